@@ -1,0 +1,276 @@
+#!/usr/bin/env python3
+"""Benchmark of the D3Q15 fp64 collide-and-stream hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one lattice time step (collide + stream) of the whole grid.
+  N = 1 : BASELINE.json configs[1] -- uniform single-level periodic pulse, 256^3, fp64.
+  N > 1 : configs[2] -- uniform 1024^3 periodic shear wave, z-slabs over N GPUs
+          (launched under torchrun, one rank per GPU).
+value   = MLUPS with the populations resident in HBM (device-timed, CUDA events).
+e2e     = MLUPS through the host-buffer API: pinned-host rho,u -> H2D -> equilibrium
+          -> K steps -> moments -> D2H of rho,u, all inside the timed region.
+roofline= fused kernel against the measured HBM copy bandwidth, 240 B/cell/step.
+cpu_baseline / --impl reference = the oracle's restatement of the reference's own
+          pass structure (ghosted 32^3 boxes, FillPatch copy, in-place dense collide,
+          FillBoundary, stream into a fresh fab, swap) timed on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MLUPS (fp64 D3Q15 BGK)"
+BYTES_PER_CELL = 240.0       # 15 fp64 loads + 15 fp64 stores
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax = float(c[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def base_grid_edges(n, max_grid=32):
+    """AMReX MakeBaseGrids chop of one direction -- the
+    max_grid_size-32 boxes the reference runs on."""
+    from lambrex_b200.boxes import chop_1d
+    return chop_1d(n, max_grid)
+
+
+def cpu_reference(sample_n, steps, warmup, tau=0.5):
+    """Time the oracle's restatement of the reference's pass structure (CPU)."""
+    from lambrex_b200 import workloads
+    from oracle import lbm_oracle as orc
+    co = orc.COracle()
+    n = sample_n
+    w = workloads.omega(tau)
+    rho = orc.user_to_fab(workloads.pulse_density(n, n, n), n, n, n)
+    f = co.equilibrium(rho, np.zeros((3, n, n, n)))
+    edges = [base_grid_edges(n)] * 3
+    if warmup:
+        f, _ = co.ref_passes(f, w, w, warmup, edges)
+    f, secs = co.ref_passes(f, w, w, steps, edges)
+    cells = float(n) ** 3
+    return {"mlups": cells * steps / secs / 1e6, "secs": secs, "cores": co.max_threads(),
+            "sample": "%d^3 periodic pulse, %d steps after %d warm-up, 32^3 ghosted boxes, "
+                      "reference pass structure, gcc -O3 -fopenmp" % (n, steps, warmup)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    warm = max(0, min(args.warmup, 1))
+    r = cpu_reference(args.cpu_sample, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["mlups"], "unit": "MLUPS",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": r["secs"] / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["mlups"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def workload_config(ngpus):
+    if ngpus == 1:
+        return {"workload": "uniform single-level periodic pulse 256^3 fp64 (BASELINE configs[1])",
+                "grid": [256, 256, 256], "tau": 0.5, "l2": "inputs (2 x 2.0 GB) larger than L2"}
+    return {"workload": "uniform 1024^3 periodic shear wave, z-slabs over %d GPUs (BASELINE configs[2])" % ngpus,
+            "grid": [1024, 1024, 1024], "tau": 0.1, "l2": "inputs larger than L2"}
+
+
+def run_single(args):
+    from lambrex_b200 import lbx, workloads
+    lbx.init()
+    n = args.grid
+    cfg = workload_config(1)
+    cfg["grid"] = [n, n, n]
+    cfg["scheme"] = args.scheme
+    scheme = lbx.PUSH if args.scheme == "push" else lbx.PULL
+    w = workloads.omega(0.5)
+    lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
+    bx, dom = lbx.box(lo, hi), lbx.domain(lo, hi)
+    cells = float(n) ** 3
+    A, B = lbx.Fab(lo, hi, 15, zero=False), lbx.Fab(lo, hi, 15, zero=False)
+    R, U = lbx.Fab(lo, hi, 1), lbx.Fab(lo, hi, 3)
+
+    # pinned host buffers in fab order (x fastest): the host side of the e2e leg
+    L = lbx.lib()
+    nb_r, nb_u = int(cells) * 8, int(cells) * 24
+    hp = ctypes.c_void_p()
+    lbx.check(L.lbx_host_alloc(ctypes.byref(hp), nb_r + nb_u))
+    host = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_double)), shape=(4 * int(cells),))
+    from lambrex_b200.layout import user_to_fab
+    host[:int(cells)] = user_to_fab(workloads.pulse_density(n, n, n), n, n, n).reshape(-1)
+    host[int(cells):] = 0.0
+
+    def upload_init():
+        lbx.check(L.lbx_h2d(R.ptr, hp.value, nb_r))
+        lbx.check(L.lbx_h2d(U.ptr, hp.value + nb_r, nb_u))
+        lbx.equilibrium(A, R, U, bx)
+
+    def steps(k):
+        nonlocal A, B
+        for _ in range(k):
+            lbx.collide_stream(A, B, bx, dom, w, w, scheme)
+            A, B = B, A
+
+    def download_moments():
+        lbx.moments(A, R, U, bx)
+        lbx.check(L.lbx_d2h(hp.value, R.ptr, nb_r))
+        lbx.check(L.lbx_d2h(hp.value + nb_r, U.ptr, nb_u))
+
+    # ---- device-resident leg -------------------------------------------------
+    upload_init()
+    steps(args.warmup)
+    lbx.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = lbx.launch_count()
+    with lbx.Timer() as t:
+        steps(args.steps)
+    launches = lbx.launch_count() - l0
+    clocks = sampler.stop()
+    ms_step = t.ms / args.steps
+    mlups = cells * args.steps / (t.ms * 1e-3) / 1e6
+    download_moments()
+    lbx.sync()
+    mass = float(host[:int(cells)].sum())
+
+    # ---- end-to-end leg ------------------------------------------------------
+    host[:int(cells)] = user_to_fab(workloads.pulse_density(n, n, n), n, n, n).reshape(-1)
+    host[int(cells):] = 0.0
+    lbx.sync()
+    t0 = time.perf_counter()
+    upload_init()
+    steps(args.steps)
+    download_moments()
+    lbx.sync()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": cells * args.steps / e2e_s / 1e6, "unit": "MLUPS",
+           "h2d_bytes_per_step": (nb_r + nb_u) / args.steps, "d2h_bytes_per_step": (nb_r + nb_u) / args.steps,
+           "note": "one job = H2D rho,u (pinned) + equilibrium + %d steps + moments + D2H rho,u" % args.steps}
+
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9
+    tr = recorded_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_collide_stream<%s>" % args.scheme, "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source")}
+
+    cpu = None
+    if not args.no_cpu:
+        r = cpu_reference(args.cpu_sample, 4, 1)
+        cpu = {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {"metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "check": {"total_mass_over_cells": mass / cells}}
+    print(json.dumps(line), flush=True)
+    lbx.check(L.lbx_host_free(hp))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=256, help="N=1 cubic grid edge (default 256 = configs[1])")
+    ap.add_argument("--scheme", default="push", choices=["push", "pull"])
+    ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU-baseline sample grid")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus == 1:
+        return run_single(args)
+    from lambrex_b200.multi_gpu_bench import run_multi   # torchrun path
+    return run_multi(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,115 @@
+/*
+ * lbx.h -- C ABI of the B200-native LAMBReX hot path (liblbx.so).
+ *
+ * This is the thin device layer the C++ host code (lambrex_b200/host/AmrSim.*)
+ * calls; nothing above AmrSim sees it.  The reference has no FFI layer: its
+ * boundary is the C++ class API (/root/reference/include/AmrSim.h:127-155,
+ * include/lambrex.h:6-7), whose private/protected members do the work these
+ * entry points replace.  Each entry point cites the reference member it
+ * replaces.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     lbx_last_error() then returns a message (per thread).
+ *   - all calls come from one host thread; kernels and copies are queued
+ *     asynchronously on the library's stream (or the one given to
+ *     lbx_set_stream) unless the name says _sync.
+ *   - device memory is owned by the library (lbx_malloc/lbx_free); host
+ *     buffers are owned by the caller.
+ *   - a "fab" is a rectangular box of cells (valid region + ghosts) stored
+ *     SoA: x fastest, then y, z, component slowest -- the FArrayBox order the
+ *     reference runs on.  Cells are addressed by GLOBAL integer indices.
+ *   - no CPU fallback: without a CUDA device lbx_init fails.
+ */
+#ifndef LBX_H
+#define LBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBX_NV 15   /* populations per cell (NMODES, include/AmrSim.h:21) */
+#define LBX_ND 3    /* dimensions          (NDIMS,  include/AmrSim.h:20) */
+#define LBX_HALO 2  /* DistFn ghost width  (include/d3q15_bgk.h:11)      */
+
+typedef struct lbx_fab {
+  void *data;      /* device pointer: component 0 of cell lo[]           */
+  int32_t lo[3];   /* lower corner of the ALLOCATED box (valid - ghosts) */
+  int32_t n[3];    /* allocated extents                                  */
+  int32_t ncomp;   /* components (15 DistFn, 1 Density, 3 velocity ...)  */
+  int32_t dtype;   /* LBX_F64 or LBX_I32                                 */
+} lbx_fab;
+enum { LBX_F64 = 0, LBX_I32 = 1 };
+
+typedef struct lbx_box { int32_t lo[3], hi[3]; } lbx_box;   /* inclusive */
+
+typedef struct lbx_domain {   /* index domain of a level + periodicity flags */
+  int32_t lo[3], hi[3], periodic[3];
+} lbx_domain;
+
+/* options for lbx_set_option */
+enum {
+  LBX_OPT_COLLIDE_LITERAL = 1, /* 1: reference operation order, no FMA (bit-exact vs a
+                                  non-FMA CPU build); 0 (default): fast structured form */
+};
+/* fused step schemes for lbx_collide_stream */
+enum {
+  LBX_PUSH = 0,  /* dst(x + c_p, p) = collide(src(x, .))_p : F <- S(C(F)), one reference step */
+  LBX_PULL = 1,  /* dst(x, .) = collide(src(x - c_p, p))   : G <- C(S(G))                    */
+};
+
+/* ---- context: replaces lambrexInit / lambrexFinalise (src/lambrex.cpp:4-14) ---- */
+int lbx_init(int device);            /* device < 0: use $LOCAL_RANK or 0 */
+int lbx_finalize(void);
+int lbx_initialized(void);
+const char *lbx_last_error(void);
+int lbx_device_count(int *count);
+int lbx_device_info(char *name, int name_cap, int *sm_count, size_t *total_bytes, size_t *free_bytes);
+int lbx_set_option(int key, int value);
+int lbx_set_stream(void *cuda_stream);   /* NULL: back to the library's own stream */
+int lbx_sync(void);
+uint64_t lbx_launch_count(void);         /* kernels launched by this library so far */
+
+/* ---- memory: replaces amrex::MultiFab allocation (include/field.h:124-129) ---- */
+int lbx_malloc(void **dev_ptr, size_t bytes);
+int lbx_free(void *dev_ptr);
+int lbx_memset(void *dev_ptr, int byte, size_t bytes);
+int lbx_host_alloc(void **host_ptr, size_t bytes);   /* pinned */
+int lbx_host_free(void *host_ptr);
+int lbx_h2d(void *dev_dst, const void *host_src, size_t bytes);
+int lbx_d2h(void *host_dst, const void *dev_src, size_t bytes);
+int lbx_d2d(void *dev_dst, const void *dev_src, size_t bytes);
+
+/* ---- timing on the launching stream (CUDA events) ---- */
+int lbx_timer_start(void);
+int lbx_timer_stop(float *milliseconds);   /* synchronises on the stop event */
+
+/* ---- kernels ---- */
+/* CalcEquilibriumDist, src/AmrSim.cpp:845-931: f <- f_eq(rho, u) on box. */
+int lbx_equilibrium(const lbx_fab *f, const lbx_fab *rho, const lbx_fab *u, const lbx_box *box);
+/* CalcHydroVars, src/AmrSim.cpp:938-979: rho, u <- moments of f on box. */
+int lbx_moments(const lbx_fab *f, const lbx_fab *rho, const lbx_fab *u, const lbx_box *box);
+/* Collide / CoarseCollide, src/AmrSim.cpp:25-107, 487-580: dst <- collide(src) on box
+ * (src may equal dst).  mask != NULL: cells with mask == fine_val get 15 zeros. */
+int lbx_collide(const lbx_fab *src, const lbx_fab *dst, const lbx_box *box, double omega_s,
+                double omega_b, const lbx_fab *mask, int fine_val);
+/* Stream + PropagatePoint, src/AmrSim.cpp:109-122, include/component.h:22-29:
+ * dst(x,p) = src(x - c_p, p) for x in box; wraps where dom->periodic, else reads ghosts. */
+int lbx_stream(const lbx_fab *src, const lbx_fab *dst, const lbx_box *box, const lbx_domain *dom);
+/* CollideAndStream, include/AmrSim.h:89-94 (CollideLevel + Stream + UpdateNow) fused into
+ * one pass over the box: 15 loads + 15 stores per cell. */
+int lbx_collide_stream(const lbx_fab *src, const lbx_fab *dst, const lbx_box *box,
+                       const lbx_domain *dom, double omega_s, double omega_b, int scheme);
+
+/* lattice constants and moment basis the kernels use (host-side query; no GPU needed):
+ * M[15][15], Minv[15][15] row-major, c[15][3], w[15].  src/AmrSim.cpp:1037-1073,
+ * include/d3q15_bgk.h:14-28. */
+void lbx_d3q15_tables(double *M, double *Minv, int32_t *c, double *w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBX_H */

@@ -1,0 +1,312 @@
+// C ABI of liblbx.so (declared in include/lbx.h).  Thin: argument checks,
+// POD -> device-view conversion, one kernel launch per call.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/lbx.h"
+#include "launch.h"
+
+namespace {
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t own = nullptr;      // the library's stream
+  cudaStream_t cur = nullptr;      // stream kernels are queued on (own or external)
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool literal = false;
+  uint64_t launches = 0;
+};
+Ctx g;
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define LBX_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                   \
+  } while (0)
+#define LBX_NEED_INIT() \
+  if (!g.ready) return fail("lbx: not initialised (call lbx_init / lambrexInit first)")
+
+int check_fab(const lbx_fab* f, int ncomp, int dtype, const char* what) {
+  if (!f || !f->data) return fail(std::string(what) + ": null fab");
+  if (f->ncomp < ncomp) return fail(std::string(what) + ": too few components");
+  if (f->dtype != dtype) return fail(std::string(what) + ": wrong dtype");
+  if (f->n[0] <= 0 || f->n[1] <= 0 || f->n[2] <= 0) return fail(std::string(what) + ": empty fab");
+  return 0;
+}
+// every cell of box grown by `grow` (clipped by wrap in periodic directions) must exist in f
+int check_cover(const lbx_fab* f, const lbx_box* b, int grow, const lbx_domain* dom, const char* what) {
+  for (int d = 0; d < 3; ++d) {
+    if (b->hi[d] < b->lo[d]) return fail(std::string(what) + ": empty box");
+    int lo = b->lo[d] - grow, hi = b->hi[d] + grow;
+    if (dom && dom->periodic[d]) {
+      // wrapped neighbours stay inside the domain
+      if (lo < dom->lo[d]) lo = dom->lo[d];
+      if (hi > dom->hi[d]) hi = dom->hi[d];
+      if (grow && (b->lo[d] == dom->lo[d] || b->hi[d] == dom->hi[d])) {
+        // wrap reaches the opposite side of the domain: fab must span it
+        if (f->lo[d] > dom->lo[d] || f->lo[d] + f->n[d] - 1 < dom->hi[d])
+          return fail(std::string(what) + ": periodic wrap needs a fab spanning the domain");
+      }
+    }
+    if (lo < f->lo[d] || hi > f->lo[d] + f->n[d] - 1)
+      return fail(std::string(what) + ": box (+stencil) not covered by fab");
+  }
+  if ((long long)(b->hi[1] - b->lo[1]) >= 65535 || (long long)(b->hi[2] - b->lo[2]) >= 65535)
+    return fail(std::string(what) + ": box exceeds 65535 rows/planes per launch");
+  return 0;
+}
+
+lbx::DFab dfab(const lbx_fab* f) {
+  lbx::DFab d;
+  d.p = static_cast<double*>(f->data);
+  for (int a = 0; a < 3; ++a) { d.lo[a] = f->lo[a]; d.n[a] = f->n[a]; }
+  return d;
+}
+lbx::DBox dbox(const lbx_box* b) {
+  lbx::DBox d;
+  for (int a = 0; a < 3; ++a) { d.lo[a] = b->lo[a]; d.hi[a] = b->hi[a]; }
+  return d;
+}
+lbx::DDom ddom(const lbx_domain* b) {
+  lbx::DDom d;
+  for (int a = 0; a < 3; ++a) { d.lo[a] = b->lo[a]; d.hi[a] = b->hi[a]; d.periodic[a] = b->periodic[a]; }
+  return d;
+}
+const lbx::Launchers& L() { return g.literal ? lbx::launchers_literal() : lbx::launchers_fast(); }
+
+int after_launch(const char* what) {
+  ++g.launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lbx_last_error(void) { return g_err.c_str(); }
+
+int lbx_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+  *count = n;
+  return 0;
+}
+
+int lbx_init(int device) {
+  if (g.ready) return 0;
+  int n = 0;
+  if (lbx_device_count(&n) || n == 0)
+    return fail("lbx_init: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0) {
+    const char* lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % n : 0;
+  }
+  if (device >= n) return fail("lbx_init: device index out of range");
+  LBX_CUDA(cudaSetDevice(device));
+  LBX_CUDA(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
+  LBX_CUDA(cudaEventCreate(&g.t0));
+  LBX_CUDA(cudaEventCreate(&g.t1));
+  g.cur = g.own;
+  g.device = device;
+  g.ready = true;
+  return 0;
+}
+
+int lbx_finalize(void) {
+  if (!g.ready) return 0;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.own);
+  cudaEventDestroy(g.t0);
+  cudaEventDestroy(g.t1);
+  cudaStreamDestroy(g.own);
+  g = Ctx();
+  return 0;
+}
+
+int lbx_initialized(void) { return g.ready ? 1 : 0; }
+
+int lbx_device_info(char* name, int name_cap, int* sm_count, size_t* total_bytes, size_t* free_bytes) {
+  LBX_NEED_INIT();
+  cudaDeviceProp p;
+  LBX_CUDA(cudaGetDeviceProperties(&p, g.device));
+  if (name && name_cap > 0) { strncpy(name, p.name, name_cap - 1); name[name_cap - 1] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  size_t fr = 0, tot = 0;
+  LBX_CUDA(cudaMemGetInfo(&fr, &tot));
+  if (total_bytes) *total_bytes = tot;
+  if (free_bytes) *free_bytes = fr;
+  return 0;
+}
+
+int lbx_set_option(int key, int value) {
+  switch (key) {
+    case LBX_OPT_COLLIDE_LITERAL: g.literal = (value != 0); return 0;
+    default: return fail("lbx_set_option: unknown key");
+  }
+}
+
+int lbx_set_stream(void* s) {
+  LBX_NEED_INIT();
+  g.cur = s ? static_cast<cudaStream_t>(s) : g.own;
+  return 0;
+}
+
+int lbx_sync(void) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaStreamSynchronize(g.cur));
+  return 0;
+}
+
+uint64_t lbx_launch_count(void) { return g.launches; }
+
+int lbx_malloc(void** p, size_t bytes) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+  return 0;
+}
+int lbx_free(void* p) {
+  if (!p) return 0;
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaStreamSynchronize(g.cur));
+  LBX_CUDA(cudaFree(p));
+  return 0;
+}
+int lbx_memset(void* p, int byte, size_t bytes) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaMemsetAsync(p, byte, bytes, g.cur));
+  return 0;
+}
+int lbx_host_alloc(void** p, size_t bytes) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+int lbx_host_free(void* p) {
+  if (!p) return 0;
+  LBX_CUDA(cudaFreeHost(p));
+  return 0;
+}
+int lbx_h2d(void* d, const void* h, size_t bytes) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g.cur));
+  return 0;
+}
+int lbx_d2h(void* h, const void* d, size_t bytes) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, g.cur));
+  return 0;
+}
+int lbx_d2d(void* dst, const void* src, size_t bytes) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g.cur));
+  return 0;
+}
+
+int lbx_timer_start(void) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaEventRecord(g.t0, g.cur));
+  return 0;
+}
+int lbx_timer_stop(float* ms) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaEventRecord(g.t1, g.cur));
+  LBX_CUDA(cudaEventSynchronize(g.t1));
+  LBX_CUDA(cudaEventElapsedTime(ms, g.t0, g.t1));
+  return 0;
+}
+
+int lbx_equilibrium(const lbx_fab* f, const lbx_fab* rho, const lbx_fab* u, const lbx_box* box) {
+  LBX_NEED_INIT();
+  if (check_fab(f, LBX_NV, LBX_F64, "lbx_equilibrium f") || check_fab(rho, 1, LBX_F64, "lbx_equilibrium rho") ||
+      check_fab(u, 3, LBX_F64, "lbx_equilibrium u"))
+    return 1;
+  if (check_cover(f, box, 0, nullptr, "lbx_equilibrium f") || check_cover(rho, box, 0, nullptr, "lbx_equilibrium rho") ||
+      check_cover(u, box, 0, nullptr, "lbx_equilibrium u"))
+    return 1;
+  L().equilibrium(g.cur, dfab(f), dfab(rho), dfab(u), dbox(box));
+  return after_launch("lbx_equilibrium");
+}
+
+int lbx_moments(const lbx_fab* f, const lbx_fab* rho, const lbx_fab* u, const lbx_box* box) {
+  LBX_NEED_INIT();
+  if (check_fab(f, LBX_NV, LBX_F64, "lbx_moments f") || check_fab(rho, 1, LBX_F64, "lbx_moments rho") ||
+      check_fab(u, 3, LBX_F64, "lbx_moments u"))
+    return 1;
+  if (check_cover(f, box, 0, nullptr, "lbx_moments f") || check_cover(rho, box, 0, nullptr, "lbx_moments rho") ||
+      check_cover(u, box, 0, nullptr, "lbx_moments u"))
+    return 1;
+  L().moments(g.cur, dfab(f), dfab(rho), dfab(u), dbox(box));
+  return after_launch("lbx_moments");
+}
+
+int lbx_collide(const lbx_fab* src, const lbx_fab* dst, const lbx_box* box, double omega_s, double omega_b,
+                const lbx_fab* mask, int fine_val) {
+  LBX_NEED_INIT();
+  if (check_fab(src, LBX_NV, LBX_F64, "lbx_collide src") || check_fab(dst, LBX_NV, LBX_F64, "lbx_collide dst")) return 1;
+  if (check_cover(src, box, 0, nullptr, "lbx_collide src") || check_cover(dst, box, 0, nullptr, "lbx_collide dst")) return 1;
+  lbx::DMask m;
+  memset(&m, 0, sizeof(m));
+  if (mask) {
+    if (check_fab(mask, 1, LBX_I32, "lbx_collide mask") || check_cover(mask, box, 0, nullptr, "lbx_collide mask")) return 1;
+    m.p = static_cast<const int*>(mask->data);
+    for (int a = 0; a < 3; ++a) { m.lo[a] = mask->lo[a]; m.n[a] = mask->n[a]; }
+  }
+  L().collide(g.cur, dfab(src), dfab(dst), dbox(box), omega_s, omega_b, m, fine_val);
+  return after_launch("lbx_collide");
+}
+
+int lbx_stream(const lbx_fab* src, const lbx_fab* dst, const lbx_box* box, const lbx_domain* dom) {
+  LBX_NEED_INIT();
+  if (!dom) return fail("lbx_stream: null domain");
+  if (check_fab(src, LBX_NV, LBX_F64, "lbx_stream src") || check_fab(dst, LBX_NV, LBX_F64, "lbx_stream dst")) return 1;
+  if (src->data == dst->data) return fail("lbx_stream: src and dst must not alias");
+  if (check_cover(src, box, 1, dom, "lbx_stream src") || check_cover(dst, box, 0, nullptr, "lbx_stream dst")) return 1;
+  L().stream(g.cur, dfab(src), dfab(dst), dbox(box), ddom(dom));
+  return after_launch("lbx_stream");
+}
+
+int lbx_collide_stream(const lbx_fab* src, const lbx_fab* dst, const lbx_box* box, const lbx_domain* dom,
+                       double omega_s, double omega_b, int scheme) {
+  LBX_NEED_INIT();
+  if (!dom) return fail("lbx_collide_stream: null domain");
+  if (scheme != LBX_PUSH && scheme != LBX_PULL) return fail("lbx_collide_stream: unknown scheme");
+  if (check_fab(src, LBX_NV, LBX_F64, "lbx_collide_stream src") ||
+      check_fab(dst, LBX_NV, LBX_F64, "lbx_collide_stream dst"))
+    return 1;
+  if (src->data == dst->data) return fail("lbx_collide_stream: src and dst must not alias");
+  const bool push = (scheme == LBX_PUSH);
+  if (check_cover(src, box, push ? 0 : 1, push ? nullptr : dom, "lbx_collide_stream src") ||
+      check_cover(dst, box, push ? 1 : 0, push ? dom : nullptr, "lbx_collide_stream dst"))
+    return 1;
+  L().collide_stream(g.cur, dfab(src), dfab(dst), dbox(box), ddom(dom), omega_s, omega_b, scheme);
+  return after_launch("lbx_collide_stream");
+}
+
+void lbx_d3q15_tables(double* M, double* Minv, int32_t* c, double* w) {
+  for (int m = 0; m < LBX_NV; ++m)
+    for (int p = 0; p < LBX_NV; ++p) {
+      M[m * LBX_NV + p] = lbx::mode_entry(m, p);
+      Minv[p * LBX_NV + m] = lbx::inv_entry(p, m);
+    }
+  for (int p = 0; p < LBX_NV; ++p) {
+    c[3 * p + 0] = lbx::cx(p);
+    c[3 * p + 1] = lbx::cy(p);
+    c[3 * p + 2] = lbx::cz(p);
+    w[p] = (double)lbx::w_num(p) / (double)lbx::w_den(p);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+"""ctypes binding of the C ABI in include/lbx.h (liblbx.so).
+
+Plumbing only: loads the in-tree shared library, mirrors the POD structs, and
+offers a small ``Fab`` convenience (device allocation + host<->device copies in
+fab order).  All compute happens in the CUDA library; nothing here falls back to
+the CPU -- a missing library or device raises ``LbxError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+NV, ND, HALO = 15, 3, 2
+F64, I32 = 0, 1
+PUSH, PULL = 0, 1
+OPT_COLLIDE_LITERAL = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblbx.so")
+
+
+class LbxError(RuntimeError):
+    pass
+
+
+class lbx_fab(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("lo", ctypes.c_int32 * 3), ("n", ctypes.c_int32 * 3),
+                ("ncomp", ctypes.c_int32), ("dtype", ctypes.c_int32)]
+
+
+class lbx_box(ctypes.Structure):
+    _fields_ = [("lo", ctypes.c_int32 * 3), ("hi", ctypes.c_int32 * 3)]
+
+
+class lbx_domain(ctypes.Structure):
+    _fields_ = [("lo", ctypes.c_int32 * 3), ("hi", ctypes.c_int32 * 3), ("periodic", ctypes.c_int32 * 3)]
+
+
+# every symbol include/lbx.h declares: name -> (restype, argtypes)
+_vp, _sz, _i, _d = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_double
+_fp, _bp, _dp = ctypes.POINTER(lbx_fab), ctypes.POINTER(lbx_box), ctypes.POINTER(lbx_domain)
+SYMBOLS = {
+    "lbx_init": (_i, [_i]),
+    "lbx_finalize": (_i, []),
+    "lbx_initialized": (_i, []),
+    "lbx_last_error": (ctypes.c_char_p, []),
+    "lbx_device_count": (_i, [ctypes.POINTER(_i)]),
+    "lbx_device_info": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(_i), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "lbx_set_option": (_i, [_i, _i]),
+    "lbx_set_stream": (_i, [_vp]),
+    "lbx_sync": (_i, []),
+    "lbx_launch_count": (ctypes.c_uint64, []),
+    "lbx_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "lbx_free": (_i, [_vp]),
+    "lbx_memset": (_i, [_vp, _i, _sz]),
+    "lbx_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "lbx_host_free": (_i, [_vp]),
+    "lbx_h2d": (_i, [_vp, _vp, _sz]),
+    "lbx_d2h": (_i, [_vp, _vp, _sz]),
+    "lbx_d2d": (_i, [_vp, _vp, _sz]),
+    "lbx_timer_start": (_i, []),
+    "lbx_timer_stop": (_i, [ctypes.POINTER(ctypes.c_float)]),
+    "lbx_equilibrium": (_i, [_fp, _fp, _fp, _bp]),
+    "lbx_moments": (_i, [_fp, _fp, _fp, _bp]),
+    "lbx_collide": (_i, [_fp, _fp, _bp, _d, _d, _fp, _i]),
+    "lbx_stream": (_i, [_fp, _fp, _bp, _dp]),
+    "lbx_collide_stream": (_i, [_fp, _fp, _bp, _dp, _d, _d, _i]),
+    "lbx_d3q15_tables": (None, [ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int32),
+                                ctypes.POINTER(_d)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load liblbx.so (once).  Raises LbxError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LbxError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(no CPU fallback exists)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)      # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise LbxError(lib().lbx_last_error().decode())
+
+
+def init(device=-1):
+    check(lib().lbx_init(device))
+
+
+def finalize():
+    check(lib().lbx_finalize())
+
+
+def sync():
+    check(lib().lbx_sync())
+
+
+def set_option(key, value):
+    check(lib().lbx_set_option(key, int(value)))
+
+
+def launch_count():
+    return int(lib().lbx_launch_count())
+
+
+def device_info():
+    name = ctypes.create_string_buffer(256)
+    sm = _i(0)
+    tot, fr = _sz(0), _sz(0)
+    check(lib().lbx_device_info(name, 256, ctypes.byref(sm), ctypes.byref(tot), ctypes.byref(fr)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "total_bytes": tot.value, "free_bytes": fr.value}
+
+
+def tables():
+    M = np.empty((NV, NV))
+    Mi = np.empty((NV, NV))
+    c = np.empty((NV, 3), dtype=np.int32)
+    w = np.empty(NV)
+    P = ctypes.POINTER(_d)
+    lib().lbx_d3q15_tables(M.ctypes.data_as(P), Mi.ctypes.data_as(P),
+                           c.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), w.ctypes.data_as(P))
+    return M, Mi, c, w
+
+
+def box(lo, hi):
+    b = lbx_box()
+    b.lo[:] = [int(x) for x in lo]
+    b.hi[:] = [int(x) for x in hi]
+    return b
+
+
+def domain(lo, hi, periodic=(1, 1, 1)):
+    d = lbx_domain()
+    d.lo[:] = [int(x) for x in lo]
+    d.hi[:] = [int(x) for x in hi]
+    d.periodic[:] = [int(x) for x in periodic]
+    return d
+
+
+class Timer:
+    def __enter__(self):
+        check(lib().lbx_timer_start())
+        return self
+
+    def __exit__(self, *exc):
+        ms = ctypes.c_float(0)
+        check(lib().lbx_timer_stop(ctypes.byref(ms)))
+        self.ms = float(ms.value)
+        return False
+
+
+class Fab:
+    """One device fab: valid box [lo, hi] grown by ``ng`` ghosts per direction,
+    ``ncomp`` SoA planes, x fastest.  Host mirror arrays are [comp, z, y, x]."""
+
+    def __init__(self, lo, hi, ncomp, ng=(0, 0, 0), dtype=F64, zero=True):
+        if isinstance(ng, int):
+            ng = (ng, ng, ng)
+        self.valid = (tuple(int(x) for x in lo), tuple(int(x) for x in hi))
+        self.ng = tuple(int(g) for g in ng)
+        self.ncomp, self.dtype = int(ncomp), dtype
+        self.alo = tuple(l - g for l, g in zip(self.valid[0], self.ng))
+        self.n = tuple(h - l + 1 + 2 * g for l, h, g in zip(self.valid[0], self.valid[1], self.ng))
+        self.itemsize = 8 if dtype == F64 else 4
+        self.nbytes = self.ncomp * self.n[0] * self.n[1] * self.n[2] * self.itemsize
+        p = _vp()
+        check(lib().lbx_malloc(ctypes.byref(p), self.nbytes))
+        self.ptr = p.value
+        if zero:
+            check(lib().lbx_memset(self.ptr, 0, self.nbytes))
+        self.c = lbx_fab()
+        self.c.data = self.ptr
+        self.c.lo[:] = self.alo
+        self.c.n[:] = self.n
+        self.c.ncomp, self.c.dtype = self.ncomp, dtype
+
+    @property
+    def shape(self):            # host mirror shape
+        return (self.ncomp, self.n[2], self.n[1], self.n[0])
+
+    @property
+    def npdtype(self):
+        return np.float64 if self.dtype == F64 else np.int32
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+    def valid_box(self, grow=0):
+        return box([l - grow for l in self.valid[0]], [h + grow for h in self.valid[1]])
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=self.npdtype)
+        assert a.shape == self.shape, (a.shape, self.shape)
+        check(lib().lbx_h2d(self.ptr, a.ctypes.data, self.nbytes))
+        sync()
+
+    def download(self):
+        a = np.empty(self.shape, dtype=self.npdtype)
+        check(lib().lbx_d2h(a.ctypes.data, self.ptr, self.nbytes))
+        sync()
+        return a
+
+    def upload_valid(self, a):
+        """a: [comp, nz, ny, nx] over the valid box; ghosts keep their content."""
+        full = self.download()
+        gx, gy, gz = self.ng
+        full[:, gz:self.n[2] - gz, gy:self.n[1] - gy, gx:self.n[0] - gx] = a
+        self.upload(full)
+
+    def download_valid(self):
+        gx, gy, gz = self.ng
+        return np.ascontiguousarray(self.download()[:, gz:self.n[2] - gz, gy:self.n[1] - gy, gx:self.n[0] - gx])
+
+    def free(self):
+        if self.ptr:
+            check(lib().lbx_free(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None and _lib.lbx_initialized():
+                _lib.lbx_free(self.ptr)
+        except Exception:
+            pass
+
+
+def equilibrium(f, rho, u, bx):
+    check(lib().lbx_equilibrium(f.ref(), rho.ref(), u.ref(), ctypes.byref(bx)))
+
+
+def moments(f, rho, u, bx):
+    check(lib().lbx_moments(f.ref(), rho.ref(), u.ref(), ctypes.byref(bx)))
+
+
+def collide(src, dst, bx, omega_s, omega_b, mask=None, fine_val=1):
+    check(lib().lbx_collide(src.ref(), dst.ref(), ctypes.byref(bx), omega_s, omega_b,
+                            mask.ref() if mask is not None else None, fine_val))
+
+
+def stream(src, dst, bx, dom):
+    check(lib().lbx_stream(src.ref(), dst.ref(), ctypes.byref(bx), ctypes.byref(dom)))
+
+
+def collide_stream(src, dst, bx, dom, omega_s, omega_b, scheme=PUSH):
+    check(lib().lbx_collide_stream(src.ref(), dst.ref(), ctypes.byref(bx), ctypes.byref(dom),
+                                   omega_s, omega_b, scheme))
