@@ -132,7 +132,7 @@ def cpu_reference(sample_n, steps, warmup, tau=0.5):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return                      # under torchrun only rank 0 measures the CPU arm
     steps = max(1, min(args.steps, 8))
     warm = max(0, min(args.warmup, 1))
     r = cpu_reference(args.cpu_sample, steps, warm)
@@ -165,7 +165,7 @@ def run_single(args):
     cfg = workload_config(1)
     cfg["grid"] = [n, n, n]
     cfg["scheme"] = args.scheme
-    scheme = lbx.PUSH if args.scheme == "push" else lbx.PULL
+    scheme = {"push": lbx.PUSH, "pull": lbx.PULL, "slab": None}[args.scheme]
     w = workloads.omega(0.5)
     lo, hi = (0, 0, 0), (n - 1, n - 1, n - 1)
     bx, dom = lbx.box(lo, hi), lbx.domain(lo, hi)
@@ -191,7 +191,10 @@ def run_single(args):
     def steps(k):
         nonlocal A, B
         for _ in range(k):
-            lbx.collide_stream(A, B, bx, dom, w, w, scheme)
+            if scheme is None:      # the multi-GPU kernel with both neighbours = this GPU
+                lbx.collide_stream_slab(A, B, B, B, bx, dom, w, w)
+            else:
+                lbx.collide_stream(A, B, bx, dom, w, w, scheme)
             A, B = B, A
 
     def download_moments():
@@ -234,7 +237,8 @@ def run_single(args):
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9
     tr = recorded_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_collide_stream<%s>" % args.scheme, "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "k_collide_stream_slab" if scheme is None else
+                "k_collide_stream<%s>" % args.scheme, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source")}
 
@@ -259,7 +263,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256, help="N=1 cubic grid edge (default 256 = configs[1])")
-    ap.add_argument("--scheme", default="push", choices=["push", "pull"])
+    ap.add_argument("--scheme", default="push", choices=["push", "pull", "slab"])
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 face exchange: peer stores fused into the step kernel, or packed NCCL send/recv")
+    ap.add_argument("--grid-multi", type=int, default=1024, help="N>1 cubic grid edge (default 1024 = configs[2])")
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU-baseline sample grid")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -269,7 +276,9 @@ def main():
     if args.gpus == 1:
         return run_single(args)
     from lambrex_b200.multi_gpu_bench import run_multi   # torchrun path
-    return run_multi(args)
+    helpers = {"ClockSampler": ClockSampler, "measured_peak": measured_peak, "recorded_traffic": lambda: None,
+               "workload_config": workload_config, "METRIC": METRIC, "BYTES_PER_CELL": BYTES_PER_CELL}
+    return run_multi(args, helpers)
 
 
 if __name__ == "__main__":

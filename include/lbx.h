@@ -54,6 +54,8 @@ typedef struct lbx_domain {   /* index domain of a level + periodicity flags */
 enum {
   LBX_OPT_COLLIDE_LITERAL = 1, /* 1: reference operation order, no FMA (bit-exact vs a
                                   non-FMA CPU build); 0 (default): fast structured form */
+  LBX_OPT_SMEM_PAD = 2,        /* bytes of dynamic shared memory added to the fused kernels' launches to
+                                  cap resident CTAs per SM (tuning knob; 0 = uncapped, max 49152) */
 };
 /* fused step schemes for lbx_collide_stream */
 enum {
@@ -69,7 +71,8 @@ const char *lbx_last_error(void);
 int lbx_device_count(int *count);
 int lbx_device_info(char *name, int name_cap, int *sm_count, size_t *total_bytes, size_t *free_bytes);
 int lbx_set_option(int key, int value);
-int lbx_set_stream(void *cuda_stream);   /* NULL: back to the library's own stream */
+int lbx_set_stream(void *cuda_stream);   /* NULL: back to the library's own stream;
+                                            the legacy default stream is cudaStreamLegacy (0x1) */
 int lbx_sync(void);
 uint64_t lbx_launch_count(void);         /* kernels launched by this library so far */
 
@@ -103,6 +106,35 @@ int lbx_stream(const lbx_fab *src, const lbx_fab *dst, const lbx_box *box, const
  * one pass over the box: 15 loads + 15 stores per cell. */
 int lbx_collide_stream(const lbx_fab *src, const lbx_fab *dst, const lbx_box *box,
                        const lbx_domain *dom, double omega_s, double omega_b, int scheme);
+
+/* ---- multi-GPU uniform path: z-slabs, one per GPU ----
+ * Replaces the FillBoundary of CollideLevel (src/AmrSim.cpp:132) between boxes owned by
+ * different GPUs.  Two transports:
+ *   peer stores : lbx_collide_stream_slab writes the 5 populations crossing each z face
+ *                 straight into the neighbour's fab through CUDA-IPC peer pointers
+ *                 (lbx_ipc_*), ordered per step by lbx_peer_signal / lbx_peer_wait;
+ *   packed halos: lbx_halo_pack / lbx_halo_unpack move the 5 crossing populations of a
+ *                 face between a fab and a contiguous buffer the caller sends (NCCL). */
+#define LBX_IPC_HANDLE_BYTES 64
+int lbx_ipc_get_handle(void *dev_ptr, unsigned char *handle /* [LBX_IPC_HANDLE_BYTES] */);
+int lbx_ipc_open_handle(const unsigned char *handle, void **peer_ptr);
+int lbx_ipc_close_handle(void *peer_ptr);
+/* store `value` (release, system scope) to up to two flags (NULL is skipped), after all
+ * work queued so far on the stream. */
+int lbx_peer_signal(uint64_t *flag_a, uint64_t *flag_b, uint64_t value);
+/* block the STREAM (not the host) until both flags hold >= value; after timeout_ns the
+ * wait gives up and lbx_peer_error() / lbx_sync() report it. */
+int lbx_peer_wait(const uint64_t *flag_a, const uint64_t *flag_b, uint64_t value, uint64_t timeout_ns);
+int lbx_peer_error(void);   /* 1 if a wait timed out since the last call; clears the flag */
+/* One reference step (CollideAndStream, include/AmrSim.h:89-94) of this rank's slab `box`
+ * (global indices).  Destination planes outside `dst` after the periodic wrap of `dom` are
+ * taken from `dst_dn` (k-1) / `dst_up` (k+1): peer fabs, or `dst` itself on one GPU. */
+int lbx_collide_stream_slab(const lbx_fab *src, const lbx_fab *dst, const lbx_fab *dst_dn,
+                            const lbx_fab *dst_up, const lbx_box *box, const lbx_domain *dom,
+                            double omega_s, double omega_b);
+/* face: 0 +x, 1 -x, 2 +y, 3 -y, 4 +z, 5 -z; buf holds [5][cells of region] doubles. */
+int lbx_halo_pack(const lbx_fab *f, const lbx_box *region, int face, double *buf);
+int lbx_halo_unpack(const lbx_fab *f, const lbx_box *region, int face, const double *buf);
 
 /* lattice constants and moment basis the kernels use (host-side query; no GPU needed):
  * M[15][15], Minv[15][15] row-major, c[15][3], w[15].  src/AmrSim.cpp:1037-1073,

@@ -101,6 +101,71 @@ __global__ void __launch_bounds__(BX) k_collide_stream(DFab src, DFab dst, DBox 
 }
 
 // ---------------------------------------------------------------------------
+// Fused collide + stream + z-face exchange for the slab-decomposed uniform path
+// (one z-slab per GPU).  Push form.  Cells are addressed by GLOBAL
+// k; a destination plane that is not part of this rank's fab (k+1 above the slab,
+// k-1 below it, after the periodic wrap of the global domain) lives in the
+// neighbour's fab, reached through a CUDA-IPC peer pointer: the 5 populations
+// crossing the face are stored straight into the neighbour's HBM over NVLink by
+// the boundary-plane CTAs while the interior CTAs keep the local HBM busy.  This
+// replaces CollideLevel + FillBoundary + Stream + UpdateNow
+// (src/AmrSim.cpp:124-135, 109-122; include/AmrSim.h:89-94).  With up = dn = dst
+// (one GPU) it degenerates to k_collide_stream<.., true>.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool has_plane(const DFab& f, int k) {
+  return k >= f.lo[2] && k < f.lo[2] + f.n[2];
+}
+
+template <class C>
+__global__ void __launch_bounds__(BX) k_collide_stream_slab(DFab src, DFab dst, DFab dn, DFab up, DBox box,
+                                                            DDom dom, double omega_s, double omega_b) {
+  const int i = box.lo[0] + blockIdx.x * BX + threadIdx.x;
+  const int j = box.lo[1] + blockIdx.y;
+  const int k = box.lo[2] + blockIdx.z;
+  if (i > box.hi[0]) return;
+
+  int ip = i + 1, im = i - 1, jp = j + 1, jm = j - 1, kp = k + 1, km = k - 1;
+  if (dom.periodic[0]) { if (ip > dom.hi[0]) ip = dom.lo[0]; if (im < dom.lo[0]) im = dom.hi[0]; }
+  if (dom.periodic[1]) { if (jp > dom.hi[1]) jp = dom.lo[1]; if (jm < dom.lo[1]) jm = dom.hi[1]; }
+  if (dom.periodic[2]) { if (kp > dom.hi[2]) kp = dom.lo[2]; if (km < dom.lo[2]) km = dom.hi[2]; }
+
+  // block-uniform choice of the fab that owns plane k+1 / k-1
+  const DFab& fp = has_plane(dst, kp) ? dst : up;
+  const DFab& fm = has_plane(dst, km) ? dst : dn;
+  const long long sc0 = plane_stride(dst), scp = plane_stride(fp), scm = plane_stride(fm);
+  double* const b0 = dst.p;
+  double* const bp = fp.p;
+  double* const bm = fm.p;
+  const long long r00 = row_off(dst, j, k), rp0 = row_off(dst, jp, k), rm0 = row_off(dst, jm, k);
+  const long long r0p = row_off(fp, j, kp), rpp = row_off(fp, jp, kp), rmp = row_off(fp, jm, kp);
+  const long long r0m = row_off(fm, j, km), rpm = row_off(fm, jp, km), rmm = row_off(fm, jm, km);
+
+  const long long ssc = plane_stride(src), o = row_off(src, j, k) + i;
+  double f[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) f[p] = __ldcs(src.p + p * ssc + o);
+  C::collide(f, omega_s, omega_b);
+  // same-plane populations (c_z = 0)
+  __stcs(b0 + 0 * sc0 + r00 + i, f[0]);
+  __stcs(b0 + 1 * sc0 + r00 + ip, f[1]);
+  __stcs(b0 + 2 * sc0 + r00 + im, f[2]);
+  __stcs(b0 + 3 * sc0 + rp0 + i, f[3]);
+  __stcs(b0 + 4 * sc0 + rm0 + i, f[4]);
+  // c_z = +1 : plane k+1 (local or the upper neighbour's fab)
+  __stcs(bp + 5 * scp + r0p + i, f[5]);
+  __stcs(bp + 7 * scp + rpp + ip, f[7]);
+  __stcs(bp + 9 * scp + rmp + ip, f[9]);
+  __stcs(bp + 11 * scp + rpp + im, f[11]);
+  __stcs(bp + 13 * scp + rmp + im, f[13]);
+  // c_z = -1 : plane k-1 (local or the lower neighbour's fab)
+  __stcs(bm + 6 * scm + r0m + i, f[6]);
+  __stcs(bm + 8 * scm + rpm + ip, f[8]);
+  __stcs(bm + 10 * scm + rmm + ip, f[10]);
+  __stcs(bm + 12 * scm + rpm + im, f[12]);
+  __stcs(bm + 14 * scm + rmm + im, f[14]);
+}
+
+// ---------------------------------------------------------------------------
 // Collide valid cells (src -> dst, may alias).  Optional int mask (1 comp, any
 // ghost width): cells with mask == fine_val get all 15 populations zeroed
 // (CoarseCollide, src/AmrSim.cpp:499-500).

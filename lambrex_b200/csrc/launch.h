@@ -4,12 +4,17 @@
 #include "kernels.cuh"
 
 namespace lbx {
+// dynamic shared memory added to the fused kernels' launches purely to cap resident CTAs/SM
+// (occupancy tuning knob, LBX_OPT_SMEM_PAD); 0 = no cap
+extern int g_smem_pad;
 struct Launchers {
   void (*equilibrium)(cudaStream_t, DFab f, DFab rho, DFab u, DBox box);
   void (*moments)(cudaStream_t, DFab f, DFab rho, DFab u, DBox box);
   void (*collide)(cudaStream_t, DFab src, DFab dst, DBox box, double ws, double wb, DMask mask, int fine_val);
   void (*stream)(cudaStream_t, DFab src, DFab dst, DBox box, DDom dom);
   void (*collide_stream)(cudaStream_t, DFab src, DFab dst, DBox box, DDom dom, double ws, double wb, int scheme);
+  void (*collide_stream_slab)(cudaStream_t, DFab src, DFab dst, DFab dn, DFab up, DBox box, DDom dom, double ws,
+                              double wb);
 };
 const Launchers& launchers_fast();
 const Launchers& launchers_literal();

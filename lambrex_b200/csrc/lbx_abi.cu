@@ -8,6 +8,9 @@
 
 #include "../../include/lbx.h"
 #include "launch.h"
+#include "kernels_util.cuh"
+
+namespace lbx { int g_smem_pad = 0; }
 
 namespace {
 
@@ -18,6 +21,7 @@ struct Ctx {
   cudaStream_t cur = nullptr;      // stream kernels are queued on (own or external)
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   bool literal = false;
+  int* peer_err = nullptr;         // host-mapped: set by k_peer_wait on timeout
   uint64_t launches = 0;
 };
 Ctx g;
@@ -119,6 +123,8 @@ int lbx_init(int device) {
   LBX_CUDA(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
   LBX_CUDA(cudaEventCreate(&g.t0));
   LBX_CUDA(cudaEventCreate(&g.t1));
+  LBX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g.peer_err), sizeof(int), cudaHostAllocMapped));
+  *g.peer_err = 0;
   g.cur = g.own;
   g.device = device;
   g.ready = true;
@@ -132,6 +138,7 @@ int lbx_finalize(void) {
   cudaEventDestroy(g.t0);
   cudaEventDestroy(g.t1);
   cudaStreamDestroy(g.own);
+  if (g.peer_err) cudaFreeHost(g.peer_err);
   g = Ctx();
   return 0;
 }
@@ -154,12 +161,17 @@ int lbx_device_info(char* name, int name_cap, int* sm_count, size_t* total_bytes
 int lbx_set_option(int key, int value) {
   switch (key) {
     case LBX_OPT_COLLIDE_LITERAL: g.literal = (value != 0); return 0;
+    case LBX_OPT_SMEM_PAD:
+      if (value < 0 || value > 48 * 1024) return fail("lbx_set_option: LBX_OPT_SMEM_PAD must be 0..49152");
+      lbx::g_smem_pad = value;
+      return 0;
     default: return fail("lbx_set_option: unknown key");
   }
 }
 
 int lbx_set_stream(void* s) {
   LBX_NEED_INIT();
+  // NULL: the library's own stream; pass cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2) for the default streams
   g.cur = s ? static_cast<cudaStream_t>(s) : g.own;
   return 0;
 }
@@ -167,6 +179,7 @@ int lbx_set_stream(void* s) {
 int lbx_sync(void) {
   LBX_NEED_INIT();
   LBX_CUDA(cudaStreamSynchronize(g.cur));
+  if (*g.peer_err) return fail("lbx_sync: a peer wait timed out (neighbour GPU did not signal)");
   return 0;
 }
 
@@ -293,6 +306,108 @@ int lbx_collide_stream(const lbx_fab* src, const lbx_fab* dst, const lbx_box* bo
     return 1;
   L().collide_stream(g.cur, dfab(src), dfab(dst), dbox(box), ddom(dom), omega_s, omega_b, scheme);
   return after_launch("lbx_collide_stream");
+}
+
+int lbx_ipc_get_handle(void* p, unsigned char* handle) {
+  LBX_NEED_INIT();
+  static_assert(sizeof(cudaIpcMemHandle_t) == LBX_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  LBX_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+int lbx_ipc_open_handle(const unsigned char* handle, void** p) {
+  LBX_NEED_INIT();
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  LBX_CUDA(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int lbx_ipc_close_handle(void* p) {
+  if (!p) return 0;
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaStreamSynchronize(g.cur));
+  LBX_CUDA(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+
+int lbx_peer_signal(uint64_t* a, uint64_t* b, uint64_t value) {
+  LBX_NEED_INIT();
+  lbx::k_peer_signal<<<1, 1, 0, g.cur>>>(reinterpret_cast<unsigned long long*>(a),
+                                         reinterpret_cast<unsigned long long*>(b), value);
+  return after_launch("lbx_peer_signal");
+}
+int lbx_peer_wait(const uint64_t* a, const uint64_t* b, uint64_t value, uint64_t timeout_ns) {
+  LBX_NEED_INIT();
+  int* derr = nullptr;
+  LBX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&derr), g.peer_err, 0));
+  lbx::k_peer_wait<<<1, 1, 0, g.cur>>>(reinterpret_cast<const unsigned long long*>(a),
+                                       reinterpret_cast<const unsigned long long*>(b), value, timeout_ns, derr);
+  return after_launch("lbx_peer_wait");
+}
+int lbx_peer_error(void) {   // returns the flag and clears it
+  if (!g.ready || !g.peer_err) return 0;
+  const int e = *g.peer_err;
+  *g.peer_err = 0;
+  return e;
+}
+
+int lbx_collide_stream_slab(const lbx_fab* src, const lbx_fab* dst, const lbx_fab* dn, const lbx_fab* up,
+                            const lbx_box* box, const lbx_domain* dom, double omega_s, double omega_b) {
+  LBX_NEED_INIT();
+  if (!dom) return fail("lbx_collide_stream_slab: null domain");
+  if (check_fab(src, LBX_NV, LBX_F64, "lbx_collide_stream_slab src") ||
+      check_fab(dst, LBX_NV, LBX_F64, "lbx_collide_stream_slab dst") ||
+      check_fab(dn, LBX_NV, LBX_F64, "lbx_collide_stream_slab dst_dn") ||
+      check_fab(up, LBX_NV, LBX_F64, "lbx_collide_stream_slab dst_up"))
+    return 1;
+  if (src->data == dst->data) return fail("lbx_collide_stream_slab: src and dst must not alias");
+  if (check_cover(src, box, 0, nullptr, "lbx_collide_stream_slab src")) return 1;
+  // x,y: the destination must hold box grown by 1 (wrapped where periodic); z: every plane
+  // k+-1 must exist in dst or in the neighbour given for that side
+  lbx_box xy = *box;
+  xy.lo[2] = xy.hi[2] = box->lo[2];
+  for (const lbx_fab* f : {dst, dn, up}) {
+    lbx_box b = xy;
+    b.lo[2] = b.hi[2] = f->lo[2];
+    lbx_fab flat = *f;           // check x,y coverage only
+    flat.n[2] = 1;
+    if (check_cover(&flat, &b, 0, nullptr, "lbx_collide_stream_slab dst") ) return 1;
+    for (int d = 0; d < 2; ++d) {
+      const int lo = box->lo[d] - 1, hi = box->hi[d] + 1;
+      const bool wrap = dom->periodic[d] && box->lo[d] == dom->lo[d] && box->hi[d] == dom->hi[d];
+      if (!wrap && (lo < f->lo[d] || hi > f->lo[d] + f->n[d] - 1))
+        return fail("lbx_collide_stream_slab: destination fab lacks the x/y stencil rim");
+    }
+  }
+  auto has = [](const lbx_fab* f, int k) { return k >= f->lo[2] && k < f->lo[2] + f->n[2]; };
+  if (!has(dst, box->lo[2]) || !has(dst, box->hi[2])) return fail("lbx_collide_stream_slab: box not inside dst in z");
+  int kp = box->hi[2] + 1, km = box->lo[2] - 1;
+  if (dom->periodic[2]) { if (kp > dom->hi[2]) kp = dom->lo[2]; if (km < dom->lo[2]) km = dom->hi[2]; }
+  if (!has(dst, kp) && !has(up, kp)) return fail("lbx_collide_stream_slab: plane above the slab is in neither dst nor dst_up");
+  if (!has(dst, km) && !has(dn, km)) return fail("lbx_collide_stream_slab: plane below the slab is in neither dst nor dst_dn");
+  L().collide_stream_slab(g.cur, dfab(src), dfab(dst), dfab(dn), dfab(up), dbox(box), ddom(dom), omega_s, omega_b);
+  return after_launch("lbx_collide_stream_slab");
+}
+
+static int halo_common(const lbx_fab* f, const lbx_box* reg, int face, const void* buf, const char* what) {
+  if (check_fab(f, LBX_NV, LBX_F64, what) || check_cover(f, reg, 0, nullptr, what)) return 1;
+  if (face < 0 || face > 5) return fail(std::string(what) + ": face must be 0..5");
+  if (!buf) return fail(std::string(what) + ": null buffer");
+  return 0;
+}
+int lbx_halo_pack(const lbx_fab* f, const lbx_box* reg, int face, double* buf) {
+  LBX_NEED_INIT();
+  if (halo_common(f, reg, face, buf, "lbx_halo_pack")) return 1;
+  lbx::k_halo<true><<<lbx::grid_for(dbox(reg)), lbx::BX, 0, g.cur>>>(dfab(f), dbox(reg), face, buf);
+  return after_launch("lbx_halo_pack");
+}
+int lbx_halo_unpack(const lbx_fab* f, const lbx_box* reg, int face, const double* buf) {
+  LBX_NEED_INIT();
+  if (halo_common(f, reg, face, buf, "lbx_halo_unpack")) return 1;
+  lbx::k_halo<false><<<lbx::grid_for(dbox(reg)), lbx::BX, 0, g.cur>>>(dfab(f), dbox(reg), face,
+                                                                     const_cast<double*>(buf));
+  return after_launch("lbx_halo_unpack");
 }
 
 void lbx_d3q15_tables(double* M, double* Minv, int32_t* c, double* w) {

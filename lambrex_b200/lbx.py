@@ -14,6 +14,9 @@ NV, ND, HALO = 15, 3, 2
 F64, I32 = 0, 1
 PUSH, PULL = 0, 1
 OPT_COLLIDE_LITERAL = 1
+OPT_SMEM_PAD = 2
+IPC_HANDLE_BYTES = 64
+FACE_XP, FACE_XM, FACE_YP, FACE_YM, FACE_ZP, FACE_ZM = range(6)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "liblbx.so")
@@ -65,6 +68,15 @@ SYMBOLS = {
     "lbx_collide": (_i, [_fp, _fp, _bp, _d, _d, _fp, _i]),
     "lbx_stream": (_i, [_fp, _fp, _bp, _dp]),
     "lbx_collide_stream": (_i, [_fp, _fp, _bp, _dp, _d, _d, _i]),
+    "lbx_ipc_get_handle": (_i, [_vp, ctypes.c_char_p]),
+    "lbx_ipc_open_handle": (_i, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "lbx_ipc_close_handle": (_i, [_vp]),
+    "lbx_peer_signal": (_i, [_vp, _vp, ctypes.c_uint64]),
+    "lbx_peer_wait": (_i, [_vp, _vp, ctypes.c_uint64, ctypes.c_uint64]),
+    "lbx_peer_error": (_i, []),
+    "lbx_collide_stream_slab": (_i, [_fp, _fp, _fp, _fp, _bp, _dp, _d, _d]),
+    "lbx_halo_pack": (_i, [_fp, _bp, _i, _vp]),
+    "lbx_halo_unpack": (_i, [_fp, _bp, _i, _vp]),
     "lbx_d3q15_tables": (None, [ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(_d)]),
 }
@@ -249,6 +261,55 @@ def collide(src, dst, bx, omega_s, omega_b, mask=None, fine_val=1):
 
 def stream(src, dst, bx, dom):
     check(lib().lbx_stream(src.ref(), dst.ref(), ctypes.byref(bx), ctypes.byref(dom)))
+
+
+def collide_stream_slab(src, dst, dn, up, bx, dom, omega_s, omega_b):
+    """src, dst: Fab; dn, up: Fab or lbx_fab descriptor of a peer fab."""
+    r = lambda x: x.ref() if isinstance(x, Fab) else ctypes.byref(x)
+    check(lib().lbx_collide_stream_slab(src.ref(), dst.ref(), r(dn), r(up), ctypes.byref(bx), ctypes.byref(dom),
+                                        omega_s, omega_b))
+
+
+def halo_pack(f, region, face, buf_ptr):
+    check(lib().lbx_halo_pack(f.ref(), ctypes.byref(region), face, buf_ptr))
+
+
+def halo_unpack(f, region, face, buf_ptr):
+    check(lib().lbx_halo_unpack(f.ref(), ctypes.byref(region), face, buf_ptr))
+
+
+def ipc_get_handle(ptr):
+    h = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+    check(lib().lbx_ipc_get_handle(ptr, h))
+    return h.raw
+
+
+def ipc_open_handle(handle):
+    p = _vp()
+    check(lib().lbx_ipc_open_handle(handle, ctypes.byref(p)))
+    return p.value
+
+
+def ipc_close_handle(ptr):
+    check(lib().lbx_ipc_close_handle(ptr))
+
+
+def peer_signal(flag_a, flag_b, value):
+    check(lib().lbx_peer_signal(flag_a, flag_b, value))
+
+
+def peer_wait(flag_a, flag_b, value, timeout_ns=5_000_000_000):
+    check(lib().lbx_peer_wait(flag_a, flag_b, value, timeout_ns))
+
+
+def fab_desc(ptr, alo, n, ncomp=NV, dtype=F64):
+    """lbx_fab descriptor of memory this process did not allocate (a peer's fab)."""
+    c = lbx_fab()
+    c.data = ptr
+    c.lo[:] = [int(x) for x in alo]
+    c.n[:] = [int(x) for x in n]
+    c.ncomp, c.dtype = ncomp, dtype
+    return c
 
 
 def collide_stream(src, dst, bx, dom, omega_s, omega_b, scheme=PUSH):

@@ -1,0 +1,94 @@
+"""Host-side logic of the multi-GPU uniform path (lambrex_b200/slab.py) on CPU:
+slab ownership, neighbour maps, and the halo message pairing over torch.distributed
+(gloo, world_size 2 and 3)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from lambrex_b200.boxes import chop_1d, slab_partition
+from lambrex_b200.slab import SlabLayout, allgather_objects, exchange_z_halos, pulse_slab, shear_slab
+from lambrex_b200 import workloads
+from lambrex_b200.layout import user_to_fab
+
+
+def test_slab_partition_covers_domain():
+    for nz, w in [(1024, 8), (50, 3), (7, 7), (130, 4)]:
+        lay = SlabLayout(8, 8, nz, w)
+        planes = []
+        for r in range(w):
+            lo, hi = lay.slab(r)
+            assert hi >= lo
+            planes += list(range(lo, hi + 1))
+            assert lay.owner(hi + 1) == lay.up(r) and lay.owner(lo - 1) == lay.dn(r)
+        assert planes == list(range(nz))
+        assert sum(lay.cells(r) for r in range(w)) == 64 * nz
+    with pytest.raises(ValueError):
+        SlabLayout(4, 4, 2, 3)
+
+
+def test_base_grid_chop_matches_amrex_examples():
+    # 10x10x50 -> z pieces [0,23],[24,49]; 256 -> 8 x 32
+    assert chop_1d(50) == [0, 24, 50]
+    assert chop_1d(10) == [0, 10]
+    assert chop_1d(256) == list(range(0, 257, 32))
+    assert slab_partition(10, 3) == [(0, 3), (4, 6), (7, 9)]
+
+
+def test_slab_initial_conditions_match_global_workloads():
+    nx, ny, nz = 6, 5, 20
+    rho = user_to_fab(workloads.pulse_density(nx, ny, nz), nx, ny, nz)
+    assert np.array_equal(pulse_slab(nx, ny, nz, 4, 11)[0], rho[4:12])
+    rc, uc = workloads.shear_wave(nx, ny, nz)
+    r, u = shear_slab(nx, ny, nz, 3, 9)
+    assert np.array_equal(u, user_to_fab(uc, nx, ny, nz, 3)[:, 3:10])
+    assert np.array_equal(r[0], user_to_fab(rc, nx, ny, nz)[3:10])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lay = SlabLayout(4, 4, 12, world)
+        got = allgather_objects({"rank": rank, "slab": lay.slab(rank)})
+        assert [g["rank"] for g in got] == list(range(world))
+        assert [tuple(g["slab"]) for g in got] == lay.slabs
+        for rep in range(3):     # repeated exchanges must keep pairing up
+            su = torch.full((5,), 100.0 * rank + 1 + rep, dtype=torch.float64)    # to the rank above
+            sd = torch.full((5,), 100.0 * rank + 2 + rep, dtype=torch.float64)    # to the rank below
+            rd, ru = torch.zeros(5, dtype=torch.float64), torch.zeros(5, dtype=torch.float64)
+            exchange_z_halos(su, sd, rd, ru, rank, lay)
+            assert rd[0].item() == 100.0 * lay.dn(rank) + 1 + rep      # what the rank below sent up
+            assert ru[0].item() == 100.0 * lay.up(rank) + 2 + rep      # what the rank above sent down
+        q.put((rank, "ok"))
+    except Exception as e:       # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_message_pairing_over_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
