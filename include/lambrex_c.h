@@ -1,0 +1,113 @@
+/*
+ * lambrex_c.h -- flat C mirror of the reference's C++ surface (liblambrex.so), for bindings
+ * from other languages (ctypes / cgo / JNI).  One function per public member of
+ * /root/reference/include/AmrSim.h:127-155 and include/lambrex.h:6-7, plus the inherited
+ * amrex::AmrCore members the reference's callers use and the protected members its own test
+ * subclass re-exports (/root/reference/tests/AmrTest.h:6-50), so the reference's tests can be
+ * restated against this library.
+ *
+ * Conventions: int functions return 0 on success; on failure lbx_sim_last_error() holds the
+ * message (amrex::Abort, std::out_of_range and CUDA errors are all reported this way instead
+ * of terminating the process).  Host buffers are owned by the caller.  Levels are 0-based.
+ * Boxes are 6 ints: lo[3], hi[3], inclusive.
+ */
+#ifndef LAMBREX_C_H
+#define LAMBREX_C_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lbx_sim lbx_sim;
+
+/* lambrexInit / lambrexFinalise (include/lambrex.h:6-7) */
+int lbx_sim_global_init(void);
+int lbx_sim_global_finalise(void);
+const char *lbx_sim_last_error(void);
+
+/* AmrSim::AmrSim (include/AmrSim.h:128-129) */
+int lbx_sim_create(int nx, int ny, int nz, int max_level, const int periodicity[3], double tau_s,
+                   double tau_b, lbx_sim **out);
+int lbx_sim_destroy(lbx_sim *sim);
+/* inherited AmrMesh knobs, callable before InitFromScratch */
+int lbx_sim_set_max_grid_size(lbx_sim *sim, int n);
+int lbx_sim_set_uniform_fast_path(lbx_sim *sim, int on);
+
+/* SetInitialDensity / SetInitialVelocity (:141-144); n == 1 selects the scalar overloads */
+int lbx_sim_set_initial_density(lbx_sim *sim, const double *rho, size_t n);
+int lbx_sim_set_initial_velocity(lbx_sim *sim, const double *u, size_t n);
+/* AmrCore::InitFromScratch, regrid */
+int lbx_sim_init_from_scratch(lbx_sim *sim, double time);
+int lbx_sim_regrid(lbx_sim *sim, int lbase, double time);
+/* Iterate, CalcHydroVars, CalcEquilibriumDist (:147-149) */
+int lbx_sim_iterate(lbx_sim *sim, int nsteps);
+int lbx_sim_calc_hydro_vars(lbx_sim *sim, int level);
+int lbx_sim_calc_equilibrium_dist(lbx_sim *sim, int level);
+/* GetDensity / GetVelocity (:145-146): value through *out; sentinels -1.0 / -3e8 off-level */
+int lbx_sim_get_density(const lbx_sim *sim, int i, int j, int k, int level, double *out);
+int lbx_sim_get_velocity(const lbx_sim *sim, int i, int j, int k, int n, int level, double *out);
+/* bulk output (addition): dense over the level's domain, C-ordered [i][j][k]([n]) */
+int lbx_sim_get_density_field(const lbx_sim *sim, int level, double *out, size_t n);
+int lbx_sim_get_velocity_field(const lbx_sim *sim, int level, double *out, size_t n);
+/* GetTime, GetTimeStep, GetDims, GetExtent (:130-139, 154) */
+int lbx_sim_get_time(const lbx_sim *sim, int level, double *out);
+int lbx_sim_get_time_step(const lbx_sim *sim, int level, int *out);
+int lbx_sim_get_dims(const lbx_sim *sim, int dims[3]);
+int lbx_sim_get_extent(const lbx_sim *sim, int level, int lo[3], int hi[3]);
+/* SetStaticRefinement / UnsetStaticRefinement (:150-152) */
+int lbx_sim_set_static_refinement(lbx_sim *sim, int level, const int lo[3], const int hi[3]);
+int lbx_sim_unset_static_refinement(lbx_sim *sim, int level);
+/* AmrCore: maxLevel, finestLevel, refRatio, boxArray(level) */
+int lbx_sim_max_level(const lbx_sim *sim);
+int lbx_sim_finest_level(const lbx_sim *sim);
+int lbx_sim_ref_ratio(const lbx_sim *sim, int level, int ratio[3]);
+int lbx_sim_num_boxes(const lbx_sim *sim, int level);             /* AmrCore::boxArray(level).size() */
+int lbx_sim_get_boxes(const lbx_sim *sim, int level, int *boxes /* [6 * num_boxes] */);
+
+/* ---- white-box access, as tests/AmrTest.h re-exports it ---- */
+enum { LBX_FIELD_DISTFN = 0, LBX_FIELD_DENSITY = 1, LBX_FIELD_VELOCITY = 2, LBX_FIELD_DISTFN_NEXT = 3,
+       LBX_FIELD_FINE_MASK = 4 };
+int lbx_sim_field_empty(const lbx_sim *sim, int level, int field);    /* 1 empty, 0 not, <0 error */
+int lbx_sim_field_num_boxes(const lbx_sim *sim, int level, int field);
+int lbx_sim_field_boxes(const lbx_sim *sim, int level, int field, int *boxes);
+/* box `b` of the field incl. ghost cells as [comp][z][y][x]; n = capacity of out in elements.
+ * Mask data is returned converted to double. */
+int lbx_sim_field_fab(const lbx_sim *sim, int level, int field, int b, double *out, size_t n, int shape[4]);
+int lbx_sim_get_tau(const lbx_sim *sim, int level, double *tau_s, double *tau_b);
+int lbx_sim_get_mass(const lbx_sim *sim, int level, double *mass);
+int lbx_sim_get_dt(const lbx_sim *sim, int level, double *dt);
+int lbx_sim_num_levels_allocated(const lbx_sim *sim);   /* levels.size() == tau_s.size() == ... */
+/* ErrorEst on a TagBoxArray built on the boxes of `tag_level_boxes` (6 ints each), pre-set to
+ * `preset` (0 CLEAR, 2 SET) on the level's AmrCore boxArray; out: one char per cell of each box, box after box */
+int lbx_sim_call_error_est(lbx_sim *sim, int level, const int *tag_boxes, int ntag_boxes, int preset,
+                           char *out, size_t n);
+int lbx_sim_call_make_new_level_from_scratch(lbx_sim *sim, int level, const int *boxes, int nboxes, double time);
+int lbx_sim_call_make_new_level_from_coarse(lbx_sim *sim, int level, const int *boxes, int nboxes);
+int lbx_sim_call_remake_level(lbx_sim *sim, int level, double time, const int *boxes, int nboxes);
+int lbx_sim_call_clear_level(lbx_sim *sim, int level);
+
+/* ---- grid-generation metadata only (no GPU needed): the amrex-mini box calculus behind
+ * AmrCore::InitFromScratch / regrid.  Functions returning boxes write up to `cap` boxes
+ * (6 ints each) and return the number of boxes, or -1 on error. ---- */
+int lbx_meta_base_grids(const int dims[3], int max_grid_size, int *boxes, int cap);
+int lbx_meta_max_size(const int *in_boxes, int n, int chunk, int *boxes, int cap);
+int lbx_meta_simplify(const int *in_boxes, int n, int *boxes, int cap);
+int lbx_meta_complement(const int region[6], const int *in_boxes, int n, int *boxes, int cap);
+int lbx_meta_cluster(const int *points /* [3 * npoints] */, int npoints, double efficiency, int *boxes, int cap);
+/* A field-less AmrCore with the reference's static-box tagging (TagCell, src/AmrSim.cpp:413-417):
+ * create, InitFromScratch, then set / unset static boxes (each triggers regrid(level)), query grids. */
+typedef struct lbx_meta_mesh lbx_meta_mesh;
+int lbx_meta_mesh_create(const int dims[3], int max_level, int max_grid_size, lbx_meta_mesh **out);
+int lbx_meta_mesh_destroy(lbx_meta_mesh *m);
+int lbx_meta_mesh_set_static(lbx_meta_mesh *m, int level, const int lo[3], const int hi[3]);
+int lbx_meta_mesh_unset_static(lbx_meta_mesh *m, int level);
+int lbx_meta_mesh_finest_level(const lbx_meta_mesh *m);
+int lbx_meta_mesh_boxes(const lbx_meta_mesh *m, int level, int *boxes, int cap);
+/* log of hook calls since creation: "S<l>" scratch, "C<l>" from coarse, "R<l>" remake, "X<l>" clear */
+int lbx_meta_mesh_log(const lbx_meta_mesh *m, char *out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAMBREX_C_H */

@@ -136,6 +136,60 @@ int lbx_collide_stream_slab(const lbx_fab *src, const lbx_fab *dst, const lbx_fa
 int lbx_halo_pack(const lbx_fab *f, const lbx_box *region, int face, double *buf);
 int lbx_halo_unpack(const lbx_fab *f, const lbx_box *region, int face, const double *buf);
 
+/* ---- AMR path: batched per-level operations ----
+ * A "fab set" (lbx_mf) is every box of one level/field in ONE device allocation, each box
+ * grown by `ngrow` ghosts, `ncomp` SoA planes, zero-filled at creation -- the device side of
+ * an amrex::MultiFab / iMultiFab (include/field.h:124-129, src/AmrSim.cpp:668).  Every call
+ * below is ONE kernel launch over all boxes of the set. */
+typedef struct lbx_mf lbx_mf;
+int lbx_mf_create(const lbx_box *valid, int nfabs, int ncomp, int ngrow, int dtype, lbx_mf **out);
+int lbx_mf_destroy(lbx_mf *mf);
+int lbx_mf_info(const lbx_mf *mf, int *nfabs, int *ncomp, int *ngrow, int *dtype, size_t *bytes);
+/* descriptor of fab i (usable with the single-fab kernels above), its valid box, and its
+ * byte offset inside the allocation (host mirrors: fab after fab, [comp][z][y][x]) */
+int lbx_mf_fab(const lbx_mf *mf, int i, lbx_fab *fab, lbx_box *valid, size_t *byte_offset);
+int lbx_mf_upload(lbx_mf *mf, const void *host, size_t bytes);
+int lbx_mf_download(const lbx_mf *mf, void *host, size_t bytes);
+int lbx_mf_setval(lbx_mf *mf, double value);                       /* all cells incl. ghosts */
+/* CalcEquilibriumDist :845-931 / CalcHydroVars :938-979 on the valid cells of every box */
+int lbx_mf_equilibrium(lbx_mf *f, const lbx_mf *rho, const lbx_mf *u);
+int lbx_mf_moments(const lbx_mf *f, lbx_mf *rho, lbx_mf *u);
+/* Collide :25-107, CoarseCollide :487-580 (mask != NULL), FineCollide :582-590: in place */
+int lbx_mf_collide(lbx_mf *f, double omega_s, double omega_b, const lbx_mf *mask, int fine_val);
+/* Stream :109-122 into a "fresh" fab: dst(x,p) = src(x - c_p, p) on valid grown by 1, every
+ * other cell of dst zeroed (the reference never writes ghost ring 2 of its new fab) */
+int lbx_mf_stream(const lbx_mf *src, lbx_mf *dst);
+/* ZeroInvalidComponents :604-617: in the ghost shell, f_m = 0 unless pos - 2 c_m is valid */
+int lbx_mf_zero_invalid(lbx_mf *f);
+/* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */
+int lbx_mf_zero_ring(lbx_mf *f, int depth, int comp);
+
+/* Gather plans: the box-intersection metadata of AMReX's ParallelCopy-type calls, computed
+ * once on the host, executed as one launch (one thread per destination cell).
+ * COPY: the last matching descriptor of a destination fab wins; ADD: all matches are added
+ * in list order (deterministic).  Replaces FillBoundary :21,:132, FillPatchSingleLevel :371,
+ * FillPatchTwoLevels+PCInterp :385, InterpFromCoarseLevel :406, sum_fine_to_coarse :598,
+ * makeFineMask :425. */
+enum { LBX_G_COPY = 0,   /* dst(x) = src(x + shift)                                  */
+       LBX_G_PC = 1,     /* dst(x) = src(floor(x / ratio) + shift)   (PCInterp)      */
+       LBX_G_AVG = 2,    /* dst(x) = mean of the ratio^3 cells src(ratio x + shift..) */
+       LBX_G_CONST = 3   /* dst(x) = value                                           */ };
+enum { LBX_OP_COPY = 0, LBX_OP_ADD = 1 };
+typedef struct lbx_gather {
+  int32_t dst_fab;      /* index into the destination set; descriptors sorted by it   */
+  int32_t src_set;      /* 0 or 1: which of the two source sets given to apply        */
+  int32_t src_fab;      /* index into that set                                        */
+  int32_t kind;         /* LBX_G_*                                                    */
+  int32_t ratio;        /* refinement ratio for PC / AVG                              */
+  int32_t shift[3];     /* added in SOURCE index space after the map                  */
+  lbx_box region;       /* destination cells                                          */
+  double value;         /* LBX_G_CONST                                                */
+} lbx_gather;
+typedef struct lbx_plan lbx_plan;
+int lbx_plan_create(const lbx_gather *g, int n, lbx_plan **out);
+int lbx_plan_apply(lbx_plan *plan, lbx_mf *dst, const lbx_mf *src0, const lbx_mf *src1, int op);
+int lbx_plan_destroy(lbx_plan *plan);
+
 /* lattice constants and moment basis the kernels use (host-side query; no GPU needed):
  * M[15][15], Minv[15][15] row-major, c[15][3], w[15].  src/AmrSim.cpp:1037-1073,
  * include/d3q15_bgk.h:14-28. */

@@ -133,36 +133,39 @@ __global__ void __launch_bounds__(BX) k_collide_stream_slab(DFab src, DFab dst, 
   const DFab& fp = has_plane(dst, kp) ? dst : up;
   const DFab& fm = has_plane(dst, km) ? dst : dn;
   const long long sc0 = plane_stride(dst), scp = plane_stride(fp), scm = plane_stride(fm);
-  double* const b0 = dst.p;
-  double* const bp = fp.p;
-  double* const bm = fm.p;
-  const long long r00 = row_off(dst, j, k), rp0 = row_off(dst, jp, k), rm0 = row_off(dst, jm, k);
-  const long long r0p = row_off(fp, j, kp), rpp = row_off(fp, jp, kp), rmp = row_off(fp, jm, kp);
-  const long long r0m = row_off(fm, j, km), rpm = row_off(fm, jp, km), rmm = row_off(fm, jm, km);
-
+  // 15 destination addresses up front (like k_collide_stream's off[]): the register
+  // footprint this costs caps residency at 6 CTAs/SM, which measured FASTER than the
+  // 10 CTAs/SM of an address-on-the-fly formulation (profiles/r01_occupancy_sweep.md)
+  double* d[NV];
+  {
+    const long long r00 = row_off(dst, j, k), rp0 = row_off(dst, jp, k), rm0 = row_off(dst, jm, k);
+    d[0] = dst.p + r00 + i;
+    d[1] = dst.p + 1 * sc0 + r00 + ip;
+    d[2] = dst.p + 2 * sc0 + r00 + im;
+    d[3] = dst.p + 3 * sc0 + rp0 + i;
+    d[4] = dst.p + 4 * sc0 + rm0 + i;
+    // c_z = +1 : plane k+1 (local or the upper neighbour's fab)
+    const long long r0p = row_off(fp, j, kp), rpp = row_off(fp, jp, kp), rmp = row_off(fp, jm, kp);
+    d[5] = fp.p + 5 * scp + r0p + i;
+    d[7] = fp.p + 7 * scp + rpp + ip;
+    d[9] = fp.p + 9 * scp + rmp + ip;
+    d[11] = fp.p + 11 * scp + rpp + im;
+    d[13] = fp.p + 13 * scp + rmp + im;
+    // c_z = -1 : plane k-1 (local or the lower neighbour's fab)
+    const long long r0m = row_off(fm, j, km), rpm = row_off(fm, jp, km), rmm = row_off(fm, jm, km);
+    d[6] = fm.p + 6 * scm + r0m + i;
+    d[8] = fm.p + 8 * scm + rpm + ip;
+    d[10] = fm.p + 10 * scm + rmm + ip;
+    d[12] = fm.p + 12 * scm + rpm + im;
+    d[14] = fm.p + 14 * scm + rmm + im;
+  }
   const long long ssc = plane_stride(src), o = row_off(src, j, k) + i;
   double f[NV];
 #pragma unroll
   for (int p = 0; p < NV; ++p) f[p] = __ldcs(src.p + p * ssc + o);
   C::collide(f, omega_s, omega_b);
-  // same-plane populations (c_z = 0)
-  __stcs(b0 + 0 * sc0 + r00 + i, f[0]);
-  __stcs(b0 + 1 * sc0 + r00 + ip, f[1]);
-  __stcs(b0 + 2 * sc0 + r00 + im, f[2]);
-  __stcs(b0 + 3 * sc0 + rp0 + i, f[3]);
-  __stcs(b0 + 4 * sc0 + rm0 + i, f[4]);
-  // c_z = +1 : plane k+1 (local or the upper neighbour's fab)
-  __stcs(bp + 5 * scp + r0p + i, f[5]);
-  __stcs(bp + 7 * scp + rpp + ip, f[7]);
-  __stcs(bp + 9 * scp + rmp + ip, f[9]);
-  __stcs(bp + 11 * scp + rpp + im, f[11]);
-  __stcs(bp + 13 * scp + rmp + im, f[13]);
-  // c_z = -1 : plane k-1 (local or the lower neighbour's fab)
-  __stcs(bm + 6 * scm + r0m + i, f[6]);
-  __stcs(bm + 8 * scm + rpm + ip, f[8]);
-  __stcs(bm + 10 * scm + rmm + ip, f[10]);
-  __stcs(bm + 12 * scm + rpm + im, f[12]);
-  __stcs(bm + 14 * scm + rmm + im, f[14]);
+#pragma unroll
+  for (int p = 0; p < NV; ++p) __stcs(d[p], f[p]);
 }
 
 // ---------------------------------------------------------------------------
@@ -263,6 +266,119 @@ __global__ void __launch_bounds__(BX) k_equilibrium(DFab f_, DFab rho_, DFab u_,
   const long long fo = row_off(f_, j, k) + i;
 #pragma unroll
   for (int p = 0; p < NV; ++p) f_.p[p * fsc + fo] = f[p];
+}
+
+// ===========================================================================
+// Batched per-level kernels (AMR path): a level's field is ONE device allocation
+// holding all its boxes (each grown by its ghosts) plus a device table of DFabT
+// descriptors; one launch covers every box of the level.
+// grid = (tiles of MFT cells, fab index); a tile is MFT consecutive cells (x
+// fastest) of the fab's operating region = valid box grown by `grow`.
+// ===========================================================================
+struct DFabT {
+  void* p;           // component 0 of the allocated box
+  int lo[3], n[3];   // allocated box: lower corner, extents
+  int vlo[3], vhi[3];  // valid box (inclusive)
+};
+constexpr int MFT = 256;
+
+__device__ __forceinline__ int mf_fab_index() { return blockIdx.y + gridDim.y * blockIdx.z; }
+
+__device__ __forceinline__ bool mf_cell(const DFabT& f, int grow, int& i, int& j, int& k) {
+  const int nx = f.vhi[0] - f.vlo[0] + 1 + 2 * grow, ny = f.vhi[1] - f.vlo[1] + 1 + 2 * grow,
+            nz = f.vhi[2] - f.vlo[2] + 1 + 2 * grow;
+  long long t = (long long)blockIdx.x * MFT + threadIdx.x;
+  if (t >= (long long)nx * ny * nz) return false;
+  i = f.vlo[0] - grow + (int)(t % nx);
+  t /= nx;
+  j = f.vlo[1] - grow + (int)(t % ny);
+  k = f.vlo[2] - grow + (int)(t / ny);
+  return true;
+}
+__device__ __forceinline__ long long mf_stride(const DFabT& f) { return (long long)f.n[0] * f.n[1] * f.n[2]; }
+__device__ __forceinline__ long long mf_off(const DFabT& f, int i, int j, int k) {
+  return (i - f.lo[0]) + (long long)f.n[0] * ((j - f.lo[1]) + (long long)f.n[1] * (k - f.lo[2]));
+}
+__device__ __forceinline__ bool mf_in_valid(const DFabT& f, int i, int j, int k) {
+  return i >= f.vlo[0] && i <= f.vhi[0] && j >= f.vlo[1] && j <= f.vhi[1] && k >= f.vlo[2] && k <= f.vhi[2];
+}
+
+// Collide / CoarseCollide / FineCollide on the valid cells of every box, in place
+// (src/AmrSim.cpp:25-107, 487-590).  mask != null: cells with mask == fine_val are zeroed.
+template <class C>
+__global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ ft, const DFabT* __restrict__ mt,
+                                                    int nfabs, double omega_s, double omega_b, int fine_val) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT F = ft[b];
+  int i, j, k;
+  if (!mf_cell(F, 0, i, j, k)) return;
+  double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
+  const long long sc = mf_stride(F);
+  if (mt) {
+    const DFabT M = mt[b];
+    if (static_cast<const int*>(M.p)[mf_off(M, i, j, k)] == fine_val) {
+#pragma unroll
+      for (int p = 0; p < NV; ++p) fp[p * sc] = 0.0;
+      return;
+    }
+  }
+  double f[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) f[p] = fp[p * sc];
+  C::collide(f, omega_s, omega_b);
+#pragma unroll
+  for (int p = 0; p < NV; ++p) fp[p * sc] = f[p];
+}
+
+// CalcHydroVars (src/AmrSim.cpp:938-979) on the valid cells of every box.
+template <class C>
+__global__ void __launch_bounds__(MFT) k_mf_moments(const DFabT* __restrict__ ft, const DFabT* __restrict__ rt,
+                                                    const DFabT* __restrict__ ut, int nfabs) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT F = ft[b];
+  int i, j, k;
+  if (!mf_cell(F, 0, i, j, k)) return;
+  const double* fp = static_cast<const double*>(F.p) + mf_off(F, i, j, k);
+  const long long sc = mf_stride(F);
+  double f[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) f[p] = fp[p * sc];
+  double rho, ux, uy, uz;
+  C::moments(f, rho, ux, uy, uz);
+  const DFabT R = rt[b], U = ut[b];
+  static_cast<double*>(R.p)[mf_off(R, i, j, k)] = rho;
+  double* up = static_cast<double*>(U.p) + mf_off(U, i, j, k);
+  const long long usc = mf_stride(U);
+  up[0] = ux;
+  up[usc] = uy;
+  up[2 * usc] = uz;
+}
+
+// CalcEquilibriumDist (src/AmrSim.cpp:845-931) on the valid cells of every box.
+template <class C>
+__global__ void __launch_bounds__(MFT) k_mf_equilibrium(const DFabT* __restrict__ ft, const DFabT* __restrict__ rt,
+                                                        const DFabT* __restrict__ ut, int nfabs) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT F = ft[b];
+  int i, j, k;
+  if (!mf_cell(F, 0, i, j, k)) return;
+  const DFabT R = rt[b], U = ut[b];
+  const double* up = static_cast<const double*>(U.p) + mf_off(U, i, j, k);
+  const long long usc = mf_stride(U);
+  double f[NV];
+  equilibrium_cell(static_cast<const double*>(R.p)[mf_off(R, i, j, k)], up[0], up[usc], up[2 * usc], f);
+  double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
+  const long long sc = mf_stride(F);
+#pragma unroll
+  for (int p = 0; p < NV; ++p) fp[p * sc] = f[p];
+}
+
+inline dim3 mf_grid(long long max_cells, int nfabs) {
+  const unsigned gy = (unsigned)(nfabs < 65535 ? nfabs : 65535);
+  return dim3((unsigned)((max_cells + MFT - 1) / MFT), gy, (unsigned)((nfabs + gy - 1) / gy));
 }
 
 inline dim3 grid_for(const DBox& b) {

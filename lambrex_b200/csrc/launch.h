@@ -15,6 +15,11 @@ struct Launchers {
   void (*collide_stream)(cudaStream_t, DFab src, DFab dst, DBox box, DDom dom, double ws, double wb, int scheme);
   void (*collide_stream_slab)(cudaStream_t, DFab src, DFab dst, DFab dn, DFab up, DBox box, DDom dom, double ws,
                               double wb);
+  void (*mf_collide)(cudaStream_t, const DFabT* f, const DFabT* mask, int nfabs, long long max_cells, double ws,
+                     double wb, int fine_val);
+  void (*mf_moments)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs, long long max_cells);
+  void (*mf_equilibrium)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs,
+                         long long max_cells);
 };
 const Launchers& launchers_fast();
 const Launchers& launchers_literal();

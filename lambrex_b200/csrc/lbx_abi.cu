@@ -7,38 +7,31 @@
 #include <string>
 
 #include "../../include/lbx.h"
+#include "ctx.h"
 #include "launch.h"
 #include "kernels_util.cuh"
 
-namespace lbx { int g_smem_pad = 0; }
-
-namespace {
-
-struct Ctx {
-  bool ready = false;
-  int device = -1;
-  cudaStream_t own = nullptr;      // the library's stream
-  cudaStream_t cur = nullptr;      // stream kernels are queued on (own or external)
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
-  bool literal = false;
-  int* peer_err = nullptr;         // host-mapped: set by k_peer_wait on timeout
-  uint64_t launches = 0;
-};
-Ctx g;
+namespace lbx {
+int g_smem_pad = 0;
+Ctx g_ctx;
 thread_local std::string g_err;
-
 int fail(const std::string& msg) {
   g_err = msg;
   return 1;
 }
-#define LBX_CUDA(expr)                                                                   \
-  do {                                                                                   \
-    cudaError_t e_ = (expr);                                                             \
-    if (e_ != cudaSuccess)                                                               \
-      return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                   \
-  } while (0)
-#define LBX_NEED_INIT() \
-  if (!g.ready) return fail("lbx: not initialised (call lbx_init / lambrexInit first)")
+int after_launch(const char* what) {
+  ++g_ctx.launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
+  return 0;
+}
+}  // namespace lbx
+
+namespace {
+using lbx::after_launch;
+using lbx::fail;
+using lbx::g_err;
+lbx::Ctx& g = lbx::g_ctx;
 
 int check_fab(const lbx_fab* f, int ncomp, int dtype, const char* what) {
   if (!f || !f->data) return fail(std::string(what) + ": null fab");
@@ -88,13 +81,6 @@ lbx::DDom ddom(const lbx_domain* b) {
 }
 const lbx::Launchers& L() { return g.literal ? lbx::launchers_literal() : lbx::launchers_fast(); }
 
-int after_launch(const char* what) {
-  ++g.launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
-  return 0;
-}
-
 }  // namespace
 
 extern "C" {
@@ -139,7 +125,7 @@ int lbx_finalize(void) {
   cudaEventDestroy(g.t1);
   cudaStreamDestroy(g.own);
   if (g.peer_err) cudaFreeHost(g.peer_err);
-  g = Ctx();
+  g = lbx::Ctx();
   return 0;
 }
 

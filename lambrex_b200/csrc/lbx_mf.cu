@@ -1,0 +1,339 @@
+// C ABI of the batched AMR-path operations (lbx_mf_*, lbx_plan_*; declared in include/lbx.h).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstring>
+#include <set>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/lbx.h"
+#include "ctx.h"
+#include "launch.h"
+#include "mf_kernels.cuh"
+
+struct lbx_mf {
+  int nfabs = 0, ncomp = 0, ngrow = 0, dtype = LBX_F64;
+  size_t bytes = 0;
+  char* base = nullptr;                 // one device allocation
+  lbx::DFabT* table = nullptr;          // device table [nfabs]
+  std::vector<lbx::DFabT> host;         // same, host side
+  std::vector<size_t> offset;           // byte offset of fab i in `base`
+  long long max_valid = 0;              // largest valid-box cell count
+  uint64_t geom = 0;                    // signature of (boxes, ngrow, ncomp, dtype)
+  long long max_cells(int grow) const {
+    long long m = 0;
+    for (const auto& f : host) {
+      long long c = 1;
+      for (int d = 0; d < 3; ++d) c *= (f.vhi[d] - f.vlo[d] + 1 + 2 * grow);
+      m = std::max(m, c);
+    }
+    return m;
+  }
+};
+
+struct lbx_plan {
+  std::vector<lbx::GDesc> descs;
+  std::vector<lbx::GDst> dsts;
+  lbx::GDesc* d_descs = nullptr;
+  lbx::GDst* d_dsts = nullptr;
+  long long max_cells = 0;
+  std::set<std::tuple<uint64_t, uint64_t, uint64_t>> validated;
+};
+
+namespace {
+using lbx::fail;
+lbx::Ctx& g = lbx::g_ctx;
+const lbx::Launchers& L() { return g.literal ? lbx::launchers_literal() : lbx::launchers_fast(); }
+
+uint64_t mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  return h;
+}
+int same_boxes(const lbx_mf* a, const lbx_mf* b, const char* what) {
+  if (!a || !b) return fail(std::string(what) + ": null fab set");
+  if (a->nfabs != b->nfabs) return fail(std::string(what) + ": fab sets differ in size");
+  for (int i = 0; i < a->nfabs; ++i)
+    for (int d = 0; d < 3; ++d)
+      if (a->host[i].vlo[d] != b->host[i].vlo[d] || a->host[i].vhi[d] != b->host[i].vhi[d])
+        return fail(std::string(what) + ": fab sets have different valid boxes");
+  return 0;
+}
+int need(const lbx_mf* f, int ncomp, int dtype, int ngrow_min, const char* what) {
+  if (!f || !f->base) return fail(std::string(what) + ": null or empty fab set");
+  if (f->ncomp < ncomp) return fail(std::string(what) + ": too few components");
+  if (f->dtype != dtype) return fail(std::string(what) + ": wrong dtype");
+  if (f->ngrow < ngrow_min) return fail(std::string(what) + ": too few ghost cells");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int lbx_mf_create(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dtype, lbx_mf** out) {
+  LBX_NEED_INIT();
+  if (!valid || nfabs <= 0 || ncomp <= 0 || ngrow < 0 || !out) return fail("lbx_mf_create: bad arguments");
+  if (dtype != LBX_F64 && dtype != LBX_I32) return fail("lbx_mf_create: unknown dtype");
+  auto* m = new lbx_mf;
+  m->nfabs = nfabs; m->ncomp = ncomp; m->ngrow = ngrow; m->dtype = dtype;
+  const size_t item = dtype == LBX_F64 ? 8 : 4;
+  m->host.resize(nfabs);
+  m->offset.resize(nfabs);
+  size_t off = 0;
+  uint64_t h = mix(mix(mix(0x1234, ncomp), ngrow), dtype);
+  for (int i = 0; i < nfabs; ++i) {
+    lbx::DFabT& f = m->host[i];
+    size_t cells = 1;
+    for (int d = 0; d < 3; ++d) {
+      if (valid[i].hi[d] < valid[i].lo[d]) { delete m; return fail("lbx_mf_create: empty box"); }
+      f.vlo[d] = valid[i].lo[d]; f.vhi[d] = valid[i].hi[d];
+      f.lo[d] = f.vlo[d] - ngrow; f.n[d] = f.vhi[d] - f.vlo[d] + 1 + 2 * ngrow;
+      cells *= (size_t)f.n[d];
+      h = mix(mix(h, (uint64_t)(uint32_t)f.vlo[d]), (uint64_t)(uint32_t)f.vhi[d]);
+    }
+    m->offset[i] = off;
+    off += (cells * ncomp * item + 255) / 256 * 256;
+  }
+  m->bytes = off;
+  m->geom = h;
+  m->max_valid = m->max_cells(0);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->base), m->bytes);
+  if (e != cudaSuccess) { delete m; return fail(std::string("lbx_mf_create: cudaMalloc: ") + cudaGetErrorString(e)); }
+  for (int i = 0; i < nfabs; ++i) m->host[i].p = m->base + m->offset[i];
+  e = cudaMalloc(reinterpret_cast<void**>(&m->table), sizeof(lbx::DFabT) * nfabs);
+  if (e != cudaSuccess) { cudaFree(m->base); delete m; return fail("lbx_mf_create: cudaMalloc(table)"); }
+  // pageable-host async copy: the driver stages it before returning, so `host` may change later
+  LBX_CUDA(cudaMemcpyAsync(m->table, m->host.data(), sizeof(lbx::DFabT) * nfabs, cudaMemcpyHostToDevice, g.cur));
+  LBX_CUDA(cudaMemsetAsync(m->base, 0, m->bytes, g.cur));     // NEW_FAB_FILL = 0
+  *out = m;
+  return 0;
+}
+
+int lbx_mf_destroy(lbx_mf* m) {
+  if (!m) return 0;
+  if (g.ready) {
+    cudaStreamSynchronize(g.cur);
+    cudaFree(m->base);
+    cudaFree(m->table);
+  }
+  delete m;
+  return 0;
+}
+
+int lbx_mf_info(const lbx_mf* m, int* nfabs, int* ncomp, int* ngrow, int* dtype, size_t* bytes) {
+  if (!m) return fail("lbx_mf_info: null fab set");
+  if (nfabs) *nfabs = m->nfabs;
+  if (ncomp) *ncomp = m->ncomp;
+  if (ngrow) *ngrow = m->ngrow;
+  if (dtype) *dtype = m->dtype;
+  if (bytes) *bytes = m->bytes;
+  return 0;
+}
+
+int lbx_mf_fab(const lbx_mf* m, int i, lbx_fab* fab, lbx_box* valid, size_t* byte_offset) {
+  if (!m || i < 0 || i >= m->nfabs) return fail("lbx_mf_fab: index out of range");
+  const lbx::DFabT& f = m->host[i];
+  if (fab) {
+    fab->data = f.p;
+    for (int d = 0; d < 3; ++d) { fab->lo[d] = f.lo[d]; fab->n[d] = f.n[d]; }
+    fab->ncomp = m->ncomp;
+    fab->dtype = m->dtype;
+  }
+  if (valid)
+    for (int d = 0; d < 3; ++d) { valid->lo[d] = f.vlo[d]; valid->hi[d] = f.vhi[d]; }
+  if (byte_offset) *byte_offset = m->offset[i];
+  return 0;
+}
+
+int lbx_mf_upload(lbx_mf* m, const void* host, size_t bytes) {
+  LBX_NEED_INIT();
+  if (!m || !host || bytes != m->bytes) return fail("lbx_mf_upload: size mismatch");
+  LBX_CUDA(cudaMemcpyAsync(m->base, host, bytes, cudaMemcpyHostToDevice, g.cur));
+  return 0;
+}
+int lbx_mf_download(const lbx_mf* m, void* host, size_t bytes) {
+  LBX_NEED_INIT();
+  if (!m || !host || bytes != m->bytes) return fail("lbx_mf_download: size mismatch");
+  LBX_CUDA(cudaMemcpyAsync(host, m->base, bytes, cudaMemcpyDeviceToHost, g.cur));
+  return 0;
+}
+
+int lbx_mf_setval(lbx_mf* m, double value) {
+  LBX_NEED_INIT();
+  if (!m) return fail("lbx_mf_setval: null fab set");
+  const dim3 grid = lbx::mf_grid(m->max_cells(m->ngrow), m->nfabs);
+  if (m->dtype == LBX_F64)
+    lbx::k_mf_setval<double><<<grid, lbx::MFT, 0, g.cur>>>(m->table, m->nfabs, m->ngrow, m->ncomp, value);
+  else
+    lbx::k_mf_setval<int><<<grid, lbx::MFT, 0, g.cur>>>(m->table, m->nfabs, m->ngrow, m->ncomp, (int)value);
+  return lbx::after_launch("lbx_mf_setval");
+}
+
+int lbx_mf_equilibrium(lbx_mf* f, const lbx_mf* rho, const lbx_mf* u) {
+  LBX_NEED_INIT();
+  if (need(f, LBX_NV, LBX_F64, 0, "lbx_mf_equilibrium f") || need(rho, 1, LBX_F64, 0, "lbx_mf_equilibrium rho") ||
+      need(u, 3, LBX_F64, 0, "lbx_mf_equilibrium u") || same_boxes(f, rho, "lbx_mf_equilibrium") ||
+      same_boxes(f, u, "lbx_mf_equilibrium"))
+    return 1;
+  L().mf_equilibrium(g.cur, f->table, rho->table, u->table, f->nfabs, f->max_valid);
+  return lbx::after_launch("lbx_mf_equilibrium");
+}
+
+int lbx_mf_moments(const lbx_mf* f, lbx_mf* rho, lbx_mf* u) {
+  LBX_NEED_INIT();
+  if (need(f, LBX_NV, LBX_F64, 0, "lbx_mf_moments f") || need(rho, 1, LBX_F64, 0, "lbx_mf_moments rho") ||
+      need(u, 3, LBX_F64, 0, "lbx_mf_moments u") || same_boxes(f, rho, "lbx_mf_moments") ||
+      same_boxes(f, u, "lbx_mf_moments"))
+    return 1;
+  L().mf_moments(g.cur, f->table, rho->table, u->table, f->nfabs, f->max_valid);
+  return lbx::after_launch("lbx_mf_moments");
+}
+
+int lbx_mf_collide(lbx_mf* f, double omega_s, double omega_b, const lbx_mf* mask, int fine_val) {
+  LBX_NEED_INIT();
+  if (need(f, LBX_NV, LBX_F64, 0, "lbx_mf_collide f")) return 1;
+  if (mask && (need(mask, 1, LBX_I32, 0, "lbx_mf_collide mask") || same_boxes(f, mask, "lbx_mf_collide"))) return 1;
+  L().mf_collide(g.cur, f->table, mask ? mask->table : nullptr, f->nfabs, f->max_valid, omega_s, omega_b, fine_val);
+  return lbx::after_launch("lbx_mf_collide");
+}
+
+int lbx_mf_stream(const lbx_mf* src, lbx_mf* dst) {
+  LBX_NEED_INIT();
+  if (need(src, LBX_NV, LBX_F64, 2, "lbx_mf_stream src") || need(dst, LBX_NV, LBX_F64, 1, "lbx_mf_stream dst") ||
+      same_boxes(src, dst, "lbx_mf_stream"))
+    return 1;
+  if (src->base == dst->base) return fail("lbx_mf_stream: src and dst must not alias");
+  lbx::k_mf_stream<<<lbx::mf_grid(dst->max_cells(dst->ngrow), dst->nfabs), lbx::MFT, 0, g.cur>>>(
+      src->table, dst->table, dst->nfabs, dst->ngrow);
+  return lbx::after_launch("lbx_mf_stream");
+}
+
+int lbx_mf_zero_invalid(lbx_mf* f) {
+  LBX_NEED_INIT();
+  if (need(f, LBX_NV, LBX_F64, 1, "lbx_mf_zero_invalid")) return 1;
+  lbx::k_mf_zero_invalid<<<lbx::mf_grid(f->max_cells(f->ngrow), f->nfabs), lbx::MFT, 0, g.cur>>>(f->table, f->nfabs,
+                                                                                               f->ngrow);
+  return lbx::after_launch("lbx_mf_zero_invalid");
+}
+
+int lbx_mf_zero_ring(lbx_mf* f, int depth, int comp) {
+  LBX_NEED_INIT();
+  if (need(f, 1, LBX_F64, 1, "lbx_mf_zero_ring")) return 1;
+  if (comp < 0 || comp >= f->ncomp || depth < 1 || depth > f->ngrow) return fail("lbx_mf_zero_ring: bad comp/depth");
+  lbx::k_mf_zero_ring<<<lbx::mf_grid(f->max_cells(f->ngrow), f->nfabs), lbx::MFT, 0, g.cur>>>(f->table, f->nfabs,
+                                                                                            f->ngrow, depth, comp);
+  return lbx::after_launch("lbx_mf_zero_ring");
+}
+
+// ----------------------------------------------------------------------------- gather plans
+int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
+  LBX_NEED_INIT();
+  if (!out || n < 0 || (n > 0 && !gs)) return fail("lbx_plan_create: bad arguments");
+  auto* p = new lbx_plan;
+  p->descs.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const lbx_gather& a = gs[i];
+    lbx::GDesc& d = p->descs[i];
+    if (i > 0 && a.dst_fab < gs[i - 1].dst_fab) { delete p; return fail("lbx_plan_create: descriptors must be grouped by ascending dst_fab"); }
+    if (a.kind < LBX_G_COPY || a.kind > LBX_G_CONST) { delete p; return fail("lbx_plan_create: unknown kind"); }
+    if ((a.kind == LBX_G_PC || a.kind == LBX_G_AVG) && a.ratio < 1) { delete p; return fail("lbx_plan_create: ratio must be >= 1"); }
+    if (a.src_set != 0 && a.src_set != 1) { delete p; return fail("lbx_plan_create: src_set must be 0 or 1"); }
+    for (int k = 0; k < 3; ++k) {
+      if (a.region.hi[k] < a.region.lo[k]) { delete p; return fail("lbx_plan_create: empty region"); }
+      d.lo[k] = a.region.lo[k]; d.hi[k] = a.region.hi[k]; d.shift[k] = a.shift[k];
+    }
+    d.src_set = a.src_set; d.src_fab = a.src_fab; d.kind = a.kind; d.ratio = a.ratio > 0 ? a.ratio : 1; d.value = a.value;
+    if (p->dsts.empty() || p->dsts.back().fab != a.dst_fab) {
+      lbx::GDst t;
+      t.fab = a.dst_fab; t.first = i; t.count = 0; t.pad = 0;
+      for (int k = 0; k < 3; ++k) { t.blo[k] = d.lo[k]; t.bhi[k] = d.hi[k]; }
+      p->dsts.push_back(t);
+    }
+    lbx::GDst& t = p->dsts.back();
+    ++t.count;
+    for (int k = 0; k < 3; ++k) { t.blo[k] = std::min(t.blo[k], d.lo[k]); t.bhi[k] = std::max(t.bhi[k], d.hi[k]); }
+  }
+  for (const auto& t : p->dsts) {
+    long long c = 1;
+    for (int k = 0; k < 3; ++k) c *= (t.bhi[k] - t.blo[k] + 1);
+    p->max_cells = std::max(p->max_cells, c);
+  }
+  if (n > 0) {
+    LBX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_descs), sizeof(lbx::GDesc) * n));
+    LBX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_dsts), sizeof(lbx::GDst) * p->dsts.size()));
+    LBX_CUDA(cudaMemcpyAsync(p->d_descs, p->descs.data(), sizeof(lbx::GDesc) * n, cudaMemcpyHostToDevice, g.cur));
+    LBX_CUDA(cudaMemcpyAsync(p->d_dsts, p->dsts.data(), sizeof(lbx::GDst) * p->dsts.size(), cudaMemcpyHostToDevice, g.cur));
+    LBX_CUDA(cudaStreamSynchronize(g.cur));
+  }
+  *out = p;
+  return 0;
+}
+
+int lbx_plan_destroy(lbx_plan* p) {
+  if (!p) return 0;
+  if (g.ready) {
+    cudaStreamSynchronize(g.cur);
+    cudaFree(p->d_descs);
+    cudaFree(p->d_dsts);
+  }
+  delete p;
+  return 0;
+}
+
+static int validate_plan(lbx_plan* p, const lbx_mf* dst, const lbx_mf* s0, const lbx_mf* s1) {
+  const auto key = std::make_tuple(dst->geom, s0 ? s0->geom : 0, s1 ? s1->geom : 0);
+  if (p->validated.count(key)) return 0;
+  auto inside = [](const lbx::DFabT& f, const int* lo, const int* hi) {
+    for (int d = 0; d < 3; ++d)
+      if (lo[d] < f.lo[d] || hi[d] > f.lo[d] + f.n[d] - 1) return false;
+    return true;
+  };
+  for (const auto& t : p->dsts) {
+    if (t.fab < 0 || t.fab >= dst->nfabs) return fail("lbx_plan_apply: destination fab index out of range");
+    for (int q = t.first; q < t.first + t.count; ++q) {
+      const lbx::GDesc& d = p->descs[q];
+      if (!inside(dst->host[t.fab], d.lo, d.hi)) return fail("lbx_plan_apply: region outside the destination fab");
+      if (d.kind == lbx::G_CONST) continue;
+      const lbx_mf* s = d.src_set ? s1 : s0;
+      if (!s) return fail("lbx_plan_apply: plan needs a source set that was not given");
+      if (d.src_fab < 0 || d.src_fab >= s->nfabs) return fail("lbx_plan_apply: source fab index out of range");
+      if (s->dtype != dst->dtype || s->ncomp < dst->ncomp) return fail("lbx_plan_apply: source dtype/components mismatch");
+      int lo[3], hi[3];
+      for (int k = 0; k < 3; ++k) {
+        auto fd = [](int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); };
+        if (d.kind == lbx::G_COPY) { lo[k] = d.lo[k] + d.shift[k]; hi[k] = d.hi[k] + d.shift[k]; }
+        else if (d.kind == lbx::G_PC) { lo[k] = fd(d.lo[k], d.ratio) + d.shift[k]; hi[k] = fd(d.hi[k], d.ratio) + d.shift[k]; }
+        else { lo[k] = d.lo[k] * d.ratio + d.shift[k]; hi[k] = d.hi[k] * d.ratio + d.shift[k] + d.ratio - 1; }
+      }
+      if (!inside(s->host[d.src_fab], lo, hi)) return fail("lbx_plan_apply: mapped source region outside the source fab");
+    }
+  }
+  p->validated.insert(key);
+  return 0;
+}
+
+int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* src1, int op) {
+  LBX_NEED_INIT();
+  if (!p || !dst) return fail("lbx_plan_apply: null plan or destination");
+  if (op != LBX_OP_COPY && op != LBX_OP_ADD) return fail("lbx_plan_apply: unknown op");
+  if (p->descs.empty()) return 0;
+  if (validate_plan(p, dst, src0, src1)) return 1;
+  const dim3 grid = lbx::mf_grid(p->max_cells, (int)p->dsts.size());
+  const lbx::DFabT* t0 = src0 ? src0->table : nullptr;
+  const lbx::DFabT* t1 = src1 ? src1->table : nullptr;
+  const int nd = (int)p->dsts.size();
+  if (dst->dtype == LBX_F64) {
+    if (op == LBX_OP_COPY)
+      lbx::k_plan_apply<double, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+    else
+      lbx::k_plan_apply<double, true><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+  } else {
+    if (op == LBX_OP_COPY)
+      lbx::k_plan_apply<int, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+    else
+      lbx::k_plan_apply<int, true><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+  }
+  return lbx::after_launch("lbx_plan_apply");
+}
+
+}  // extern "C"

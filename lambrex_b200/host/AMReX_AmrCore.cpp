@@ -1,0 +1,278 @@
+// amrex-mini AmrMesh/AmrCore (see AMReX_AmrCore.H).  [AMReX, unverified] throughout: restated
+// from upstream semantics recorded in SURVEY.md appendix C, not from AMReX source.
+#include "AMReX_AmrCore.H"
+
+#include <iostream>
+#include <list>
+
+#include "AMReX_FillPatch.H"
+
+namespace amrex {
+
+// ----------------------------------------------------------------------------- clustering
+namespace {
+enum CutStatus { HoleCut = 0, SteepCut = 1, BisectCut = 2, InvalidCut = 3 };
+
+int find_cut(const std::vector<int>& hist, CutStatus& status) {
+  const int len = (int)hist.size();
+  status = InvalidCut;
+  if (len <= 1) return 0;
+  const int mid = len / 2;
+  int cut = -1;
+  for (int i = 0; i < len; ++i) {
+    if (hist[i] == 0) {                        // centre-most empty plane
+      status = HoleCut;
+      if (std::abs(cut - mid) > std::abs(i - mid)) {
+        cut = i;
+        if (i > mid) break;
+      }
+    }
+  }
+  if (status == HoleCut) return cut;
+  std::vector<int> dh(len, 0);                 // discrete Laplacian of the signature
+  for (int i = 1; i < len - 1; ++i) dh[i] = hist[i + 1] - 2 * hist[i] + hist[i - 1];
+  int locmax = -1;
+  for (int i = 2; i < len - 2; ++i) {          // strongest sign change, at least 2 cells from the ends
+    const int ip = dh[i - 1], ic = dh[i], dif = std::abs(ip - ic);
+    if (ip * ic < 0 && dif >= locmax) {
+      if (dif > locmax) { status = SteepCut; cut = i; locmax = dif; }
+      else if (std::abs(i - mid) < std::abs(cut - mid)) cut = i;
+    }
+  }
+  if (locmax <= 2) { status = BisectCut; return mid; }
+  return cut;
+}
+
+Box min_box(const IntVect* p, size_t n) {
+  Box b(p[0], p[0]);
+  for (size_t i = 1; i < n; ++i) b.minBox(Box(p[i], p[i]));
+  return b;
+}
+}  // namespace
+
+BoxList ClusterTags(std::vector<IntVect>& tags, Real eff) {
+  struct Cl { size_t first, count; Box box; };
+  BoxList out;
+  if (tags.empty()) return out;
+  std::list<Cl> lst;
+  lst.push_back({0, tags.size(), min_box(tags.data(), tags.size())});
+  for (auto it = lst.begin(); it != lst.end();) {
+    Cl& c = *it;
+    if ((Real)c.count / (Real)c.box.numPts() >= eff) { ++it; continue; }
+    IntVect* p = tags.data() + c.first;
+    CutStatus st[3], mincut = InvalidCut;
+    int cut[3];
+    for (int d = 0; d < 3; ++d) {
+      std::vector<int> hist(c.box.length(d), 0);
+      for (size_t q = 0; q < c.count; ++q) ++hist[p[q][d] - c.box.smallEnd(d)];
+      cut[d] = c.box.smallEnd(d) + find_cut(hist, st[d]);
+      if (st[d] < mincut) mincut = st[d];
+    }
+    int dir = -1;
+    for (int d = 0; d < 3; ++d)
+      if (st[d] == mincut && (dir < 0 || c.box.length(d) > c.box.length(dir))) dir = d;
+    IntVect* mid = std::stable_partition(p, p + c.count, [&](const IntVect& v) { return v[dir] < cut[dir]; });
+    const size_t nlo = (size_t)(mid - p), nhi = c.count - nlo;
+    if (nlo == 0 || nhi == 0) { ++it; continue; }   // cannot split further
+    lst.push_back({c.first + nlo, nhi, min_box(mid, nhi)});
+    c.count = nlo;
+    c.box = min_box(p, nlo);
+    // the low part is examined again before moving on
+  }
+  for (const Cl& c : lst) out.push_back(c.box);
+  return out;
+}
+
+// ----------------------------------------------------------------------------- AmrMesh
+AmrMesh::AmrMesh(const Geometry& g0, const AmrInfo& info)
+    : verbose(info.verbose), max_level(info.max_level), grid_eff(info.grid_eff), n_proper(info.n_proper),
+      refine_grid_layout(info.refine_grid_layout) {
+  const int nlev = max_level + 1;
+  auto spread = [nlev](const Vector<IntVect>& v, const IntVect& dflt) {
+    Vector<IntVect> r(nlev, dflt);
+    for (int i = 0; i < nlev; ++i) r[i] = v.empty() ? dflt : v[std::min<size_t>(i, v.size() - 1)];
+    return r;
+  };
+  ref_ratio = spread(info.ref_ratio, IntVect(2));
+  blocking_factor = spread(info.blocking_factor, IntVect(8));
+  max_grid_size = spread(info.max_grid_size, IntVect(32));
+  n_error_buf = spread(info.n_error_buf, IntVect(1));
+  geom.resize(nlev);
+  grids.resize(nlev);
+  dmap.resize(nlev);
+  geom[0] = g0;
+  for (int l = 1; l < nlev; ++l) geom[l] = amrex::refine(geom[l - 1], ref_ratio[l - 1]);
+}
+
+BoxArray AmrMesh::MakeBaseGrids() const {
+  const Box& dom = geom[0].Domain();
+  IntVect fac(2);
+  for (int d = 0; d < 3; ++d)
+    if (dom.length(d) % 2 != 0) fac[d] = 1;     // odd extents are not coarsened
+  BoxArray ba(amrex::coarsen(dom, fac));
+  IntVect chunk;
+  for (int d = 0; d < 3; ++d) chunk[d] = std::max(1, max_grid_size[0][d] / fac[d]);
+  ba.maxSize(chunk);
+  ba.refine(fac);
+  return ba;
+}
+
+namespace {
+void proj_periodic(BoxList& bl, const Box& domain, const Geometry& g) {
+  const BoxList orig(bl);
+  for (const Box& b : orig)
+    for (const IntVect& s : g.periodicity().shiftIntVect()) {
+      if (s == IntVect(0)) continue;
+      const Box r = amrex::shift(b, s) & domain;
+      if (r.ok()) bl.push_back(r);
+    }
+}
+}  // namespace
+
+void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArray>& new_grids) {
+  const int max_crse = std::min(finest_level, max_level - 1);
+  if ((int)new_grids.size() < max_crse + 2) new_grids.resize(max_crse + 2);
+  // proper-nesting domains (blocking factor 1 on this path: no tag coarsening)
+  Vector<BoxList> p_n(max_level), p_n_comp(max_level);
+  {
+    BoxList bl = grids[lbase].boxList();
+    simplify(bl);
+    p_n_comp[lbase] = complementIn(geom[lbase].Domain(), bl);
+    simplify(p_n_comp[lbase]);
+    for (Box& b : p_n_comp[lbase]) b.grow(n_proper);
+    if (geom[lbase].isAnyPeriodic()) proj_periodic(p_n_comp[lbase], geom[lbase].Domain(), geom[lbase]);
+    p_n[lbase] = complementIn(geom[lbase].Domain(), p_n_comp[lbase]);
+    simplify(p_n[lbase]);
+  }
+  for (int i = lbase + 1; i <= max_crse; ++i) {
+    p_n_comp[i] = p_n_comp[i - 1];
+    simplify(p_n_comp[i]);
+    for (Box& b : p_n_comp[i]) { b.refine(ref_ratio[i - 1]); b.grow(n_proper); }
+    if (geom[i].isAnyPeriodic()) proj_periodic(p_n_comp[i], geom[i].Domain(), geom[i]);
+    p_n[i] = complementIn(geom[i].Domain(), p_n_comp[i]);
+    simplify(p_n[i]);
+  }
+  new_finest = lbase;
+  for (int levc = max_crse; levc >= lbase; --levc) {
+    const int levf = levc + 1;
+    const int nbuf = n_error_buf[levc][0];
+    TagBoxArray tags(grids[levc], dmap[levc], nbuf);
+    ErrorEst(levc, tags, time, 0);
+    tags.buffer(nbuf);
+    if (levf < new_finest) {
+      // project the new grids two levels up down to levc so that the new levf contains them
+      BoxList proj;
+      for (const Box& b : new_grids[levf + 1].boxList()) {
+        Box c = amrex::coarsen(b, ref_ratio[levf]);
+        c.grow(n_proper);
+        c.coarsen(ref_ratio[levc]);
+        proj.push_back(c);
+      }
+      tags.setVal(proj, TagBox::SET);
+    }
+    std::vector<IntVect> tagvec;
+    tags.collate(tagvec, geom[levc].Domain(), geom[levc].isPeriodicArray());
+    if (!p_n_comp[levc].empty()) {             // remove cells outside the proper nesting domain
+      auto bad = [&](const IntVect& p) {
+        for (const Box& b : p_n_comp[levc])
+          if (b.contains(p)) return true;
+        return false;
+      };
+      tagvec.erase(std::remove_if(tagvec.begin(), tagvec.end(), bad), tagvec.end());
+    }
+    if (tagvec.empty()) continue;
+    new_finest = std::max(new_finest, levf);
+    BoxList clusters = ClusterTags(tagvec, grid_eff);
+    BoxList clipped;                           // ClusterList::intersect(p_n)
+    for (const Box& b : clusters) {
+      bool whole = false;
+      for (const Box& q : p_n[levc])
+        if (q.contains(b)) { whole = true; break; }
+      if (whole) { clipped.push_back(b); continue; }
+      for (const Box& q : p_n[levc]) {
+        const Box r = b & q;
+        if (r.ok()) clipped.push_back(r);
+      }
+    }
+    simplify(clipped);
+    IntVect largest;
+    for (int d = 0; d < 3; ++d) largest[d] = std::max(1, max_grid_size[levf][d] / ref_ratio[levc][d]);
+    maxSize(clipped, largest);
+    for (Box& b : clipped) b.refine(ref_ratio[levc]);
+    new_grids[levf].define(clipped);
+  }
+}
+
+void AmrMesh::MakeNewGrids(Real time) {
+  finest_level = 0;
+  {
+    const BoxArray ba = MakeBaseGrids();
+    const DistributionMapping dm(ba);
+    MakeNewLevelFromScratch(0, time, ba, dm);
+    SetBoxArray(0, ba);
+    SetDistributionMap(0, dm);
+  }
+  if (max_level > 0) {
+    Vector<BoxArray> new_grids(max_level + 1);
+    new_grids[0] = grids[0];
+    do {
+      int new_finest;
+      MakeNewGrids(finest_level, time, new_finest, new_grids);
+      if (new_finest <= finest_level) break;
+      finest_level = new_finest;
+      const DistributionMapping dm(new_grids[new_finest]);
+      MakeNewLevelFromScratch(new_finest, time, new_grids[new_finest], dm);
+      SetBoxArray(new_finest, new_grids[new_finest]);
+      SetDistributionMap(new_finest, dm);
+    } while (finest_level < max_level);
+  }
+}
+
+// ----------------------------------------------------------------------------- AmrCore
+void AmrCore::InitFromScratch(Real time) {
+  MakeNewGrids(time);
+  if (verbose > 0)
+    for (int l = 0; l <= finest_level; ++l)
+      std::cout << "INITIAL GRIDS: level " << l << " has " << grids[l].size() << " grids, " << grids[l].numPts()
+                << " cells" << std::endl;
+}
+
+void AmrCore::regrid(int lbase, Real time, bool) {
+  if (lbase >= max_level) return;
+  int new_finest;
+  Vector<BoxArray> new_grids(finest_level + 2);
+  MakeNewGrids(lbase, time, new_finest, new_grids);
+  bool coarse_ba_changed = false;
+  for (int lev = lbase + 1; lev <= new_finest; ++lev) {
+    if (lev <= finest_level) {                 // an existing level
+      const bool ba_changed = (new_grids[lev] != grids[lev]);
+      if (ba_changed || coarse_ba_changed) {
+        BoxArray level_grids = grids[lev];
+        DistributionMapping level_dmap = dmap[lev];
+        if (ba_changed) {
+          level_grids = new_grids[lev];
+          level_dmap = DistributionMapping(level_grids);
+        }
+        RemakeLevel(lev, time, level_grids, level_dmap);
+        SetBoxArray(lev, level_grids);
+        SetDistributionMap(lev, level_dmap);
+      }
+      coarse_ba_changed = ba_changed;
+    } else {                                   // a new level
+      const DistributionMapping new_dmap(new_grids[lev]);
+      MakeNewLevelFromCoarse(lev, time, new_grids[lev], new_dmap);
+      SetBoxArray(lev, new_grids[lev]);
+      SetDistributionMap(lev, new_dmap);
+    }
+  }
+  for (int lev = new_finest + 1; lev <= finest_level; ++lev) {
+    ClearLevel(lev);
+    ClearBoxArray(lev);
+    ClearDistributionMap(lev);
+  }
+  finest_level = new_finest;
+  if (verbose > 0)
+    std::cout << "REGRID: finest level " << finest_level << std::endl;
+}
+
+}  // namespace amrex

@@ -1,0 +1,469 @@
+// amrex-mini: device field containers, host tag boxes, and the gather-plan builders that stand
+// in for AMReX's ParallelCopy family (see AMReX_MultiFab.H, AMReX_FillPatch.H).
+#include "AMReX_MultiFab.H"
+
+#include <cstring>
+#include <functional>
+#include <map>
+#include <unordered_map>
+
+#include "AMReX_FillPatch.H"
+
+namespace amrex {
+
+void lbx_check(int rc, const char* where) {
+  if (rc != 0) Abort(std::string(where) + ": " + lbx_last_error());
+}
+
+// ----------------------------------------------------------------------------- DeviceFabArray
+template <class T, int DTYPE>
+DeviceFabArray<T, DTYPE>::Storage::~Storage() {
+  if (mf) lbx_mf_destroy(mf);
+}
+
+template <class T, int DTYPE>
+void DeviceFabArray<T, DTYPE>::define(const BoxArray& ba, const DistributionMapping& dm, int ncomp, int ngrow,
+                                      Layout lay) {
+  clear();
+  ba_ = ba;
+  dm_ = dm;
+  ncomp_ = ncomp;
+  ngrow_ = ngrow;
+  lay_ = lay;
+  if (ba.empty()) return;
+  std::vector<lbx_box> vb;
+  int sg = ngrow;
+  if (lay == Layout::FLAT) {
+    const Box mb = ba.minimalBox();
+    if (mb.numPts() != ba.numPts()) Abort("FLAT layout needs a BoxArray that tiles its minimal box");
+    vb.resize(1);
+    for (int d = 0; d < 3; ++d) { vb[0].lo[d] = mb.smallEnd(d); vb[0].hi[d] = mb.bigEnd(d); }
+    sg = 0;
+  } else {
+    vb.resize(ba.size());
+    for (long i = 0; i < ba.size(); ++i)
+      for (int d = 0; d < 3; ++d) { vb[i].lo[d] = ba[i].smallEnd(d); vb[i].hi[d] = ba[i].bigEnd(d); }
+  }
+  st_ = std::make_shared<Storage>();
+  lbx_check(lbx_mf_create(vb.data(), (int)vb.size(), ncomp, sg, DTYPE, &st_->mf), "MultiFab::define");
+  size_t bytes = 0;
+  lbx_check(lbx_mf_info(st_->mf, nullptr, nullptr, nullptr, nullptr, &bytes), "MultiFab::define");
+  st_->elems = bytes / sizeof(T);
+  st_->offset.resize(vb.size());
+  for (size_t s = 0; s < vb.size(); ++s) {
+    size_t off = 0;
+    lbx_check(lbx_mf_fab(st_->mf, (int)s, nullptr, nullptr, &off), "MultiFab::define");
+    st_->offset[s] = off / sizeof(T);
+  }
+  mirror_ok_ = false;
+}
+
+template <class T, int DTYPE>
+void DeviceFabArray<T, DTYPE>::clear() {
+  st_.reset();
+  ba_.clear();
+  dm_ = DistributionMapping();
+  ncomp_ = ngrow_ = 0;
+  mirror_.clear();
+  mirror_ok_ = false;
+}
+
+template <class T, int DTYPE>
+lbx_fab DeviceFabArray<T, DTYPE>::fabDesc(int s) const {
+  lbx_fab f;
+  lbx_check(lbx_mf_fab(st_->mf, s, &f, nullptr, nullptr), "MultiFab::fabDesc");
+  return f;
+}
+
+template <class T, int DTYPE>
+void DeviceFabArray<T, DTYPE>::setVal(T v) {
+  if (!st_) return;
+  lbx_check(lbx_mf_setval(st_->mf, (double)v), "MultiFab::setVal");
+  touch();
+}
+
+template <class T, int DTYPE>
+const std::vector<T>& DeviceFabArray<T, DTYPE>::hostMirror() const {
+  if (!mirror_ok_) {
+    mirror_.resize(st_ ? st_->elems : 0);
+    if (st_) {
+      lbx_check(lbx_mf_download(st_->mf, mirror_.data(), mirror_.size() * sizeof(T)), "MultiFab::hostMirror");
+      lbx_check(lbx_sync(), "MultiFab::hostMirror");
+    }
+    mirror_ok_ = true;
+  }
+  return mirror_;
+}
+
+template <class T, int DTYPE>
+void DeviceFabArray<T, DTYPE>::upload(const std::vector<T>& host) {
+  if (!st_ || host.size() != st_->elems) Abort("MultiFab::upload: size mismatch");
+  lbx_check(lbx_mf_upload(st_->mf, host.data(), host.size() * sizeof(T)), "MultiFab::upload");
+  lbx_check(lbx_sync(), "MultiFab::upload");
+  touch();
+}
+
+template <class T, int DTYPE>
+T DeviceFabArray<T, DTYPE>::hostValue(int bi, const IntVect& p, int comp) const {
+  const std::vector<T>& m = hostMirror();
+  const int s = isFlat() ? 0 : bi;
+  const Box a = storageBox(s);
+  if (!a.contains(p)) Abort("MultiFab::hostValue: cell outside the fab");
+  const size_t nx = a.length(0), ny = a.length(1), nz = a.length(2);
+  const size_t c = (size_t)(p[0] - a.smallEnd(0)) + nx * ((size_t)(p[1] - a.smallEnd(1)) + ny * (size_t)(p[2] - a.smallEnd(2)));
+  return m[st_->offset[s] + (size_t)comp * nx * ny * nz + c];
+}
+
+template <>
+void DeviceFabArray<double, LBX_F64>::relayout(Layout lay) {
+  if (lay == lay_ || !st_) { lay_ = st_ ? lay_ : lay; return; }
+  MultiFab fresh(ba_, dm_, ncomp_, ngrow_, lay);
+  CopyValid(fresh, *this);
+  st_ = fresh.st_;
+  lay_ = lay;
+  touch();
+}
+template <>
+void DeviceFabArray<int, LBX_I32>::relayout(Layout lay) {
+  if (lay != lay_) Abort("iMultiFab::relayout is not supported");
+}
+
+template class DeviceFabArray<double, LBX_F64>;
+template class DeviceFabArray<int, LBX_I32>;
+
+// ----------------------------------------------------------------------------- tags
+void TagBox::setVal(char v, const Box& region) {
+  const Box r = region & box_;
+  if (!r.ok()) return;
+  for (int k = r.smallEnd(2); k <= r.bigEnd(2); ++k)
+    for (int j = r.smallEnd(1); j <= r.bigEnd(1); ++j) {
+      char* row = &d_[index(IntVect(r.smallEnd(0), j, k))];
+      std::memset(row, v, (size_t)r.length(0));
+    }
+}
+
+void TagBox::buffer(int nbuf, const Box& interior) {
+  if (nbuf <= 0) return;
+  const Box in = interior & box_;
+  if (!in.ok()) return;
+  std::vector<IntVect> set;
+  for (int k = in.smallEnd(2); k <= in.bigEnd(2); ++k)
+    for (int j = in.smallEnd(1); j <= in.bigEnd(1); ++j)
+      for (int i = in.smallEnd(0); i <= in.bigEnd(0); ++i)
+        if ((*this)(IntVect(i, j, k)) == SET) set.push_back(IntVect(i, j, k));
+  for (const IntVect& p : set) {
+    const Box nb = Box(p - IntVect(nbuf), p + IntVect(nbuf)) & box_;
+    for (int k = nb.smallEnd(2); k <= nb.bigEnd(2); ++k)
+      for (int j = nb.smallEnd(1); j <= nb.bigEnd(1); ++j)
+        for (int i = nb.smallEnd(0); i <= nb.bigEnd(0); ++i) {
+          char& t = (*this)(IntVect(i, j, k));
+          if (t == CLEAR) t = BUF;
+        }
+  }
+}
+
+TagBoxArray::TagBoxArray(const BoxArray& ba, const DistributionMapping& dm, int ngrow) {
+  ba_ = ba;
+  dm_ = dm;
+  ncomp_ = 1;
+  ngrow_ = ngrow;
+  fabs_.reserve(ba.size());
+  for (long i = 0; i < ba.size(); ++i) fabs_.emplace_back(amrex::grow(ba[i], ngrow));
+}
+void TagBoxArray::setVal(const BoxArray& ba, TagBox::TagVal v) { setVal(ba.boxList(), v); }
+void TagBoxArray::setVal(const BoxList& bl, TagBox::TagVal v) {
+  for (TagBox& t : fabs_)
+    for (const Box& b : bl) t.setVal((char)v, b);
+}
+void TagBoxArray::buffer(int nbuf) {
+  for (long i = 0; i < size(); ++i) fabs_[i].buffer(nbuf, ba_[i]);
+}
+void TagBoxArray::collate(std::vector<IntVect>& out, const Box& domain, const std::array<int, 3>& is_per) const {
+  out.clear();
+  for (const TagBox& t : fabs_) {
+    const Box& b = t.box();
+    for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
+      for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j)
+        for (int i = b.smallEnd(0); i <= b.bigEnd(0); ++i) {
+          if (t(IntVect(i, j, k)) == TagBox::CLEAR) continue;
+          IntVect p(i, j, k);
+          bool inside = true;
+          for (int d = 0; d < 3; ++d) {
+            const int len = domain.length(d), lo = domain.smallEnd(d);
+            if (is_per[d]) p[d] = lo + (((p[d] - lo) % len) + len) % len;
+            else if (p[d] < lo || p[d] > domain.bigEnd(d)) inside = false;
+          }
+          if (inside) out.push_back(p);
+        }
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+// ----------------------------------------------------------------------------- gather plans
+namespace {
+
+struct PlanDeleter { void operator()(lbx_plan* p) const { lbx_plan_destroy(p); } };
+std::map<std::string, std::unique_ptr<lbx_plan, PlanDeleter>> g_plans;
+
+uint64_t fnv(uint64_t h, int64_t v) {
+  for (int b = 0; b < 8; ++b) { h ^= (uint64_t)((v >> (8 * b)) & 0xff); h *= 1099511628211ull; }
+  return h;
+}
+// identity of a MultiFab's storage geometry
+std::string geom_key(const FabArrayBase& fa, bool flat, int storage_ng) {
+  uint64_t h = 1469598103934665603ull;
+  for (long i = 0; i < fa.size(); ++i)
+    for (int d = 0; d < 3; ++d) { h = fnv(h, fa.box((int)i).smallEnd(d)); h = fnv(h, fa.box((int)i).bigEnd(d)); }
+  char buf[96];
+  std::snprintf(buf, sizeof(buf), "%016llx:%ld:%d:%d", (unsigned long long)h, fa.size(), flat ? 1 : 0, storage_ng);
+  return buf;
+}
+template <class FA>
+std::string gkey(const FA& m) { return geom_key(m, m.isFlat(), m.isFlat() ? 0 : m.nGrow()); }
+std::string pkey(const Periodicity& p) {
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), "p%d,%d,%d", p.period()[0], p.period()[1], p.period()[2]);
+  return buf;
+}
+
+// uniform-bin spatial index over a list of boxes
+class BoxHash {
+ public:
+  explicit BoxHash(const std::vector<Box>& boxes) : boxes_(boxes) {
+    bin_ = IntVect(1);
+    for (const Box& b : boxes)
+      for (int d = 0; d < 3; ++d) bin_[d] = std::max(bin_[d], b.length(d));
+    for (size_t i = 0; i < boxes.size(); ++i) {
+      const IntVect c = cell(boxes[i].smallEnd());
+      map_[key(c)].push_back((int)i);
+    }
+  }
+  // indices (ascending) of boxes intersecting q
+  std::vector<int> query(const Box& q) const {
+    std::vector<int> r;
+    if (!q.ok()) return r;
+    IntVect lo = cell(q.smallEnd()), hi = cell(q.bigEnd());
+    for (int d = 0; d < 3; ++d) lo[d] -= 1;      // a box registered by its low corner may start one bin earlier
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          auto it = map_.find(key(IntVect(i, j, k)));
+          if (it == map_.end()) continue;
+          for (int b : it->second)
+            if (boxes_[b].intersects(q)) r.push_back(b);
+        }
+    std::sort(r.begin(), r.end());
+    return r;
+  }
+
+ private:
+  IntVect cell(const IntVect& p) const {
+    return IntVect(IntVect::floor_div(p[0], bin_[0]), IntVect::floor_div(p[1], bin_[1]), IntVect::floor_div(p[2], bin_[2]));
+  }
+  static uint64_t key(const IntVect& c) {
+    return ((uint64_t)(uint32_t)(c[0] + (1 << 20)) << 42) ^ ((uint64_t)(uint32_t)(c[1] + (1 << 20)) << 21) ^
+           (uint64_t)(uint32_t)(c[2] + (1 << 20));
+  }
+  const std::vector<Box>& boxes_;
+  IntVect bin_;
+  std::unordered_map<uint64_t, std::vector<int>> map_;
+};
+
+lbx_gather make_desc(int dst_fab, int src_set, int src_fab, int kind, int ratio, const IntVect& shift, const Box& r,
+                     double value = 0.0) {
+  lbx_gather g;
+  g.dst_fab = dst_fab; g.src_set = src_set; g.src_fab = src_fab; g.kind = kind; g.ratio = ratio;
+  for (int d = 0; d < 3; ++d) { g.shift[d] = shift[d]; g.region.lo[d] = r.smallEnd(d); g.region.hi[d] = r.bigEnd(d); }
+  g.value = value;
+  return g;
+}
+
+template <class FA>
+std::vector<Box> storage_valid(const FA& m) {
+  std::vector<Box> v(m.numStorageFabs());
+  for (int s = 0; s < m.numStorageFabs(); ++s) v[s] = m.storageValid(s);
+  return v;
+}
+
+lbx_plan* cached(const std::string& key, const std::function<void(std::vector<lbx_gather>&)>& build) {
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) return it->second.get();
+  std::vector<lbx_gather> descs;
+  build(descs);
+  lbx_plan* p = nullptr;
+  lbx_check(lbx_plan_create(descs.data(), (int)descs.size(), &p), "gather plan");
+  g_plans[key].reset(p);
+  return p;
+}
+
+// COPY descriptors: dst fab k <- every (source box, shift) that meets its region `want`
+void copy_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::vector<Box>& svalid, const BoxHash& sh,
+                int src_ng, const std::vector<IntVect>& shifts, int src_set, bool skip_self, int self_index) {
+  // collect (i, shift) pairs, then order by source index, then shift order (ParallelCopy order)
+  std::vector<std::pair<int, int>> hits;
+  for (size_t si = 0; si < shifts.size(); ++si) {
+    const Box q = amrex::grow(amrex::shift(want, IntVect(0) - shifts[si]), src_ng);
+    for (int i : sh.query(q)) {
+      if (skip_self && i == self_index && shifts[si] == IntVect(0)) continue;
+      hits.emplace_back(i, (int)si);
+    }
+  }
+  std::sort(hits.begin(), hits.end());
+  for (auto& h : hits) {
+    const IntVect& s = shifts[h.second];
+    const Box r = amrex::shift(amrex::grow(svalid[h.first], src_ng), s) & want;
+    if (r.ok()) out.push_back(make_desc(k, src_set, h.first, LBX_G_COPY, 1, IntVect(0) - s, r));
+  }
+}
+
+// PC descriptors: fine fab k region `want` <- coarse boxes (valid cells, periodic images)
+void pc_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::vector<Box>& cvalid, const BoxHash& ch,
+              const std::vector<IntVect>& cshifts, int ratio, int src_set) {
+  const Box cw = amrex::coarsen(want, ratio);
+  std::vector<std::pair<int, int>> hits;
+  for (size_t si = 0; si < cshifts.size(); ++si)
+    for (int i : ch.query(amrex::shift(cw, IntVect(0) - cshifts[si]))) hits.emplace_back(i, (int)si);
+  std::sort(hits.begin(), hits.end());
+  for (auto& h : hits) {
+    const IntVect& s = cshifts[h.second];
+    const Box rc = amrex::shift(cvalid[h.first], s) & cw;
+    if (!rc.ok()) continue;
+    const Box rf = amrex::refine(rc, ratio) & want;
+    if (rf.ok()) out.push_back(make_desc(k, src_set, h.first, LBX_G_PC, ratio, IntVect(0) - s, rf));
+  }
+}
+
+}  // namespace
+
+void ClearPlanCache() { g_plans.clear(); }
+size_t PlanCacheSize() { return g_plans.size(); }
+
+void ParallelCopy(MultiFab& dst, const MultiFab& src, int src_ng, int dst_ng, const Periodicity& period, bool add) {
+  if (dst.empty() || src.empty()) return;
+  if (src.isFlat()) src_ng = 0;
+  if (dst.isFlat()) dst_ng = 0;
+  if (src_ng > src.nGrow() || dst_ng > dst.nGrow()) Abort("ParallelCopy: ghost width exceeds the MultiFab's");
+  char tail[64];
+  std::snprintf(tail, sizeof(tail), "|%d|%d|%d", src_ng, dst_ng, add ? 1 : 0);
+  const std::string key = "PC|" + gkey(dst) + "|" + gkey(src) + "|" + pkey(period) + tail;
+  lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
+    const std::vector<Box> sv = storage_valid(src);
+    const BoxHash sh(sv);
+    const std::vector<IntVect> shifts = period.shiftIntVect();
+    for (int k = 0; k < dst.numStorageFabs(); ++k)
+      copy_descs(d, k, amrex::grow(dst.storageValid(k), dst_ng), sv, sh, src_ng, shifts, 0, false, -1);
+  });
+  lbx_check(lbx_plan_apply(p, dst.mf(), src.mf(), nullptr, add ? LBX_OP_ADD : LBX_OP_COPY), "ParallelCopy");
+  dst.touch();
+}
+
+void CopyValid(MultiFab& dst, const MultiFab& src) { ParallelCopy(dst, src, 0, 0, Periodicity::NonPeriodic()); }
+
+void FillBoundary(MultiFab& mf, const Periodicity& period) {
+  if (mf.empty() || mf.isFlat() || mf.nGrow() == 0) return;    // FLAT storage has no ghost cells
+  const std::string key = "FB|" + gkey(mf) + "|" + pkey(period);
+  lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
+    const std::vector<Box> sv = storage_valid(mf);
+    const BoxHash sh(sv);
+    const std::vector<IntVect> shifts = period.shiftIntVect();
+    for (int k = 0; k < mf.numStorageFabs(); ++k) copy_descs(d, k, mf.storageBox(k), sv, sh, 0, shifts, 0, true, k);
+  });
+  lbx_check(lbx_plan_apply(p, mf.mf(), mf.mf(), nullptr, LBX_OP_COPY), "FillBoundary");
+  mf.touch();
+}
+
+void FillPatchSingleLevel(MultiFab& dst, const MultiFab& src, const Geometry& geom) {
+  ParallelCopy(dst, src, 0, dst.nGrow(), geom.periodicity());
+}
+
+static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* fine, const Geometry& cgeom,
+                           const Geometry& fgeom, const IntVect& ratio, const char* tag) {
+  if (dst.empty()) return;
+  if (ratio[0] != ratio[1] || ratio[0] != ratio[2]) Abort("anisotropic refinement ratios are not supported");
+  if (dst.isFlat()) Abort("two-level fills need BOXES storage on the fine level");
+  const std::string key = std::string(tag) + "|" + gkey(dst) + "|" + gkey(crse) + "|" + (fine ? gkey(*fine) : "-") + "|" +
+                          pkey(cgeom.periodicity()) + "|" + pkey(fgeom.periodicity()) + "|" + std::to_string(ratio[0]);
+  lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
+    const std::vector<Box> cv = storage_valid(crse);
+    const BoxHash ch(cv);
+    const std::vector<IntVect> cs = cgeom.periodicity().shiftIntVect();
+    std::vector<Box> fv;
+    if (fine) fv = storage_valid(*fine);
+    const BoxHash fh(fv);
+    const std::vector<IntVect> fs = fgeom.periodicity().shiftIntVect();
+    for (int k = 0; k < dst.numStorageFabs(); ++k) {
+      const Box want = dst.storageBox(k);
+      pc_descs(d, k, want, cv, ch, cs, ratio[0], 1);                        // coarse first ...
+      if (fine) copy_descs(d, k, want, fv, fh, 0, fs, 0, false, -1);      // ... fine data wins
+    }
+  });
+  lbx_check(lbx_plan_apply(p, dst.mf(), fine ? fine->mf() : nullptr, crse.mf(), LBX_OP_COPY), tag);
+  dst.touch();
+}
+
+void FillPatchTwoLevels(MultiFab& dst, const MultiFab& crse, const MultiFab& fine, const Geometry& cgeom,
+                        const Geometry& fgeom, const IntVect& ratio) {
+  two_level_fill(dst, crse, &fine, cgeom, fgeom, ratio, "FillPatchTwoLevels");
+}
+
+void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& cgeom, const Geometry& fgeom,
+                           const IntVect& ratio) {
+  two_level_fill(dst, crse, nullptr, cgeom, fgeom, ratio, "InterpFromCoarseLevel");
+}
+
+void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, const IntVect& ratio,
+                        const Geometry& cgeom, const Geometry& /*fgeom*/) {
+  if (fine.empty() || crse.empty()) return;
+  if (scomp != 0 || ncomp != crse.nComp()) Abort("sum_fine_to_coarse: only all components are supported");
+  if (fine.isFlat()) Abort("sum_fine_to_coarse: fine level must use BOXES storage");
+  const int r = ratio[0];
+  if (fine.nGrow() % r != 0) Abort("sum_fine_to_coarse: fine.nGrow() must be a multiple of the ratio");
+  const int cng = fine.nGrow() / r;
+  const std::string key = "SF|" + gkey(crse) + "|" + gkey(fine) + "|" + pkey(cgeom.periodicity()) + "|" + std::to_string(r);
+  lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
+    std::vector<Box> cf(fine.size());        // coarsened fine boxes grown by the coarse ghost width
+    for (long i = 0; i < fine.size(); ++i) {
+      cf[i] = amrex::grow(amrex::coarsen(fine.box((int)i), r), cng);
+      if (amrex::refine(cf[i], r) != fine.fabbox((int)i)) Abort("sum_fine_to_coarse: fine box not aligned to the coarse grid");
+    }
+    const BoxHash fh(cf);
+    const std::vector<IntVect> shifts = cgeom.periodicity().shiftIntVect();
+    for (int k = 0; k < crse.numStorageFabs(); ++k) {
+      const Box want = crse.storageValid(k);
+      std::vector<std::pair<int, int>> hits;
+      for (size_t si = 0; si < shifts.size(); ++si)
+        for (int i : fh.query(amrex::shift(want, IntVect(0) - shifts[si]))) hits.emplace_back(i, (int)si);
+      std::sort(hits.begin(), hits.end());
+      for (auto& h : hits) {
+        const IntVect& s = shifts[h.second];
+        const Box reg = amrex::shift(cf[h.first], s) & want;
+        if (reg.ok()) d.push_back(make_desc(k, 0, h.first, LBX_G_AVG, r, (IntVect(0) - s) * r, reg));
+      }
+    }
+  });
+  lbx_check(lbx_plan_apply(p, crse.mf(), fine.mf(), nullptr, LBX_OP_ADD), "sum_fine_to_coarse");
+  crse.touch();
+}
+
+iMultiFab makeFineMask(const MultiFab& cmf, const BoxArray& fba, const IntVect& ratio, int crse_value, int fine_value) {
+  iMultiFab mask(cmf.boxArray(), cmf.DistributionMap(), 1, cmf.nGrow());
+  if (mask.empty()) return mask;
+  mask.setVal(crse_value);
+  std::vector<Box> cf(fba.size());
+  for (long i = 0; i < fba.size(); ++i) cf[i] = amrex::coarsen(fba[i], ratio);
+  const BoxHash fh(cf);
+  std::vector<lbx_gather> d;
+  for (int k = 0; k < (int)mask.size(); ++k) {
+    const Box want = mask.fabbox(k);
+    for (int i : fh.query(want)) d.push_back(make_desc(k, 0, 0, LBX_G_CONST, 1, IntVect(0), cf[i] & want, (double)fine_value));
+  }
+  lbx_plan* p = nullptr;
+  lbx_check(lbx_plan_create(d.data(), (int)d.size(), &p), "makeFineMask");
+  lbx_check(lbx_plan_apply(p, mask.mf(), nullptr, nullptr, LBX_OP_COPY), "makeFineMask");
+  lbx_plan_destroy(p);
+  mask.touch();
+  return mask;
+}
+
+}  // namespace amrex

@@ -1,0 +1,222 @@
+// amrex-mini: box calculus (see AMReX_mini.H).  Restated from AMReX semantics
+//  [AMReX, unverified]; nothing here is copied from AMReX or the reference.
+#include "AMReX_mini.H"
+
+#include <cstring>
+#include <iostream>
+
+namespace amrex {
+
+namespace {
+bool g_abort_throws = false;
+int g_myproc = 0, g_nprocs = 1;
+}  // namespace
+
+void SetAbortThrows(bool on) { g_abort_throws = on; }
+
+void Abort(const char* msg) {
+  if (g_abort_throws) throw AbortException(msg ? msg : "amrex::Abort");
+  std::cerr << "amrex::Abort::" << g_myproc << "::" << (msg ? msg : "") << " !!!" << std::endl;
+  std::abort();
+}
+
+// ----------------------------------------------------------------------------- BoxList ops
+void boxDiff(BoxList& out, const Box& b1, const Box& b2) {
+  if (!b2.contains(b1)) {
+    if (!b1.intersects(b2)) {
+      out.push_back(b1);
+      return;
+    }
+    Box rest(b1);
+    for (int d = 0; d < 3; ++d) {
+      if (rest.smallEnd(d) < b2.smallEnd(d) && b2.smallEnd(d) <= rest.bigEnd(d)) {
+        Box low(rest);
+        low.setBig(d, b2.smallEnd(d) - 1);
+        out.push_back(low);
+        rest.setSmall(d, b2.smallEnd(d));
+      }
+      if (rest.smallEnd(d) <= b2.bigEnd(d) && b2.bigEnd(d) < rest.bigEnd(d)) {
+        Box high(rest);
+        high.setSmall(d, b2.bigEnd(d) + 1);
+        out.push_back(high);
+        rest.setBig(d, b2.bigEnd(d));
+      }
+    }
+  }
+}
+
+BoxList complementIn(const Box& region, const BoxList& bl) {
+  BoxList cur(1, region);
+  for (const Box& cut : bl) {
+    BoxList next;
+    for (const Box& b : cur) boxDiff(next, b, cut);
+    cur.swap(next);
+    if (cur.empty()) break;
+  }
+  return cur;
+}
+
+void simplify(BoxList& bl) {
+  // repeatedly coalesce pairs that abut along exactly one direction with equal extents in
+  // the others; a joined box replaces the LATER of the two (list order otherwise kept)
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    for (size_t a = 0; a < bl.size() && !changed; ++a) {
+      for (size_t b = a + 1; b < bl.size(); ++b) {
+        int lo[3], hi[3], joincnt = 0;
+        bool canjoin = true;
+        for (int d = 0; d < 3 && canjoin; ++d) {
+          const int alo = bl[a].smallEnd(d), ahi = bl[a].bigEnd(d), blo = bl[b].smallEnd(d), bhi = bl[b].bigEnd(d);
+          if (alo == blo && ahi == bhi) { lo[d] = alo; hi[d] = ahi; }
+          else if (alo <= blo && blo <= ahi + 1) { lo[d] = alo; hi[d] = std::max(ahi, bhi); ++joincnt; }
+          else if (blo <= alo && alo <= bhi + 1) { lo[d] = blo; hi[d] = std::max(ahi, bhi); ++joincnt; }
+          else canjoin = false;
+        }
+        if (canjoin && joincnt <= 1) {
+          bl[b] = Box(IntVect(lo), IntVect(hi));
+          bl.erase(bl.begin() + a);
+          changed = true;
+          break;
+        }
+      }
+    }
+  }
+}
+
+void maxSize(BoxList& bl, const IntVect& chunk) {
+  for (int d = 0; d < 3; ++d) {
+    BoxList chopped;
+    for (Box& bx : bl) {
+      const int len = bx.length(d);
+      if (len <= chunk[d]) continue;
+      int ratio = 1, bs = chunk[d], nlen = len;
+      while (bs % 2 == 0 && nlen % 2 == 0) { ratio *= 2; bs /= 2; nlen /= 2; }
+      const int numblk = nlen / bs + (nlen % bs ? 1 : 0);
+      const int sz = nlen / numblk, extra = nlen % numblk;
+      for (int k = 0; k < numblk - 1; ++k) {
+        const int ksize = (k < extra ? sz + 1 : sz) * ratio;
+        chopped.push_back(bx.chop(d, bx.bigEnd(d) - ksize + 1));   // from the high end
+      }
+    }
+    bl.insert(bl.end(), chopped.begin(), chopped.end());
+  }
+}
+
+BoxList intersect(const BoxList& bl, const Box& b) {
+  BoxList out;
+  for (const Box& x : bl) {
+    const Box i = x & b;
+    if (i.ok()) out.push_back(i);
+  }
+  return out;
+}
+
+Box minimalBox(const BoxList& bl) {
+  Box m;
+  for (const Box& b : bl) m.minBox(b);
+  return m;
+}
+
+// ----------------------------------------------------------------------------- Periodicity
+std::vector<IntVect> Periodicity::shiftIntVect() const {
+  std::vector<IntVect> r;
+  const int jx = p_[0] > 0 ? 1 : 0, jy = p_[1] > 0 ? 1 : 0, jz = p_[2] > 0 ? 1 : 0;
+  for (int i = -jx; i <= jx; ++i)
+    for (int j = -jy; j <= jy; ++j)
+      for (int k = -jz; k <= jz; ++k) r.push_back(IntVect(i * p_[0], j * p_[1], k * p_[2]));
+  return r;
+}
+
+// ----------------------------------------------------------------------------- BoxArray
+void BoxArray::detach() {
+  if (b_.use_count() > 1) b_ = std::make_shared<BoxList>(*b_);
+}
+bool BoxArray::ok() const {
+  for (const Box& b : *b_)
+    if (!b.ok()) return false;
+  return !b_->empty();
+}
+bool BoxArray::contains(const IntVect& p) const {
+  for (const Box& b : *b_)
+    if (b.contains(p)) return true;
+  return false;
+}
+bool BoxArray::contains(const Box& b) const {
+  if (!b.ok()) return false;
+  return complementIn(b, *b_).empty();
+}
+bool BoxArray::contains(const BoxArray& ba) const {
+  for (const Box& b : *ba.b_)
+    if (!contains(b)) return false;
+  return true;
+}
+bool BoxArray::intersects(const Box& b) const {
+  for (const Box& x : *b_)
+    if (x.intersects(b)) return true;
+  return false;
+}
+std::vector<std::pair<int, Box>> BoxArray::intersections(const Box& b) const {
+  std::vector<std::pair<int, Box>> r;
+  for (size_t i = 0; i < b_->size(); ++i) {
+    const Box x = (*b_)[i] & b;
+    if (x.ok()) r.emplace_back((int)i, x);
+  }
+  return r;
+}
+long BoxArray::numPts() const {
+  long n = 0;
+  for (const Box& b : *b_) n += b.numPts();
+  return n;
+}
+bool BoxArray::isDisjoint() const {
+  for (size_t a = 0; a < b_->size(); ++a)
+    for (size_t b = a + 1; b < b_->size(); ++b)
+      if ((*b_)[a].intersects((*b_)[b])) return false;
+  return true;
+}
+BoxArray& BoxArray::coarsen(const IntVect& r) {
+  detach();
+  for (Box& b : *b_) b.coarsen(r);
+  return *this;
+}
+BoxArray& BoxArray::refine(const IntVect& r) {
+  detach();
+  for (Box& b : *b_) b.refine(r);
+  return *this;
+}
+BoxArray& BoxArray::grow(int n) {
+  detach();
+  for (Box& b : *b_) b.grow(n);
+  return *this;
+}
+BoxArray& BoxArray::maxSize(const IntVect& n) {
+  detach();
+  amrex::maxSize(*b_, n);
+  return *this;
+}
+
+// ----------------------------------------------------------------------------- DistributionMapping
+int DistributionMapping::NProcs() { return g_nprocs; }
+int DistributionMapping::MyProc() { return g_myproc; }
+void DistributionMapping::SetParallel(int myproc, int nprocs) {
+  g_myproc = myproc;
+  g_nprocs = nprocs;
+}
+
+DistributionMapping::DistributionMapping(const BoxArray& ba, int nprocs) {
+  // contiguous chunks of the box list balanced by cell count (boxes of one level are listed in
+  // a spatially coherent order by the grid generator); a single rank owns everything.
+  const long n = ba.size();
+  p_.assign(n, 0);
+  if (nprocs <= 1 || n == 0) return;
+  const double total = (double)ba.numPts();
+  double acc = 0.0;
+  for (long i = 0; i < n; ++i) {
+    const double mid = acc + 0.5 * ba[i].numPts();
+    p_[i] = std::min(nprocs - 1, (int)(mid / total * nprocs));
+    acc += (double)ba[i].numPts();
+  }
+}
+
+}  // namespace amrex

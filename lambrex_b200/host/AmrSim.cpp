@@ -1,0 +1,473 @@
+// AmrSim on the GPU: host control flow of the reference's time stepping
+// (/root/reference/src/AmrSim.cpp), every field operation a kernel launch through
+// include/lbx.h.  Reference lines are cited per member.
+#include "AmrSim.h"
+
+#include <iostream>
+#include <stdexcept>
+
+using amrex::Box;
+using amrex::BoxArray;
+using amrex::DistributionMapping;
+using amrex::IntVect;
+using amrex::Layout;
+using amrex::lbx_check;
+using amrex::MultiFab;
+
+namespace {
+amrex::AmrInfo make_info(int max_ref_level) {
+  amrex::AmrInfo info;
+  info.verbose = 1;                                                        // src/AmrSim.cpp:763
+  info.max_level = max_ref_level;
+  info.ref_ratio.assign((size_t)max_ref_level + 1, IntVect(2, 2, 2));       // :765-766
+  info.blocking_factor.assign((size_t)max_ref_level + 1, IntVect(1, 1, 1)); // :767-768
+  return info;
+}
+lbx_box to_lbx(const Box& b) {
+  lbx_box r;
+  for (int d = 0; d < 3; ++d) { r.lo[d] = b.smallEnd(d); r.hi[d] = b.bigEnd(d); }
+  return r;
+}
+}  // namespace
+
+// src/AmrSim.cpp:753-802
+AmrSim::AmrSim(int const nx, int const ny, int const nz, int const max_ref_level,
+               const std::array<int, NDIMS>& periodicity, double const tau_s_0, double const tau_b_0)
+    : AmrCore(amrex::Geometry(Box(IntVect(0, 0, 0), IntVect(nx - 1, ny - 1, nz - 1)),
+                              amrex::RealBox({{0.0, 0.0, 0.0}}, {{1.0, 1.0, 1.0}}), 0, periodicity),
+              make_info(max_ref_level)),
+      NX(geom[0].Domain().length(0)), NY(geom[0].Domain().length(1)), NZ(geom[0].Domain().length(2)),
+      NUMEL(NX * NY * NZ), COORD_SYS(0),
+      PERIODICITY{{geom[0].period(0), geom[0].period(1), geom[0].period(2)}}, levels((size_t)max_ref_level + 1) {
+  std::cout << "NX: " << NX << " NY: " << NY << " NZ: " << NZ << std::endl;
+  const int num_levels = max_level + 1;
+  velocity.resize(num_levels);
+  stream_scratch.resize(num_levels);
+  tau_s.resize(num_levels);
+  tau_b.resize(num_levels);
+  mass.resize(num_levels);
+  static_tags.resize(num_levels);
+  fine_masks.resize(num_levels);
+  for (int d = 0; d < NDIMS; ++d)
+    if (!PERIODICITY[d]) amrex::Abort("Currently only periodic boundary conditions allowed.");
+  tau_s.at(0) = tau_s_0;
+  tau_b.at(0) = tau_b_0;
+  if (!lbx_initialized()) amrex::Abort("AmrSim: call lambrexInit() first (no CUDA context; there is no CPU path)");
+}
+
+AmrSim::~AmrSim() {
+  if (lbx_initialized()) lbx_sync();
+}
+
+// ----------------------------------------------------------------------------- input / output
+void AmrSim::SetInitialDensity(double const rho_init) { initial_density.assign(NUMEL, rho_init); }
+void AmrSim::SetInitialDensity(std::vector<double> const rho_init) { initial_density = rho_init; }
+void AmrSim::SetInitialVelocity(double const u_init) { initial_velocity.assign(3 * (size_t)NUMEL, u_init); }
+void AmrSim::SetInitialVelocity(std::vector<double> const u_init) { initial_velocity = u_init; }
+
+// user array (C-ordered, i slowest, component fastest) -> device field in fab order
+void AmrSim::upload_user_field(MultiFab& mf, const std::vector<double>& user, int ncomp) {
+  if (user.size() < (size_t)NUMEL * ncomp)
+    throw std::out_of_range("AmrSim: initial field has fewer than NX*NY*NZ*ncomp entries");
+  std::vector<double> host(mf.hostMirror().size(), 0.0);
+  const IntVect dims(NX, NY, NZ);
+  for (int s = 0; s < mf.numStorageFabs(); ++s) {
+    const Box a = mf.storageBox(s), v = mf.storageValid(s);
+    const size_t nx = a.length(0), ny = a.length(1), plane = nx * ny * a.length(2);
+    double* base = host.data() + mf.storageOffset(s);
+    for (int k = v.smallEnd(2); k <= v.bigEnd(2); ++k)
+      for (int j = v.smallEnd(1); j <= v.bigEnd(1); ++j)
+        for (int i = v.smallEnd(0); i <= v.bigEnd(0); ++i) {
+          const size_t c = (size_t)(i - a.smallEnd(0)) + nx * ((size_t)(j - a.smallEnd(1)) + ny * (size_t)(k - a.smallEnd(2)));
+          for (int n = 0; n < ncomp; ++n) base[n * plane + c] = user[(size_t)CLindex(i, j, k, n, dims, ncomp)];
+        }
+  }
+  mf.upload(host);
+}
+
+// src/AmrSim.cpp:138-214
+void AmrSim::InitDensity(int const level) {
+  if (level) amrex::Abort("Only level 0 should be initialised from scratch currently.");
+  upload_user_field(levels.at(level).now.get<Density>(), initial_density, 1);
+}
+// src/AmrSim.cpp:217-295
+void AmrSim::InitVelocity(int const level) {
+  if (level) amrex::Abort("Only LEVEL 0 should be initialised from scratch currently.");
+  upload_user_field(velocity.at(level), initial_velocity, NDIMS);
+}
+
+// src/AmrSim.cpp:824-843
+double AmrSim::GetDensity(int const i, int const j, int const k, int const level) const {
+  const IntVect pos(i, j, k);
+  const MultiFab& rho = levels[level].now.get<Density>();
+  for (amrex::MFIter mfi(rho); mfi.isValid(); ++mfi)
+    if (mfi.validbox().contains(pos)) return rho.hostValue(mfi.index(), pos, 0);
+  return NL_DENSITY;
+}
+double AmrSim::GetVelocity(int const i, int const j, int const k, int const n, int const level) const {
+  const IntVect pos(i, j, k);
+  const MultiFab& u = velocity.at(level);
+  for (amrex::MFIter mfi(u); mfi.isValid(); ++mfi)
+    if (mfi.validbox().contains(pos)) return u.hostValue(mfi.index(), pos, n);
+  return NL_VELOCITY;
+}
+
+std::vector<double> AmrSim::dense_field(const MultiFab& mf, int level, double sentinel) const {
+  const Box dom = geom[level].Domain();
+  const int nc = mf.nComp();
+  const size_t ny = dom.length(1), nz = dom.length(2);
+  std::vector<double> out((size_t)dom.numPts() * nc, sentinel);
+  if (mf.empty()) return out;
+  const std::vector<double>& host = mf.hostMirror();
+  for (int s = 0; s < mf.numStorageFabs(); ++s) {
+    const Box a = mf.storageBox(s), v = mf.storageValid(s);
+    const size_t ax = a.length(0), ay = a.length(1), plane = ax * ay * a.length(2);
+    const double* base = host.data() + mf.storageOffset(s);
+    for (int k = v.smallEnd(2); k <= v.bigEnd(2); ++k)
+      for (int j = v.smallEnd(1); j <= v.bigEnd(1); ++j)
+        for (int i = v.smallEnd(0); i <= v.bigEnd(0); ++i) {
+          const size_t c = (size_t)(i - a.smallEnd(0)) + ax * ((size_t)(j - a.smallEnd(1)) + ay * (size_t)(k - a.smallEnd(2)));
+          for (int n = 0; n < nc; ++n) out[(((size_t)i * ny + j) * nz + k) * nc + n] = base[n * plane + c];
+        }
+  }
+  return out;
+}
+std::vector<double> AmrSim::GetDensityField(int const level) const {
+  return dense_field(levels.at(level).now.get<Density>(), level, NL_DENSITY);
+}
+std::vector<double> AmrSim::GetVelocityField(int const level) const {
+  return dense_field(velocity.at(level), level, NL_VELOCITY);
+}
+
+// src/AmrSim.cpp:1019-1030
+std::pair<std::array<int, NDIMS>, std::array<int, NDIMS>> AmrSim::GetExtent(int const level) const {
+  const Box mb = levels[level].now.get<DistFn>().boxArray().minimalBox();
+  return {{{mb.smallEnd(0), mb.smallEnd(1), mb.smallEnd(2)}}, {{mb.bigEnd(0), mb.bigEnd(1), mb.bigEnd(2)}}};
+}
+
+// ----------------------------------------------------------------------------- layouts
+Layout AmrSim::PreferredLayout(int const level) const {
+  const bool alone = (level == 0 && finest_level == 0 && uniform_fast_path && DistributionMapping::NProcs() == 1);
+  return alone ? Layout::FLAT : Layout::BOXES;
+}
+
+void AmrSim::SetLevelLayout(int const level, Layout lay) {
+  auto& lvl = levels.at(level);
+  if (lvl.now.get<DistFn>().empty() || lvl.now.get<DistFn>().layout() == lay) return;
+  lvl.now.Relayout(lay);                         // keeps the valid cells of f and rho
+  velocity.at(level).relayout(lay);
+  const BoxArray ba = lvl.now.get<DistFn>().boxArray();
+  const DistributionMapping dm = lvl.now.get<DistFn>().DistributionMap();
+  lvl.next.Define(ba, dm, lay);                  // next is scratch between steps
+  stream_scratch.at(level).clear();
+}
+
+// ----------------------------------------------------------------------------- physics
+// src/AmrSim.cpp:845-936: f <- f_eq(rho, u) on the valid cells of NOW; then (sic, SURVEY.md
+// B-6) the boundary fill goes to NEXT.
+void AmrSim::CalcEquilibriumDist(int const level) {
+  auto& lvl = levels.at(level);
+  MultiFab& f = lvl.now.get<DistFn>();
+  lbx_check(lbx_mf_equilibrium(f.mf(), lvl.now.get<Density>().mf(), velocity.at(level).mf()), "CalcEquilibriumDist");
+  f.touch();
+  UpdateBoundaries(level);
+}
+
+// src/AmrSim.cpp:938-979
+void AmrSim::CalcHydroVars(int const level) {
+  auto& state = levels.at(level).now;
+  Density::fill(state.get<Density>(), velocity.at(level), state.get<DistFn>());
+}
+
+// src/AmrSim.cpp:19-23
+void AmrSim::UpdateBoundaries(int const level) {
+  amrex::FillBoundary(levels.at(level).next.get<DistFn>(), geom[level].periodicity());
+}
+
+// src/AmrSim.cpp:25-107 (valid cells, in place)
+void AmrSim::Collide(MultiFab& f, const double omega_s, const double omega_b) {
+  lbx_check(lbx_mf_collide(f.mf(), omega_s, omega_b, nullptr, FINE_VAL), "Collide");
+  f.touch();
+}
+
+// src/AmrSim.cpp:109-122: pull-stream NEXT into a "fresh" fab over valid grown by one, swap
+void AmrSim::Stream(int const level) {
+  MultiFab& f_nxt = levels[level].next.get<DistFn>();
+  MultiFab& f_prop = stream_scratch.at(level);
+  if (f_prop.empty() || f_prop.boxArray() != f_nxt.boxArray() || f_prop.layout() != f_nxt.layout())
+    f_prop = field_traits<DistFn>::MakeLevelData(f_nxt.boxArray(), f_nxt.DistributionMap(), f_nxt.layout());
+  DistFn::Propagate(f_nxt, f_prop);
+  std::swap(f_nxt, f_prop);
+}
+
+// src/AmrSim.cpp:124-135
+void AmrSim::CollideLevel(int const level) {
+  const double omega_s = 1.0 / (tau_s.at(level) + 0.5);
+  const double omega_b = 1.0 / (tau_b.at(level) + 0.5);
+  MultiFab& f_pc = levels.at(level).next.get<DistFn>();
+  DistFnFillPatch(level, f_pc);
+  Collide(f_pc, omega_s, omega_b);
+  amrex::FillBoundary(f_pc, geom[level].periodicity());
+}
+
+// include/AmrSim.h:89-94.  FLAT storage: CollideLevel + Stream collapse into one fused launch
+// (15 loads + 15 stores per cell); the result lands in NEXT exactly as after the reference's
+// Stream, then UpdateNow swaps the states.
+void AmrSim::CollideAndStream(int const level) {
+  auto& lvl = levels.at(level);
+  MultiFab& now_f = lvl.now.get<DistFn>();
+  if (now_f.isFlat()) {
+    MultiFab& next_f = lvl.next.get<DistFn>();
+    const lbx_fab src = now_f.fabDesc(0), dst = next_f.fabDesc(0);
+    const lbx_box box = to_lbx(geom[level].Domain());
+    lbx_domain dom;
+    for (int d = 0; d < 3; ++d) {
+      dom.lo[d] = box.lo[d];
+      dom.hi[d] = box.hi[d];
+      dom.periodic[d] = geom[level].isPeriodic(d) ? 1 : 0;
+    }
+    lbx_check(lbx_collide_stream(&src, &dst, &box, &dom, 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5),
+                                 LBX_PUSH),
+              "CollideAndStream");
+    next_f.touch();
+  } else {
+    CollideLevel(level);
+    Stream(level);
+  }
+  lvl.UpdateNow();
+}
+
+// src/AmrSim.cpp:324-333
+void AmrSim::IterateLevel(int const level) {
+  CollideAndStream(level);
+  auto& time = levels.at(level).time;
+  time.current += time.delta;
+  ++time.step;
+}
+
+// src/AmrSim.cpp:335-344 (never called by the reference either)
+void AmrSim::SubCycle(int const base_level, int const num_steps) {
+  if (base_level == finest_level) {
+    for (int iter = 0; iter < num_steps; ++iter) IterateLevel(base_level);
+  } else {
+    IterateLevel(base_level);
+    SubCycle(base_level + 1, refRatio(base_level)[0]);
+  }
+}
+
+// src/AmrSim.cpp:297-322
+void AmrSim::ComputeDt(int const level) {
+  auto& fine_time = levels[level].time;
+  if (level) {
+    const int r = refRatio(level - 1)[0];
+    fine_time.delta = levels[level - 1].time.delta / r;
+    mass.at(level) = mass.at(level - 1) / r;
+    tau_s.at(level) = r * (tau_s.at(level - 1) - 0.5) + 0.5;
+    tau_b.at(level) = r * (tau_b.at(level - 1) - 0.5) + 0.5;
+  } else {
+    fine_time.delta = 1.0;
+    mass.at(level) = 1.0;
+  }
+}
+
+// src/AmrSim.cpp:359-391
+void AmrSim::DistFnFillPatch(int const level, MultiFab& dest) {
+  if (!level) {
+    amrex::FillPatchSingleLevel(dest, levels[level].now.get<DistFn>(), geom[level]);
+  } else {
+    amrex::FillPatchTwoLevels(dest, levels[level - 1].now.get<DistFn>(), levels[level].now.get<DistFn>(), geom[level - 1],
+                              geom[level], refRatio(level - 1));
+  }
+}
+
+// src/AmrSim.cpp:393-411
+void AmrSim::DistFnFillFromCoarse(int const level, MultiFab& fine_mf) {
+  if (!level) amrex::Abort("Cannot fill level 0 from coarse.");
+  amrex::InterpFromCoarseLevel(fine_mf, levels[level - 1].now.get<DistFn>(), geom[level - 1], geom[level],
+                               refRatio(level - 1));
+}
+
+// src/AmrSim.cpp:413-417
+bool AmrSim::TagCell(int const level, const IntVect& pos) { return static_tags.at(level).contains(pos); }
+
+// src/AmrSim.cpp:419-428 -- sic: the level's OWN BoxArray is handed over as the fine one
+// (SURVEY.md B-1), so the mask marks coarsen(level grids), not the cells under level+1.
+void AmrSim::MakeFineMask(int const coarse_level) {
+  const MultiFab& cmf = levels[coarse_level].now.get<DistFn>();
+  const BoxArray& fba = levels[coarse_level].now.get<DistFn>().boxArray();
+  fine_masks[coarse_level] = amrex::makeFineMask(cmf, fba, refRatio(coarse_level), COARSE_VAL, FINE_VAL);
+}
+
+// ----------------------------------------------------------------------------- Rohde cycle
+// src/AmrSim.cpp:430-469
+void AmrSim::RohdeCycle(int const coarse_level) {
+  const int ref_ratio_here = refRatio(coarse_level)[0];
+  InitPostCollision(coarse_level);
+  CoarseCollide(coarse_level);
+  if (coarse_level + 1 == finest_level) {
+    InitPostCollision(finest_level);
+    FineCollide(finest_level);
+    Stream(finest_level);
+    FineCollide(finest_level);
+    Stream(finest_level);
+    ZeroInvalidComponents(finest_level);
+    UpdateDistribution(finest_level);
+  } else {
+    for (int iter = 0; iter < ref_ratio_here; ++iter) RohdeCycle(coarse_level + 1);
+  }
+  Stream(coarse_level);
+  SumFromFine(coarse_level);
+  ZeroInvalidComponents(coarse_level);
+  if (coarse_level == 0) UpdateBoundaries(coarse_level);
+  UpdateDistribution(coarse_level);
+}
+
+// src/AmrSim.cpp:471-485
+void AmrSim::InitPostCollision(int const level) {
+  MultiFab& f_pc = levels[level].next.get<DistFn>();
+  DistFnFillPatch(level, f_pc);
+  if (level != 0) {
+    // sic: component 0 only, outermost ghost ring
+    lbx_check(lbx_mf_zero_ring(f_pc.mf(), 1, 0), "InitPostCollision");
+    f_pc.touch();
+  }
+}
+
+// src/AmrSim.cpp:487-580
+void AmrSim::CoarseCollide(int const level) {
+  MultiFab& f_pc = levels[level].next.get<DistFn>();
+  const amrex::iMultiFab& mask = fine_masks.at(level);
+  if (mask.empty()) amrex::Abort("CoarseCollide: no fine mask on this level");
+  lbx_check(lbx_mf_collide(f_pc.mf(), 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5), mask.mf(), FINE_VAL),
+            "CoarseCollide");
+  f_pc.touch();
+}
+
+// src/AmrSim.cpp:582-590
+void AmrSim::FineCollide(int const level) {
+  Collide(levels.at(level).next.get<DistFn>(), 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5));
+}
+
+// src/AmrSim.cpp:592-602
+void AmrSim::SumFromFine(int const coarse_level) {
+  amrex::sum_fine_to_coarse(levels[coarse_level + 1].now.get<DistFn>(), levels[coarse_level].next.get<DistFn>(), 0, NMODES,
+                            refRatio(coarse_level), geom[coarse_level], geom[coarse_level + 1]);
+}
+
+// src/AmrSim.cpp:604-617
+void AmrSim::ZeroInvalidComponents(int const level) {
+  MultiFab& f_pc = levels[level].next.get<DistFn>();
+  lbx_check(lbx_mf_zero_invalid(f_pc.mf()), "ZeroInvalidComponents");
+  f_pc.touch();
+}
+
+// src/AmrSim.cpp:619-631
+void AmrSim::UpdateDistribution(int const level) {
+  auto& lvl = levels[level];
+  if (level && level == finest_level) {
+    lvl.time.current += 2 * lvl.time.delta;
+    lvl.time.step += 2;
+  } else {
+    lvl.time.current += lvl.time.delta;
+    ++lvl.time.step;
+  }
+  std::swap(lvl.now.get<DistFn>(), lvl.next.get<DistFn>());
+}
+
+// src/AmrSim.cpp:981-993
+void AmrSim::Iterate(int const nsteps) {
+  if (!finest_level) {
+    SetLevelLayout(0, PreferredLayout(0));
+    for (int t = 0; t < nsteps; ++t) IterateLevel(0);
+  } else {
+    for (int l = 0; l <= finest_level; ++l) SetLevelLayout(l, Layout::BOXES);
+    for (int t = 0; t < nsteps; ++t) RohdeCycle(0);
+  }
+}
+
+// ----------------------------------------------------------------------------- regrid hooks
+// src/AmrSim.cpp:633-663
+void AmrSim::ErrorEst(int level, amrex::TagBoxArray& tba, double /*time*/, int /*ngrow*/) {
+  const MultiFab& f = levels[level].now.get<DistFn>();
+  for (amrex::MFIter mfi(f); mfi.isValid(); ++mfi) {
+    const Box box = mfi.validbox();
+    amrex::TagBox& tagfab = tba[mfi];
+    tagfab.setVal(amrex::TagBox::CLEAR, box);
+    for (const auto& hit : static_tags.at(level).intersections(box)) tagfab.setVal(amrex::TagBox::SET, hit.second);
+  }
+}
+
+// src/AmrSim.cpp:665-687
+void AmrSim::MakeNewLevelFromScratch(int level, double time, const BoxArray& ba, const DistributionMapping& dm) {
+  auto& lvl = levels[level];
+  const Layout lay = (level == 0) ? PreferredLayout(0) : Layout::BOXES;
+  velocity[level].define(ba, dm, NDIMS, 0, lay);
+  lvl.Define(ba, dm, lay);
+  stream_scratch[level].clear();
+  lvl.time.current = time;
+  ComputeDt(level);
+  lvl.time.step = 0;
+  if (!level) {
+    InitDensity(level);
+    InitVelocity(level);
+    CalcEquilibriumDist(level);
+  }
+}
+
+// src/AmrSim.cpp:689-713
+void AmrSim::MakeNewLevelFromCoarse(int level, double time, const BoxArray& ba, const DistributionMapping& dm) {
+  if (!level) amrex::Abort("Cannot construct level 0 from a coarser level.");
+  velocity[level].define(ba, dm, NDIMS, 0);
+  auto& lvl = levels[level];
+  lvl.Define(ba, dm);
+  stream_scratch[level].clear();
+  lvl.time.current = time;
+  ComputeDt(level);
+  lvl.time.step = 0;
+  DistFnFillFromCoarse(level, lvl.now.get<DistFn>());
+  CalcHydroVars(level);
+  MakeFineMask(level - 1);
+}
+
+// src/AmrSim.cpp:715-744.  DEVIATION: the reference swaps in new NOW fabs only and
+// leaves NEXT on the old BoxArray, which breaks the following step whenever the grids really
+// changed; NEXT is redefined on the new BoxArray here.
+void AmrSim::RemakeLevel(int level, double time, const BoxArray& ba, const DistributionMapping& dm) {
+  auto& lvl = levels[level];
+  const Layout lay = lvl.now.get<DistFn>().empty() ? Layout::BOXES : lvl.now.get<DistFn>().layout();
+  MultiFab new_u(ba, dm, NDIMS, 0, lay);
+  MultiFab new_f = field_traits<DistFn>::MakeLevelData(ba, dm, lay);
+  MultiFab new_rho = field_traits<Density>::MakeLevelData(ba, dm, lay);
+  DistFnFillPatch(level, new_f);
+  auto& state = lvl.now;
+  std::swap(new_f, state.get<DistFn>());
+  std::swap(new_rho, state.get<Density>());
+  std::swap(new_u, velocity[level]);
+  lvl.next.Define(ba, dm, lay);
+  stream_scratch[level].clear();
+  lvl.time.current = time;
+  CalcHydroVars(level);
+  if (level < finest_level) MakeFineMask(level);
+}
+
+// src/AmrSim.cpp:746-751
+void AmrSim::ClearLevel(int level) {
+  velocity.at(level).clear();
+  levels.at(level).Clear();
+  stream_scratch.at(level).clear();
+}
+
+// src/AmrSim.cpp:995-1009
+void AmrSim::SetStaticRefinement(int const level, const std::array<int, NDIMS>& lo_corner,
+                                 const std::array<int, NDIMS>& hi_corner) {
+  static_tags.at(level).define(Box(IntVect(lo_corner), IntVect(hi_corner)));
+  regrid(level, GetTime(level));
+  MakeFineMask(level);
+}
+
+// src/AmrSim.cpp:1011-1017
+void AmrSim::UnsetStaticRefinement(int const level) {
+  static_tags.at(level).clear();
+  regrid(level, GetTime(level));
+  MakeFineMask(level);
+}

@@ -1,0 +1,142 @@
+// -*- mode: c++ -*-
+// AmrSim: the reference's simulation class (/root/reference/include/AmrSim.h:23-155) with the
+// same public and protected member names, argument meaning and error behaviour, implemented
+// as host control flow over device kernels (include/lbx.h).  Each member cites the reference
+// lines it replaces in AmrSim.cpp.
+//
+// What differs by design:
+//  * field data lives in HBM; members launch kernels, the getters read a lazily refreshed host
+//    mirror (GetDensity/GetVelocity keep the reference's per-cell signature and sentinels).
+//  * while level 0 is the only level it is stored FLAT (one ghost-free fab over the periodic
+//    domain) and one Iterate step is ONE fused kernel; with finer levels present every level
+//    uses per-box storage and the Rohde cycle runs as batched per-level kernels.
+//  * Stream() reuses a third population buffer instead of allocating a fab per call; the
+//    buffer's ghost ring 2 is zeroed by the kernel (a "fresh" fab).
+#ifndef LBX_AMRSIM_H
+#define LBX_AMRSIM_H
+
+#include <array>
+#include <utility>
+#include <vector>
+
+#include "AMReX_AmrCore.H"
+#include "AMReX_FillPatch.H"
+#include "d3q15_bgk.h"
+
+#define NDIMS 3
+#define NMODES 15
+
+class AmrSim : public amrex::AmrCore {
+ public:
+  AmrSim(int const nx, int const ny, int const nz, int const max_ref_level,
+         const std::array<int, NDIMS>& periodicity, double const tau_s_0, double const tau_b_0);
+  ~AmrSim() override;
+
+  // clocks and extents
+  double GetTime(int const level) const { return levels.at(level).time.current; }
+  int GetTimeStep(int const level) const { return levels.at(level).time.step; }
+  std::array<int, NDIMS> GetDims() const { return {{NX, NY, NZ}}; }
+  std::pair<std::array<int, NDIMS>, std::array<int, NDIMS>> GetExtent(int const level) const;
+
+  // initial condition: scalars or C-ordered arrays rho[(i*NY+j)*NZ+k], u[((i*NY+j)*NZ+k)*3+n]
+  void SetInitialDensity(double const rho_init);
+  void SetInitialDensity(std::vector<double> const rho_init);
+  void SetInitialVelocity(double const u_init);
+  void SetInitialVelocity(std::vector<double> const u_init);
+
+  // output; cells the level does not hold give the sentinels NL_DENSITY / NL_VELOCITY
+  double GetDensity(int const i, int const j, int const k, int const level) const;
+  double GetVelocity(int const i, int const j, int const k, int const n, int const level) const;
+  bool OnProcessDensity(double const rho) const { return rho != NL_DENSITY; }
+  bool OnProcessVelocity(double const u) const { return u != NL_VELOCITY; }
+
+  void CalcEquilibriumDist(int const level);
+  void CalcHydroVars(int const level);
+  void Iterate(int const nsteps);
+  void SetStaticRefinement(int const level, const std::array<int, NDIMS>& lo_corner,
+                           const std::array<int, NDIMS>& hi_corner);
+  void UnsetStaticRefinement(int const level);
+
+  // ---- additions (not in the reference) -------------------------------------------------
+  // dense copies of the level's fields over its index domain, C-ordered like the inputs;
+  // cells the level does not hold carry the sentinels.  One device->host copy per call.
+  std::vector<double> GetDensityField(int const level) const;
+  std::vector<double> GetVelocityField(int const level) const;
+  // false: run level 0 through the reference's literal pass structure on per-box storage even
+  // when it is the only level (FillPatch, collide, FillBoundary, stream, swap).  Default true.
+  void SetUniformFastPath(bool on) { uniform_fast_path = on; }
+
+ protected:
+  const int NX, NY, NZ, NUMEL, COORD_SYS;
+  std::array<int, NDIMS> PERIODICITY;
+
+  constexpr static double CS2 = 1.0 / 3.0;
+  constexpr static double NL_DENSITY = -1.0;
+  constexpr static double NL_VELOCITY = -3E8;
+  std::vector<double> initial_density;
+  std::vector<double> initial_velocity;
+  std::vector<amrex::BoxArray> static_tags;
+
+  std::vector<double> tau_s;
+  std::vector<double> tau_b;
+  std::vector<double> mass;
+  std::vector<amrex::MultiFab> velocity;    // output, 3 comps, no ghosts
+  std::vector<SimLevelData> levels;         // now/next x {DistFn, Density} + clock
+
+  const int COARSE_VAL = 0;
+  const int FINE_VAL = 1;
+  std::vector<amrex::iMultiFab> fine_masks;
+
+  int CLindex(int const i, int const j, int const k, int const n, amrex::IntVect const dims,
+              int const n_comps) const {
+    return ((i * dims[1] + j) * dims[2] + k) * n_comps + n;
+  }
+
+  // single-level step
+  void UpdateBoundaries(int const level);
+  void Collide(amrex::MultiFab& f, const double omega_s, const double omega_b);
+  void Stream(int const level);
+  void CollideLevel(int const level);
+  void CollideAndStream(int const level);
+  void IterateLevel(int const level);
+  void SubCycle(int const base_level, int const num_steps);
+
+  // set-up
+  void InitDensity(int const level);
+  void InitVelocity(int const level);
+  void ComputeDt(int const level);
+  void DistFnFillPatch(int const level, amrex::MultiFab& dest);
+  void DistFnFillFromCoarse(int const level, amrex::MultiFab& fine_mf);
+  bool TagCell(int const level, const amrex::IntVect& pos);
+  void MakeFineMask(int const coarse_level);
+
+  // Rohde et al. (2006) volumetric two-level coupling
+  void RohdeCycle(int const coarse_level);
+  void InitPostCollision(int const level);
+  void CoarseCollide(int const level);
+  void FineCollide(int const level);
+  void SumFromFine(int const coarse_level);
+  void ZeroInvalidComponents(int const level);
+  void UpdateDistribution(int const level);
+
+  // amrex::AmrCore hooks
+  void ErrorEst(int level, amrex::TagBoxArray& tags, double time, int ngrow) override;
+  void MakeNewLevelFromScratch(int level, double time, const amrex::BoxArray& ba,
+                               const amrex::DistributionMapping& dm) override;
+  void MakeNewLevelFromCoarse(int level, double time, const amrex::BoxArray& ba,
+                              const amrex::DistributionMapping& dm) override;
+  void RemakeLevel(int level, double time, const amrex::BoxArray& ba, const amrex::DistributionMapping& dm) override;
+  void ClearLevel(int level) override;
+
+  // storage layout of a level (see AMReX_MultiFab.H)
+  void SetLevelLayout(int const level, amrex::Layout lay);
+  amrex::Layout PreferredLayout(int const level) const;
+
+ private:
+  std::vector<amrex::MultiFab> stream_scratch;   // third population buffer per level
+  bool uniform_fast_path = true;
+  void upload_user_field(amrex::MultiFab& mf, const std::vector<double>& user, int ncomp);
+  std::vector<double> dense_field(const amrex::MultiFab& mf, int level, double sentinel) const;
+};
+
+#endif

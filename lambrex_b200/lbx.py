@@ -39,6 +39,15 @@ class lbx_domain(ctypes.Structure):
     _fields_ = [("lo", ctypes.c_int32 * 3), ("hi", ctypes.c_int32 * 3), ("periodic", ctypes.c_int32 * 3)]
 
 
+class lbx_gather(ctypes.Structure):
+    _fields_ = [("dst_fab", ctypes.c_int32), ("src_set", ctypes.c_int32), ("src_fab", ctypes.c_int32),
+                ("kind", ctypes.c_int32), ("ratio", ctypes.c_int32), ("shift", ctypes.c_int32 * 3),
+                ("region", lbx_box), ("value", ctypes.c_double)]
+
+
+G_COPY, G_PC, G_AVG, G_CONST = 0, 1, 2, 3
+OP_COPY, OP_ADD = 0, 1
+
 # every symbol include/lbx.h declares: name -> (restype, argtypes)
 _vp, _sz, _i, _d = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_double
 _fp, _bp, _dp = ctypes.POINTER(lbx_fab), ctypes.POINTER(lbx_box), ctypes.POINTER(lbx_domain)
@@ -77,6 +86,23 @@ SYMBOLS = {
     "lbx_collide_stream_slab": (_i, [_fp, _fp, _fp, _fp, _bp, _dp, _d, _d]),
     "lbx_halo_pack": (_i, [_fp, _bp, _i, _vp]),
     "lbx_halo_unpack": (_i, [_fp, _bp, _i, _vp]),
+    "lbx_mf_create": (_i, [_bp, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "lbx_mf_destroy": (_i, [_vp]),
+    "lbx_mf_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
+                         ctypes.POINTER(_sz)]),
+    "lbx_mf_fab": (_i, [_vp, _i, _fp, _bp, ctypes.POINTER(_sz)]),
+    "lbx_mf_upload": (_i, [_vp, _vp, _sz]),
+    "lbx_mf_download": (_i, [_vp, _vp, _sz]),
+    "lbx_mf_setval": (_i, [_vp, _d]),
+    "lbx_mf_equilibrium": (_i, [_vp, _vp, _vp]),
+    "lbx_mf_moments": (_i, [_vp, _vp, _vp]),
+    "lbx_mf_collide": (_i, [_vp, _d, _d, _vp, _i]),
+    "lbx_mf_stream": (_i, [_vp, _vp]),
+    "lbx_mf_zero_invalid": (_i, [_vp]),
+    "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
+    "lbx_plan_create": (_i, [ctypes.POINTER(lbx_gather), _i, ctypes.POINTER(_vp)]),
+    "lbx_plan_apply": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "lbx_plan_destroy": (_i, [_vp]),
     "lbx_d3q15_tables": (None, [ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(_d)]),
 }
@@ -315,3 +341,118 @@ def fab_desc(ptr, alo, n, ncomp=NV, dtype=F64):
 def collide_stream(src, dst, bx, dom, omega_s, omega_b, scheme=PUSH):
     check(lib().lbx_collide_stream(src.ref(), dst.ref(), ctypes.byref(bx), ctypes.byref(dom),
                                    omega_s, omega_b, scheme))
+
+
+class MF:
+    """Device fab set (lbx_mf): all boxes of one level/field.  ``boxes`` = [(lo, hi)] valid
+    boxes.  Host mirrors are lists of numpy arrays [comp, z, y, x] over the GROWN boxes."""
+
+    def __init__(self, boxes, ncomp, ngrow=0, dtype=F64):
+        self.boxes = [(tuple(int(x) for x in lo), tuple(int(x) for x in hi)) for lo, hi in boxes]
+        self.ncomp, self.ngrow, self.dtype = int(ncomp), int(ngrow), dtype
+        arr = (lbx_box * len(self.boxes))()
+        for a, (lo, hi) in zip(arr, self.boxes):
+            a.lo[:] = lo
+            a.hi[:] = hi
+        h = _vp()
+        check(lib().lbx_mf_create(arr, len(self.boxes), self.ncomp, self.ngrow, dtype, ctypes.byref(h)))
+        self.h = h.value
+        nb = _sz(0)
+        check(lib().lbx_mf_info(self.h, None, None, None, None, ctypes.byref(nb)))
+        self.nbytes = nb.value
+        self.item = 8 if dtype == F64 else 4
+        self.npdtype = np.float64 if dtype == F64 else np.int32
+        self.offsets, self.shapes = [], []
+        for i in range(len(self.boxes)):
+            f, off = lbx_fab(), _sz(0)
+            check(lib().lbx_mf_fab(self.h, i, ctypes.byref(f), None, ctypes.byref(off)))
+            self.offsets.append(off.value)
+            self.shapes.append((self.ncomp, f.n[2], f.n[1], f.n[0]))
+
+    def fab(self, i):
+        f = lbx_fab()
+        check(lib().lbx_mf_fab(self.h, i, ctypes.byref(f), None, None))
+        return f
+
+    def upload(self, arrays):
+        buf = np.zeros(self.nbytes // self.item, dtype=self.npdtype)
+        for a, off, shp in zip(arrays, self.offsets, self.shapes):
+            a = np.ascontiguousarray(a, dtype=self.npdtype)
+            assert a.shape == shp, (a.shape, shp)
+            buf[off // self.item: off // self.item + a.size] = a.reshape(-1)
+        check(lib().lbx_mf_upload(self.h, buf.ctypes.data, self.nbytes))
+        sync()
+
+    def download(self):
+        buf = np.empty(self.nbytes // self.item, dtype=self.npdtype)
+        check(lib().lbx_mf_download(self.h, buf.ctypes.data, self.nbytes))
+        sync()
+        return [buf[off // self.item: off // self.item + int(np.prod(shp))].reshape(shp).copy()
+                for off, shp in zip(self.offsets, self.shapes)]
+
+    def setval(self, v):
+        check(lib().lbx_mf_setval(self.h, float(v)))
+
+    def free(self):
+        if self.h:
+            check(lib().lbx_mf_destroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.h and _lib is not None and _lib.lbx_initialized():
+                _lib.lbx_mf_destroy(self.h)
+        except Exception:
+            pass
+
+
+def mf_equilibrium(f, rho, u):
+    check(lib().lbx_mf_equilibrium(f.h, rho.h, u.h))
+
+
+def mf_moments(f, rho, u):
+    check(lib().lbx_mf_moments(f.h, rho.h, u.h))
+
+
+def mf_collide(f, omega_s, omega_b, mask=None, fine_val=1):
+    check(lib().lbx_mf_collide(f.h, omega_s, omega_b, mask.h if mask is not None else None, fine_val))
+
+
+def mf_stream(src, dst):
+    check(lib().lbx_mf_stream(src.h, dst.h))
+
+
+def mf_zero_invalid(f):
+    check(lib().lbx_mf_zero_invalid(f.h))
+
+
+def mf_zero_ring(f, depth, comp):
+    check(lib().lbx_mf_zero_ring(f.h, depth, comp))
+
+
+class Plan:
+    """descs: iterable of dicts(dst_fab, src_set, src_fab, kind, ratio, shift, lo, hi, value),
+    grouped by ascending dst_fab."""
+
+    def __init__(self, descs):
+        descs = list(descs)
+        arr = (lbx_gather * max(len(descs), 1))()
+        for a, d in zip(arr, descs):
+            a.dst_fab, a.src_set, a.src_fab = d["dst_fab"], d.get("src_set", 0), d.get("src_fab", 0)
+            a.kind, a.ratio = d.get("kind", G_COPY), d.get("ratio", 1)
+            a.shift[:] = [int(x) for x in d.get("shift", (0, 0, 0))]
+            a.region.lo[:] = [int(x) for x in d["lo"]]
+            a.region.hi[:] = [int(x) for x in d["hi"]]
+            a.value = float(d.get("value", 0.0))
+        h = _vp()
+        check(lib().lbx_plan_create(arr, len(descs), ctypes.byref(h)))
+        self.h, self.n = h.value, len(descs)
+
+    def apply(self, dst, src0=None, src1=None, op=OP_COPY):
+        check(lib().lbx_plan_apply(self.h, dst.h, src0.h if src0 is not None else None,
+                                   src1.h if src1 is not None else None, op))
+
+    def free(self):
+        if self.h:
+            check(lib().lbx_plan_destroy(self.h))
+            self.h = None

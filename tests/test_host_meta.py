@@ -1,0 +1,118 @@
+"""CPU tests of the C++ host library's grid-generation metadata (liblambrex.so, no GPU):
+bit-exact agreement of box lists with the oracle's restatement -- base grids, maxSize,
+simplify, complement, Berger-Rigoutsos clustering, and whole regrid sequences with the
+reference's static-box tagging -- plus the C-ABI export check for include/lambrex_c.h."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from lambrex_b200 import amrsim
+from oracle import amr_oracle as ao
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = amrsim.lib()
+    txt = open(os.path.join(ROOT, "include", "lambrex_c.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set(re.findall(r"\b(lbx_(?:sim|meta)_[a-z0-9_]+)\s*\(", txt))
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(L, n), "liblambrex.so does not export " + n
+    assert names == set(amrsim.SYMBOLS), names ^ set(amrsim.SYMBOLS)
+
+
+def test_sim_needs_initialised_gpu_context():
+    from lambrex_b200 import lbx
+    import ctypes
+    n = ctypes.c_int(0)
+    lbx.lib().lbx_device_count(ctypes.byref(n))
+    if n.value == 0:
+        with pytest.raises(amrsim.LambrexError):
+            amrsim.lambrexInit()
+        with pytest.raises(amrsim.LambrexError):
+            amrsim.AmrSim(4, 4, 4, 0, (1, 1, 1), 0.5, 0.5)
+
+
+@pytest.mark.parametrize("dims", [(10, 10, 50), (48, 24, 12), (11, 12, 13), (256, 256, 256), (16, 9, 8), (100, 70, 33)])
+def test_base_grids_match_oracle(dims):
+    want = ao.make_base_grids(((0, 0, 0), tuple(d - 1 for d in dims)))
+    assert amrsim.meta_base_grids(dims) == want
+    assert sum(ao.numpts(b) for b in want) == int(np.prod(dims))
+
+
+def test_box_calculus_matches_oracle():
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        lo = rng.integers(-5, 10, 3)
+        hi = lo + rng.integers(0, 70, 3)
+        b = ao.bx(lo, hi)
+        chunk = int(rng.choice([4, 8, 16, 32]))
+        assert amrsim.meta_max_size([b], chunk) == ao.max_size([b], chunk)
+        cuts = []
+        for _ in range(3):
+            cl = lo + rng.integers(-3, 40, 3)
+            cuts.append(ao.bx(cl, cl + rng.integers(0, 30, 3)))
+        comp = ao.complement_in(b, cuts)
+        assert amrsim.meta_complement(b, cuts) == comp
+        assert amrsim.meta_simplify(comp) == ao.simplify(comp)
+        assert sum(ao.numpts(x) for x in ao.simplify(comp)) == sum(ao.numpts(x) for x in comp)
+
+
+def test_cluster_matches_oracle():
+    rng = np.random.default_rng(3)
+    for trial in range(12):
+        pts = set()
+        for _ in range(int(rng.integers(1, 5))):
+            lo = rng.integers(0, 40, 3)
+            ext = rng.integers(1, 12, 3)
+            for i in range(ext[0]):
+                for j in range(ext[1]):
+                    for k in range(ext[2]):
+                        if rng.random() < 0.9:
+                            pts.add((int(lo[0] + i), int(lo[1] + j), int(lo[2] + k)))
+        p = np.array(sorted(pts, key=lambda v: (v[2], v[1], v[0])))
+        want, _ = ao.cluster(p, 0.7)
+        assert amrsim.meta_cluster(p, 0.7) == want, trial
+
+
+REGRID_CASES = [
+    ((48, 24, 12), 1, [("set", 0, (12, 6, 3), (36, 18, 9))]),
+    ((48, 24, 12), 1, [("set", 0, (0, 0, 0), (47, 23, 11)), ("unset", 0)]),
+    ((16, 16, 32), 1, [("set", 0, (4, 4, 8), (12, 12, 24)), ("set", 0, (2, 2, 2), (9, 9, 20))]),
+    ((32, 32, 32), 2, [("set", 0, (8, 8, 8), (23, 23, 23)), ("set", 1, (24, 24, 24), (39, 39, 39))]),
+    ((32, 32, 32), 2, [("set", 0, (0, 8, 8), (10, 23, 23)), ("set", 1, (4, 20, 20), (15, 30, 30)),
+                       ("set", 0, (4, 8, 8), (14, 23, 23)), ("unset", 1)]),
+    ((64, 64, 64), 2, [("set", 0, (10, 12, 14), (50, 41, 30)), ("set", 1, (30, 30, 34), (90, 70, 52))]),
+]
+
+
+@pytest.mark.parametrize("dims,max_level,ops", REGRID_CASES)
+def test_regrid_sequences_match_oracle(dims, max_level, ops, coracle):
+    mesh = amrsim.MetaMesh(dims, max_level)
+    sim = ao.AmrSimOracle(*dims, max_level, 0.5, 0.5, coracle=coracle)
+    sim.set_initial_density(1.0)
+    sim.set_initial_velocity(0.0)
+    sim.init_from_scratch(0.0)
+    assert mesh.boxes(0) == sim.grids[0]
+    for op in ops:
+        if op[0] == "set":
+            mesh.set_static(op[1], op[2], op[3])
+            sim.set_static_refinement(op[1], op[2], op[3])
+        else:
+            mesh.unset_static(op[1])
+            sim.unset_static_refinement(op[1])
+        assert mesh.finest_level() == sim.finest_level, op
+        for lev in range(max_level + 1):
+            assert mesh.boxes(lev) == sim.grids[lev], (op, lev)
+    # proper nesting: every level-(l+1) box, coarsened and grown by n_proper, lies in level l
+    for lev in range(1, sim.finest_level + 1):
+        for b in sim.grids[lev]:
+            c = ao.grow(ao.coarsen(b, 2), 1)
+            dom = sim.domain(lev - 1)
+            cells = ao.complement_in(c, sim.grids[lev - 1])
+            for r in cells:      # anything uncovered must be outside the domain (periodic wrap)
+                assert ao.isect(r, dom) is None or lev - 1 == 0
