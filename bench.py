@@ -159,6 +159,96 @@ def workload_config(ngpus):
 
 
 def run_single(args):
+    """N = 1.  Both legs go through the reference-facing API (AmrSim, include/lambrex_c.h):
+    value = K x AmrSim::Iterate steps with the populations resident in HBM (CUDA events on the
+    library's stream); e2e = SetInitialDensity/Velocity (host arrays) + InitFromScratch +
+    Iterate(K) + CalcHydroVars + bulk getters back to host arrays.  --api raw times the bare
+    C-ABI kernels instead (kernel comparisons: --scheme push|pull|slab)."""
+    from lambrex_b200 import lbx, workloads
+    if args.api == "raw":
+        return run_single_raw(args)
+    from lambrex_b200 import amrsim
+    amrsim.lambrexInit()
+    n = args.grid
+    cfg = workload_config(1)
+    cfg["grid"] = [n, n, n]
+    cfg["api"] = "AmrSim (liblambrex.so) -> lbx_collide_stream, FLAT level-0 storage"
+    cells = float(n) ** 3
+    # pinned host buffers: [rho | u] inputs and [rho | u] outputs, C-ordered like the reference's API
+    L = lbx.lib()
+    ncell = n ** 3
+    hp = ctypes.c_void_p()
+    lbx.check(L.lbx_host_alloc(ctypes.byref(hp), 8 * ncell * 8))
+    host = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_double)), shape=(8 * ncell,))
+    rho0, u0 = host[:ncell], host[ncell:4 * ncell]
+    rho_out, u_out = host[4 * ncell:5 * ncell], host[5 * ncell:]
+    rho0[:] = workloads.pulse_density(n, n, n)
+    u0[:] = 0.0
+
+    def make_sim():
+        sim = amrsim.AmrSim(n, n, n, 0, (1, 1, 1), 0.5, 0.5)
+        sim.SetInitialDensityView(rho0)       # read from the pinned arrays at InitFromScratch
+        sim.SetInitialVelocityView(u0)
+        sim.InitFromScratch(0.0)
+        return sim
+
+    # ---- device-resident leg -------------------------------------------------
+    sim = make_sim()
+    sim.Iterate(args.warmup)
+    lbx.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = lbx.launch_count()
+    with lbx.Timer() as t:
+        sim.Iterate(args.steps)
+    launches = lbx.launch_count() - l0
+    clocks = sampler.stop()
+    ms_step = t.ms / args.steps
+    mlups = cells * args.steps / (t.ms * 1e-3) / 1e6
+    sim.CalcHydroVars(0)
+    rho = sim.GetDensityField(0, rho_out)
+    mass = float(rho.sum())
+    sim.close()
+
+    # ---- end-to-end leg ------------------------------------------------------
+    lbx.sync()
+    t0 = time.perf_counter()
+    sim = make_sim()
+    sim.Iterate(args.steps)
+    sim.CalcHydroVars(0)
+    rho = sim.GetDensityField(0, rho_out)
+    vel = sim.GetVelocityField(0, u_out)
+    e2e_s = time.perf_counter() - t0
+    io = 32.0 * cells
+    e2e = {"value": cells * args.steps / e2e_s / 1e6, "unit": "MLUPS",
+           "h2d_bytes_per_step": io / args.steps, "d2h_bytes_per_step": io / args.steps,
+           "note": "one job = AmrSim ctor + SetInitialDensity/VelocityView (pinned host arrays) + InitFromScratch (H2D, "
+                   "equilibrium) + Iterate(%d) + CalcHydroVars + GetDensityField/GetVelocityField (D2H)" % args.steps,
+           "check_rho_minmax": [float(rho.min()), float(rho.max())], "check_u_absmax": float(np.abs(vel).max())}
+    sim.close()
+
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9
+    tr = recorded_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_collide_stream<push>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source")}
+    cpu = None
+    if not args.no_cpu:
+        r = cpu_reference(args.cpu_sample, 4, 1)
+        cpu = {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    line = {"metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "check": {"total_mass_over_cells": mass / cells}}
+    print(json.dumps(line), flush=True)
+    del rho, vel, rho0, u0, rho_out, u_out, host
+    lbx.check(L.lbx_host_free(hp))
+
+
+def run_single_raw(args):
     from lambrex_b200 import lbx, workloads
     lbx.init()
     n = args.grid
@@ -263,7 +353,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256, help="N=1 cubic grid edge (default 256 = configs[1])")
-    ap.add_argument("--scheme", default="push", choices=["push", "pull", "slab"])
+    ap.add_argument("--api", default="amrsim", choices=["amrsim", "raw"],
+                    help="N=1: time AmrSim::Iterate (default) or the bare C-ABI kernels")
+    ap.add_argument("--scheme", default="push", choices=["push", "pull", "slab"], help="kernel for --api raw")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 face exchange: peer stores fused into the step kernel, or packed NCCL send/recv")
     ap.add_argument("--grid-multi", type=int, default=1024, help="N>1 cubic grid edge (default 1024 = configs[2])")

@@ -37,6 +37,10 @@ int lbx_sim_set_uniform_fast_path(lbx_sim *sim, int on);
 /* SetInitialDensity / SetInitialVelocity (:141-144); n == 1 selects the scalar overloads */
 int lbx_sim_set_initial_density(lbx_sim *sim, const double *rho, size_t n);
 int lbx_sim_set_initial_velocity(lbx_sim *sim, const double *u, size_t n);
+/* zero-copy variants (addition): the arrays are read by lbx_sim_init_from_scratch straight from
+ * caller memory (one DMA when it is pinned, see lbx_host_alloc) and must stay valid until then */
+int lbx_sim_set_initial_density_view(lbx_sim *sim, const double *rho, size_t n);
+int lbx_sim_set_initial_velocity_view(lbx_sim *sim, const double *u, size_t n);
 /* AmrCore::InitFromScratch, regrid */
 int lbx_sim_init_from_scratch(lbx_sim *sim, double time);
 int lbx_sim_regrid(lbx_sim *sim, int lbase, double time);

@@ -156,6 +156,10 @@ int lbx_mf_equilibrium(lbx_mf *f, const lbx_mf *rho, const lbx_mf *u);
 int lbx_mf_moments(const lbx_mf *f, lbx_mf *rho, lbx_mf *u);
 /* Collide :25-107, CoarseCollide :487-580 (mask != NULL), FineCollide :582-590: in place */
 int lbx_mf_collide(lbx_mf *f, double omega_s, double omega_b, const lbx_mf *mask, int fine_val);
+/* same, out of place: dst valid cells <- collide(src valid cells); src and dst hold the same boxes.
+ * Fuses the valid-cell copy of FillPatch (src/AmrSim.cpp:129) with the collision that follows it. */
+int lbx_mf_collide2(const lbx_mf *src, lbx_mf *dst, double omega_s, double omega_b, const lbx_mf *mask,
+                    int fine_val);
 /* Stream :109-122 into a "fresh" fab: dst(x,p) = src(x - c_p, p) on valid grown by 1, every
  * other cell of dst zeroed (the reference never writes ghost ring 2 of its new fab) */
 int lbx_mf_stream(const lbx_mf *src, lbx_mf *dst);
@@ -163,6 +167,15 @@ int lbx_mf_stream(const lbx_mf *src, lbx_mf *dst);
 int lbx_mf_zero_invalid(lbx_mf *f);
 /* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */
 int lbx_mf_zero_ring(lbx_mf *f, int depth, int comp);
+
+/* User-facing arrays are C-ordered, i slowest, component fastest (CLindex, include/AmrSim.h:79-83):
+ * user[(((i-lo0)*NY + (j-lo1))*NZ + (k-lo2))*ncomp + n] over `domain`.  `user_dev` is DEVICE memory.
+ * from_user: valid cells of every box <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);
+ * to_user  : user <- valid cells; cells no box holds keep their content (GetDensity / GetVelocity
+ *            :824-843 in bulk; pre-fill the sentinel with lbx_fill_f64). */
+int lbx_mf_from_user(lbx_mf *mf, const double *user_dev, const lbx_box *domain, int ncomp);
+int lbx_mf_to_user(const lbx_mf *mf, double *user_dev, const lbx_box *domain, int ncomp);
+int lbx_fill_f64(double *dev, size_t n, double value);
 
 /* Gather plans: the box-intersection metadata of AMReX's ParallelCopy-type calls, computed
  * once on the host, executed as one launch (one thread per destination cell).
@@ -177,6 +190,9 @@ enum { LBX_G_COPY = 0,   /* dst(x) = src(x + shift)                             
 enum { LBX_OP_COPY = 0, LBX_OP_ADD = 1 };
 typedef struct lbx_gather {
   int32_t dst_fab;      /* index into the destination set; descriptors sorted by it   */
+  int32_t group;        /* tile group inside dst_fab (ascending): each (dst_fab, group) is
+                           tiled over the bounding box of ITS regions only -- e.g. the six
+                           slabs of a ghost shell instead of the whole grown box          */
   int32_t src_set;      /* 0 or 1: which of the two source sets given to apply        */
   int32_t src_fab;      /* index into that set                                        */
   int32_t kind;         /* LBX_G_*                                                    */

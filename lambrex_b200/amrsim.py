@@ -34,6 +34,7 @@ SYMBOLS = {
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
+    "lbx_sim_set_initial_density_view": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity_view": (_i, [_vp, _dp, _sz]),
     "lbx_sim_init_from_scratch": (_i, [_vp, _d]), "lbx_sim_regrid": (_i, [_vp, _i, _d]),
     "lbx_sim_iterate": (_i, [_vp, _i]), "lbx_sim_calc_hydro_vars": (_i, [_vp, _i]),
     "lbx_sim_calc_equilibrium_dist": (_i, [_vp, _i]),
@@ -144,6 +145,17 @@ class AmrSim:
     def SetInitialVelocity(self, u):
         self._set(lib().lbx_sim_set_initial_velocity, u)
 
+    def SetInitialDensityView(self, rho):
+        """Zero-copy: `rho` (contiguous float64 array, ideally pinned) is read at InitFromScratch."""
+        assert rho.dtype == np.float64 and rho.flags["C_CONTIGUOUS"]
+        self._keep = (self._keep or []) + [rho]
+        _check(lib().lbx_sim_set_initial_density_view(self._h, rho.ctypes.data_as(_dp), rho.size))
+
+    def SetInitialVelocityView(self, u):
+        assert u.dtype == np.float64 and u.flags["C_CONTIGUOUS"]
+        self._keep = (self._keep or []) + [u]
+        _check(lib().lbx_sim_set_initial_velocity_view(self._h, u.ctypes.data_as(_dp), u.size))
+
     def InitFromScratch(self, time=0.0):
         _check(lib().lbx_sim_init_from_scratch(self._h, time))
 
@@ -172,16 +184,19 @@ class AmrSim:
     def _level_dims(self, level):
         return tuple(d * 2 ** level for d in self.GetDims())
 
-    def GetDensityField(self, level):
-        """[NX_l, NY_l, NZ_l] array (C order); sentinel -1.0 where the level has no cell."""
-        out = np.empty(self._level_dims(level))
+    def GetDensityField(self, level, out=None):
+        """[NX_l, NY_l, NZ_l] array (C order); sentinel -1.0 where the level has no cell.
+        `out`: optional preallocated (e.g. pinned) float64 array of that size."""
+        if out is None:
+            out = np.empty(self._level_dims(level))
         _check(lib().lbx_sim_get_density_field(self._h, level, out.ctypes.data_as(_dp), out.size))
-        return out
+        return out.reshape(self._level_dims(level))
 
-    def GetVelocityField(self, level):
-        out = np.empty(self._level_dims(level) + (3,))
+    def GetVelocityField(self, level, out=None):
+        if out is None:
+            out = np.empty(self._level_dims(level) + (3,))
         _check(lib().lbx_sim_get_velocity_field(self._h, level, out.ctypes.data_as(_dp), out.size))
-        return out
+        return out.reshape(self._level_dims(level) + (3,))
 
     def GetTime(self, level):
         v = _d()

@@ -303,11 +303,13 @@ __device__ __forceinline__ bool mf_in_valid(const DFabT& f, int i, int j, int k)
   return i >= f.vlo[0] && i <= f.vhi[0] && j >= f.vlo[1] && j <= f.vhi[1] && k >= f.vlo[2] && k <= f.vhi[2];
 }
 
-// Collide / CoarseCollide / FineCollide on the valid cells of every box, in place
-// (src/AmrSim.cpp:25-107, 487-590).  mask != null: cells with mask == fine_val are zeroed.
+// Collide / CoarseCollide / FineCollide on the valid cells of every box: dst <- collide(src)
+// (src/AmrSim.cpp:25-107, 487-590; in place when src == dst).  mask != null: cells with
+// mask == fine_val are zeroed.
 template <class C>
-__global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ ft, const DFabT* __restrict__ mt,
-                                                    int nfabs, double omega_s, double omega_b, int fine_val) {
+__global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ st, const DFabT* __restrict__ ft,
+                                                    const DFabT* __restrict__ mt, int nfabs, double omega_s,
+                                                    double omega_b, int fine_val) {
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
@@ -323,9 +325,12 @@ __global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ ft
       return;
     }
   }
+  const DFabT S = st[b];      // source set: same boxes, may be the destination itself
+  const double* sp = static_cast<const double*>(S.p) + mf_off(S, i, j, k);
+  const long long ssc = mf_stride(S);
   double f[NV];
 #pragma unroll
-  for (int p = 0; p < NV; ++p) f[p] = fp[p * sc];
+  for (int p = 0; p < NV; ++p) f[p] = sp[p * ssc];
   C::collide(f, omega_s, omega_b);
 #pragma unroll
   for (int p = 0; p < NV; ++p) fp[p * sc] = f[p];

@@ -15,7 +15,7 @@ struct Launchers {
   void (*collide_stream)(cudaStream_t, DFab src, DFab dst, DBox box, DDom dom, double ws, double wb, int scheme);
   void (*collide_stream_slab)(cudaStream_t, DFab src, DFab dst, DFab dn, DFab up, DBox box, DDom dom, double ws,
                               double wb);
-  void (*mf_collide)(cudaStream_t, const DFabT* f, const DFabT* mask, int nfabs, long long max_cells, double ws,
+  void (*mf_collide)(cudaStream_t, const DFabT* src, const DFabT* f, const DFabT* mask, int nfabs, long long max_cells, double ws,
                      double wb, int fine_val);
   void (*mf_moments)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs, long long max_cells);
   void (*mf_equilibrium)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs,

@@ -189,12 +189,18 @@ int lbx_mf_moments(const lbx_mf* f, lbx_mf* rho, lbx_mf* u) {
   return lbx::after_launch("lbx_mf_moments");
 }
 
-int lbx_mf_collide(lbx_mf* f, double omega_s, double omega_b, const lbx_mf* mask, int fine_val) {
+int lbx_mf_collide2(const lbx_mf* src, lbx_mf* dst, double omega_s, double omega_b, const lbx_mf* mask, int fine_val) {
   LBX_NEED_INIT();
-  if (need(f, LBX_NV, LBX_F64, 0, "lbx_mf_collide f")) return 1;
-  if (mask && (need(mask, 1, LBX_I32, 0, "lbx_mf_collide mask") || same_boxes(f, mask, "lbx_mf_collide"))) return 1;
-  L().mf_collide(g.cur, f->table, mask ? mask->table : nullptr, f->nfabs, f->max_valid, omega_s, omega_b, fine_val);
+  if (need(src, LBX_NV, LBX_F64, 0, "lbx_mf_collide src") || need(dst, LBX_NV, LBX_F64, 0, "lbx_mf_collide dst") ||
+      same_boxes(src, dst, "lbx_mf_collide"))
+    return 1;
+  if (mask && (need(mask, 1, LBX_I32, 0, "lbx_mf_collide mask") || same_boxes(dst, mask, "lbx_mf_collide"))) return 1;
+  L().mf_collide(g.cur, src->table, dst->table, mask ? mask->table : nullptr, dst->nfabs, dst->max_valid, omega_s, omega_b,
+                 fine_val);
   return lbx::after_launch("lbx_mf_collide");
+}
+int lbx_mf_collide(lbx_mf* f, double omega_s, double omega_b, const lbx_mf* mask, int fine_val) {
+  return lbx_mf_collide2(f, f, omega_s, omega_b, mask, fine_val);
 }
 
 int lbx_mf_stream(const lbx_mf* src, lbx_mf* dst) {
@@ -225,6 +231,39 @@ int lbx_mf_zero_ring(lbx_mf* f, int depth, int comp) {
   return lbx::after_launch("lbx_mf_zero_ring");
 }
 
+static int user_common(const lbx_mf* m, const void* user, const lbx_box* dom, int ncomp, const char* what) {
+  if (need(m, ncomp, LBX_F64, 0, what)) return 1;
+  if (!user || !dom) return fail(std::string(what) + ": null argument");
+  for (const auto& f : m->host)
+    for (int d = 0; d < 3; ++d)
+      if (f.vlo[d] < dom->lo[d] || f.vhi[d] > dom->hi[d]) return fail(std::string(what) + ": a box lies outside the user array's domain");
+  return 0;
+}
+int lbx_mf_from_user(lbx_mf* m, const double* user_dev, const lbx_box* dom, int ncomp) {
+  LBX_NEED_INIT();
+  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_from_user")) return 1;
+  lbx::k_mf_user<true><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
+      m->table, m->nfabs, const_cast<double*>(user_dev), dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
+      dom->hi[2] - dom->lo[2] + 1, ncomp);
+  return lbx::after_launch("lbx_mf_from_user");
+}
+int lbx_mf_to_user(const lbx_mf* m, double* user_dev, const lbx_box* dom, int ncomp) {
+  LBX_NEED_INIT();
+  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_to_user")) return 1;
+  lbx::k_mf_user<false><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
+      m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
+      dom->hi[2] - dom->lo[2] + 1, ncomp);
+  return lbx::after_launch("lbx_mf_to_user");
+}
+int lbx_fill_f64(double* dev, size_t n, double value) {
+  LBX_NEED_INIT();
+  if (!dev) return fail("lbx_fill_f64: null pointer");
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+  lbx::k_fill_f64<<<blocks, 256, 0, g.cur>>>(dev, (long long)n, value);
+  return lbx::after_launch("lbx_fill_f64");
+}
+
 // ----------------------------------------------------------------------------- gather plans
 int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
   LBX_NEED_INIT();
@@ -234,7 +273,10 @@ int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
   for (int i = 0; i < n; ++i) {
     const lbx_gather& a = gs[i];
     lbx::GDesc& d = p->descs[i];
-    if (i > 0 && a.dst_fab < gs[i - 1].dst_fab) { delete p; return fail("lbx_plan_create: descriptors must be grouped by ascending dst_fab"); }
+    if (i > 0 && (a.dst_fab < gs[i - 1].dst_fab || (a.dst_fab == gs[i - 1].dst_fab && a.group < gs[i - 1].group))) {
+      delete p;
+      return fail("lbx_plan_create: descriptors must be sorted by (dst_fab, group)");
+    }
     if (a.kind < LBX_G_COPY || a.kind > LBX_G_CONST) { delete p; return fail("lbx_plan_create: unknown kind"); }
     if ((a.kind == LBX_G_PC || a.kind == LBX_G_AVG) && a.ratio < 1) { delete p; return fail("lbx_plan_create: ratio must be >= 1"); }
     if (a.src_set != 0 && a.src_set != 1) { delete p; return fail("lbx_plan_create: src_set must be 0 or 1"); }
@@ -243,7 +285,7 @@ int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
       d.lo[k] = a.region.lo[k]; d.hi[k] = a.region.hi[k]; d.shift[k] = a.shift[k];
     }
     d.src_set = a.src_set; d.src_fab = a.src_fab; d.kind = a.kind; d.ratio = a.ratio > 0 ? a.ratio : 1; d.value = a.value;
-    if (p->dsts.empty() || p->dsts.back().fab != a.dst_fab) {
+    if (p->dsts.empty() || p->dsts.back().fab != a.dst_fab || gs[i - 1].group != a.group) {
       lbx::GDst t;
       t.fab = a.dst_fab; t.first = i; t.count = 0; t.pad = 0;
       for (int k = 0; k < 3; ++k) { t.blo[k] = d.lo[k]; t.bhi[k] = d.hi[k]; }
@@ -322,17 +364,21 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   const lbx::DFabT* t0 = src0 ? src0->table : nullptr;
   const lbx::DFabT* t1 = src1 ? src1->table : nullptr;
   const int nd = (int)p->dsts.size();
+#define LBX_PLAN_LAUNCH(T, ADD, NC) \
+  lbx::k_plan_apply<T, ADD, NC><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp)
   if (dst->dtype == LBX_F64) {
-    if (op == LBX_OP_COPY)
-      lbx::k_plan_apply<double, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
-    else
-      lbx::k_plan_apply<double, true><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+    if (dst->ncomp == LBX_NV) {          // the populations: compile-time component count
+      if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, LBX_NV);
+      else LBX_PLAN_LAUNCH(double, true, LBX_NV);
+    } else {
+      if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, 0);
+      else LBX_PLAN_LAUNCH(double, true, 0);
+    }
   } else {
-    if (op == LBX_OP_COPY)
-      lbx::k_plan_apply<int, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
-    else
-      lbx::k_plan_apply<int, true><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+    if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(int, false, 0);
+    else LBX_PLAN_LAUNCH(int, true, 0);
   }
+#undef LBX_PLAN_LAUNCH
   return lbx::after_launch("lbx_plan_apply");
 }
 

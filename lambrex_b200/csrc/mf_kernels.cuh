@@ -71,6 +71,32 @@ __global__ void __launch_bounds__(MFT) k_mf_zero_ring(const DFabT* __restrict__ 
   static_cast<double*>(F.p)[comp * mf_stride(F) + mf_off(F, i, j, k)] = 0.0;
 }
 
+// User arrays of the reference's API are C-ordered, i slowest, component fastest
+// (CLindex, include/AmrSim.h:79-83): user[(((i-d0)*NY + (j-d1))*NZ + (k-d2))*ncomp + n].
+// TO_FAB: valid cells of every fab <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);
+// else  : user <- valid cells (bulk form of GetDensity / GetVelocity, :824-843).
+template <bool TO_FAB>
+__global__ void __launch_bounds__(MFT) k_mf_user(const DFabT* __restrict__ ft, int nfabs, double* __restrict__ user,
+                                                 int d0, int d1, int d2, int ny, int nz, int ncomp) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT F = ft[b];
+  int i, j, k;
+  if (!mf_cell(F, 0, i, j, k)) return;
+  double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
+  const long long sc = mf_stride(F);
+  double* up = user + ((((long long)(i - d0) * ny + (j - d1)) * nz + (k - d2)) * ncomp);
+  for (int n = 0; n < ncomp; ++n) {
+    if (TO_FAB) fp[n * sc] = up[n];
+    else up[n] = fp[n * sc];
+  }
+}
+
+__global__ void k_fill_f64(double* __restrict__ p, long long n, double v) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    p[t] = v;
+}
+
 template <class T>
 __global__ void __launch_bounds__(MFT) k_mf_setval(const DFabT* __restrict__ ft, int nfabs, int grow_all, int ncomp,
                                                    T value) {
@@ -98,12 +124,14 @@ __global__ void __launch_bounds__(MFT) k_mf_setval(const DFabT* __restrict__ ft,
 //   G_CONST value                                setVal on a region (masks)
 // ---------------------------------------------------------------------------
 enum { G_COPY = 0, G_PC = 1, G_AVG = 2, G_CONST = 3 };
-struct GDesc {
+struct alignas(16) GDesc {   // 64 bytes
   int lo[3], hi[3];   // destination region (destination index space)
   int shift[3];       // added in SOURCE index space after the map
   int src_set, src_fab, kind, ratio;
+  int pad;
   double value;
 };
+static_assert(sizeof(GDesc) == 64, "GDesc must be 64 bytes (staged to shared memory as int4 words)");
 struct GDst {
   int fab, first, count, pad;
   int blo[3], bhi[3];   // bounding box of this fab's regions
@@ -111,53 +139,118 @@ struct GDst {
 
 __device__ __forceinline__ int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
 
-template <class T>
-__device__ __forceinline__ T g_value(const GDesc& g, const DFabT* s0, const DFabT* s1, int i, int j, int k, int c) {
-  if (g.kind == G_CONST) return (T)g.value;
+// one matching descriptor applied to one destination cell, all components.  NC > 0: component
+// count known at compile time (15 populations): every load of the cell is issued before the
+// first store, which is what keeps these gather kernels bandwidth- rather than latency-bound.
+template <class T, bool ADD, int NC>
+__device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
+                                        int i, int j, int k, T* __restrict__ dp, long long dsc, int ncomp_rt) {
+  const int ncomp = NC > 0 ? NC : ncomp_rt;
+  if (g.kind == G_CONST) {
+#pragma unroll
+    for (int c = 0; c < ncomp; ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + (T)g.value) : (T)g.value;
+    return;
+  }
   const DFabT S = (g.src_set ? s1 : s0)[g.src_fab];
-  const T* sp = static_cast<const T*>(S.p) + c * mf_stride(S);
-  if (g.kind == G_COPY) return sp[mf_off(S, i + g.shift[0], j + g.shift[1], k + g.shift[2])];
-  if (g.kind == G_PC)
-    return sp[mf_off(S, fdiv(i, g.ratio) + g.shift[0], fdiv(j, g.ratio) + g.shift[1], fdiv(k, g.ratio) + g.shift[2])];
-  // G_AVG
-  const int r = g.ratio, i0 = i * r + g.shift[0], j0 = j * r + g.shift[1], k0 = k * r + g.shift[2];
-  T acc = 0;
-  for (int kr = 0; kr < r; ++kr)
-    for (int jr = 0; jr < r; ++jr)
-      for (int ir = 0; ir < r; ++ir) acc += sp[mf_off(S, i0 + ir, j0 + jr, k0 + kr)];
-  return (T)(acc * (1.0 / (double)(r * r * r)));
+  const long long ssc = mf_stride(S);
+  if (g.kind == G_AVG) {
+    const int r = g.ratio;
+    const int i0 = i * r + g.shift[0];
+    const T* sp = static_cast<const T*>(S.p) + mf_off(S, i0, j * r + g.shift[1], k * r + g.shift[2]);
+    const long long sy = S.n[0], sz = (long long)S.n[0] * S.n[1];
+    if (sizeof(T) == 8 && r == 2 && NC > 0 && ((i0 - S.lo[0]) & 1) == 0 && (S.n[0] & 1) == 0) {
+      // ratio 2, 16-byte aligned pairs: four 16-byte loads per component, summed in
+      // amrex_avgdown order (iref fastest, then jref, then kref)
+      const double* dpp = reinterpret_cast<const double*>(sp);
+      double v[NC > 0 ? NC : 1];
+#pragma unroll
+      for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
+        const double2 a = *reinterpret_cast<const double2*>(dpp + c * ssc);
+        const double2 b = *reinterpret_cast<const double2*>(dpp + c * ssc + sy);
+        const double2 cc = *reinterpret_cast<const double2*>(dpp + c * ssc + sz);
+        const double2 d = *reinterpret_cast<const double2*>(dpp + c * ssc + sz + sy);
+        v[c] = ((((((a.x + a.y) + b.x) + b.y) + cc.x) + cc.y) + d.x + d.y) * 0.125;
+      }
+#pragma unroll
+      for (int c = 0; c < (NC > 0 ? NC : 1); ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + (T)v[c]) : (T)v[c];
+      return;
+    }
+    const double w = 1.0 / (double)(r * r * r);
+    for (int c = 0; c < ncomp; ++c) {
+      T acc = 0;
+      for (int kr = 0; kr < r; ++kr)          // amrex_avgdown order: iref fastest
+        for (int jr = 0; jr < r; ++jr)
+          for (int ir = 0; ir < r; ++ir) acc += sp[c * ssc + kr * sz + jr * sy + ir];
+      const T val = (T)(acc * w);
+      dp[c * dsc] = ADD ? (T)(dp[c * dsc] + val) : val;
+    }
+    return;
+  }
+  int si = i, sj = j, sk = k;
+  if (g.kind == G_PC) { si = fdiv(i, g.ratio); sj = fdiv(j, g.ratio); sk = fdiv(k, g.ratio); }
+  const T* sp = static_cast<const T*>(S.p) + mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
+  if (NC > 0) {
+    T v[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < (NC > 0 ? NC : 1); ++c) v[c] = sp[c * ssc];
+#pragma unroll
+    for (int c = 0; c < (NC > 0 ? NC : 1); ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + v[c]) : v[c];
+  } else {
+    for (int c = 0; c < ncomp; ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + sp[c * ssc]) : sp[c * ssc];
+  }
 }
 
-template <class T, bool ADD>
+constexpr int PLAN_CHUNK = 64;   // descriptors staged in shared memory at a time (4 KB)
+
+template <class T, bool ADD, int NC>
 __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dsts, int ndst,
                                                     const GDesc* __restrict__ descs, const DFabT* __restrict__ dt,
                                                     const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
                                                     int ncomp) {
+  __shared__ GDesc sd[PLAN_CHUNK];
   const int q = mf_fab_index();
-  if (q >= ndst) return;
+  if (q >= ndst) return;                       // block-uniform
   const GDst D = dsts[q];
   const int nx = D.bhi[0] - D.blo[0] + 1, ny = D.bhi[1] - D.blo[1] + 1, nz = D.bhi[2] - D.blo[2] + 1;
   long long t = (long long)blockIdx.x * MFT + threadIdx.x;
-  if (t >= (long long)nx * ny * nz) return;
+  if ((long long)blockIdx.x * MFT >= (long long)nx * ny * nz) return;   // whole block idle: uniform exit
+  bool active = t < (long long)nx * ny * nz;
   const int i = D.blo[0] + (int)(t % nx);
   t /= nx;
   const int j = D.blo[1] + (int)(t % ny), k = D.blo[2] + (int)(t / ny);
   const DFabT F = dt[D.fab];
-  T* dp = static_cast<T*>(F.p) + mf_off(F, i, j, k);
+  T* dp = static_cast<T*>(F.p) + (active ? mf_off(F, i, j, k) : 0);
   const long long dsc = mf_stride(F);
-  if (!ADD) {
-    for (int d = D.count - 1; d >= 0; --d) {
-      const GDesc& g = descs[D.first + d];
-      if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
-      for (int c = 0; c < ncomp; ++c) dp[c * dsc] = g_value<T>(g, s0, s1, i, j, k, c);
-      return;
+  const int nchunks = (D.count + PLAN_CHUNK - 1) / PLAN_CHUNK;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    // COPY walks the list backwards (the last match wins), ADD forwards (list order)
+    const int c0 = ADD ? ch * PLAN_CHUNK : max(D.count - (ch + 1) * PLAN_CHUNK, 0);
+    const int c1 = ADD ? min(c0 + PLAN_CHUNK, D.count) : D.count - ch * PLAN_CHUNK;
+    const int n = c1 - c0;
+    {  // cooperative copy of n descriptors as 16-byte words
+      const int4* src = reinterpret_cast<const int4*>(descs + D.first + c0);
+      int4* dst = reinterpret_cast<int4*>(sd);
+      for (int w = threadIdx.x; w < n * (int)(sizeof(GDesc) / 16); w += MFT) dst[w] = src[w];
     }
-  } else {
-    for (int d = 0; d < D.count; ++d) {
-      const GDesc& g = descs[D.first + d];
-      if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
-      for (int c = 0; c < ncomp; ++c) dp[c * dsc] += g_value<T>(g, s0, s1, i, j, k, c);
+    __syncthreads();
+    if (active) {
+      if (!ADD) {
+        for (int d = n - 1; d >= 0; --d) {
+          const GDesc& g = sd[d];
+          if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
+          g_apply<T, false, NC>(g, s0, s1, i, j, k, dp, dsc, ncomp);
+          active = false;
+          break;
+        }
+      } else {
+        for (int d = 0; d < n; ++d) {
+          const GDesc& g = sd[d];
+          if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
+          g_apply<T, true, NC>(g, s0, s1, i, j, k, dp, dsc, ncomp);
+        }
+      }
     }
+    __syncthreads();
   }
 }
 

@@ -270,10 +270,12 @@ class BoxHash {
   std::unordered_map<uint64_t, std::vector<int>> map_;
 };
 
+int g_group = 0;    // tile group stamped on the descriptors being built (see lbx_gather.group)
+
 lbx_gather make_desc(int dst_fab, int src_set, int src_fab, int kind, int ratio, const IntVect& shift, const Box& r,
                      double value = 0.0) {
   lbx_gather g;
-  g.dst_fab = dst_fab; g.src_set = src_set; g.src_fab = src_fab; g.kind = kind; g.ratio = ratio;
+  g.dst_fab = dst_fab; g.group = g_group; g.src_set = src_set; g.src_fab = src_fab; g.kind = kind; g.ratio = ratio;
   for (int d = 0; d < 3; ++d) { g.shift[d] = shift[d]; g.region.lo[d] = r.smallEnd(d); g.region.hi[d] = r.bigEnd(d); }
   g.value = value;
   return g;
@@ -284,6 +286,15 @@ std::vector<Box> storage_valid(const FA& m) {
   std::vector<Box> v(m.numStorageFabs());
   for (int s = 0; s < m.numStorageFabs(); ++s) v[s] = m.storageValid(s);
   return v;
+}
+
+// what to tile for one destination fab: the whole wanted box, or (ghost shell only) its up to
+// six slabs around the valid box, each its own tile group
+BoxList tile_regions(const Box& want, const Box& valid, bool shell_only) {
+  BoxList r;
+  if (shell_only) boxDiff(r, want, valid);
+  else r.push_back(want);
+  return r;
 }
 
 lbx_plan* cached(const std::string& key, const std::function<void(std::vector<lbx_gather>&)>& build) {
@@ -298,8 +309,24 @@ lbx_plan* cached(const std::string& key, const std::function<void(std::vector<lb
 }
 
 // COPY descriptors: dst fab k <- every (source box, shift) that meets its region `want`
+// COPY regions of one destination fab come from disjoint sources, so their order is free:
+// smallest first, because the kernel walks the list backwards and most cells sit in the
+// largest region.  (ADD keeps the ParallelCopy order: it fixes the summation order.)
+void by_volume(std::vector<lbx_gather>& v, size_t from) {
+  std::stable_sort(v.begin() + from, v.end(), [](const lbx_gather& a, const lbx_gather& b) {
+    auto vol = [](const lbx_gather& g) {
+      long n = 1;
+      for (int d = 0; d < 3; ++d) n *= (g.region.hi[d] - g.region.lo[d] + 1);
+      return n;
+    };
+    return vol(a) < vol(b);
+  });
+}
+
 void copy_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::vector<Box>& svalid, const BoxHash& sh,
-                int src_ng, const std::vector<IntVect>& shifts, int src_set, bool skip_self, int self_index) {
+                int src_ng, const std::vector<IntVect>& shifts, int src_set, bool skip_self, int self_index,
+                bool keep_order = false) {
+  const size_t from = out.size();
   // collect (i, shift) pairs, then order by source index, then shift order (ParallelCopy order)
   std::vector<std::pair<int, int>> hits;
   for (size_t si = 0; si < shifts.size(); ++si) {
@@ -315,11 +342,13 @@ void copy_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std:
     const Box r = amrex::shift(amrex::grow(svalid[h.first], src_ng), s) & want;
     if (r.ok()) out.push_back(make_desc(k, src_set, h.first, LBX_G_COPY, 1, IntVect(0) - s, r));
   }
+  if (!keep_order) by_volume(out, from);
 }
 
 // PC descriptors: fine fab k region `want` <- coarse boxes (valid cells, periodic images)
 void pc_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::vector<Box>& cvalid, const BoxHash& ch,
-              const std::vector<IntVect>& cshifts, int ratio, int src_set) {
+              const std::vector<IntVect>& cshifts, int ratio, int src_set, const Box* exclude = nullptr) {
+  const size_t from = out.size();
   const Box cw = amrex::coarsen(want, ratio);
   std::vector<std::pair<int, int>> hits;
   for (size_t si = 0; si < cshifts.size(); ++si)
@@ -330,8 +359,13 @@ void pc_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::v
     const Box rc = amrex::shift(cvalid[h.first], s) & cw;
     if (!rc.ok()) continue;
     const Box rf = amrex::refine(rc, ratio) & want;
-    if (rf.ok()) out.push_back(make_desc(k, src_set, h.first, LBX_G_PC, ratio, IntVect(0) - s, rf));
+    if (!rf.ok()) continue;
+    BoxList parts;
+    if (exclude) boxDiff(parts, rf, *exclude);
+    else parts.push_back(rf);
+    for (const Box& part : parts) out.push_back(make_desc(k, src_set, h.first, LBX_G_PC, ratio, IntVect(0) - s, part));
   }
+  by_volume(out, from);
 }
 
 }  // namespace
@@ -339,20 +373,29 @@ void pc_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::v
 void ClearPlanCache() { g_plans.clear(); }
 size_t PlanCacheSize() { return g_plans.size(); }
 
-void ParallelCopy(MultiFab& dst, const MultiFab& src, int src_ng, int dst_ng, const Periodicity& period, bool add) {
+void ParallelCopy(MultiFab& dst, const MultiFab& src, int src_ng, int dst_ng, const Periodicity& period, bool add,
+                  bool ghosts_only) {
   if (dst.empty() || src.empty()) return;
+  if (ghosts_only && (add || dst.boxArray() != src.boxArray() || dst.layout() != src.layout()))
+    Abort("ParallelCopy: ghosts_only needs identical source and destination boxes");
   if (src.isFlat()) src_ng = 0;
   if (dst.isFlat()) dst_ng = 0;
   if (src_ng > src.nGrow() || dst_ng > dst.nGrow()) Abort("ParallelCopy: ghost width exceeds the MultiFab's");
   char tail[64];
-  std::snprintf(tail, sizeof(tail), "|%d|%d|%d", src_ng, dst_ng, add ? 1 : 0);
+  std::snprintf(tail, sizeof(tail), "|%d|%d|%d|%d", src_ng, dst_ng, add ? 1 : 0, ghosts_only ? 1 : 0);
   const std::string key = "PC|" + gkey(dst) + "|" + gkey(src) + "|" + pkey(period) + tail;
   lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
     const std::vector<Box> sv = storage_valid(src);
     const BoxHash sh(sv);
     const std::vector<IntVect> shifts = period.shiftIntVect();
-    for (int k = 0; k < dst.numStorageFabs(); ++k)
-      copy_descs(d, k, amrex::grow(dst.storageValid(k), dst_ng), sv, sh, src_ng, shifts, 0, false, -1);
+    for (int k = 0; k < dst.numStorageFabs(); ++k) {
+      g_group = 0;
+      for (const Box& reg : tile_regions(amrex::grow(dst.storageValid(k), dst_ng), dst.storageValid(k), ghosts_only)) {
+        copy_descs(d, k, reg, sv, sh, src_ng, shifts, 0, ghosts_only, k, add);
+        ++g_group;
+      }
+    }
+    g_group = 0;
   });
   lbx_check(lbx_plan_apply(p, dst.mf(), src.mf(), nullptr, add ? LBX_OP_ADD : LBX_OP_COPY), "ParallelCopy");
   dst.touch();
@@ -367,23 +410,33 @@ void FillBoundary(MultiFab& mf, const Periodicity& period) {
     const std::vector<Box> sv = storage_valid(mf);
     const BoxHash sh(sv);
     const std::vector<IntVect> shifts = period.shiftIntVect();
-    for (int k = 0; k < mf.numStorageFabs(); ++k) copy_descs(d, k, mf.storageBox(k), sv, sh, 0, shifts, 0, true, k);
+    for (int k = 0; k < mf.numStorageFabs(); ++k) {
+      g_group = 0;
+      for (const Box& reg : tile_regions(mf.storageBox(k), mf.storageValid(k), true)) {
+        copy_descs(d, k, reg, sv, sh, 0, shifts, 0, true, k);
+        ++g_group;
+      }
+    }
+    g_group = 0;
   });
   lbx_check(lbx_plan_apply(p, mf.mf(), mf.mf(), nullptr, LBX_OP_COPY), "FillBoundary");
   mf.touch();
 }
 
-void FillPatchSingleLevel(MultiFab& dst, const MultiFab& src, const Geometry& geom) {
-  ParallelCopy(dst, src, 0, dst.nGrow(), geom.periodicity());
+void FillPatchSingleLevel(MultiFab& dst, const MultiFab& src, const Geometry& geom, bool ghosts_only) {
+  ParallelCopy(dst, src, 0, dst.nGrow(), geom.periodicity(), false, ghosts_only);
 }
 
 static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* fine, const Geometry& cgeom,
-                           const Geometry& fgeom, const IntVect& ratio, const char* tag) {
+                           const Geometry& fgeom, const IntVect& ratio, const char* tag, bool ghosts_only = false) {
   if (dst.empty()) return;
+  if (ghosts_only && (!fine || dst.boxArray() != fine->boxArray() || fine->isFlat()))
+    Abort("FillPatchTwoLevels: ghosts_only needs identical fine source and destination boxes");
   if (ratio[0] != ratio[1] || ratio[0] != ratio[2]) Abort("anisotropic refinement ratios are not supported");
   if (dst.isFlat()) Abort("two-level fills need BOXES storage on the fine level");
   const std::string key = std::string(tag) + "|" + gkey(dst) + "|" + gkey(crse) + "|" + (fine ? gkey(*fine) : "-") + "|" +
-                          pkey(cgeom.periodicity()) + "|" + pkey(fgeom.periodicity()) + "|" + std::to_string(ratio[0]);
+                          pkey(cgeom.periodicity()) + "|" + pkey(fgeom.periodicity()) + "|" + std::to_string(ratio[0]) +
+                          (ghosts_only ? "|g" : "|a");
   lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
     const std::vector<Box> cv = storage_valid(crse);
     const BoxHash ch(cv);
@@ -393,18 +446,22 @@ static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* 
     const BoxHash fh(fv);
     const std::vector<IntVect> fs = fgeom.periodicity().shiftIntVect();
     for (int k = 0; k < dst.numStorageFabs(); ++k) {
-      const Box want = dst.storageBox(k);
-      pc_descs(d, k, want, cv, ch, cs, ratio[0], 1);                        // coarse first ...
-      if (fine) copy_descs(d, k, want, fv, fh, 0, fs, 0, false, -1);      // ... fine data wins
+      g_group = 0;
+      for (const Box& reg : tile_regions(dst.storageBox(k), dst.storageValid(k), ghosts_only)) {
+        pc_descs(d, k, reg, cv, ch, cs, ratio[0], 1);                              // coarse first ...
+        if (fine) copy_descs(d, k, reg, fv, fh, 0, fs, 0, ghosts_only, k);        // ... fine data wins
+        ++g_group;
+      }
     }
+    g_group = 0;
   });
   lbx_check(lbx_plan_apply(p, dst.mf(), fine ? fine->mf() : nullptr, crse.mf(), LBX_OP_COPY), tag);
   dst.touch();
 }
 
 void FillPatchTwoLevels(MultiFab& dst, const MultiFab& crse, const MultiFab& fine, const Geometry& cgeom,
-                        const Geometry& fgeom, const IntVect& ratio) {
-  two_level_fill(dst, crse, &fine, cgeom, fgeom, ratio, "FillPatchTwoLevels");
+                        const Geometry& fgeom, const IntVect& ratio, bool ghosts_only) {
+  two_level_fill(dst, crse, &fine, cgeom, fgeom, ratio, "FillPatchTwoLevels", ghosts_only);
 }
 
 void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& cgeom, const Geometry& fgeom,

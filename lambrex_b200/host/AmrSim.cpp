@@ -43,6 +43,7 @@ AmrSim::AmrSim(int const nx, int const ny, int const nz, int const max_ref_level
   const int num_levels = max_level + 1;
   velocity.resize(num_levels);
   stream_scratch.resize(num_levels);
+  valid_pending.assign(num_levels, false);
   tau_s.resize(num_levels);
   tau_b.resize(num_levels);
   mass.resize(num_levels);
@@ -60,40 +61,38 @@ AmrSim::~AmrSim() {
 }
 
 // ----------------------------------------------------------------------------- input / output
-void AmrSim::SetInitialDensity(double const rho_init) { initial_density.assign(NUMEL, rho_init); }
-void AmrSim::SetInitialDensity(std::vector<double> const rho_init) { initial_density = rho_init; }
-void AmrSim::SetInitialVelocity(double const u_init) { initial_velocity.assign(3 * (size_t)NUMEL, u_init); }
-void AmrSim::SetInitialVelocity(std::vector<double> const u_init) { initial_velocity = u_init; }
+void AmrSim::SetInitialDensity(double const rho_init) { density_view = nullptr; initial_density.assign(NUMEL, rho_init); }
+void AmrSim::SetInitialDensity(std::vector<double> rho_init) { density_view = nullptr; initial_density = std::move(rho_init); }
+void AmrSim::SetInitialVelocity(double const u_init) { velocity_view = nullptr; initial_velocity.assign(3 * (size_t)NUMEL, u_init); }
+void AmrSim::SetInitialVelocity(std::vector<double> u_init) { velocity_view = nullptr; initial_velocity = std::move(u_init); }
 
-// user array (C-ordered, i slowest, component fastest) -> device field in fab order
-void AmrSim::upload_user_field(MultiFab& mf, const std::vector<double>& user, int ncomp) {
-  if (user.size() < (size_t)NUMEL * ncomp)
-    throw std::out_of_range("AmrSim: initial field has fewer than NX*NY*NZ*ncomp entries");
-  std::vector<double> host(mf.hostMirror().size(), 0.0);
-  const IntVect dims(NX, NY, NZ);
-  for (int s = 0; s < mf.numStorageFabs(); ++s) {
-    const Box a = mf.storageBox(s), v = mf.storageValid(s);
-    const size_t nx = a.length(0), ny = a.length(1), plane = nx * ny * a.length(2);
-    double* base = host.data() + mf.storageOffset(s);
-    for (int k = v.smallEnd(2); k <= v.bigEnd(2); ++k)
-      for (int j = v.smallEnd(1); j <= v.bigEnd(1); ++j)
-        for (int i = v.smallEnd(0); i <= v.bigEnd(0); ++i) {
-          const size_t c = (size_t)(i - a.smallEnd(0)) + nx * ((size_t)(j - a.smallEnd(1)) + ny * (size_t)(k - a.smallEnd(2)));
-          for (int n = 0; n < ncomp; ++n) base[n * plane + c] = user[(size_t)CLindex(i, j, k, n, dims, ncomp)];
-        }
-  }
-  mf.upload(host);
+// user array (C-ordered, i slowest, component fastest) -> device field in fab order: one
+// host->device copy of the raw array, then a transposing kernel
+void AmrSim::upload_user_field(MultiFab& mf, const double* user, size_t n, int ncomp) {
+  const size_t need = (size_t)NUMEL * ncomp;
+  if (n < need) throw std::out_of_range("AmrSim: initial field has fewer than NX*NY*NZ*ncomp entries");
+  void* dev = nullptr;
+  lbx_check(lbx_malloc(&dev, need * sizeof(double)), "upload_user_field");
+  const lbx_box dom = to_lbx(geom[0].Domain());
+  int rc = lbx_h2d(dev, user, need * sizeof(double));
+  if (!rc) rc = lbx_mf_from_user(mf.mf(), static_cast<const double*>(dev), &dom, ncomp);
+  const int rc2 = lbx_free(dev);          // synchronises the stream first
+  lbx_check(rc, "upload_user_field");
+  lbx_check(rc2, "upload_user_field");
+  mf.touch();
 }
 
 // src/AmrSim.cpp:138-214
 void AmrSim::InitDensity(int const level) {
   if (level) amrex::Abort("Only level 0 should be initialised from scratch currently.");
-  upload_user_field(levels.at(level).now.get<Density>(), initial_density, 1);
+  if (density_view) upload_user_field(levels.at(level).now.get<Density>(), density_view, density_view_n, 1);
+  else upload_user_field(levels.at(level).now.get<Density>(), initial_density.data(), initial_density.size(), 1);
 }
 // src/AmrSim.cpp:217-295
 void AmrSim::InitVelocity(int const level) {
   if (level) amrex::Abort("Only LEVEL 0 should be initialised from scratch currently.");
-  upload_user_field(velocity.at(level), initial_velocity, NDIMS);
+  if (velocity_view) upload_user_field(velocity.at(level), velocity_view, velocity_view_n, NDIMS);
+  else upload_user_field(velocity.at(level), initial_velocity.data(), initial_velocity.size(), NDIMS);
 }
 
 // src/AmrSim.cpp:824-843
@@ -112,31 +111,38 @@ double AmrSim::GetVelocity(int const i, int const j, int const k, int const n, i
   return NL_VELOCITY;
 }
 
-std::vector<double> AmrSim::dense_field(const MultiFab& mf, int level, double sentinel) const {
-  const Box dom = geom[level].Domain();
-  const int nc = mf.nComp();
-  const size_t ny = dom.length(1), nz = dom.length(2);
-  std::vector<double> out((size_t)dom.numPts() * nc, sentinel);
-  if (mf.empty()) return out;
-  const std::vector<double>& host = mf.hostMirror();
-  for (int s = 0; s < mf.numStorageFabs(); ++s) {
-    const Box a = mf.storageBox(s), v = mf.storageValid(s);
-    const size_t ax = a.length(0), ay = a.length(1), plane = ax * ay * a.length(2);
-    const double* base = host.data() + mf.storageOffset(s);
-    for (int k = v.smallEnd(2); k <= v.bigEnd(2); ++k)
-      for (int j = v.smallEnd(1); j <= v.bigEnd(1); ++j)
-        for (int i = v.smallEnd(0); i <= v.bigEnd(0); ++i) {
-          const size_t c = (size_t)(i - a.smallEnd(0)) + ax * ((size_t)(j - a.smallEnd(1)) + ay * (size_t)(k - a.smallEnd(2)));
-          for (int n = 0; n < nc; ++n) out[(((size_t)i * ny + j) * nz + k) * nc + n] = base[n * plane + c];
-        }
-  }
-  return out;
+// dense C-ordered copy of a field into caller memory (device-side transpose, one D2H copy)
+void AmrSim::dense_field_into(const MultiFab& mf, int level, double sentinel, double* out, size_t n) const {
+  const Box domb = geom.at(level).Domain();
+  const int nc = mf.nComp() > 0 ? mf.nComp() : 1;
+  if (mf.empty()) amrex::Abort("dense field requested on an empty level");
+  if (n != (size_t)domb.numPts() * nc) amrex::Abort("dense field: buffer size mismatch");
+  void* dev = nullptr;
+  lbx_check(lbx_malloc(&dev, n * sizeof(double)), "dense_field");
+  const lbx_box dom = to_lbx(domb);
+  int rc = 0;
+  if (mf.boxArray().numPts() != domb.numPts()) rc = lbx_fill_f64(static_cast<double*>(dev), n, sentinel);
+  if (!rc) rc = lbx_mf_to_user(mf.mf(), static_cast<double*>(dev), &dom, nc);
+  if (!rc) rc = lbx_d2h(out, dev, n * sizeof(double));
+  const int rc2 = lbx_free(dev);          // synchronises the stream first
+  lbx_check(rc, "dense_field");
+  lbx_check(rc2, "dense_field");
+}
+void AmrSim::GetDensityField(int const level, double* out, size_t n) const {
+  dense_field_into(levels.at(level).now.get<Density>(), level, NL_DENSITY, out, n);
+}
+void AmrSim::GetVelocityField(int const level, double* out, size_t n) const {
+  dense_field_into(velocity.at(level), level, NL_VELOCITY, out, n);
 }
 std::vector<double> AmrSim::GetDensityField(int const level) const {
-  return dense_field(levels.at(level).now.get<Density>(), level, NL_DENSITY);
+  std::vector<double> out((size_t)geom.at(level).Domain().numPts());
+  GetDensityField(level, out.data(), out.size());
+  return out;
 }
 std::vector<double> AmrSim::GetVelocityField(int const level) const {
-  return dense_field(velocity.at(level), level, NL_VELOCITY);
+  std::vector<double> out((size_t)geom.at(level).Domain().numPts() * NDIMS);
+  GetVelocityField(level, out.data(), out.size());
+  return out;
 }
 
 // src/AmrSim.cpp:1019-1030
@@ -193,6 +199,10 @@ void AmrSim::Collide(MultiFab& f, const double omega_s, const double omega_b) {
 // src/AmrSim.cpp:109-122: pull-stream NEXT into a "fresh" fab over valid grown by one, swap
 void AmrSim::Stream(int const level) {
   MultiFab& f_nxt = levels[level].next.get<DistFn>();
+  if (valid_pending.at(level)) {      // only if a caller streams without colliding first
+    amrex::CopyValid(f_nxt, levels[level].now.get<DistFn>());
+    valid_pending.at(level) = false;
+  }
   MultiFab& f_prop = stream_scratch.at(level);
   if (f_prop.empty() || f_prop.boxArray() != f_nxt.boxArray() || f_prop.layout() != f_nxt.layout())
     f_prop = field_traits<DistFn>::MakeLevelData(f_nxt.boxArray(), f_nxt.DistributionMap(), f_nxt.layout());
@@ -205,8 +215,16 @@ void AmrSim::CollideLevel(int const level) {
   const double omega_s = 1.0 / (tau_s.at(level) + 0.5);
   const double omega_b = 1.0 / (tau_b.at(level) + 0.5);
   MultiFab& f_pc = levels.at(level).next.get<DistFn>();
-  DistFnFillPatch(level, f_pc);
-  Collide(f_pc, omega_s, omega_b);
+  const MultiFab& f_now = levels.at(level).now.get<DistFn>();
+  if (level == 0 && f_pc.boxArray() == f_now.boxArray() && f_pc.layout() == f_now.layout()) {
+    // FillPatch's valid-cell copy fused into the collision (next <- collide(now)); its ghost
+    // fill is dead work here because the FillBoundary below rewrites every ghost cell
+    lbx_check(lbx_mf_collide2(f_now.mf(), f_pc.mf(), omega_s, omega_b, nullptr, FINE_VAL), "CollideLevel");
+    f_pc.touch();
+  } else {
+    DistFnFillPatch(level, f_pc);
+    Collide(f_pc, omega_s, omega_b);
+  }
   amrex::FillBoundary(f_pc, geom[level].periodicity());
 }
 
@@ -271,12 +289,15 @@ void AmrSim::ComputeDt(int const level) {
 }
 
 // src/AmrSim.cpp:359-391
-void AmrSim::DistFnFillPatch(int const level, MultiFab& dest) {
+void AmrSim::DistFnFillPatch(int const level, MultiFab& dest) { FillPatchImpl(level, dest, false); }
+
+// ghosts_only: dest's valid cells are left for an out-of-place collision to produce
+void AmrSim::FillPatchImpl(int const level, MultiFab& dest, bool ghosts_only) {
   if (!level) {
-    amrex::FillPatchSingleLevel(dest, levels[level].now.get<DistFn>(), geom[level]);
+    amrex::FillPatchSingleLevel(dest, levels[level].now.get<DistFn>(), geom[level], ghosts_only);
   } else {
     amrex::FillPatchTwoLevels(dest, levels[level - 1].now.get<DistFn>(), levels[level].now.get<DistFn>(), geom[level - 1],
-                              geom[level], refRatio(level - 1));
+                              geom[level], refRatio(level - 1), ghosts_only);
   }
 }
 
@@ -325,7 +346,12 @@ void AmrSim::RohdeCycle(int const coarse_level) {
 // src/AmrSim.cpp:471-485
 void AmrSim::InitPostCollision(int const level) {
   MultiFab& f_pc = levels[level].next.get<DistFn>();
-  DistFnFillPatch(level, f_pc);
+  // ghost cells now; the valid cells (= NOW's valid cells) are produced by the collision that
+  // always follows, out of place (CoarseCollide / FineCollide below)
+  const MultiFab& f_now = levels[level].now.get<DistFn>();
+  const bool fuse = f_pc.boxArray() == f_now.boxArray() && f_pc.layout() == f_now.layout() && !f_now.isFlat();
+  FillPatchImpl(level, f_pc, fuse);
+  valid_pending.at(level) = fuse;
   if (level != 0) {
     // sic: component 0 only, outermost ghost ring
     lbx_check(lbx_mf_zero_ring(f_pc.mf(), 1, 0), "InitPostCollision");
@@ -338,14 +364,23 @@ void AmrSim::CoarseCollide(int const level) {
   MultiFab& f_pc = levels[level].next.get<DistFn>();
   const amrex::iMultiFab& mask = fine_masks.at(level);
   if (mask.empty()) amrex::Abort("CoarseCollide: no fine mask on this level");
-  lbx_check(lbx_mf_collide(f_pc.mf(), 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5), mask.mf(), FINE_VAL),
+  const MultiFab& src = valid_pending.at(level) ? levels[level].now.get<DistFn>() : f_pc;
+  lbx_check(lbx_mf_collide2(src.mf(), f_pc.mf(), 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5), mask.mf(),
+                            FINE_VAL),
             "CoarseCollide");
+  valid_pending.at(level) = false;
   f_pc.touch();
 }
 
 // src/AmrSim.cpp:582-590
 void AmrSim::FineCollide(int const level) {
-  Collide(levels.at(level).next.get<DistFn>(), 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5));
+  MultiFab& f_pc = levels.at(level).next.get<DistFn>();
+  const MultiFab& src = valid_pending.at(level) ? levels[level].now.get<DistFn>() : f_pc;
+  lbx_check(lbx_mf_collide2(src.mf(), f_pc.mf(), 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5), nullptr,
+                            FINE_VAL),
+            "FineCollide");
+  valid_pending.at(level) = false;
+  f_pc.touch();
 }
 
 // src/AmrSim.cpp:592-602

@@ -40,9 +40,9 @@ class AmrSim : public amrex::AmrCore {
 
   // initial condition: scalars or C-ordered arrays rho[(i*NY+j)*NZ+k], u[((i*NY+j)*NZ+k)*3+n]
   void SetInitialDensity(double const rho_init);
-  void SetInitialDensity(std::vector<double> const rho_init);
+  void SetInitialDensity(std::vector<double> rho_init);
   void SetInitialVelocity(double const u_init);
-  void SetInitialVelocity(std::vector<double> const u_init);
+  void SetInitialVelocity(std::vector<double> u_init);
 
   // output; cells the level does not hold give the sentinels NL_DENSITY / NL_VELOCITY
   double GetDensity(int const i, int const j, int const k, int const level) const;
@@ -62,6 +62,12 @@ class AmrSim : public amrex::AmrCore {
   // cells the level does not hold carry the sentinels.  One device->host copy per call.
   std::vector<double> GetDensityField(int const level) const;
   std::vector<double> GetVelocityField(int const level) const;
+  void GetDensityField(int const level, double* out, size_t n) const;    // into caller memory
+  void GetVelocityField(int const level, double* out, size_t n) const;
+  // zero-copy inputs: the arrays (same C ordering) are read at InitFromScratch directly from
+  // caller memory -- pinned memory makes that one DMA -- and must stay valid until it returns.
+  void SetInitialDensityView(const double* rho_init, size_t n) { density_view = rho_init; density_view_n = n; }
+  void SetInitialVelocityView(const double* u_init, size_t n) { velocity_view = u_init; velocity_view_n = n; }
   // false: run level 0 through the reference's literal pass structure on per-box storage even
   // when it is the only level (FillPatch, collide, FillBoundary, stream, swap).  Default true.
   void SetUniformFastPath(bool on) { uniform_fast_path = on; }
@@ -134,9 +140,16 @@ class AmrSim : public amrex::AmrCore {
 
  private:
   std::vector<amrex::MultiFab> stream_scratch;   // third population buffer per level
+  // InitPostCollision filled only the ghost cells of NEXT; its valid cells are still NOW's and
+  // the next collision reads them from there (valid-cell copy fused into the collision)
+  std::vector<char> valid_pending;
+  void FillPatchImpl(int const level, amrex::MultiFab& dest, bool ghosts_only);
   bool uniform_fast_path = true;
-  void upload_user_field(amrex::MultiFab& mf, const std::vector<double>& user, int ncomp);
-  std::vector<double> dense_field(const amrex::MultiFab& mf, int level, double sentinel) const;
+  void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp);
+  const double* density_view = nullptr;
+  const double* velocity_view = nullptr;
+  size_t density_view_n = 0, velocity_view_n = 0;
+  void dense_field_into(const amrex::MultiFab& mf, int level, double sentinel, double* out, size_t n) const;
 };
 
 #endif

@@ -90,7 +90,7 @@ int lbx_sim_set_uniform_fast_path(lbx_sim* sim, int on) { return guarded([&] { s
 int lbx_sim_set_initial_density(lbx_sim* sim, const double* rho, size_t n) {
   return guarded([&] {
     if (n == 1) sim->s.SetInitialDensity(rho[0]);
-    else sim->s.SetInitialDensity(std::vector<double>(rho, rho + n));
+    else sim->s.SetInitialDensity(std::vector<double>(rho, rho + n));     // the one copy the by-value API implies
   });
 }
 int lbx_sim_set_initial_velocity(lbx_sim* sim, const double* u, size_t n) {
@@ -98,6 +98,12 @@ int lbx_sim_set_initial_velocity(lbx_sim* sim, const double* u, size_t n) {
     if (n == 1) sim->s.SetInitialVelocity(u[0]);
     else sim->s.SetInitialVelocity(std::vector<double>(u, u + n));
   });
+}
+int lbx_sim_set_initial_density_view(lbx_sim* sim, const double* rho, size_t n) {
+  return guarded([&] { sim->s.SetInitialDensityView(rho, n); });
+}
+int lbx_sim_set_initial_velocity_view(lbx_sim* sim, const double* u, size_t n) {
+  return guarded([&] { sim->s.SetInitialVelocityView(u, n); });
 }
 int lbx_sim_init_from_scratch(lbx_sim* sim, double time) { return guarded([&] { sim->s.InitFromScratch(time); }); }
 int lbx_sim_regrid(lbx_sim* sim, int lbase, double time) { return guarded([&] { sim->s.regrid(lbase, time); }); }
@@ -112,18 +118,10 @@ int lbx_sim_get_velocity(const lbx_sim* sim, int i, int j, int k, int n, int lev
   return guarded([&] { *out = sim->s.GetVelocity(i, j, k, n, level); });
 }
 int lbx_sim_get_density_field(const lbx_sim* sim, int level, double* out, size_t n) {
-  return guarded([&] {
-    const std::vector<double> v = sim->s.GetDensityField(level);
-    if (v.size() != n) amrex::Abort("lbx_sim_get_density_field: buffer size mismatch");
-    std::memcpy(out, v.data(), n * sizeof(double));
-  });
+  return guarded([&] { sim->s.GetDensityField(level, out, n); });
 }
 int lbx_sim_get_velocity_field(const lbx_sim* sim, int level, double* out, size_t n) {
-  return guarded([&] {
-    const std::vector<double> v = sim->s.GetVelocityField(level);
-    if (v.size() != n) amrex::Abort("lbx_sim_get_velocity_field: buffer size mismatch");
-    std::memcpy(out, v.data(), n * sizeof(double));
-  });
+  return guarded([&] { sim->s.GetVelocityField(level, out, n); });
 }
 int lbx_sim_get_time(const lbx_sim* sim, int level, double* out) { return guarded([&] { *out = sim->s.GetTime(level); }); }
 int lbx_sim_get_time_step(const lbx_sim* sim, int level, int* out) {

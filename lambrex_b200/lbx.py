@@ -40,7 +40,7 @@ class lbx_domain(ctypes.Structure):
 
 
 class lbx_gather(ctypes.Structure):
-    _fields_ = [("dst_fab", ctypes.c_int32), ("src_set", ctypes.c_int32), ("src_fab", ctypes.c_int32),
+    _fields_ = [("dst_fab", ctypes.c_int32), ("group", ctypes.c_int32), ("src_set", ctypes.c_int32), ("src_fab", ctypes.c_int32),
                 ("kind", ctypes.c_int32), ("ratio", ctypes.c_int32), ("shift", ctypes.c_int32 * 3),
                 ("region", lbx_box), ("value", ctypes.c_double)]
 
@@ -97,9 +97,13 @@ SYMBOLS = {
     "lbx_mf_equilibrium": (_i, [_vp, _vp, _vp]),
     "lbx_mf_moments": (_i, [_vp, _vp, _vp]),
     "lbx_mf_collide": (_i, [_vp, _d, _d, _vp, _i]),
+    "lbx_mf_collide2": (_i, [_vp, _vp, _d, _d, _vp, _i]),
     "lbx_mf_stream": (_i, [_vp, _vp]),
     "lbx_mf_zero_invalid": (_i, [_vp]),
     "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
+    "lbx_mf_from_user": (_i, [_vp, _vp, _bp, _i]),
+    "lbx_mf_to_user": (_i, [_vp, _vp, _bp, _i]),
+    "lbx_fill_f64": (_i, [_vp, _sz, _d]),
     "lbx_plan_create": (_i, [ctypes.POINTER(lbx_gather), _i, ctypes.POINTER(_vp)]),
     "lbx_plan_apply": (_i, [_vp, _vp, _vp, _vp, _i]),
     "lbx_plan_destroy": (_i, [_vp]),
@@ -418,6 +422,10 @@ def mf_collide(f, omega_s, omega_b, mask=None, fine_val=1):
     check(lib().lbx_mf_collide(f.h, omega_s, omega_b, mask.h if mask is not None else None, fine_val))
 
 
+def mf_collide2(src, dst, omega_s, omega_b, mask=None, fine_val=1):
+    check(lib().lbx_mf_collide2(src.h, dst.h, omega_s, omega_b, mask.h if mask is not None else None, fine_val))
+
+
 def mf_stream(src, dst):
     check(lib().lbx_mf_stream(src.h, dst.h))
 
@@ -439,6 +447,7 @@ class Plan:
         arr = (lbx_gather * max(len(descs), 1))()
         for a, d in zip(arr, descs):
             a.dst_fab, a.src_set, a.src_fab = d["dst_fab"], d.get("src_set", 0), d.get("src_fab", 0)
+            a.group = d.get("group", 0)
             a.kind, a.ratio = d.get("kind", G_COPY), d.get("ratio", 1)
             a.shift[:] = [int(x) for x in d.get("shift", (0, 0, 0))]
             a.region.lo[:] = [int(x) for x in d["lo"]]
