@@ -33,6 +33,8 @@ int lbx_sim_destroy(lbx_sim *sim);
 /* inherited AmrMesh knobs, callable before InitFromScratch */
 int lbx_sim_set_max_grid_size(lbx_sim *sim, int n);
 int lbx_sim_set_uniform_fast_path(lbx_sim *sim, int on);
+/* 0: Rohde cycle as the reference's literal pass sequence; 1 (default): collide+Stream fused per level */
+int lbx_sim_set_rohde_fusion(lbx_sim *sim, int on);
 
 /* SetInitialDensity / SetInitialVelocity (:141-144); n == 1 selects the scalar overloads */
 int lbx_sim_set_initial_density(lbx_sim *sim, const double *rho, size_t n);

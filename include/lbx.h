@@ -77,8 +77,15 @@ int lbx_sync(void);
 uint64_t lbx_launch_count(void);         /* kernels launched by this library so far */
 
 /* ---- memory: replaces amrex::MultiFab allocation (include/field.h:124-129) ---- */
+/* Device memory comes from an arena (the role of AMReX's Arena under every MultiFab): lbx_free /
+ * lbx_mf_destroy park the block, the next request of the same (rounded) size reuses it, so
+ * rebuilding levels or whole simulations does not pay cudaMalloc/cudaFree again.  Blocks are whole
+ * device allocations (CUDA-IPC handles stay valid).  lbx_arena_release returns the parked blocks
+ * to the driver (also done by lbx_finalize, and automatically when an allocation fails). */
 int lbx_malloc(void **dev_ptr, size_t bytes);
 int lbx_free(void *dev_ptr);
+int lbx_arena_release(void);
+int lbx_arena_info(size_t *in_use_bytes, size_t *cached_bytes, uint64_t *hits, uint64_t *misses);
 int lbx_memset(void *dev_ptr, int byte, size_t bytes);
 int lbx_host_alloc(void **host_ptr, size_t bytes);   /* pinned */
 int lbx_host_free(void *host_ptr);
@@ -163,6 +170,16 @@ int lbx_mf_collide2(const lbx_mf *src, lbx_mf *dst, double omega_s, double omega
 /* Stream :109-122 into a "fresh" fab: dst(x,p) = src(x - c_p, p) on valid grown by 1, every
  * other cell of dst zeroed (the reference never writes ghost ring 2 of its new fab) */
 int lbx_mf_stream(const lbx_mf *src, lbx_mf *dst);
+/* Rohde-cycle collide + Stream in ONE pass (push form) -- CoarseCollide/FineCollide :487-590 followed
+ * by Stream :109-122, the pair RohdeCycle :441-457 runs on every level:
+ *   valid cells  : read from `src_valid`, zeroed where mask == fine_val, else collided;
+ *   ghost cells  : read from `src_ghost` UNcollided (the reference does not refresh ghosts between its
+ *                  collide and its Stream);
+ *   dst(x + c_p, p) = f_p(x) for destinations in valid grown by 1; ghost ring 2 of dst = 0 (fresh fab).
+ * zero_invalid != 0 also applies the ZeroInvalidComponents :604-617 that follows the cycle's last
+ * Stream.  The three sets hold the same boxes with 2 ghost cells; dst must not alias a source. */
+int lbx_mf_collide_stream(const lbx_mf *src_valid, const lbx_mf *src_ghost, lbx_mf *dst, double omega_s,
+                          double omega_b, const lbx_mf *mask, int fine_val, int zero_invalid);
 /* ZeroInvalidComponents :604-617: in the ghost shell, f_m = 0 unless pos - 2 c_m is valid */
 int lbx_mf_zero_invalid(lbx_mf *f);
 /* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */

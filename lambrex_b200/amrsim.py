@@ -33,6 +33,7 @@ SYMBOLS = {
     "lbx_sim_create": (_i, [_i, _i, _i, _i, _ip, _d, _d, ctypes.POINTER(_vp)]),
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
+    "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
     "lbx_sim_set_initial_density_view": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity_view": (_i, [_vp, _dp, _sz]),
     "lbx_sim_init_from_scratch": (_i, [_vp, _d]), "lbx_sim_regrid": (_i, [_vp, _i, _d]),
@@ -134,6 +135,9 @@ class AmrSim:
 
     def SetUniformFastPath(self, on):
         _check(lib().lbx_sim_set_uniform_fast_path(self._h, int(on)))
+
+    def SetRohdeFusion(self, on):
+        _check(lib().lbx_sim_set_rohde_fusion(self._h, int(on)))
 
     def _set(self, fn, v):
         a = np.ascontiguousarray(np.atleast_1d(np.asarray(v, dtype=np.float64)).reshape(-1))

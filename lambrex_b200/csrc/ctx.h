@@ -16,6 +16,15 @@ struct Ctx {
   uint64_t launches = 0;
 };
 extern Ctx g_ctx;
+// Device-memory arena (the role AMReX's Arena plays under every MultiFab): freed blocks are kept
+// and handed out again for requests of the same rounded size, so rebuilding a level or a whole
+// simulation does not go back to cudaMalloc/cudaFree (milliseconds per GB).  Blocks are whole
+// cudaMalloc allocations, never sub-allocated, so CUDA-IPC handles of arena memory stay valid.
+// arena_free expects the caller to have drained the stream that last used the block.
+cudaError_t arena_alloc(void** p, size_t bytes);
+void arena_free(void* p);
+void arena_release();                                    // cudaFree every cached block
+void arena_stats(size_t* in_use, size_t* cached, uint64_t* hits, uint64_t* misses);
 int fail(const std::string& msg);            // records the message for lbx_last_error(); returns 1
 int after_launch(const char* what);          // counts the launch, reports launch errors
 }  // namespace lbx

@@ -287,12 +287,12 @@ __device__ __forceinline__ int mf_fab_index() { return blockIdx.y + gridDim.y * 
 __device__ __forceinline__ bool mf_cell(const DFabT& f, int grow, int& i, int& j, int& k) {
   const int nx = f.vhi[0] - f.vlo[0] + 1 + 2 * grow, ny = f.vhi[1] - f.vlo[1] + 1 + 2 * grow,
             nz = f.vhi[2] - f.vlo[2] + 1 + 2 * grow;
-  long long t = (long long)blockIdx.x * MFT + threadIdx.x;
-  if (t >= (long long)nx * ny * nz) return false;
-  i = f.vlo[0] - grow + (int)(t % nx);
-  t /= nx;
-  j = f.vlo[1] - grow + (int)(t % ny);
-  k = f.vlo[2] - grow + (int)(t / ny);
+  unsigned t = blockIdx.x * MFT + threadIdx.x;      // a fab holds < 2^31 cells (lbx_mf_create)
+  if (t >= (unsigned)nx * ny * nz) return false;
+  i = f.vlo[0] - grow + (int)(t % (unsigned)nx);
+  t /= (unsigned)nx;
+  j = f.vlo[1] - grow + (int)(t % (unsigned)ny);
+  k = f.vlo[2] - grow + (int)(t / (unsigned)ny);
   return true;
 }
 __device__ __forceinline__ long long mf_stride(const DFabT& f) { return (long long)f.n[0] * f.n[1] * f.n[2]; }
@@ -334,6 +334,131 @@ __global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ st
   C::collide(f, omega_s, omega_b);
 #pragma unroll
   for (int p = 0; p < NV; ++p) fp[p * sc] = f[p];
+}
+
+// Fused Collide/CoarseCollide/FineCollide + Stream of the Rohde cycle on every box of a level
+// (src/AmrSim.cpp:487-590 then :109-122), push form, ONE pass over the level instead of two:
+//   thread = one SOURCE cell x of the box grown by its 2 ghost rings;
+//   valid cell : f <- vt(x), zeroed where mask == fine_val (CoarseCollide, :499-500), else
+//                collided;
+//   ghost cell : f <- gt(x) UNcollided -- the reference never refreshes ghosts between its
+//                collide and its Stream, so Stream pulls FillPatch values there;
+//   push       : dst(x + c_p, p) = f_p for destinations inside valid grown by 1 (Stream's
+//                iteration space); ring 2 of dst is never written by Stream and holds the fresh
+//                fab's fill, 0: the ring-2 thread zeroes its own cell.
+// zero_invalid != 0 folds the ZeroInvalidComponents that follows the last Stream of a cycle
+// (:604-617) into the stores: a ghost destination y keeps component p only if y - 2 c_p is a
+// valid cell; y - 2 c_p = x - c_p.  (Ring 2 is all zeros already, so nothing else remains.)
+// CTAs have one of two roles (block-uniform, no divergence between the two code paths):
+// blockIdx.x < tiles_valid walks the valid box; the others walk the six slabs of the ghost
+// shell, loading only the populations that have a destination.
+__device__ __forceinline__ bool mf_shell_cell(const DFabT& f, unsigned t, int& i, int& j, int& k) {
+  constexpr unsigned h = HALO;
+  const unsigned v0 = f.vhi[0] - f.vlo[0] + 1, v1 = f.vhi[1] - f.vlo[1] + 1, v2 = f.vhi[2] - f.vlo[2] + 1;
+  const unsigned n0 = v0 + 2 * h, n1 = v1 + 2 * h;
+  const unsigned A = n0 * n1 * h, B = n0 * h * v2, Cc = h * v1 * v2;     // a fab holds < 2^31 cells
+  if (t < 2 * A) {                      // z-low / z-high slabs: full x-y planes
+    const unsigned s = t >= A, r = t - s * A;
+    i = f.vlo[0] - (int)h + (int)(r % n0);
+    j = f.vlo[1] - (int)h + (int)((r / n0) % n1);
+    k = (s ? f.vhi[2] + 1 : f.vlo[2] - (int)h) + (int)(r / (n0 * n1));
+    return true;
+  }
+  t -= 2 * A;
+  if (t < 2 * B) {                      // y-low / y-high slabs over the valid z range
+    const unsigned s = t >= B, r = t - s * B;
+    i = f.vlo[0] - (int)h + (int)(r % n0);
+    j = (s ? f.vhi[1] + 1 : f.vlo[1] - (int)h) + (int)((r / n0) % h);
+    k = f.vlo[2] + (int)(r / (n0 * h));
+    return true;
+  }
+  t -= 2 * B;
+  if (t < 2 * Cc) {                     // x-low / x-high slabs over the valid y-z range
+    const unsigned s = t >= Cc, r = t - s * Cc;
+    i = (s ? f.vhi[0] + 1 : f.vlo[0] - (int)h) + (int)(r % h);
+    j = f.vlo[1] + (int)((r / h) % v1);
+    k = f.vlo[2] + (int)(r / (h * v1));
+    return true;
+  }
+  return false;
+}
+
+template <class C>
+__global__ void __launch_bounds__(MFT) k_mf_collide_stream(const DFabT* __restrict__ vt, const DFabT* __restrict__ gt,
+                                                           const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
+                                                           int nfabs, int tiles_valid, double omega_s, double omega_b,
+                                                           int fine_val, int zero_invalid) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT D = dt[b];
+  const long long dsc = mf_stride(D), dy = D.n[0], dz = (long long)D.n[0] * D.n[1];
+  int i, j, k;
+  double f[NV];
+  if ((int)blockIdx.x < tiles_valid) {
+    // ---- valid source cells ------------------------------------------------------------
+    if (!mf_cell(D, 0, i, j, k)) return;
+    double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
+    bool zero = false;
+    if (mt) {
+      const DFabT M = mt[b];
+      zero = static_cast<const int*>(M.p)[mf_off(M, i, j, k)] == fine_val;
+    }
+    if (zero) {
+#pragma unroll
+      for (int p = 0; p < NV; ++p) f[p] = 0.0;
+    } else {
+      const DFabT S = vt[b];
+      const double* sp = static_cast<const double*>(S.p) + mf_off(S, i, j, k);
+      const long long ssc = mf_stride(S);
+#pragma unroll
+      for (int p = 0; p < NV; ++p) f[p] = __ldcs(sp + p * ssc);
+      C::collide(f, omega_s, omega_b);
+    }
+    // a valid source on the rim of its box pushes into ghost ring 1: that component survives
+    // ZeroInvalidComponents only if x - c_p is valid too (false only for boxes one cell thick)
+    if (zero_invalid && (i == D.vlo[0] || i == D.vhi[0] || j == D.vlo[1] || j == D.vhi[1] || k == D.vlo[2] ||
+                         k == D.vhi[2])) {
+#pragma unroll
+      for (int p = 1; p < NV; ++p)
+        if (!mf_in_valid(D, i + cx(p), j + cy(p), k + cz(p)) && !mf_in_valid(D, i - cx(p), j - cy(p), k - cz(p)))
+          f[p] = 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < NV; ++p) __stcs(dp + p * dsc + cx(p) + cy(p) * dy + cz(p) * dz, f[p]);
+    return;
+  }
+  // ---- ghost source cells: destination x + c_p must lie inside valid grown by 1 -----------
+  if (!mf_shell_cell(D, (blockIdx.x - tiles_valid) * MFT + threadIdx.x, i, j, k)) return;
+  double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
+  // signed ring distance of x from the valid box per direction: <0 below, >0 above, 0 inside
+  const int ex = i < D.vlo[0] ? i - D.vlo[0] : i > D.vhi[0] ? i - D.vhi[0] : 0;
+  const int ey = j < D.vlo[1] ? j - D.vlo[1] : j > D.vhi[1] ? j - D.vhi[1] : 0;
+  const int ez = k < D.vlo[2] ? k - D.vlo[2] : k > D.vhi[2] ? k - D.vhi[2] : 0;
+  const DFabT S = gt[b];
+  const double* sp = static_cast<const double*>(S.p) + mf_off(S, i, j, k);
+  const long long ssc = mf_stride(S);
+  bool go[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) {
+    // ring of the destination per direction: moving inward from ring |e| lands in |e|-1
+    const int rx = ex == 0 ? 0 : (ex > 0 ? ex + cx(p) : -(ex + cx(p)));
+    const int ry = ey == 0 ? 0 : (ey > 0 ? ey + cy(p) : -(ey + cy(p)));
+    const int rz = ez == 0 ? 0 : (ez > 0 ? ez + cz(p) : -(ez + cz(p)));
+    go[p] = rx <= 1 && ry <= 1 && rz <= 1;
+    // kept by ZeroInvalidComponents if the destination is valid, or if x - c_p is valid
+    if (zero_invalid && go[p] && !mf_in_valid(D, i + cx(p), j + cy(p), k + cz(p)) &&
+        !mf_in_valid(D, i - cx(p), j - cy(p), k - cz(p)))
+      f[p] = 0.0;
+    else
+      f[p] = go[p] ? __ldcs(sp + p * ssc) : 0.0;
+  }
+#pragma unroll
+  for (int p = 0; p < NV; ++p)
+    if (go[p]) __stcs(dp + p * dsc + cx(p) + cy(p) * dy + cz(p) * dz, f[p]);
+  if (ex < -1 || ex > 1 || ey < -1 || ey > 1 || ez < -1 || ez > 1) {   // own cell is in ring 2
+#pragma unroll
+    for (int p = 0; p < NV; ++p) dp[p * dsc] = 0.0;
+  }
 }
 
 // CalcHydroVars (src/AmrSim.cpp:938-979) on the valid cells of every box.
@@ -381,9 +506,9 @@ __global__ void __launch_bounds__(MFT) k_mf_equilibrium(const DFabT* __restrict_
   for (int p = 0; p < NV; ++p) fp[p * sc] = f[p];
 }
 
-inline dim3 mf_grid(long long max_cells, int nfabs) {
+inline dim3 mf_grid(long long max_cells, int nfabs, long long extra_tiles = 0, int tile_mult = 1) {
   const unsigned gy = (unsigned)(nfabs < 65535 ? nfabs : 65535);
-  return dim3((unsigned)((max_cells + MFT - 1) / MFT), gy, (unsigned)((nfabs + gy - 1) / gy));
+  return dim3((unsigned)(((max_cells + MFT - 1) / MFT + extra_tiles) * tile_mult), gy, (unsigned)((nfabs + gy - 1) / gy));
 }
 
 inline dim3 grid_for(const DBox& b) {

@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/lbx.h"
 #include "ctx.h"
@@ -19,6 +21,70 @@ int fail(const std::string& msg) {
   g_err = msg;
   return 1;
 }
+// ---- arena -------------------------------------------------------------------------------
+namespace {
+std::unordered_map<void*, size_t> a_live;        // block -> rounded size
+std::multimap<size_t, void*> a_cache;            // rounded size -> free block
+size_t a_in_use = 0, a_cached = 0;
+uint64_t a_hits = 0, a_misses = 0;
+size_t a_round(size_t b) {
+  const size_t g = b >= (size_t(2) << 20) ? (size_t(2) << 20) : 512;   // 2 MiB pages for big blocks
+  return (b + g - 1) / g * g;
+}
+}  // namespace
+void arena_release() {
+  for (auto& kv : a_cache) cudaFree(kv.second);
+  a_cache.clear();
+  a_cached = 0;
+}
+cudaError_t arena_alloc(void** p, size_t bytes) {
+  const size_t rb = a_round(bytes ? bytes : 1);
+  auto it = a_cache.find(rb);
+  if (it != a_cache.end()) {
+    *p = it->second;
+    a_cache.erase(it);
+    a_cached -= rb;
+    ++a_hits;
+  } else {
+    cudaError_t e = cudaMalloc(p, rb);
+    if (e != cudaSuccess) {          // give the cached blocks back to the driver and retry once
+      cudaGetLastError();
+      arena_release();
+      e = cudaMalloc(p, rb);
+      if (e != cudaSuccess) return e;
+    }
+    ++a_misses;
+  }
+  a_live[*p] = rb;
+  a_in_use += rb;
+  return cudaSuccess;
+}
+void arena_free(void* p) {
+  if (!p) return;
+  auto it = a_live.find(p);
+  if (it == a_live.end()) { cudaFree(p); return; }     // not ours (defensive)
+  const size_t rb = it->second;
+  a_live.erase(it);
+  a_in_use -= rb;
+  a_cache.emplace(rb, p);
+  a_cached += rb;
+  // keep at most half of the device's memory parked in the cache: evict the largest blocks first
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return; }
+  while (a_cached > tot / 2 && !a_cache.empty()) {
+    auto last = std::prev(a_cache.end());
+    cudaFree(last->second);
+    a_cached -= last->first;
+    a_cache.erase(last);
+  }
+}
+void arena_stats(size_t* in_use, size_t* cached, uint64_t* hits, uint64_t* misses) {
+  if (in_use) *in_use = a_in_use;
+  if (cached) *cached = a_cached;
+  if (hits) *hits = a_hits;
+  if (misses) *misses = a_misses;
+}
+
 int after_launch(const char* what) {
   ++g_ctx.launches;
   cudaError_t e = cudaGetLastError();
@@ -121,6 +187,7 @@ int lbx_finalize(void) {
   if (!g.ready) return 0;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.own);
+  lbx::arena_release();
   cudaEventDestroy(g.t0);
   cudaEventDestroy(g.t1);
   cudaStreamDestroy(g.own);
@@ -173,14 +240,24 @@ uint64_t lbx_launch_count(void) { return g.launches; }
 
 int lbx_malloc(void** p, size_t bytes) {
   LBX_NEED_INIT();
-  LBX_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+  LBX_CUDA(lbx::arena_alloc(p, bytes));
   return 0;
 }
 int lbx_free(void* p) {
   if (!p) return 0;
   LBX_NEED_INIT();
   LBX_CUDA(cudaStreamSynchronize(g.cur));
-  LBX_CUDA(cudaFree(p));
+  lbx::arena_free(p);
+  return 0;
+}
+int lbx_arena_release(void) {
+  LBX_NEED_INIT();
+  LBX_CUDA(cudaStreamSynchronize(g.cur));
+  lbx::arena_release();
+  return 0;
+}
+int lbx_arena_info(size_t* in_use_bytes, size_t* cached_bytes, uint64_t* hits, uint64_t* misses) {
+  lbx::arena_stats(in_use_bytes, cached_bytes, hits, misses);
   return 0;
 }
 int lbx_memset(void* p, int byte, size_t bytes) {

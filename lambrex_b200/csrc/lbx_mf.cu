@@ -21,6 +21,15 @@ struct lbx_mf {
   std::vector<size_t> offset;           // byte offset of fab i in `base`
   long long max_valid = 0;              // largest valid-box cell count
   uint64_t geom = 0;                    // signature of (boxes, ngrow, ncomp, dtype)
+  long long max_shell(int grow) const {     // most ghost-shell cells (grown minus valid) of any fab
+    long long m = 0;
+    for (const auto& f : host) {
+      long long v = 1, c = 1;
+      for (int d = 0; d < 3; ++d) { v *= (f.vhi[d] - f.vlo[d] + 1); c *= (f.vhi[d] - f.vlo[d] + 1 + 2 * grow); }
+      m = std::max(m, c - v);
+    }
+    return m;
+  }
   long long max_cells(int grow) const {
     long long m = 0;
     for (const auto& f : host) {
@@ -38,6 +47,7 @@ struct lbx_plan {
   lbx::GDesc* d_descs = nullptr;
   lbx::GDst* d_dsts = nullptr;
   long long max_cells = 0;
+  bool has_avg = false;
   std::set<std::tuple<uint64_t, uint64_t, uint64_t>> validated;
 };
 
@@ -89,6 +99,7 @@ int lbx_mf_create(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dty
       f.vlo[d] = valid[i].lo[d]; f.vhi[d] = valid[i].hi[d];
       f.lo[d] = f.vlo[d] - ngrow; f.n[d] = f.vhi[d] - f.vlo[d] + 1 + 2 * ngrow;
       cells *= (size_t)f.n[d];
+      if (cells >= (size_t(1) << 31)) { delete m; return fail("lbx_mf_create: a fab exceeds 2^31 cells"); }
       h = mix(mix(h, (uint64_t)(uint32_t)f.vlo[d]), (uint64_t)(uint32_t)f.vhi[d]);
     }
     m->offset[i] = off;
@@ -97,11 +108,11 @@ int lbx_mf_create(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dty
   m->bytes = off;
   m->geom = h;
   m->max_valid = m->max_cells(0);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->base), m->bytes);
+  cudaError_t e = lbx::arena_alloc(reinterpret_cast<void**>(&m->base), m->bytes);
   if (e != cudaSuccess) { delete m; return fail(std::string("lbx_mf_create: cudaMalloc: ") + cudaGetErrorString(e)); }
   for (int i = 0; i < nfabs; ++i) m->host[i].p = m->base + m->offset[i];
-  e = cudaMalloc(reinterpret_cast<void**>(&m->table), sizeof(lbx::DFabT) * nfabs);
-  if (e != cudaSuccess) { cudaFree(m->base); delete m; return fail("lbx_mf_create: cudaMalloc(table)"); }
+  e = lbx::arena_alloc(reinterpret_cast<void**>(&m->table), sizeof(lbx::DFabT) * nfabs);
+  if (e != cudaSuccess) { lbx::arena_free(m->base); delete m; return fail("lbx_mf_create: cudaMalloc(table)"); }
   // pageable-host async copy: the driver stages it before returning, so `host` may change later
   LBX_CUDA(cudaMemcpyAsync(m->table, m->host.data(), sizeof(lbx::DFabT) * nfabs, cudaMemcpyHostToDevice, g.cur));
   LBX_CUDA(cudaMemsetAsync(m->base, 0, m->bytes, g.cur));     // NEW_FAB_FILL = 0
@@ -113,8 +124,8 @@ int lbx_mf_destroy(lbx_mf* m) {
   if (!m) return 0;
   if (g.ready) {
     cudaStreamSynchronize(g.cur);
-    cudaFree(m->base);
-    cudaFree(m->table);
+    lbx::arena_free(m->base);
+    lbx::arena_free(m->table);
   }
   delete m;
   return 0;
@@ -203,6 +214,22 @@ int lbx_mf_collide(lbx_mf* f, double omega_s, double omega_b, const lbx_mf* mask
   return lbx_mf_collide2(f, f, omega_s, omega_b, mask, fine_val);
 }
 
+int lbx_mf_collide_stream(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
+                          const lbx_mf* mask, int fine_val, int zero_invalid) {
+  LBX_NEED_INIT();
+  if (need(src_valid, LBX_NV, LBX_F64, 0, "lbx_mf_collide_stream src_valid") ||
+      need(src_ghost, LBX_NV, LBX_F64, 2, "lbx_mf_collide_stream src_ghost") ||
+      need(dst, LBX_NV, LBX_F64, 2, "lbx_mf_collide_stream dst") || same_boxes(src_valid, dst, "lbx_mf_collide_stream") ||
+      same_boxes(src_ghost, dst, "lbx_mf_collide_stream"))
+    return 1;
+  if (dst->ngrow != 2 || src_ghost->ngrow != 2) return fail("lbx_mf_collide_stream: needs exactly 2 ghost cells");
+  if (dst->base == src_valid->base || dst->base == src_ghost->base) return fail("lbx_mf_collide_stream: dst aliases a source");
+  if (mask && (need(mask, 1, LBX_I32, 0, "lbx_mf_collide_stream mask") || same_boxes(dst, mask, "lbx_mf_collide_stream"))) return 1;
+  L().mf_collide_stream(g.cur, src_valid->table, src_ghost->table, dst->table, mask ? mask->table : nullptr, dst->nfabs,
+                        dst->max_valid, dst->max_shell(2), omega_s, omega_b, fine_val, zero_invalid);
+  return lbx::after_launch("lbx_mf_collide_stream");
+}
+
 int lbx_mf_stream(const lbx_mf* src, lbx_mf* dst) {
   LBX_NEED_INIT();
   if (need(src, LBX_NV, LBX_F64, 2, "lbx_mf_stream src") || need(dst, LBX_NV, LBX_F64, 1, "lbx_mf_stream dst") ||
@@ -239,20 +266,43 @@ static int user_common(const lbx_mf* m, const void* user, const lbx_box* dom, in
       if (f.vlo[d] < dom->lo[d] || f.vhi[d] > dom->hi[d]) return fail(std::string(what) + ": a box lies outside the user array's domain");
   return 0;
 }
+}  // extern "C"
+// tiled launch when the shape allows it (1 or 3 components, grid limits), else the plain kernel
+template <bool TO_FAB>
+static bool user_tiled(const lbx_mf* m, double* user, const lbx_box* dom, int ncomp) {
+  int mx = 0, my = 0, mz = 0;
+  for (const auto& f : m->host) {
+    mx = std::max(mx, f.vhi[0] - f.vlo[0] + 1);
+    my = std::max(my, f.vhi[1] - f.vlo[1] + 1);
+    mz = std::max(mz, f.vhi[2] - f.vlo[2] + 1);
+  }
+  if ((ncomp != 1 && ncomp != 3) || m->nfabs > 65535 || my > 65535) return false;
+  const int tx = (mx + lbx::UT - 1) / lbx::UT, tz = (mz + lbx::UT - 1) / lbx::UT;
+  const dim3 grid((unsigned)(tx * tz), (unsigned)my, (unsigned)m->nfabs), block(lbx::UT, 8);
+  const int ny = dom->hi[1] - dom->lo[1] + 1, nz = dom->hi[2] - dom->lo[2] + 1;
+  if (ncomp == 1)
+    lbx::k_mf_user_tiled<TO_FAB, 1><<<grid, block, 0, g.cur>>>(m->table, user, tx, dom->lo[0], dom->lo[1], dom->lo[2], ny, nz);
+  else
+    lbx::k_mf_user_tiled<TO_FAB, 3><<<grid, block, 0, g.cur>>>(m->table, user, tx, dom->lo[0], dom->lo[1], dom->lo[2], ny, nz);
+  return true;
+}
+extern "C" {
 int lbx_mf_from_user(lbx_mf* m, const double* user_dev, const lbx_box* dom, int ncomp) {
   LBX_NEED_INIT();
   if (user_common(m, user_dev, dom, ncomp, "lbx_mf_from_user")) return 1;
-  lbx::k_mf_user<true><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
-      m->table, m->nfabs, const_cast<double*>(user_dev), dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
-      dom->hi[2] - dom->lo[2] + 1, ncomp);
+  if (!user_tiled<true>(m, const_cast<double*>(user_dev), dom, ncomp))
+    lbx::k_mf_user<true><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
+        m->table, m->nfabs, const_cast<double*>(user_dev), dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
+        dom->hi[2] - dom->lo[2] + 1, ncomp);
   return lbx::after_launch("lbx_mf_from_user");
 }
 int lbx_mf_to_user(const lbx_mf* m, double* user_dev, const lbx_box* dom, int ncomp) {
   LBX_NEED_INIT();
   if (user_common(m, user_dev, dom, ncomp, "lbx_mf_to_user")) return 1;
-  lbx::k_mf_user<false><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
-      m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
-      dom->hi[2] - dom->lo[2] + 1, ncomp);
+  if (!user_tiled<false>(m, user_dev, dom, ncomp))
+    lbx::k_mf_user<false><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
+        m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
+        dom->hi[2] - dom->lo[2] + 1, ncomp);
   return lbx::after_launch("lbx_mf_to_user");
 }
 int lbx_fill_f64(double* dev, size_t n, double value) {
@@ -284,6 +334,7 @@ int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
       if (a.region.hi[k] < a.region.lo[k]) { delete p; return fail("lbx_plan_create: empty region"); }
       d.lo[k] = a.region.lo[k]; d.hi[k] = a.region.hi[k]; d.shift[k] = a.shift[k];
     }
+    if (a.kind == LBX_G_AVG) p->has_avg = true;
     d.src_set = a.src_set; d.src_fab = a.src_fab; d.kind = a.kind; d.ratio = a.ratio > 0 ? a.ratio : 1; d.value = a.value;
     if (p->dsts.empty() || p->dsts.back().fab != a.dst_fab || gs[i - 1].group != a.group) {
       lbx::GDst t;
@@ -300,9 +351,10 @@ int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
     for (int k = 0; k < 3; ++k) c *= (t.bhi[k] - t.blo[k] + 1);
     p->max_cells = std::max(p->max_cells, c);
   }
+  if (p->max_cells >= (1ll << 31)) { delete p; return fail("lbx_plan_create: a destination region exceeds 2^31 cells"); }
   if (n > 0) {
-    LBX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_descs), sizeof(lbx::GDesc) * n));
-    LBX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_dsts), sizeof(lbx::GDst) * p->dsts.size()));
+    LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&p->d_descs), sizeof(lbx::GDesc) * n));
+    LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&p->d_dsts), sizeof(lbx::GDst) * p->dsts.size()));
     LBX_CUDA(cudaMemcpyAsync(p->d_descs, p->descs.data(), sizeof(lbx::GDesc) * n, cudaMemcpyHostToDevice, g.cur));
     LBX_CUDA(cudaMemcpyAsync(p->d_dsts, p->dsts.data(), sizeof(lbx::GDst) * p->dsts.size(), cudaMemcpyHostToDevice, g.cur));
     LBX_CUDA(cudaStreamSynchronize(g.cur));
@@ -315,8 +367,8 @@ int lbx_plan_destroy(lbx_plan* p) {
   if (!p) return 0;
   if (g.ready) {
     cudaStreamSynchronize(g.cur);
-    cudaFree(p->d_descs);
-    cudaFree(p->d_dsts);
+    lbx::arena_free(p->d_descs);
+    lbx::arena_free(p->d_dsts);
   }
   delete p;
   return 0;
@@ -365,11 +417,15 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   const lbx::DFabT* t1 = src1 ? src1->table : nullptr;
   const int nd = (int)p->dsts.size();
 #define LBX_PLAN_LAUNCH(T, ADD, NC) \
-  lbx::k_plan_apply<T, ADD, NC><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp)
+  lbx::k_plan_apply<T, ADD, NC, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp)
   if (dst->dtype == LBX_F64) {
     if (dst->ncomp == LBX_NV) {          // the populations: compile-time component count
       if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, LBX_NV);
-      else LBX_PLAN_LAUNCH(double, true, LBX_NV);
+      else if (p->has_avg) {             // averaging plan: one thread per (cell, component)
+        const dim3 gc = lbx::mf_grid(p->max_cells, nd, 0, dst->ncomp);
+        lbx::k_plan_apply<double, true, 1, true><<<gc, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1,
+                                                                             dst->ncomp);
+      } else LBX_PLAN_LAUNCH(double, true, LBX_NV);
     } else {
       if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, 0);
       else LBX_PLAN_LAUNCH(double, true, 0);

@@ -92,6 +92,49 @@ __global__ void __launch_bounds__(MFT) k_mf_user(const DFabT* __restrict__ ft, i
   }
 }
 
+// Same transposition through shared memory: a CTA moves a 32 (x) x 32 (z) tile of one y-row, all
+// components, so that BOTH sides are coalesced -- the fab side along x, the user side along its
+// contiguous (k, n) run.  grid = (x-tiles * z-tiles of the largest box, y extent, fab).
+constexpr int UT = 32;
+template <bool TO_FAB, int NC>
+__global__ void __launch_bounds__(UT * 8) k_mf_user_tiled(const DFabT* __restrict__ ft, double* __restrict__ user,
+                                                          int tiles_x, int d0, int d1, int d2, int ny, int nz) {
+  __shared__ double tile[NC][UT][UT + 1];     // [n][z][x]
+  const DFabT F = ft[blockIdx.z];
+  const int j = F.vlo[1] + blockIdx.y;
+  const int i0 = F.vlo[0] + (blockIdx.x % tiles_x) * UT, k0 = F.vlo[2] + (blockIdx.x / tiles_x) * UT;
+  if (j > F.vhi[1] || i0 > F.vhi[0] || k0 > F.vhi[2]) return;           // block-uniform
+  const int ni = min(UT, F.vhi[0] - i0 + 1), nk = min(UT, F.vhi[2] - k0 + 1);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long sc = mf_stride(F);
+  double* fp = static_cast<double*>(F.p);
+  if (!TO_FAB) {
+    if (tx < ni)
+      for (int kk = ty; kk < nk; kk += 8) {
+        const long long o = mf_off(F, i0 + tx, j, k0 + kk);
+#pragma unroll
+        for (int n = 0; n < NC; ++n) tile[n][kk][tx] = fp[n * sc + o];
+      }
+    __syncthreads();
+    for (int ii = ty; ii < ni; ii += 8) {
+      double* up = user + (((long long)(i0 + ii - d0) * ny + (j - d1)) * nz + (k0 - d2)) * NC;
+      for (int e = tx; e < nk * NC; e += UT) up[e] = tile[e % NC][e / NC][ii];
+    }
+  } else {
+    for (int ii = ty; ii < ni; ii += 8) {
+      const double* up = user + (((long long)(i0 + ii - d0) * ny + (j - d1)) * nz + (k0 - d2)) * NC;
+      for (int e = tx; e < nk * NC; e += UT) tile[e % NC][e / NC][ii] = up[e];
+    }
+    __syncthreads();
+    if (tx < ni)
+      for (int kk = ty; kk < nk; kk += 8) {
+        const long long o = mf_off(F, i0 + tx, j, k0 + kk);
+#pragma unroll
+        for (int n = 0; n < NC; ++n) fp[n * sc + o] = tile[n][kk][tx];
+      }
+  }
+}
+
 __global__ void k_fill_f64(double* __restrict__ p, long long n, double v) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
     p[t] = v;
@@ -139,12 +182,13 @@ struct GDst {
 
 __device__ __forceinline__ int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
 
-// one matching descriptor applied to one destination cell, all components.  NC > 0: component
-// count known at compile time (15 populations): every load of the cell is issued before the
-// first store, which is what keeps these gather kernels bandwidth- rather than latency-bound.
+// one matching descriptor applied to one destination cell, components [c0, c0 + n).  NC > 0: the
+// count n is known at compile time (15 populations, or 1 in the component-parallel launch): every
+// load of the cell is issued before the first store, which is what keeps these gather kernels
+// bandwidth- rather than latency-bound.  dp already points at component c0 of the destination.
 template <class T, bool ADD, int NC>
 __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
-                                        int i, int j, int k, T* __restrict__ dp, long long dsc, int ncomp_rt) {
+                                        int i, int j, int k, T* __restrict__ dp, long long dsc, int c0, int ncomp_rt) {
   const int ncomp = NC > 0 ? NC : ncomp_rt;
   if (g.kind == G_CONST) {
 #pragma unroll
@@ -156,7 +200,7 @@ __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict_
   if (g.kind == G_AVG) {
     const int r = g.ratio;
     const int i0 = i * r + g.shift[0];
-    const T* sp = static_cast<const T*>(S.p) + mf_off(S, i0, j * r + g.shift[1], k * r + g.shift[2]);
+    const T* sp = static_cast<const T*>(S.p) + c0 * ssc + mf_off(S, i0, j * r + g.shift[1], k * r + g.shift[2]);
     const long long sy = S.n[0], sz = (long long)S.n[0] * S.n[1];
     if (sizeof(T) == 8 && r == 2 && NC > 0 && ((i0 - S.lo[0]) & 1) == 0 && (S.n[0] & 1) == 0) {
       // ratio 2, 16-byte aligned pairs: four 16-byte loads per component, summed in
@@ -188,7 +232,7 @@ __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict_
   }
   int si = i, sj = j, sk = k;
   if (g.kind == G_PC) { si = fdiv(i, g.ratio); sj = fdiv(j, g.ratio); sk = fdiv(k, g.ratio); }
-  const T* sp = static_cast<const T*>(S.p) + mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
+  const T* sp = static_cast<const T*>(S.p) + c0 * ssc + mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
   if (NC > 0) {
     T v[NC > 0 ? NC : 1];
 #pragma unroll
@@ -202,7 +246,10 @@ __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict_
 
 constexpr int PLAN_CHUNK = 64;   // descriptors staged in shared memory at a time (4 KB)
 
-template <class T, bool ADD, int NC>
+// CPAR: component-parallel launch -- gridDim.x = tiles * ncomp and a thread handles ONE component
+// of its cell (NC must be 1).  Used for the averaging plans (sum_fine_to_coarse), whose 60 loads
+// per cell otherwise leave a 15-component thread latency-bound at low occupancy.
+template <class T, bool ADD, int NC, bool CPAR>
 __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dsts, int ndst,
                                                     const GDesc* __restrict__ descs, const DFabT* __restrict__ dt,
                                                     const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
@@ -211,24 +258,27 @@ __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dst
   const int q = mf_fab_index();
   if (q >= ndst) return;                       // block-uniform
   const GDst D = dsts[q];
-  const int nx = D.bhi[0] - D.blo[0] + 1, ny = D.bhi[1] - D.blo[1] + 1, nz = D.bhi[2] - D.blo[2] + 1;
-  long long t = (long long)blockIdx.x * MFT + threadIdx.x;
-  if ((long long)blockIdx.x * MFT >= (long long)nx * ny * nz) return;   // whole block idle: uniform exit
-  bool active = t < (long long)nx * ny * nz;
+  const unsigned tile = CPAR ? blockIdx.x / (unsigned)ncomp : blockIdx.x;
+  const int c0 = CPAR ? (int)(blockIdx.x % (unsigned)ncomp) : 0;
+  const unsigned nx = D.bhi[0] - D.blo[0] + 1, ny = D.bhi[1] - D.blo[1] + 1, nz = D.bhi[2] - D.blo[2] + 1;
+  const unsigned cells = nx * ny * nz;         // < 2^31 (checked at plan creation)
+  if (tile * MFT >= cells) return;             // whole block idle: uniform exit
+  unsigned t = tile * MFT + threadIdx.x;
+  bool active = t < cells;
   const int i = D.blo[0] + (int)(t % nx);
   t /= nx;
   const int j = D.blo[1] + (int)(t % ny), k = D.blo[2] + (int)(t / ny);
   const DFabT F = dt[D.fab];
-  T* dp = static_cast<T*>(F.p) + (active ? mf_off(F, i, j, k) : 0);
   const long long dsc = mf_stride(F);
+  T* dp = static_cast<T*>(F.p) + c0 * dsc + (active ? mf_off(F, i, j, k) : 0);
   const int nchunks = (D.count + PLAN_CHUNK - 1) / PLAN_CHUNK;
   for (int ch = 0; ch < nchunks; ++ch) {
     // COPY walks the list backwards (the last match wins), ADD forwards (list order)
-    const int c0 = ADD ? ch * PLAN_CHUNK : max(D.count - (ch + 1) * PLAN_CHUNK, 0);
-    const int c1 = ADD ? min(c0 + PLAN_CHUNK, D.count) : D.count - ch * PLAN_CHUNK;
-    const int n = c1 - c0;
+    const int cb = ADD ? ch * PLAN_CHUNK : max(D.count - (ch + 1) * PLAN_CHUNK, 0);
+    const int ce = ADD ? min(cb + PLAN_CHUNK, D.count) : D.count - ch * PLAN_CHUNK;
+    const int n = ce - cb;
     {  // cooperative copy of n descriptors as 16-byte words
-      const int4* src = reinterpret_cast<const int4*>(descs + D.first + c0);
+      const int4* src = reinterpret_cast<const int4*>(descs + D.first + cb);
       int4* dst = reinterpret_cast<int4*>(sd);
       for (int w = threadIdx.x; w < n * (int)(sizeof(GDesc) / 16); w += MFT) dst[w] = src[w];
     }
@@ -238,7 +288,7 @@ __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dst
         for (int d = n - 1; d >= 0; --d) {
           const GDesc& g = sd[d];
           if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
-          g_apply<T, false, NC>(g, s0, s1, i, j, k, dp, dsc, ncomp);
+          g_apply<T, false, NC>(g, s0, s1, i, j, k, dp, dsc, c0, ncomp);
           active = false;
           break;
         }
@@ -246,7 +296,7 @@ __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dst
         for (int d = 0; d < n; ++d) {
           const GDesc& g = sd[d];
           if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
-          g_apply<T, true, NC>(g, s0, s1, i, j, k, dp, dsc, ncomp);
+          g_apply<T, true, NC>(g, s0, s1, i, j, k, dp, dsc, c0, ncomp);
         }
       }
     }

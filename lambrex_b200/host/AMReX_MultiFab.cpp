@@ -421,6 +421,10 @@ void FillBoundary(MultiFab& mf, const Periodicity& period) {
   });
   lbx_check(lbx_plan_apply(p, mf.mf(), mf.mf(), nullptr, LBX_OP_COPY), "FillBoundary");
   mf.touch();
+  // all directions periodic and the boxes tile the whole period: every ghost cell is now a copy
+  // of the valid cell that covers it
+  const IntVect& pp = period.period();
+  if (pp[0] > 0 && pp[1] > 0 && pp[2] > 0 && mf.boxArray().numPts() == (long)pp[0] * pp[1] * pp[2]) mf.markGhostsFresh();
 }
 
 void FillPatchSingleLevel(MultiFab& dst, const MultiFab& src, const Geometry& geom, bool ghosts_only) {

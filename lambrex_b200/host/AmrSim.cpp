@@ -322,6 +322,7 @@ void AmrSim::MakeFineMask(int const coarse_level) {
 // ----------------------------------------------------------------------------- Rohde cycle
 // src/AmrSim.cpp:430-469
 void AmrSim::RohdeCycle(int const coarse_level) {
+  if (rohde_fused && CanFuseRohde(coarse_level)) return RohdeCycleFused(coarse_level);
   const int ref_ratio_here = refRatio(coarse_level)[0];
   InitPostCollision(coarse_level);
   CoarseCollide(coarse_level);
@@ -339,6 +340,71 @@ void AmrSim::RohdeCycle(int const coarse_level) {
   Stream(coarse_level);
   SumFromFine(coarse_level);
   ZeroInvalidComponents(coarse_level);
+  if (coarse_level == 0) UpdateBoundaries(coarse_level);
+  UpdateDistribution(coarse_level);
+}
+
+// The same cycle with each level's collide + Stream pair fused into one pass over the level
+// (lbx_mf_collide_stream): every pass of the reference's sequence is still performed on the same
+// data in the same order per cell, so the result is identical to the unfused sequence above.
+//  * CoarseCollide is deferred to just before Stream(coarse): between the two the reference only
+//    works on finer levels, which read this level's NOW (FillPatchTwoLevels :385), never its NEXT.
+//  * ZeroInvalidComponents is folded into the stores of the cycle's last Stream (on the coarse
+//    level it commutes with SumFromFine, which adds into valid cells only).
+//  * InitPostCollision's zeroing of component 0 in the outermost ghost ring (:477-482) is not
+//    observable: the rest population never moves, and Stream leaves ring 2 of its fresh
+//    destination at the fill value.
+bool AmrSim::CanFuseRohde(int const level) const {
+  for (int l = level; l <= finest_level; ++l) {
+    const MultiFab& a = levels[l].now.get<DistFn>();
+    const MultiFab& b = levels[l].next.get<DistFn>();
+    if (a.empty() || b.empty() || a.isFlat() || b.isFlat() || a.nGrow() != 2 || b.nGrow() != 2 ||
+        a.boxArray() != b.boxArray())
+      return false;
+  }
+  return true;
+}
+
+void AmrSim::CollideStreamFused(int const level, bool masked, bool zero_invalid, bool ghosts_from_now) {
+  MultiFab& f_nxt = levels[level].next.get<DistFn>();
+  const MultiFab& f_now = levels[level].now.get<DistFn>();
+  const MultiFab& vsrc = valid_pending.at(level) ? f_now : f_nxt;
+  const MultiFab& gsrc = ghosts_from_now ? f_now : f_nxt;
+  MultiFab& f_prop = stream_scratch.at(level);
+  if (f_prop.empty() || f_prop.boxArray() != f_nxt.boxArray() || f_prop.layout() != f_nxt.layout())
+    f_prop = field_traits<DistFn>::MakeLevelData(f_nxt.boxArray(), f_nxt.DistributionMap(), f_nxt.layout());
+  const amrex::iMultiFab* mask = nullptr;
+  if (masked) {
+    mask = &fine_masks.at(level);
+    if (mask->empty()) amrex::Abort("CoarseCollide: no fine mask on this level");
+  }
+  lbx_check(lbx_mf_collide_stream(vsrc.mf(), gsrc.mf(), f_prop.mf(), 1.0 / (tau_s.at(level) + 0.5),
+                                  1.0 / (tau_b.at(level) + 0.5), mask ? mask->mf() : nullptr, FINE_VAL, zero_invalid ? 1 : 0),
+            "CollideStreamFused");
+  valid_pending.at(level) = false;
+  std::swap(f_nxt, f_prop);
+  f_nxt.touch();
+}
+
+void AmrSim::RohdeCycleFused(int const coarse_level) {
+  const int ref_ratio_here = refRatio(coarse_level)[0];
+  // InitPostCollision, ghost cells.  On level 0 FillPatchSingleLevel gives every ghost cell the
+  // value of the NOW valid cell covering it -- exactly what NOW's own ghost cells hold when the
+  // previous cycle's UpdateBoundaries was the last thing to touch that fab: read them in place.
+  const bool now_ghosts = coarse_level == 0 && levels[0].now.get<DistFn>().ghostsFresh();
+  if (!now_ghosts) FillPatchImpl(coarse_level, levels[coarse_level].next.get<DistFn>(), true);
+  valid_pending.at(coarse_level) = true;
+  if (coarse_level + 1 == finest_level) {
+    FillPatchImpl(finest_level, levels[finest_level].next.get<DistFn>(), true);
+    valid_pending.at(finest_level) = true;
+    CollideStreamFused(finest_level, false, false);     // FineCollide + Stream
+    CollideStreamFused(finest_level, false, true);      // FineCollide + Stream + ZeroInvalidComponents
+    UpdateDistribution(finest_level);
+  } else {
+    for (int iter = 0; iter < ref_ratio_here; ++iter) RohdeCycle(coarse_level + 1);
+  }
+  CollideStreamFused(coarse_level, true, true, now_ghosts);   // CoarseCollide + Stream + ZeroInvalidComponents
+  SumFromFine(coarse_level);
   if (coarse_level == 0) UpdateBoundaries(coarse_level);
   UpdateDistribution(coarse_level);
 }

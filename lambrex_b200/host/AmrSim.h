@@ -71,6 +71,9 @@ class AmrSim : public amrex::AmrCore {
   // false: run level 0 through the reference's literal pass structure on per-box storage even
   // when it is the only level (FillPatch, collide, FillBoundary, stream, swap).  Default true.
   void SetUniformFastPath(bool on) { uniform_fast_path = on; }
+  // false: run the Rohde cycle as the reference's literal sequence of passes (collide, Stream and
+  // ZeroInvalidComponents as separate launches).  Default true: one fused pass per collide+Stream.
+  void SetRohdeFusion(bool on) { rohde_fused = on; }
 
  protected:
   const int NX, NY, NZ, NUMEL, COORD_SYS;
@@ -145,6 +148,10 @@ class AmrSim : public amrex::AmrCore {
   std::vector<char> valid_pending;
   void FillPatchImpl(int const level, amrex::MultiFab& dest, bool ghosts_only);
   bool uniform_fast_path = true;
+  bool rohde_fused = true;
+  bool CanFuseRohde(int const level) const;
+  void RohdeCycleFused(int const coarse_level);
+  void CollideStreamFused(int const level, bool masked, bool zero_invalid, bool ghosts_from_now = false);
   void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp);
   const double* density_view = nullptr;
   const double* velocity_view = nullptr;

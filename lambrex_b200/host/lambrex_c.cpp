@@ -87,6 +87,8 @@ int lbx_sim_destroy(lbx_sim* sim) { return guarded([&] { delete sim; }); }
 int lbx_sim_set_max_grid_size(lbx_sim* sim, int n) { return guarded([&] { sim->s.SetMaxGridSize(n); }); }
 int lbx_sim_set_uniform_fast_path(lbx_sim* sim, int on) { return guarded([&] { sim->s.SetUniformFastPath(on != 0); }); }
 
+int lbx_sim_set_rohde_fusion(lbx_sim* sim, int on) { return guarded([&] { sim->s.SetRohdeFusion(on != 0); }); }
+
 int lbx_sim_set_initial_density(lbx_sim* sim, const double* rho, size_t n) {
   return guarded([&] {
     if (n == 1) sim->s.SetInitialDensity(rho[0]);

@@ -64,6 +64,9 @@ SYMBOLS = {
     "lbx_launch_count": (ctypes.c_uint64, []),
     "lbx_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "lbx_free": (_i, [_vp]),
+    "lbx_arena_release": (_i, []),
+    "lbx_arena_info": (_i, [ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(ctypes.c_uint64),
+                            ctypes.POINTER(ctypes.c_uint64)]),
     "lbx_memset": (_i, [_vp, _i, _sz]),
     "lbx_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "lbx_host_free": (_i, [_vp]),
@@ -99,6 +102,7 @@ SYMBOLS = {
     "lbx_mf_collide": (_i, [_vp, _d, _d, _vp, _i]),
     "lbx_mf_collide2": (_i, [_vp, _vp, _d, _d, _vp, _i]),
     "lbx_mf_stream": (_i, [_vp, _vp]),
+    "lbx_mf_collide_stream": (_i, [_vp, _vp, _vp, _d, _d, _vp, _i, _i]),
     "lbx_mf_zero_invalid": (_i, [_vp]),
     "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
     "lbx_mf_from_user": (_i, [_vp, _vp, _bp, _i]),
@@ -424,6 +428,11 @@ def mf_collide(f, omega_s, omega_b, mask=None, fine_val=1):
 
 def mf_collide2(src, dst, omega_s, omega_b, mask=None, fine_val=1):
     check(lib().lbx_mf_collide2(src.h, dst.h, omega_s, omega_b, mask.h if mask is not None else None, fine_val))
+
+
+def mf_collide_stream(src_valid, src_ghost, dst, omega_s, omega_b, mask=None, fine_val=1, zero_invalid=False):
+    check(lib().lbx_mf_collide_stream(src_valid.h, src_ghost.h, dst.h, omega_s, omega_b,
+                                      mask.h if mask is not None else None, fine_val, 1 if zero_invalid else 0))
 
 
 def mf_stream(src, dst):

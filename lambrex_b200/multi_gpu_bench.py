@@ -39,7 +39,7 @@ def run_multi(args, helpers):
         fits = torch.tensor([1 if need(n) < info["free_bytes"] else 0])
         dist.all_reduce(fits, op=dist.ReduceOp.MIN)
     nx = ny = nz = n
-    sim = SlabSim(nx, ny, nz, tau, tau, rank=rank, world=world, halo=args.halo)
+    sim = SlabSim(nx, ny, nz, tau, tau, rank=rank, world=world, halo=args.halo, split=not args.no_split)
     klo, khi = sim.layout.slab(rank)
     nzl = khi - klo + 1
     cells_total = float(nx) * ny * nz
@@ -121,7 +121,7 @@ def run_multi(args, helpers):
         achieved = helpers["BYTES_PER_CELL"] * cells_local / (ms_step * 1e-3) / 1e9
         tr = helpers["recorded_traffic"]()
         cfg = helpers["workload_config"](world)
-        cfg.update({"grid": [nx, ny, nz], "halo": args.halo, "partition": "z-slabs %s" % sim.layout.slabs,
+        cfg.update({"grid": [nx, ny, nz], "halo": args.halo, "split": bool(sim.split and args.halo == "p2p"), "partition": "z-slabs %s" % sim.layout.slabs,
                     "parallelism": "domain decomposition, %d slabs" % world})
         if reduced:
             cfg["workload"] += " -- REDUCED to %d^3: 1024^3 does not fit %d GPUs' free HBM" % (n, world)
@@ -129,7 +129,9 @@ def run_multi(args, helpers):
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(ln.item()),
-                "roofline": {"bound": "hbm", "kernel": "k_collide_stream_slab (per GPU, largest slab)",
+                "roofline": {"bound": "hbm", "kernel": ("k_collide_stream<push> on the interior planes + k_collide_stream_slab on the 2 boundary "
+                                        "planes (per GPU, largest slab)") if sim.split and args.halo == "p2p" else
+                             "k_collide_stream_slab (per GPU, largest slab)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "peak_source": peak_src, "traffic": (tr or {}).get("bytes_per_launch"),
                              "traffic_source": (tr or {}).get("source")},

@@ -88,7 +88,7 @@ class SlabSim:
     """Device state of one rank's slab + the step loop."""
 
     def __init__(self, nx, ny, nz, tau_s, tau_b, rank=0, world=1, halo="p2p", group=None,
-                 timeout_ns=20_000_000_000):
+                 timeout_ns=20_000_000_000, split=True):
         import torch
         self.torch = torch
         self.layout = SlabLayout(nx, ny, nz, world)
@@ -109,6 +109,10 @@ class SlabSim:
         self.U = lbx.fab_desc(self.u_t.data_ptr(), lo, (nx, ny, nzl), 3)
         self.step_id = 0
         self.cur = 0
+        # interior / boundary-plane split of the step (p2p, world > 1, slab at least 3 planes thick)
+        self.split = bool(split) and nzl >= 3
+        self.box_edges = [lbx.box(lo, (hi[0], hi[1], lo[2])), lbx.box((lo[0], lo[1], hi[2]), hi)]
+        self.box_interior = lbx.box((lo[0], lo[1], lo[2] + 1), (hi[0], hi[1], hi[2] - 1))
         glo, ghi = (0, 0, 0), (nx - 1, ny - 1, nz - 1)
         if halo == "p2p":
             self.dom = lbx.domain(glo, ghi, (1, 1, 1))
@@ -188,13 +192,26 @@ class SlabSim:
         for _ in range(n):
             src, dst = self.F[self.cur], self.F[1 - self.cur]
             if self.halo == "p2p":
-                if self.world > 1:
+                if self.world > 1 and self.split:
+                    # Only the two boundary planes touch a neighbour (they read the 5 populations it
+                    # stored last step and store 5 into its fab), so only they are ordered against
+                    # it: wait -> boundary planes -> signal, then the interior planes with the plain
+                    # push kernel while the neighbours already work on their next step.
                     lbx.peer_wait(self.flags, self.flags + 8, self.step_id, self.timeout_ns)
-                lbx.collide_stream_slab(src, dst, self.peer_dn[1 - self.cur], self.peer_up[1 - self.cur],
-                                        self.box, self.dom, self.omega_s, self.omega_b)
-                self.step_id += 1
-                if self.world > 1:
+                    for bx in self.box_edges:
+                        lbx.collide_stream_slab(src, dst, self.peer_dn[1 - self.cur], self.peer_up[1 - self.cur],
+                                                bx, self.dom, self.omega_s, self.omega_b)
+                    self.step_id += 1
                     lbx.peer_signal(self.sig_dn, self.sig_up, self.step_id)
+                    lbx.collide_stream(src, dst, self.box_interior, self.dom, self.omega_s, self.omega_b, lbx.PUSH)
+                else:
+                    if self.world > 1:
+                        lbx.peer_wait(self.flags, self.flags + 8, self.step_id, self.timeout_ns)
+                    lbx.collide_stream_slab(src, dst, self.peer_dn[1 - self.cur], self.peer_up[1 - self.cur],
+                                            self.box, self.dom, self.omega_s, self.omega_b)
+                    self.step_id += 1
+                    if self.world > 1:
+                        lbx.peer_signal(self.sig_dn, self.sig_up, self.step_id)
             else:
                 lbx.collide_stream_slab(src, dst, dst, dst, self.box, self.dom, self.omega_s, self.omega_b)
                 self.step_id += 1

@@ -319,3 +319,37 @@ def test_three_level_shear_matches_oracle(coracle):
     o.iterate(2)
     compare_levels(sim, o, (0, 1, 2))
     assert (sim.GetTime(2), sim.GetTimeStep(2)) == (o.levels[2].time, o.levels[2].step)
+
+
+@pytest.mark.parametrize("max_level", [1, 2])
+def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level):
+    """The fused collide+Stream(+ZeroInvalidComponents) passes reproduce the reference's literal
+    sequence of passes bit for bit: every cell of NOW (ghost rings included) on every level."""
+    nx, ny, nz = 16, 12, 20
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    rho = rho * workloads.pulse_density(nx, ny, nz)
+    sims = []
+    for fused in (True, False):
+        sim = AmrSim(nx, ny, nz, max_level, PER, 0.3, 0.4)
+        sim.SetRohdeFusion(fused)
+        sim.SetMaxGridSize(8)
+        sim.SetInitialDensity(rho)
+        sim.SetInitialVelocity(u)
+        sim.InitFromScratch(0.0)
+        sim.SetStaticRefinement(0, (3, 2, 4), (11, 9, 14))
+        if max_level == 2:
+            sim.SetStaticRefinement(1, (10, 8, 12), (19, 15, 25))
+        assert sim.finestLevel() == max_level
+        sims.append(sim)
+    for it in range(3):
+        for sim in sims:
+            sim.Iterate(1)
+        for lev in range(max_level + 1):
+            assert sims[0].FieldBoxes(lev, amrsim.DISTFN) == sims[1].FieldBoxes(lev, amrsim.DISTFN)
+            for b in range(len(sims[0].FieldBoxes(lev, amrsim.DISTFN))):
+                a = sims[0].FieldFab(lev, amrsim.DISTFN, b, 2, 15)
+                c = sims[1].FieldFab(lev, amrsim.DISTFN, b, 2, 15)
+                assert np.array_equal(a, c), (it, lev, b, float(np.max(np.abs(a - c))))
+            assert sims[0].GetTime(lev) == sims[1].GetTime(lev) and sims[0].GetTimeStep(lev) == sims[1].GetTimeStep(lev)
+    for sim in sims:
+        sim.close()

@@ -21,11 +21,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--levels", type=int, default=2)
     ap.add_argument("--max-grid", type=int, default=32)
+    ap.add_argument("--no-fusion", action="store_true", help="Rohde cycle as the literal pass sequence")
     args = ap.parse_args()
     n = args.grid
     amrsim.lambrexInit()
     sim = amrsim.AmrSim(n, n, n, args.levels - 1, (1, 1, 1), 0.5, 0.5)
     sim.SetMaxGridSize(args.max_grid)
+    sim.SetRohdeFusion(not args.no_fusion)
     sim.SetInitialDensity(workloads.pulse_density(n, n, n))
     sim.SetInitialVelocity(0.0)
     sim.InitFromScratch(0.0)
@@ -48,7 +50,7 @@ def main():
     launches = lbx.launch_count() - l0
     work = sum(c * s for c, s in zip(cells, substeps))
     print(json.dumps({"metric": "MLUPS (fp64 D3Q15, Rohde cycle)", "value": work * args.steps / (t.ms * 1e-3) / 1e6,
-                      "ms_per_coarse_step": t.ms / args.steps, "levels": args.levels, "base_grid": [n, n, n],
+                      "ms_per_coarse_step": t.ms / args.steps, "levels": args.levels, "fused": not args.no_fusion, "max_grid": args.max_grid, "base_grid": [n, n, n],
                       "cells_per_level": cells, "boxes_per_level": nbox, "substeps": substeps,
                       "launches_per_coarse_step": launches / args.steps, "regrid_seconds": regrid_s,
                       "first_%d_steps_seconds" % args.warmup: first_s,

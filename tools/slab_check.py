@@ -22,8 +22,9 @@ def main():
     lbx.init(local)
     nx, ny, nz, tau, steps = 64, 48, 50, 0.1, 25
     ok = True
-    for halo in ("p2p", "nccl"):
-        sim = SlabSim(nx, ny, nz, tau, tau, rank=rank, world=world, halo=halo)
+    for halo in ("p2p", "p2p-nosplit", "nccl"):
+        sim = SlabSim(nx, ny, nz, tau, tau, rank=rank, world=world, halo=halo.split("-")[0],
+                      split=not halo.endswith("nosplit"))
         klo, khi = sim.layout.slab(rank)
         rho, u = shear_slab(nx, ny, nz, klo, khi)
         rho = rho * pulse_slab(nx, ny, nz, klo, khi)            # z-dependence crosses the slab faces
