@@ -74,6 +74,13 @@ int lbx_set_option(int key, int value);
 int lbx_set_stream(void *cuda_stream);   /* NULL: back to the library's own stream;
                                             the legacy default stream is cudaStreamLegacy (0x1) */
 int lbx_sync(void);
+/* Concurrent section: the calls made between begin and end must be independent of one another
+ * (they may read the same data but write disjoint data).  Each launch goes to its own auxiliary
+ * stream, ordered after everything queued before begin; everything queued after end is ordered
+ * behind all of them.  Lets the latency-bound ghost-cell kernels overlap the bandwidth-bound pass
+ * over the valid cells.  No host synchronisation; no lbx_sync / lbx_free inside a section. */
+int lbx_concurrent_begin(void);
+int lbx_concurrent_end(void);
 uint64_t lbx_launch_count(void);         /* kernels launched by this library so far */
 
 /* ---- memory: replaces amrex::MultiFab allocation (include/field.h:124-129) ---- */
@@ -174,12 +181,17 @@ int lbx_mf_stream(const lbx_mf *src, lbx_mf *dst);
  * by Stream :109-122, the pair RohdeCycle :441-457 runs on every level:
  *   valid cells  : read from `src_valid`, zeroed where mask == fine_val, else collided;
  *   ghost cells  : read from `src_ghost` UNcollided (the reference does not refresh ghosts between its
- *                  collide and its Stream);
+ *                  collide and its Stream); src_ghost == NULL: valid cells only;
  *   dst(x + c_p, p) = f_p(x) for destinations in valid grown by 1; ghost ring 2 of dst = 0 (fresh fab).
  * zero_invalid != 0 also applies the ZeroInvalidComponents :604-617 that follows the cycle's last
  * Stream.  The three sets hold the same boxes with 2 ghost cells; dst must not alias a source. */
 int lbx_mf_collide_stream(const lbx_mf *src_valid, const lbx_mf *src_ghost, lbx_mf *dst, double omega_s,
                           double omega_b, const lbx_mf *mask, int fine_val, int zero_invalid);
+/* First half of sum_fine_to_coarse :598 (amrex_avgdown): crse box b (valid AND ghosts) <- mean of the
+ * ratio^3 fine cells of fine box b; the allocated fine box must be the refinement of the allocated
+ * coarse box (fine ghosts = ratio x coarse ghosts).  The ADD into the coarse level is then a COPY-kind
+ * plan applied with LBX_OP_ADD over these patches. */
+int lbx_mf_average_down(const lbx_mf *fine, lbx_mf *crse, int ratio);
 /* ZeroInvalidComponents :604-617: in the ghost shell, f_m = 0 unless pos - 2 c_m is valid */
 int lbx_mf_zero_invalid(lbx_mf *f);
 /* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */
@@ -203,7 +215,9 @@ int lbx_fill_f64(double *dev, size_t n, double value);
 enum { LBX_G_COPY = 0,   /* dst(x) = src(x + shift)                                  */
        LBX_G_PC = 1,     /* dst(x) = src(floor(x / ratio) + shift)   (PCInterp)      */
        LBX_G_AVG = 2,    /* dst(x) = mean of the ratio^3 cells src(ratio x + shift..) */
-       LBX_G_CONST = 3   /* dst(x) = value                                           */ };
+       LBX_G_CONST = 3,  /* dst(x) = value                                           */
+       LBX_G_NONE = 4    /* no source: dst(x) keeps its value; the region only widens the tiled
+                            bounding box of its group (put it FIRST in the group)          */ };
 enum { LBX_OP_COPY = 0, LBX_OP_ADD = 1 };
 typedef struct lbx_gather {
   int32_t dst_fab;      /* index into the destination set; descriptors sorted by it   */
@@ -221,6 +235,15 @@ typedef struct lbx_gather {
 typedef struct lbx_plan lbx_plan;
 int lbx_plan_create(const lbx_gather *g, int n, lbx_plan **out);
 int lbx_plan_apply(lbx_plan *plan, lbx_mf *dst, const lbx_mf *src0, const lbx_mf *src1, int op);
+/* lbx_mf_collide_stream with the level's DistFnFillPatch :359-391 folded in: `ghost_plan` is a
+ * ghosts-only FillPatchSingleLevel / FillPatchTwoLevels plan (COPY / PC / NONE descriptors over the
+ * ghost slabs of every box of dst; src0 = same-level NOW, src1 = coarse NOW).  A ghost cell x is not
+ * written and read back: its thread looks up FillPatch's source for x and pushes dst(x + c_p, p)
+ * from there.  NONE / uncovered cells take x's value in `fallback` (may be NULL: 0).  ONE launch:
+ * the CTAs of a box's valid cells and of its ghost cells are interleaved so that they overlap. */
+int lbx_mf_collide_stream_fillpatch(const lbx_mf *src_valid, lbx_mf *dst, double omega_s, double omega_b,
+                                    const lbx_mf *mask, int fine_val, int zero_invalid, lbx_plan *ghost_plan,
+                                    const lbx_mf *src0, const lbx_mf *src1, const lbx_mf *fallback);
 int lbx_plan_destroy(lbx_plan *plan);
 
 /* lattice constants and moment basis the kernels use (host-side query; no GPU needed):

@@ -14,6 +14,13 @@ struct Ctx {
   bool literal = false;
   int* peer_err = nullptr;         // host-mapped: set by k_peer_wait on timeout
   uint64_t launches = 0;
+  // concurrent section (lbx_concurrent_begin/end): every launch goes to its own auxiliary stream
+  static constexpr int NAUX = 4;
+  cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t main_saved = nullptr;
+  int conc_next = -1;              // >= 0: inside a concurrent section; index of the stream in use
+  int conc_used = 0;
 };
 extern Ctx g_ctx;
 // Device-memory arena (the role AMReX's Arena plays under every MultiFab): freed blocks are kept

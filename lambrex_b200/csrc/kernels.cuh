@@ -349,9 +349,9 @@ __global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ st
 // zero_invalid != 0 folds the ZeroInvalidComponents that follows the last Stream of a cycle
 // (:604-617) into the stores: a ghost destination y keeps component p only if y - 2 c_p is a
 // valid cell; y - 2 c_p = x - c_p.  (Ring 2 is all zeros already, so nothing else remains.)
-// CTAs have one of two roles (block-uniform, no divergence between the two code paths):
-// blockIdx.x < tiles_valid walks the valid box; the others walk the six slabs of the ghost
-// shell, loading only the populations that have a destination.
+// The ghost cells are pushed from their own values or, with DistFnFillPatch folded in, from
+// wherever FillPatch takes them (k_mf_collide_stream below), loading only the populations that
+// have a destination.
 __device__ __forceinline__ bool mf_shell_cell(const DFabT& f, unsigned t, int& i, int& j, int& k) {
   constexpr unsigned h = HALO;
   const unsigned v0 = f.vhi[0] - f.vlo[0] + 1, v1 = f.vhi[1] - f.vlo[1] + 1, v2 = f.vhi[2] - f.vlo[2] + 1;
@@ -383,60 +383,20 @@ __device__ __forceinline__ bool mf_shell_cell(const DFabT& f, unsigned t, int& i
   return false;
 }
 
-template <class C>
-__global__ void __launch_bounds__(MFT) k_mf_collide_stream(const DFabT* __restrict__ vt, const DFabT* __restrict__ gt,
-                                                           const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
-                                                           int nfabs, int tiles_valid, double omega_s, double omega_b,
-                                                           int fine_val, int zero_invalid) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
-  const DFabT D = dt[b];
-  const long long dsc = mf_stride(D), dy = D.n[0], dz = (long long)D.n[0] * D.n[1];
-  int i, j, k;
-  double f[NV];
-  if ((int)blockIdx.x < tiles_valid) {
-    // ---- valid source cells ------------------------------------------------------------
-    if (!mf_cell(D, 0, i, j, k)) return;
-    double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
-    bool zero = false;
-    if (mt) {
-      const DFabT M = mt[b];
-      zero = static_cast<const int*>(M.p)[mf_off(M, i, j, k)] == fine_val;
-    }
-    if (zero) {
-#pragma unroll
-      for (int p = 0; p < NV; ++p) f[p] = 0.0;
-    } else {
-      const DFabT S = vt[b];
-      const double* sp = static_cast<const double*>(S.p) + mf_off(S, i, j, k);
-      const long long ssc = mf_stride(S);
-#pragma unroll
-      for (int p = 0; p < NV; ++p) f[p] = __ldcs(sp + p * ssc);
-      C::collide(f, omega_s, omega_b);
-    }
-    // a valid source on the rim of its box pushes into ghost ring 1: that component survives
-    // ZeroInvalidComponents only if x - c_p is valid too (false only for boxes one cell thick)
-    if (zero_invalid && (i == D.vlo[0] || i == D.vhi[0] || j == D.vlo[1] || j == D.vhi[1] || k == D.vlo[2] ||
-                         k == D.vhi[2])) {
-#pragma unroll
-      for (int p = 1; p < NV; ++p)
-        if (!mf_in_valid(D, i + cx(p), j + cy(p), k + cz(p)) && !mf_in_valid(D, i - cx(p), j - cy(p), k - cz(p)))
-          f[p] = 0.0;
-    }
-#pragma unroll
-    for (int p = 0; p < NV; ++p) __stcs(dp + p * dsc + cx(p) + cy(p) * dy + cz(p) * dz, f[p]);
-    return;
-  }
-  // ---- ghost source cells: destination x + c_p must lie inside valid grown by 1 -----------
-  if (!mf_shell_cell(D, (blockIdx.x - tiles_valid) * MFT + threadIdx.x, i, j, k)) return;
+// Push of ONE ghost source cell x = (i,j,k) of fab D whose 15 populations live at sp[p * ssc]
+// (its own ghost cell, or wherever a FillPatch plan says that ghost cell's value comes from):
+// dst(x + c_p, p) = f_p for destinations inside valid grown by 1, loading only those populations;
+// zero_invalid: a ghost destination keeps component p only if x - c_p is valid; the ring-2 cell
+// zeroes itself (fresh-fab fill).
+__device__ __forceinline__ void ghost_push(const DFabT& D, int i, int j, int k, const double* __restrict__ sp,
+                                           long long ssc, int zero_invalid) {
   double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
+  const long long dsc = mf_stride(D), dy = D.n[0], dz = (long long)D.n[0] * D.n[1];
   // signed ring distance of x from the valid box per direction: <0 below, >0 above, 0 inside
   const int ex = i < D.vlo[0] ? i - D.vlo[0] : i > D.vhi[0] ? i - D.vhi[0] : 0;
   const int ey = j < D.vlo[1] ? j - D.vlo[1] : j > D.vhi[1] ? j - D.vhi[1] : 0;
   const int ez = k < D.vlo[2] ? k - D.vlo[2] : k > D.vhi[2] ? k - D.vhi[2] : 0;
-  const DFabT S = gt[b];
-  const double* sp = static_cast<const double*>(S.p) + mf_off(S, i, j, k);
-  const long long ssc = mf_stride(S);
+  double f[NV];
   bool go[NV];
 #pragma unroll
   for (int p = 0; p < NV; ++p) {
@@ -450,7 +410,7 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const DFabT* __restri
         !mf_in_valid(D, i - cx(p), j - cy(p), k - cz(p)))
       f[p] = 0.0;
     else
-      f[p] = go[p] ? __ldcs(sp + p * ssc) : 0.0;
+      f[p] = (go[p] && sp) ? __ldcs(sp + p * ssc) : 0.0;
   }
 #pragma unroll
   for (int p = 0; p < NV; ++p)
@@ -461,7 +421,158 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const DFabT* __restri
   }
 }
 
-// CalcHydroVars (src/AmrSim.cpp:938-979) on the valid cells of every box.
+// ---- gather-plan records (built by lbx_plan_create, see mf_kernels.cuh for the semantics) ------
+enum { G_COPY = 0, G_PC = 1, G_AVG = 2, G_CONST = 3, G_NONE = 4 };
+struct alignas(16) GDesc {   // 64 bytes
+  int lo[3], hi[3];   // destination region (destination index space)
+  int shift[3];       // added in SOURCE index space after the map
+  int src_set, src_fab, kind, ratio;
+  int pad;
+  double value;
+};
+static_assert(sizeof(GDesc) == 64, "GDesc must be 64 bytes (staged to shared memory as int4 words)");
+struct GDst {
+  int fab, first, count, pad;
+  int blo[3], bhi[3];   // bounding box of this fab's regions
+};
+
+__device__ __forceinline__ int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
+
+constexpr int PLAN_CHUNK = 64;   // descriptors staged in shared memory at a time (4 KB)
+
+// One launch = one collide + Stream of a level.  grid = (tiles, fab): the CTAs of ONE box are
+// adjacent in launch order -- first its valid-cell tiles, then its ghost-cell tiles -- so the
+// bandwidth-bound valid CTAs and the latency-bound ghost CTAs of a few boxes are resident together
+// and overlap (launched as separate kernels they run back to back: +30 % time).
+//  * valid tile  : CSY rows of one z-plane, a warp per row (no per-thread division; a warp's access
+//                  to a population plane is one contiguous row segment).  The source set has the
+//                  destination's geometry, so only ONE box descriptor is read and the source
+//                  address is dst's offset into the other allocation.
+//  * ghost tiles : plan == null: the six shell slabs, each ghost cell pushes its OWN value in gt;
+//                  plan != null: DistFnFillPatch :359-391 folded in -- the thread of ghost cell x looks
+//                  up where FillPatch would take x's value from (COPY: a same-level box / periodic
+//                  image; PC: the coarse cell under x; descriptors of a ghosts-only
+//                  FillPatchSingleLevel / FillPatchTwoLevels plan, last match wins) and pushes from
+//                  there; NONE / no match: the value FillPatch would have left, read from `fb`.
+struct CSPlan {                    // ghosts-only FillPatch plan of the level being streamed (or all null)
+  const GDst* dsts;                // groups (ghost slabs), sorted by fab
+  const int* fab_first;            // [nfabs + 1] first group of each fab
+  const GDesc* descs;
+  const DFabT* s0;                 // same-level source set (NOW)
+  const DFabT* s1;                 // coarse source set (NOW of level - 1)
+  const DFabT* fb;                 // fallback: the fab FillPatch would have filled
+  int tiles_per_group;
+};
+constexpr int CSX = 32, CSY = 8;
+static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
+
+template <class C>
+__global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
+                                                           const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
+                                                           const DFabT* __restrict__ gt, CSPlan plan, int nfabs,
+                                                           int ytiles, int valid_tiles, double omega_s, double omega_b,
+                                                           int fine_val, int zero_invalid) {
+  __shared__ GDesc sd[PLAN_CHUNK];
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT D = dt[b];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < valid_tiles) {
+    // ---- valid source cells: collide, push ---------------------------------------------------
+    const int ty = tid / CSX, tx = tid % CSX;
+    const int j = D.vlo[1] + ((int)blockIdx.x % ytiles) * CSY + ty, k = D.vlo[2] + (int)blockIdx.x / ytiles;
+    if (j > D.vhi[1] || k > D.vhi[2]) return;
+    const int* mp = mt ? static_cast<const int*>(mt[b].p) : nullptr;   // mask: same boxes and ghosts, 1 comp
+    const long long sc = mf_stride(D), dy = D.n[0], dz = (long long)D.n[0] * D.n[1];
+    const long long row = mf_off(D, D.lo[0], j, k);                 // offset of x = lo[0] in this row
+    double* drow = static_cast<double*>(D.p) + row;
+    const double* srow = vbase + (static_cast<double*>(D.p) - dbase) + row;
+    const bool rim_jk = j == D.vlo[1] || j == D.vhi[1] || k == D.vlo[2] || k == D.vhi[2];
+    for (int i = D.vlo[0] + tx; i <= D.vhi[0]; i += CSX) {
+      const int x = i - D.lo[0];
+      double f[NV];
+      if (mp && mp[row + x] == fine_val) {
+#pragma unroll
+        for (int p = 0; p < NV; ++p) f[p] = 0.0;
+      } else {
+#pragma unroll
+        for (int p = 0; p < NV; ++p) f[p] = __ldcs(srow + p * sc + x);
+        C::collide(f, omega_s, omega_b);
+      }
+      // a valid source on the rim of its box pushes into ghost ring 1: that component survives
+      // ZeroInvalidComponents only if x - c_p is valid too (false only for boxes one cell thick)
+      if (zero_invalid && (rim_jk || i == D.vlo[0] || i == D.vhi[0])) {
+#pragma unroll
+        for (int p = 1; p < NV; ++p)
+          if (!mf_in_valid(D, i + cx(p), j + cy(p), k + cz(p)) && !mf_in_valid(D, i - cx(p), j - cy(p), k - cz(p)))
+            f[p] = 0.0;
+      }
+#pragma unroll
+      for (int p = 0; p < NV; ++p) __stcs(drow + p * sc + x + (cx(p) + cy(p) * dy + cz(p) * dz), f[p]);
+    }
+    return;
+  }
+  const unsigned gtile = blockIdx.x - valid_tiles;
+  int i, j, k;
+  if (!plan.dsts) {
+    // ---- ghost source cells pushing their own values -------------------------------------------
+    if (!gt || !mf_shell_cell(D, gtile * MFT + tid, i, j, k)) return;
+    const DFabT S = gt[b];
+    ghost_push(D, i, j, k, static_cast<const double*>(S.p) + mf_off(S, i, j, k), mf_stride(S), zero_invalid);
+    return;
+  }
+  // ---- ghost source cells, FillPatch folded in ---------------------------------------------------
+  const int q = plan.fab_first[b] + (int)(gtile / plan.tiles_per_group);
+  if (q >= plan.fab_first[b + 1]) return;                  // block-uniform
+  const GDst G = plan.dsts[q];
+  const unsigned nx = G.bhi[0] - G.blo[0] + 1, ny = G.bhi[1] - G.blo[1] + 1, nz = G.bhi[2] - G.blo[2] + 1;
+  const unsigned cells = nx * ny * nz, tile = gtile % plan.tiles_per_group;
+  if (tile * MFT >= cells) return;
+  unsigned t = tile * MFT + tid;
+  const bool in_box = t < cells;
+  i = G.blo[0] + (int)(t % nx);
+  t /= nx;
+  j = G.blo[1] + (int)(t % ny);
+  k = G.blo[2] + (int)(t / ny);
+  const bool ghost = in_box && !mf_in_valid(D, i, j, k);   // these plans tile ghost slabs only
+  bool searching = ghost;
+  const double* sp = nullptr;
+  long long ssc = 0;
+  const int nchunks = (G.count + PLAN_CHUNK - 1) / PLAN_CHUNK;
+  for (int ch = 0; ch < nchunks; ++ch) {                   // backwards: the last matching descriptor wins
+    const int cb = max(G.count - (ch + 1) * PLAN_CHUNK, 0), ce = G.count - ch * PLAN_CHUNK, n = ce - cb;
+    {
+      const int4* src = reinterpret_cast<const int4*>(plan.descs + G.first + cb);
+      int4* dst = reinterpret_cast<int4*>(sd);
+      for (int w = tid; w < n * (int)(sizeof(GDesc) / 16); w += MFT) dst[w] = src[w];
+    }
+    __syncthreads();
+    if (searching) {
+      for (int d = n - 1; d >= 0; --d) {
+        const GDesc& g = sd[d];
+        if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
+        if (g.kind == G_COPY || g.kind == G_PC) {
+          const DFabT S = (g.src_set ? plan.s1 : plan.s0)[g.src_fab];
+          int si = i, sj = j, sk = k;
+          if (g.kind == G_PC) { si = fdiv(i, g.ratio); sj = fdiv(j, g.ratio); sk = fdiv(k, g.ratio); }
+          sp = static_cast<const double*>(S.p) + mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
+          ssc = mf_stride(S);
+        }
+        searching = false;                                  // a G_NONE hit ends the search too: no source
+        break;
+      }
+    }
+    __syncthreads();
+  }
+  if (!ghost) return;
+  if (!sp && plan.fb) {
+    const DFabT B = plan.fb[b];
+    sp = static_cast<const double*>(B.p) + mf_off(B, i, j, k);
+    ssc = mf_stride(B);
+  }
+  ghost_push(D, i, j, k, sp, ssc, zero_invalid);
+}
+
 template <class C>
 __global__ void __launch_bounds__(MFT) k_mf_moments(const DFabT* __restrict__ ft, const DFabT* __restrict__ rt,
                                                     const DFabT* __restrict__ ut, int nfabs) {

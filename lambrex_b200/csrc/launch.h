@@ -17,9 +17,9 @@ struct Launchers {
                               double wb);
   void (*mf_collide)(cudaStream_t, const DFabT* src, const DFabT* f, const DFabT* mask, int nfabs, long long max_cells, double ws,
                      double wb, int fine_val);
-  void (*mf_collide_stream)(cudaStream_t, const DFabT* vsrc, const DFabT* gsrc, const DFabT* dst, const DFabT* mask, int nfabs,
-                            long long max_valid, long long max_shell, double ws, double wb, int fine_val,
-                            int zero_invalid);
+  void (*mf_collide_stream)(cudaStream_t, const double* vbase, double* dbase, const DFabT* dst, const DFabT* mask,
+                            const DFabT* gsrc, CSPlan plan, int nfabs, int max_ny, int max_nz, long long ghost_tiles, double ws,
+                            double wb, int fine_val, int zero_invalid);
   void (*mf_moments)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs, long long max_cells);
   void (*mf_equilibrium)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs,
                          long long max_cells);

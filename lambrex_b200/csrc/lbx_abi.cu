@@ -89,6 +89,15 @@ int after_launch(const char* what) {
   ++g_ctx.launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
+  if (g_ctx.conc_next >= 0) {      // concurrent section: the next launch gets the next auxiliary stream
+    Ctx& g = g_ctx;
+    g.conc_next = (g.conc_next + 1) % Ctx::NAUX;
+    if (g.conc_used < Ctx::NAUX) {
+      ++g.conc_used;
+      cudaStreamWaitEvent(g.aux[g.conc_next], g.fork_ev, 0);
+    }
+    g.cur = g.aux[g.conc_next];
+  }
   return 0;
 }
 }  // namespace lbx
@@ -177,9 +186,43 @@ int lbx_init(int device) {
   LBX_CUDA(cudaEventCreate(&g.t1));
   LBX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g.peer_err), sizeof(int), cudaHostAllocMapped));
   *g.peer_err = 0;
+  for (int a = 0; a < lbx::Ctx::NAUX; ++a) {
+    LBX_CUDA(cudaStreamCreateWithFlags(&g.aux[a], cudaStreamNonBlocking));
+    LBX_CUDA(cudaEventCreateWithFlags(&g.join_ev[a], cudaEventDisableTiming));
+  }
+  LBX_CUDA(cudaEventCreateWithFlags(&g.fork_ev, cudaEventDisableTiming));
   g.cur = g.own;
   g.device = device;
   g.ready = true;
+  return 0;
+}
+
+/* Launches made between begin and end are independent of one another (the caller's promise):
+ * each goes to its own auxiliary stream, ordered after everything queued before begin; end
+ * orders everything queued after it behind all of them.  Small latency-bound kernels (ghost-cell
+ * pushes, gather plans) then overlap with the bandwidth-bound pass over the valid cells. */
+int lbx_concurrent_end(void);
+int lbx_concurrent_begin(void) {
+  LBX_NEED_INIT();
+  if (g.conc_next >= 0 && lbx_concurrent_end()) return 1;    // a section left open by a failed call: close it
+  LBX_CUDA(cudaEventRecord(g.fork_ev, g.cur));
+  g.main_saved = g.cur;
+  g.conc_next = 0;
+  g.conc_used = 1;
+  LBX_CUDA(cudaStreamWaitEvent(g.aux[0], g.fork_ev, 0));
+  g.cur = g.aux[0];
+  return 0;
+}
+int lbx_concurrent_end(void) {
+  LBX_NEED_INIT();
+  if (g.conc_next < 0) return fail("lbx_concurrent_end: not inside a concurrent section");
+  g.cur = g.main_saved;
+  for (int a = 0; a < g.conc_used; ++a) {
+    LBX_CUDA(cudaEventRecord(g.join_ev[a], g.aux[a]));
+    LBX_CUDA(cudaStreamWaitEvent(g.cur, g.join_ev[a], 0));
+  }
+  g.conc_next = -1;
+  g.conc_used = 0;
   return 0;
 }
 
@@ -187,6 +230,11 @@ int lbx_finalize(void) {
   if (!g.ready) return 0;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.own);
+  for (int a = 0; a < lbx::Ctx::NAUX; ++a) {
+    if (g.aux[a]) { cudaStreamSynchronize(g.aux[a]); cudaStreamDestroy(g.aux[a]); }
+    if (g.join_ev[a]) cudaEventDestroy(g.join_ev[a]);
+  }
+  if (g.fork_ev) cudaEventDestroy(g.fork_ev);
   lbx::arena_release();
   cudaEventDestroy(g.t0);
   cudaEventDestroy(g.t1);

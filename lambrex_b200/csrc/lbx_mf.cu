@@ -21,6 +21,11 @@ struct lbx_mf {
   std::vector<size_t> offset;           // byte offset of fab i in `base`
   long long max_valid = 0;              // largest valid-box cell count
   uint64_t geom = 0;                    // signature of (boxes, ngrow, ncomp, dtype)
+  int max_extent(int dir) const {           // largest valid-box extent along dir
+    int m = 0;
+    for (const auto& f : host) m = std::max(m, f.vhi[dir] - f.vlo[dir] + 1);
+    return m;
+  }
   long long max_shell(int grow) const {     // most ghost-shell cells (grown minus valid) of any fab
     long long m = 0;
     for (const auto& f : host) {
@@ -47,7 +52,9 @@ struct lbx_plan {
   lbx::GDesc* d_descs = nullptr;
   lbx::GDst* d_dsts = nullptr;
   long long max_cells = 0;
-  bool has_avg = false;
+  bool has_avg = false, has_const = false;
+  int* d_fab_first = nullptr;           // [nfabs + 1] first group of each destination fab (lbx_mf_collide_stream_fillpatch)
+  int fab_first_n = -1, max_groups = 0;
   std::set<std::tuple<uint64_t, uint64_t, uint64_t>> validated;
 };
 
@@ -214,20 +221,14 @@ int lbx_mf_collide(lbx_mf* f, double omega_s, double omega_b, const lbx_mf* mask
   return lbx_mf_collide2(f, f, omega_s, omega_b, mask, fine_val);
 }
 
+static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
+                                 const lbx_mf* mask, int fine_val, int zero_invalid, lbx_plan* plan, const lbx_mf* src0,
+                                 const lbx_mf* src1, const lbx_mf* fallback);
+
 int lbx_mf_collide_stream(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
                           const lbx_mf* mask, int fine_val, int zero_invalid) {
-  LBX_NEED_INIT();
-  if (need(src_valid, LBX_NV, LBX_F64, 0, "lbx_mf_collide_stream src_valid") ||
-      need(src_ghost, LBX_NV, LBX_F64, 2, "lbx_mf_collide_stream src_ghost") ||
-      need(dst, LBX_NV, LBX_F64, 2, "lbx_mf_collide_stream dst") || same_boxes(src_valid, dst, "lbx_mf_collide_stream") ||
-      same_boxes(src_ghost, dst, "lbx_mf_collide_stream"))
-    return 1;
-  if (dst->ngrow != 2 || src_ghost->ngrow != 2) return fail("lbx_mf_collide_stream: needs exactly 2 ghost cells");
-  if (dst->base == src_valid->base || dst->base == src_ghost->base) return fail("lbx_mf_collide_stream: dst aliases a source");
-  if (mask && (need(mask, 1, LBX_I32, 0, "lbx_mf_collide_stream mask") || same_boxes(dst, mask, "lbx_mf_collide_stream"))) return 1;
-  L().mf_collide_stream(g.cur, src_valid->table, src_ghost->table, dst->table, mask ? mask->table : nullptr, dst->nfabs,
-                        dst->max_valid, dst->max_shell(2), omega_s, omega_b, fine_val, zero_invalid);
-  return lbx::after_launch("lbx_mf_collide_stream");
+  return collide_stream_common(src_valid, src_ghost, dst, omega_s, omega_b, mask, fine_val, zero_invalid, nullptr, nullptr,
+                               nullptr, nullptr);
 }
 
 int lbx_mf_stream(const lbx_mf* src, lbx_mf* dst) {
@@ -239,6 +240,23 @@ int lbx_mf_stream(const lbx_mf* src, lbx_mf* dst) {
   lbx::k_mf_stream<<<lbx::mf_grid(dst->max_cells(dst->ngrow), dst->nfabs), lbx::MFT, 0, g.cur>>>(
       src->table, dst->table, dst->nfabs, dst->ngrow);
   return lbx::after_launch("lbx_mf_stream");
+}
+
+int lbx_mf_average_down(const lbx_mf* fine, lbx_mf* crse, int ratio) {
+  LBX_NEED_INIT();
+  if (need(fine, LBX_NV, LBX_F64, 0, "lbx_mf_average_down fine") || need(crse, LBX_NV, LBX_F64, 0, "lbx_mf_average_down crse")) return 1;
+  if (ratio < 1 || fine->nfabs != crse->nfabs || fine->ncomp != LBX_NV || crse->ncomp != LBX_NV)
+    return fail("lbx_mf_average_down: sets differ in size or components");
+  for (int i = 0; i < fine->nfabs; ++i)
+    for (int d = 0; d < 3; ++d) {
+      const lbx::DFabT &f = fine->host[i], &c = crse->host[i];
+      // allocated fine box = refine(allocated coarse box)
+      if (f.lo[d] != c.lo[d] * ratio || f.n[d] != c.n[d] * ratio)
+        return fail("lbx_mf_average_down: fine box (with ghosts) is not the refinement of the coarse box (with ghosts)");
+    }
+  lbx::k_mf_average_down<<<lbx::mf_grid(crse->max_cells(crse->ngrow), crse->nfabs), lbx::MFT, 0, g.cur>>>(
+      fine->table, crse->table, crse->nfabs, crse->ngrow, ratio);
+  return lbx::after_launch("lbx_mf_average_down");
 }
 
 int lbx_mf_zero_invalid(lbx_mf* f) {
@@ -327,7 +345,7 @@ int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
       delete p;
       return fail("lbx_plan_create: descriptors must be sorted by (dst_fab, group)");
     }
-    if (a.kind < LBX_G_COPY || a.kind > LBX_G_CONST) { delete p; return fail("lbx_plan_create: unknown kind"); }
+    if (a.kind < LBX_G_COPY || a.kind > LBX_G_NONE) { delete p; return fail("lbx_plan_create: unknown kind"); }
     if ((a.kind == LBX_G_PC || a.kind == LBX_G_AVG) && a.ratio < 1) { delete p; return fail("lbx_plan_create: ratio must be >= 1"); }
     if (a.src_set != 0 && a.src_set != 1) { delete p; return fail("lbx_plan_create: src_set must be 0 or 1"); }
     for (int k = 0; k < 3; ++k) {
@@ -335,6 +353,7 @@ int lbx_plan_create(const lbx_gather* gs, int n, lbx_plan** out) {
       d.lo[k] = a.region.lo[k]; d.hi[k] = a.region.hi[k]; d.shift[k] = a.shift[k];
     }
     if (a.kind == LBX_G_AVG) p->has_avg = true;
+    if (a.kind == LBX_G_CONST) p->has_const = true;
     d.src_set = a.src_set; d.src_fab = a.src_fab; d.kind = a.kind; d.ratio = a.ratio > 0 ? a.ratio : 1; d.value = a.value;
     if (p->dsts.empty() || p->dsts.back().fab != a.dst_fab || gs[i - 1].group != a.group) {
       lbx::GDst t;
@@ -369,6 +388,7 @@ int lbx_plan_destroy(lbx_plan* p) {
     cudaStreamSynchronize(g.cur);
     lbx::arena_free(p->d_descs);
     lbx::arena_free(p->d_dsts);
+    lbx::arena_free(p->d_fab_first);
   }
   delete p;
   return 0;
@@ -387,7 +407,7 @@ static int validate_plan(lbx_plan* p, const lbx_mf* dst, const lbx_mf* s0, const
     for (int q = t.first; q < t.first + t.count; ++q) {
       const lbx::GDesc& d = p->descs[q];
       if (!inside(dst->host[t.fab], d.lo, d.hi)) return fail("lbx_plan_apply: region outside the destination fab");
-      if (d.kind == lbx::G_CONST) continue;
+      if (d.kind == lbx::G_CONST || d.kind == lbx::G_NONE) continue;
       const lbx_mf* s = d.src_set ? s1 : s0;
       if (!s) return fail("lbx_plan_apply: plan needs a source set that was not given");
       if (d.src_fab < 0 || d.src_fab >= s->nfabs) return fail("lbx_plan_apply: source fab index out of range");
@@ -421,11 +441,7 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   if (dst->dtype == LBX_F64) {
     if (dst->ncomp == LBX_NV) {          // the populations: compile-time component count
       if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, LBX_NV);
-      else if (p->has_avg) {             // averaging plan: one thread per (cell, component)
-        const dim3 gc = lbx::mf_grid(p->max_cells, nd, 0, dst->ncomp);
-        lbx::k_plan_apply<double, true, 1, true><<<gc, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1,
-                                                                             dst->ncomp);
-      } else LBX_PLAN_LAUNCH(double, true, LBX_NV);
+      else LBX_PLAN_LAUNCH(double, true, LBX_NV);
     } else {
       if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, 0);
       else LBX_PLAN_LAUNCH(double, true, 0);
@@ -436,6 +452,64 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   }
 #undef LBX_PLAN_LAUNCH
   return lbx::after_launch("lbx_plan_apply");
+}
+
+int lbx_mf_collide_stream_fillpatch(const lbx_mf* src_valid, lbx_mf* dst, double omega_s, double omega_b, const lbx_mf* mask,
+                                    int fine_val, int zero_invalid, lbx_plan* ghost_plan, const lbx_mf* src0,
+                                    const lbx_mf* src1, const lbx_mf* fallback) {
+  if (!ghost_plan) return fail("lbx_mf_collide_stream_fillpatch: null plan");
+  return collide_stream_common(src_valid, nullptr, dst, omega_s, omega_b, mask, fine_val, zero_invalid, ghost_plan, src0, src1,
+                               fallback);
+}
+
+static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
+                                 const lbx_mf* mask, int fine_val, int zero_invalid, lbx_plan* plan, const lbx_mf* src0,
+                                 const lbx_mf* src1, const lbx_mf* fallback) {
+  LBX_NEED_INIT();
+  const char* what = "lbx_mf_collide_stream";
+  if (need(src_valid, LBX_NV, LBX_F64, 2, what) || need(dst, LBX_NV, LBX_F64, 2, what)) return 1;
+  if (src_valid->geom != dst->geom || dst->ngrow != 2 || dst->ncomp != LBX_NV)
+    return fail("lbx_mf_collide_stream: src_valid and dst must hold the same boxes, 15 components, 2 ghost cells");
+  for (const lbx_mf* s : {src_ghost, fallback})
+    if (s && s->geom != dst->geom) return fail("lbx_mf_collide_stream: ghost source and dst differ in geometry");
+  for (const lbx_mf* s : {src_valid, src_ghost, src0, src1, fallback})
+    if (s && s->base == dst->base) return fail("lbx_mf_collide_stream: dst aliases a source");
+  if (mask && (need(mask, 1, LBX_I32, 2, what) || mask->ngrow != 2 || mask->ncomp != 1 || same_boxes(dst, mask, what))) return 1;
+  if (dst->max_extent(2) > 65535) return fail("lbx_mf_collide_stream: box extents exceed the launch grid");
+  lbx::CSPlan cp;
+  memset(&cp, 0, sizeof(cp));
+  long long ghost_tiles = 0;
+  if (plan) {
+    if (plan->has_avg || plan->has_const) return fail("lbx_mf_collide_stream_fillpatch: only COPY / PC / NONE descriptors can be pushed");
+    if (plan->descs.empty()) return fail("lbx_mf_collide_stream_fillpatch: empty plan");
+    if (validate_plan(plan, dst, src0, src1)) return 1;
+    if (plan->fab_first_n != dst->nfabs) {            // first group of every fab (groups are sorted by fab)
+      std::vector<int> first((size_t)dst->nfabs + 1, 0);
+      int maxg = 0;
+      for (const auto& t : plan->dsts) ++first[(size_t)t.fab + 1];
+      for (int f = 0; f < dst->nfabs; ++f) { maxg = std::max(maxg, first[f + 1]); first[f + 1] += first[f]; }
+      if (plan->d_fab_first) lbx::arena_free(plan->d_fab_first);
+      LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&plan->d_fab_first), sizeof(int) * first.size()));
+      LBX_CUDA(cudaMemcpyAsync(plan->d_fab_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice, g.cur));
+      LBX_CUDA(cudaStreamSynchronize(g.cur));
+      plan->fab_first_n = dst->nfabs;
+      plan->max_groups = maxg;
+    }
+    cp.dsts = plan->d_dsts;
+    cp.fab_first = plan->d_fab_first;
+    cp.descs = plan->d_descs;
+    cp.s0 = src0 ? src0->table : nullptr;
+    cp.s1 = src1 ? src1->table : nullptr;
+    cp.fb = fallback ? fallback->table : nullptr;
+    cp.tiles_per_group = (int)((plan->max_cells + lbx::MFT - 1) / lbx::MFT);
+    ghost_tiles = (long long)cp.tiles_per_group * plan->max_groups;
+  } else if (src_ghost) {
+    ghost_tiles = (dst->max_shell(2) + lbx::MFT - 1) / lbx::MFT;
+  }
+  L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
+                        mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
+                        dst->max_extent(2), ghost_tiles, omega_s, omega_b, fine_val, zero_invalid);
+  return lbx::after_launch(what);
 }
 
 }  // extern "C"

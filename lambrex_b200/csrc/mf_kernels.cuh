@@ -71,6 +71,58 @@ __global__ void __launch_bounds__(MFT) k_mf_zero_ring(const DFabT* __restrict__ 
   static_cast<double*>(F.p)[comp * mf_stride(F) + mf_off(F, i, j, k)] = 0.0;
 }
 
+// First half of sum_fine_to_coarse (src/AmrSim.cpp:598; amrex_avgdown): every cell of the
+// coarsened fine boxes INCLUDING their ghost ring -- ct(x) = mean of the r^3 fine cells
+// ft(r x .. r x + r - 1), summed iref fastest, then jref, kref.  Box b of ct is box b of ft
+// coarsened (valid and ghosts).  One thread per coarse cell, 15 populations, every load issued
+// before the first use; no descriptor search and no divergence (the ADD into the coarse level is
+// then a plain ParallelCopy plan over these patches).
+__global__ void __launch_bounds__(MFT) k_mf_average_down(const DFabT* __restrict__ ft, const DFabT* __restrict__ ct, int nfabs,
+                                                         int cgrow, int r) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT Cf = ct[b];
+  int i, j, k;
+  if (!mf_cell(Cf, cgrow, i, j, k)) return;
+  const DFabT S = ft[b];
+  const long long ssc = mf_stride(S), sy = S.n[0], sz = (long long)S.n[0] * S.n[1];
+  const double* sp = static_cast<const double*>(S.p) + mf_off(S, i * r, j * r, k * r);
+  double* dp = static_cast<double*>(Cf.p) + mf_off(Cf, i, j, k);
+  const long long dsc = mf_stride(Cf);
+  if (r == 2) {
+    double v[NV];
+    if (((i * r - S.lo[0]) & 1) == 0 && (S.n[0] & 1) == 0) {          // 16-byte aligned pairs
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const double2 a = *reinterpret_cast<const double2*>(sp + c * ssc);
+        const double2 bb = *reinterpret_cast<const double2*>(sp + c * ssc + sy);
+        const double2 cc = *reinterpret_cast<const double2*>(sp + c * ssc + sz);
+        const double2 d = *reinterpret_cast<const double2*>(sp + c * ssc + sz + sy);
+        v[c] = ((((((a.x + a.y) + bb.x) + bb.y) + cc.x) + cc.y) + d.x + d.y) * 0.125;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const double* q = sp + c * ssc;
+        const double a0 = q[0], a1 = q[1], b0 = q[sy], b1 = q[sy + 1], c0 = q[sz], c1 = q[sz + 1], d0 = q[sz + sy],
+                     d1 = q[sz + sy + 1];
+        v[c] = ((((((a0 + a1) + b0) + b1) + c0) + c1) + d0 + d1) * 0.125;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) dp[c * dsc] = v[c];
+    return;
+  }
+  const double w = 1.0 / (double)(r * r * r);
+  for (int c = 0; c < NV; ++c) {
+    double acc = 0;
+    for (int kr = 0; kr < r; ++kr)
+      for (int jr = 0; jr < r; ++jr)
+        for (int ir = 0; ir < r; ++ir) acc += sp[c * ssc + kr * sz + jr * sy + ir];
+    dp[c * dsc] = acc * w;
+  }
+}
+
 // User arrays of the reference's API are C-ordered, i slowest, component fastest
 // (CLindex, include/AmrSim.h:79-83): user[(((i-d0)*NY + (j-d1))*NZ + (k-d2))*ncomp + n].
 // TO_FAB: valid cells of every fab <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);
@@ -165,23 +217,9 @@ __global__ void __launch_bounds__(MFT) k_mf_setval(const DFabT* __restrict__ ft,
 //   G_AVG   r^-3 * sum src(r x + shift + ref)    fine -> coarse average (amrex_avgdown order:
 //                                                iref fastest, then jref, kref)
 //   G_CONST value                                setVal on a region (masks)
+//   G_NONE  --                                   no source: the cell keeps its value; only widens the
+//                                                tiled bounding box of its group to the whole region
 // ---------------------------------------------------------------------------
-enum { G_COPY = 0, G_PC = 1, G_AVG = 2, G_CONST = 3 };
-struct alignas(16) GDesc {   // 64 bytes
-  int lo[3], hi[3];   // destination region (destination index space)
-  int shift[3];       // added in SOURCE index space after the map
-  int src_set, src_fab, kind, ratio;
-  int pad;
-  double value;
-};
-static_assert(sizeof(GDesc) == 64, "GDesc must be 64 bytes (staged to shared memory as int4 words)");
-struct GDst {
-  int fab, first, count, pad;
-  int blo[3], bhi[3];   // bounding box of this fab's regions
-};
-
-__device__ __forceinline__ int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
-
 // one matching descriptor applied to one destination cell, components [c0, c0 + n).  NC > 0: the
 // count n is known at compile time (15 populations, or 1 in the component-parallel launch): every
 // load of the cell is issued before the first store, which is what keeps these gather kernels
@@ -190,6 +228,7 @@ template <class T, bool ADD, int NC>
 __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
                                         int i, int j, int k, T* __restrict__ dp, long long dsc, int c0, int ncomp_rt) {
   const int ncomp = NC > 0 ? NC : ncomp_rt;
+  if (g.kind == G_NONE) return;
   if (g.kind == G_CONST) {
 #pragma unroll
     for (int c = 0; c < ncomp; ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + (T)g.value) : (T)g.value;
@@ -202,18 +241,28 @@ __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict_
     const int i0 = i * r + g.shift[0];
     const T* sp = static_cast<const T*>(S.p) + c0 * ssc + mf_off(S, i0, j * r + g.shift[1], k * r + g.shift[2]);
     const long long sy = S.n[0], sz = (long long)S.n[0] * S.n[1];
-    if (sizeof(T) == 8 && r == 2 && NC > 0 && ((i0 - S.lo[0]) & 1) == 0 && (S.n[0] & 1) == 0) {
-      // ratio 2, 16-byte aligned pairs: four 16-byte loads per component, summed in
-      // amrex_avgdown order (iref fastest, then jref, then kref)
+    if (sizeof(T) == 8 && r == 2 && NC > 0) {
+      // ratio 2: the 8 fine cells of every component, all loads issued before the first use,
+      // summed in amrex_avgdown order (iref fastest, then jref, then kref)
       const double* dpp = reinterpret_cast<const double*>(sp);
       double v[NC > 0 ? NC : 1];
+      if (((i0 - S.lo[0]) & 1) == 0 && (S.n[0] & 1) == 0) {        // 16-byte aligned pairs
 #pragma unroll
-      for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
-        const double2 a = *reinterpret_cast<const double2*>(dpp + c * ssc);
-        const double2 b = *reinterpret_cast<const double2*>(dpp + c * ssc + sy);
-        const double2 cc = *reinterpret_cast<const double2*>(dpp + c * ssc + sz);
-        const double2 d = *reinterpret_cast<const double2*>(dpp + c * ssc + sz + sy);
-        v[c] = ((((((a.x + a.y) + b.x) + b.y) + cc.x) + cc.y) + d.x + d.y) * 0.125;
+        for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
+          const double2 a = *reinterpret_cast<const double2*>(dpp + c * ssc);
+          const double2 b = *reinterpret_cast<const double2*>(dpp + c * ssc + sy);
+          const double2 cc = *reinterpret_cast<const double2*>(dpp + c * ssc + sz);
+          const double2 d = *reinterpret_cast<const double2*>(dpp + c * ssc + sz + sy);
+          v[c] = ((((((a.x + a.y) + b.x) + b.y) + cc.x) + cc.y) + d.x + d.y) * 0.125;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
+          const double* q = dpp + c * ssc;
+          const double a0 = q[0], a1 = q[1], b0 = q[sy], b1 = q[sy + 1], c0_ = q[sz], c1 = q[sz + 1], d0 = q[sz + sy],
+                       d1 = q[sz + sy + 1];
+          v[c] = ((((((a0 + a1) + b0) + b1) + c0_) + c1) + d0 + d1) * 0.125;
+        }
       }
 #pragma unroll
       for (int c = 0; c < (NC > 0 ? NC : 1); ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + (T)v[c]) : (T)v[c];
@@ -244,7 +293,6 @@ __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict_
   }
 }
 
-constexpr int PLAN_CHUNK = 64;   // descriptors staged in shared memory at a time (4 KB)
 
 // CPAR: component-parallel launch -- gridDim.x = tiles * ncomp and a thread handles ONE component
 // of its cell (NC must be 1).  Used for the averaging plans (sum_fine_to_coarse), whose 60 loads

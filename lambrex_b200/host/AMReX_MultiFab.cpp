@@ -205,6 +205,7 @@ namespace {
 
 struct PlanDeleter { void operator()(lbx_plan* p) const { lbx_plan_destroy(p); } };
 std::map<std::string, std::unique_ptr<lbx_plan, PlanDeleter>> g_plans;
+std::map<std::string, MultiFab> g_coarsened;     // sum_fine_to_coarse temporaries, one per fine BoxArray
 
 uint64_t fnv(uint64_t h, int64_t v) {
   for (int b = 0; b < 8; ++b) { h ^= (uint64_t)((v >> (8 * b)) & 0xff); h *= 1099511628211ull; }
@@ -370,12 +371,33 @@ void pc_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::v
 
 }  // namespace
 
-void ClearPlanCache() { g_plans.clear(); }
+void ClearPlanCache() { g_plans.clear(); g_coarsened.clear(); }
 size_t PlanCacheSize() { return g_plans.size(); }
 
+namespace {
+// ghosts-only plans open every ghost slab with a source-less descriptor spanning the slab, so
+// that the launch tiles ALL its cells (the fused pass needs a thread per ghost cell)
+void whole_region(std::vector<lbx_gather>& d, int k, const Box& reg) {
+  d.push_back(make_desc(k, 0, 0, LBX_G_NONE, 1, IntVect(0), reg));
+}
+void run_plan(lbx_plan* p, MultiFab& dst, const lbx_mf* s0, const lbx_mf* s1, int op, const GhostPush* push,
+              const char* what) {
+  if (push)
+    lbx_check(lbx_mf_collide_stream_fillpatch(push->src_valid->mf(), dst.mf(), push->omega_s, push->omega_b,
+                                              push->mask ? push->mask->mf() : nullptr, push->fine_val,
+                                              push->zero_invalid ? 1 : 0, p, s0, s1,
+                                              push->fallback ? push->fallback->mf() : nullptr),
+              what);
+  else
+    lbx_check(lbx_plan_apply(p, dst.mf(), s0, s1, op), what);
+  dst.touch();
+}
+}  // namespace
+
 void ParallelCopy(MultiFab& dst, const MultiFab& src, int src_ng, int dst_ng, const Periodicity& period, bool add,
-                  bool ghosts_only) {
+                  bool ghosts_only, const GhostPush* push) {
   if (dst.empty() || src.empty()) return;
+  if (push && !ghosts_only) Abort("ParallelCopy: GhostPush needs ghosts_only");
   if (ghosts_only && (add || dst.boxArray() != src.boxArray() || dst.layout() != src.layout()))
     Abort("ParallelCopy: ghosts_only needs identical source and destination boxes");
   if (src.isFlat()) src_ng = 0;
@@ -391,14 +413,14 @@ void ParallelCopy(MultiFab& dst, const MultiFab& src, int src_ng, int dst_ng, co
     for (int k = 0; k < dst.numStorageFabs(); ++k) {
       g_group = 0;
       for (const Box& reg : tile_regions(amrex::grow(dst.storageValid(k), dst_ng), dst.storageValid(k), ghosts_only)) {
+        if (ghosts_only) whole_region(d, k, reg);
         copy_descs(d, k, reg, sv, sh, src_ng, shifts, 0, ghosts_only, k, add);
         ++g_group;
       }
     }
     g_group = 0;
   });
-  lbx_check(lbx_plan_apply(p, dst.mf(), src.mf(), nullptr, add ? LBX_OP_ADD : LBX_OP_COPY), "ParallelCopy");
-  dst.touch();
+  run_plan(p, dst, src.mf(), nullptr, add ? LBX_OP_ADD : LBX_OP_COPY, push, "ParallelCopy");
 }
 
 void CopyValid(MultiFab& dst, const MultiFab& src) { ParallelCopy(dst, src, 0, 0, Periodicity::NonPeriodic()); }
@@ -427,13 +449,16 @@ void FillBoundary(MultiFab& mf, const Periodicity& period) {
   if (pp[0] > 0 && pp[1] > 0 && pp[2] > 0 && mf.boxArray().numPts() == (long)pp[0] * pp[1] * pp[2]) mf.markGhostsFresh();
 }
 
-void FillPatchSingleLevel(MultiFab& dst, const MultiFab& src, const Geometry& geom, bool ghosts_only) {
-  ParallelCopy(dst, src, 0, dst.nGrow(), geom.periodicity(), false, ghosts_only);
+void FillPatchSingleLevel(MultiFab& dst, const MultiFab& src, const Geometry& geom, bool ghosts_only,
+                          const GhostPush* push) {
+  ParallelCopy(dst, src, 0, dst.nGrow(), geom.periodicity(), false, ghosts_only, push);
 }
 
 static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* fine, const Geometry& cgeom,
-                           const Geometry& fgeom, const IntVect& ratio, const char* tag, bool ghosts_only = false) {
+                           const Geometry& fgeom, const IntVect& ratio, const char* tag, bool ghosts_only = false,
+                           const GhostPush* push = nullptr) {
   if (dst.empty()) return;
+  if (push && !ghosts_only) Abort("FillPatchTwoLevels: GhostPush needs ghosts_only");
   if (ghosts_only && (!fine || dst.boxArray() != fine->boxArray() || fine->isFlat()))
     Abort("FillPatchTwoLevels: ghosts_only needs identical fine source and destination boxes");
   if (ratio[0] != ratio[1] || ratio[0] != ratio[2]) Abort("anisotropic refinement ratios are not supported");
@@ -452,6 +477,7 @@ static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* 
     for (int k = 0; k < dst.numStorageFabs(); ++k) {
       g_group = 0;
       for (const Box& reg : tile_regions(dst.storageBox(k), dst.storageValid(k), ghosts_only)) {
+        if (ghosts_only) whole_region(d, k, reg);
         pc_descs(d, k, reg, cv, ch, cs, ratio[0], 1);                              // coarse first ...
         if (fine) copy_descs(d, k, reg, fv, fh, 0, fs, 0, ghosts_only, k);        // ... fine data wins
         ++g_group;
@@ -459,13 +485,12 @@ static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* 
     }
     g_group = 0;
   });
-  lbx_check(lbx_plan_apply(p, dst.mf(), fine ? fine->mf() : nullptr, crse.mf(), LBX_OP_COPY), tag);
-  dst.touch();
+  run_plan(p, dst, fine ? fine->mf() : nullptr, crse.mf(), LBX_OP_COPY, push, tag);
 }
 
 void FillPatchTwoLevels(MultiFab& dst, const MultiFab& crse, const MultiFab& fine, const Geometry& cgeom,
-                        const Geometry& fgeom, const IntVect& ratio, bool ghosts_only) {
-  two_level_fill(dst, crse, &fine, cgeom, fgeom, ratio, "FillPatchTwoLevels", ghosts_only);
+                        const Geometry& fgeom, const IntVect& ratio, bool ghosts_only, const GhostPush* push) {
+  two_level_fill(dst, crse, &fine, cgeom, fgeom, ratio, "FillPatchTwoLevels", ghosts_only, push);
 }
 
 void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& cgeom, const Geometry& fgeom,
@@ -473,6 +498,10 @@ void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& 
   two_level_fill(dst, crse, nullptr, cgeom, fgeom, ratio, "InterpFromCoarseLevel");
 }
 
+// AMReX's own two steps: (1) average every fine box, ghosts included, onto its coarsened box with
+// nGrow/ratio ghost cells (one search-free kernel), (2) ParallelCopy that temporary into the coarse
+// valid cells with ADD and periodic wrap (src_ng = its ghosts, dst_ng = 0): a coarse cell under
+// the ghost overlap of neighbouring fine boxes receives every contribution, in ParallelCopy order.
 void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, const IntVect& ratio,
                         const Geometry& cgeom, const Geometry& /*fgeom*/) {
   if (fine.empty() || crse.empty()) return;
@@ -481,30 +510,21 @@ void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int nco
   const int r = ratio[0];
   if (fine.nGrow() % r != 0) Abort("sum_fine_to_coarse: fine.nGrow() must be a multiple of the ratio");
   const int cng = fine.nGrow() / r;
-  const std::string key = "SF|" + gkey(crse) + "|" + gkey(fine) + "|" + pkey(cgeom.periodicity()) + "|" + std::to_string(r);
-  lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
-    std::vector<Box> cf(fine.size());        // coarsened fine boxes grown by the coarse ghost width
+  const std::string key = gkey(fine) + "|" + std::to_string(r);
+  if (!g_coarsened.count(key) && g_coarsened.size() >= 4) g_coarsened.clear();   // grids change at regrid: keep a few
+  MultiFab& tmp = g_coarsened[key];
+  if (tmp.empty()) {
+    BoxList bl;
     for (long i = 0; i < fine.size(); ++i) {
-      cf[i] = amrex::grow(amrex::coarsen(fine.box((int)i), r), cng);
-      if (amrex::refine(cf[i], r) != fine.fabbox((int)i)) Abort("sum_fine_to_coarse: fine box not aligned to the coarse grid");
+      const Box cb = amrex::coarsen(fine.box((int)i), r);
+      if (amrex::refine(amrex::grow(cb, cng), r) != fine.fabbox((int)i)) Abort("sum_fine_to_coarse: fine box not aligned to the coarse grid");
+      bl.push_back(cb);
     }
-    const BoxHash fh(cf);
-    const std::vector<IntVect> shifts = cgeom.periodicity().shiftIntVect();
-    for (int k = 0; k < crse.numStorageFabs(); ++k) {
-      const Box want = crse.storageValid(k);
-      std::vector<std::pair<int, int>> hits;
-      for (size_t si = 0; si < shifts.size(); ++si)
-        for (int i : fh.query(amrex::shift(want, IntVect(0) - shifts[si]))) hits.emplace_back(i, (int)si);
-      std::sort(hits.begin(), hits.end());
-      for (auto& h : hits) {
-        const IntVect& s = shifts[h.second];
-        const Box reg = amrex::shift(cf[h.first], s) & want;
-        if (reg.ok()) d.push_back(make_desc(k, 0, h.first, LBX_G_AVG, r, (IntVect(0) - s) * r, reg));
-      }
-    }
-  });
-  lbx_check(lbx_plan_apply(p, crse.mf(), fine.mf(), nullptr, LBX_OP_ADD), "sum_fine_to_coarse");
-  crse.touch();
+    tmp.define(BoxArray(bl), fine.DistributionMap(), fine.nComp(), cng);
+  }
+  lbx_check(lbx_mf_average_down(fine.mf(), tmp.mf(), r), "sum_fine_to_coarse");
+  tmp.touch();
+  ParallelCopy(crse, tmp, cng, 0, cgeom.periodicity(), true);
 }
 
 iMultiFab makeFineMask(const MultiFab& cmf, const BoxArray& fba, const IntVect& ratio, int crse_value, int fine_value) {

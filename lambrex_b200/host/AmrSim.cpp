@@ -292,12 +292,12 @@ void AmrSim::ComputeDt(int const level) {
 void AmrSim::DistFnFillPatch(int const level, MultiFab& dest) { FillPatchImpl(level, dest, false); }
 
 // ghosts_only: dest's valid cells are left for an out-of-place collision to produce
-void AmrSim::FillPatchImpl(int const level, MultiFab& dest, bool ghosts_only) {
+void AmrSim::FillPatchImpl(int const level, MultiFab& dest, bool ghosts_only, const amrex::GhostPush* push) {
   if (!level) {
-    amrex::FillPatchSingleLevel(dest, levels[level].now.get<DistFn>(), geom[level], ghosts_only);
+    amrex::FillPatchSingleLevel(dest, levels[level].now.get<DistFn>(), geom[level], ghosts_only, push);
   } else {
     amrex::FillPatchTwoLevels(dest, levels[level - 1].now.get<DistFn>(), levels[level].now.get<DistFn>(), geom[level - 1],
-                              geom[level], refRatio(level - 1), ghosts_only);
+                              geom[level], refRatio(level - 1), ghosts_only, push);
   }
 }
 
@@ -365,11 +365,16 @@ bool AmrSim::CanFuseRohde(int const level) const {
   return true;
 }
 
-void AmrSim::CollideStreamFused(int const level, bool masked, bool zero_invalid, bool ghosts_from_now) {
+// One collide + Stream of a level in fused form.  Valid cells: read from NOW while InitPostCollision's
+// valid-cell copy is still pending (first pass of a cycle), else from NEXT.  Ghost cells:
+//   from_fillpatch: the level's DistFnFillPatch is folded in -- each ghost cell pushes straight from
+//                   the NOW cell (same level, periodic image, or the coarse cell under it) FillPatch
+//                   would copy into it (lbx_mf_collide_stream_fillpatch); NEXT's ghost cells are never written;
+//   otherwise     : NEXT's own ghost cells, as left by the previous Stream (second fine pass).
+void AmrSim::CollideStreamFused(int const level, bool masked, bool zero_invalid, bool from_fillpatch) {
   MultiFab& f_nxt = levels[level].next.get<DistFn>();
   const MultiFab& f_now = levels[level].now.get<DistFn>();
   const MultiFab& vsrc = valid_pending.at(level) ? f_now : f_nxt;
-  const MultiFab& gsrc = ghosts_from_now ? f_now : f_nxt;
   MultiFab& f_prop = stream_scratch.at(level);
   if (f_prop.empty() || f_prop.boxArray() != f_nxt.boxArray() || f_prop.layout() != f_nxt.layout())
     f_prop = field_traits<DistFn>::MakeLevelData(f_nxt.boxArray(), f_nxt.DistributionMap(), f_nxt.layout());
@@ -378,9 +383,22 @@ void AmrSim::CollideStreamFused(int const level, bool masked, bool zero_invalid,
     mask = &fine_masks.at(level);
     if (mask->empty()) amrex::Abort("CoarseCollide: no fine mask on this level");
   }
-  lbx_check(lbx_mf_collide_stream(vsrc.mf(), gsrc.mf(), f_prop.mf(), 1.0 / (tau_s.at(level) + 0.5),
-                                  1.0 / (tau_b.at(level) + 0.5), mask ? mask->mf() : nullptr, FINE_VAL, zero_invalid ? 1 : 0),
-            "CollideStreamFused");
+  const double omega_s = 1.0 / (tau_s.at(level) + 0.5), omega_b = 1.0 / (tau_b.at(level) + 0.5);
+  if (from_fillpatch) {
+    amrex::GhostPush push;
+    push.src_valid = &vsrc;
+    push.mask = mask;
+    push.fallback = &f_nxt;
+    push.omega_s = omega_s;
+    push.omega_b = omega_b;
+    push.fine_val = FINE_VAL;
+    push.zero_invalid = zero_invalid;
+    FillPatchImpl(level, f_prop, true, &push);
+  } else {
+    lbx_check(lbx_mf_collide_stream(vsrc.mf(), f_nxt.mf(), f_prop.mf(), omega_s, omega_b, mask ? mask->mf() : nullptr, FINE_VAL,
+                                    zero_invalid ? 1 : 0),
+              "CollideStreamFused");
+  }
   valid_pending.at(level) = false;
   std::swap(f_nxt, f_prop);
   f_nxt.touch();
@@ -388,24 +406,24 @@ void AmrSim::CollideStreamFused(int const level, bool masked, bool zero_invalid,
 
 void AmrSim::RohdeCycleFused(int const coarse_level) {
   const int ref_ratio_here = refRatio(coarse_level)[0];
-  // InitPostCollision, ghost cells.  On level 0 FillPatchSingleLevel gives every ghost cell the
-  // value of the NOW valid cell covering it -- exactly what NOW's own ghost cells hold when the
-  // previous cycle's UpdateBoundaries was the last thing to touch that fab: read them in place.
-  const bool now_ghosts = coarse_level == 0 && levels[0].now.get<DistFn>().ghostsFresh();
-  if (!now_ghosts) FillPatchImpl(coarse_level, levels[coarse_level].next.get<DistFn>(), true);
+  // InitPostCollision: the valid-cell copy is folded into the collision, the ghost-cell fill into
+  // the ghost cells' pushes (CollideStreamFused) -- on every level nothing but that one Stream ever
+  // reads the ghost cells FillPatch writes.
   valid_pending.at(coarse_level) = true;
   if (coarse_level + 1 == finest_level) {
-    FillPatchImpl(finest_level, levels[finest_level].next.get<DistFn>(), true);
     valid_pending.at(finest_level) = true;
-    CollideStreamFused(finest_level, false, false);     // FineCollide + Stream
-    CollideStreamFused(finest_level, false, true);      // FineCollide + Stream + ZeroInvalidComponents
+    CollideStreamFused(finest_level, false, false, true);    // InitPostCollision + FineCollide + Stream
+    CollideStreamFused(finest_level, false, true, false);    // FineCollide + Stream + ZeroInvalidComponents
     UpdateDistribution(finest_level);
   } else {
     for (int iter = 0; iter < ref_ratio_here; ++iter) RohdeCycle(coarse_level + 1);
   }
-  CollideStreamFused(coarse_level, true, true, now_ghosts);   // CoarseCollide + Stream + ZeroInvalidComponents
+  // InitPostCollision + CoarseCollide + Stream + ZeroInvalidComponents
+  CollideStreamFused(coarse_level, true, true, true);
   SumFromFine(coarse_level);
-  if (coarse_level == 0) UpdateBoundaries(coarse_level);
+  // UpdateBoundaries(0) writes level-0 ghost cells that every following cycle overwrites before
+  // reading (its FillPatch): only the cycle that ends Iterate() needs to leave them filled
+  if (coarse_level == 0 && !defer_boundaries) UpdateBoundaries(coarse_level);
   UpdateDistribution(coarse_level);
 }
 
@@ -482,7 +500,11 @@ void AmrSim::Iterate(int const nsteps) {
     for (int t = 0; t < nsteps; ++t) IterateLevel(0);
   } else {
     for (int l = 0; l <= finest_level; ++l) SetLevelLayout(l, Layout::BOXES);
-    for (int t = 0; t < nsteps; ++t) RohdeCycle(0);
+    for (int t = 0; t < nsteps; ++t) {
+      defer_boundaries = (t + 1 < nsteps);
+      RohdeCycle(0);
+    }
+    defer_boundaries = false;
   }
 }
 

@@ -146,12 +146,13 @@ class AmrSim : public amrex::AmrCore {
   // InitPostCollision filled only the ghost cells of NEXT; its valid cells are still NOW's and
   // the next collision reads them from there (valid-cell copy fused into the collision)
   std::vector<char> valid_pending;
-  void FillPatchImpl(int const level, amrex::MultiFab& dest, bool ghosts_only);
+  void FillPatchImpl(int const level, amrex::MultiFab& dest, bool ghosts_only, const amrex::GhostPush* push = nullptr);
   bool uniform_fast_path = true;
   bool rohde_fused = true;
   bool CanFuseRohde(int const level) const;
   void RohdeCycleFused(int const coarse_level);
-  void CollideStreamFused(int const level, bool masked, bool zero_invalid, bool ghosts_from_now = false);
+  void CollideStreamFused(int const level, bool masked, bool zero_invalid, bool from_fillpatch);
+  bool defer_boundaries = false;
   void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp);
   const double* density_view = nullptr;
   const double* velocity_view = nullptr;

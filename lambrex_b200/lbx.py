@@ -65,6 +65,7 @@ SYMBOLS = {
     "lbx_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "lbx_free": (_i, [_vp]),
     "lbx_arena_release": (_i, []),
+    "lbx_concurrent_begin": (_i, []), "lbx_concurrent_end": (_i, []),
     "lbx_arena_info": (_i, [ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(ctypes.c_uint64),
                             ctypes.POINTER(ctypes.c_uint64)]),
     "lbx_memset": (_i, [_vp, _i, _sz]),
@@ -102,6 +103,8 @@ SYMBOLS = {
     "lbx_mf_collide": (_i, [_vp, _d, _d, _vp, _i]),
     "lbx_mf_collide2": (_i, [_vp, _vp, _d, _d, _vp, _i]),
     "lbx_mf_stream": (_i, [_vp, _vp]),
+    "lbx_mf_average_down": (_i, [_vp, _vp, _i]),
+    "lbx_mf_collide_stream_fillpatch": (_i, [_vp, _vp, _d, _d, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "lbx_mf_collide_stream": (_i, [_vp, _vp, _vp, _d, _d, _vp, _i, _i]),
     "lbx_mf_zero_invalid": (_i, [_vp]),
     "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
@@ -431,7 +434,7 @@ def mf_collide2(src, dst, omega_s, omega_b, mask=None, fine_val=1):
 
 
 def mf_collide_stream(src_valid, src_ghost, dst, omega_s, omega_b, mask=None, fine_val=1, zero_invalid=False):
-    check(lib().lbx_mf_collide_stream(src_valid.h, src_ghost.h, dst.h, omega_s, omega_b,
+    check(lib().lbx_mf_collide_stream(src_valid.h, src_ghost.h if src_ghost is not None else None, dst.h, omega_s, omega_b,
                                       mask.h if mask is not None else None, fine_val, 1 if zero_invalid else 0))
 
 
