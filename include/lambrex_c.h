@@ -24,6 +24,12 @@ typedef struct lbx_sim lbx_sim;
 /* lambrexInit / lambrexFinalise (include/lambrex.h:6-7) */
 int lbx_sim_global_init(void);
 int lbx_sim_global_finalise(void);
+/* addition: distributed start-up (one process per GPU): lbx_init + lbx_par_init + box ownership by
+ * rank.  allgather(send, bytes, recv, user) gathers `bytes` from every rank, rank order, returns 0. */
+int lbx_sim_global_init_parallel(int rank, int nranks,
+                                 int (*allgather)(const void *send, size_t bytes, void *recv, void *user), void *user);
+int lbx_sim_set_parallel_view(int rank, int nranks);   /* testing aid: ownership view of this process */
+int lbx_sim_owner(const lbx_sim *sim, int level, int box, int *rank);   /* DistributionMap(level)[box] */
 const char *lbx_sim_last_error(void);
 
 /* AmrSim::AmrSim (include/AmrSim.h:128-129) */

@@ -73,6 +73,18 @@ int lbx_device_info(char *name, int name_cap, int *sm_count, size_t *total_bytes
 int lbx_set_option(int key, int value);
 int lbx_set_stream(void *cuda_stream);   /* NULL: back to the library's own stream;
                                             the legacy default stream is cudaStreamLegacy (0x1) */
+/* ---- distributed runs: one process per GPU of one NVSwitch box ----
+ * Boxes of every level belong to ranks (lbx_mf_create_dist); a rank allocates only its own boxes and
+ * reaches the others' through CUDA-IPC peer pointers: gather plans and the fused FillPatch read
+ * neighbour boxes straight out of the owner's HBM over NVLink.  Ranks run the same sequence of calls;
+ * calls that read peer memory are bracketed by a device-side all-rank barrier (lbx_par_barrier,
+ * 8-byte flags in peer memory, no host round trip).  `allgather(send, bytes, recv, user)` gathers
+ * `bytes` from every rank into recv in rank order and returns 0 (torch.distributed / MPI plumbing);
+ * it only carries IPC handles when fields are created.  lbx_par_init is collective. */
+int lbx_par_init(int rank, int world, int (*allgather)(const void *send, size_t bytes, void *recv, void *user),
+                 void *user);
+int lbx_par_info(int *rank, int *world, uint64_t *barriers);
+int lbx_par_barrier(void);
 int lbx_sync(void);
 /* Concurrent section: the calls made between begin and end must be independent of one another
  * (they may read the same data but write disjoint data).  Each launch goes to its own auxiliary
@@ -157,6 +169,12 @@ int lbx_halo_unpack(const lbx_fab *f, const lbx_box *region, int face, const dou
  * below is ONE kernel launch over all boxes of the set. */
 typedef struct lbx_mf lbx_mf;
 int lbx_mf_create(const lbx_box *valid, int nfabs, int ncomp, int ngrow, int dtype, lbx_mf **out);
+/* distributed (after lbx_par_init, COLLECTIVE, same arguments on every rank): owner[i] = rank that
+ * holds box i (amrex::DistributionMapping).  This rank allocates its own boxes only; the others are
+ * mapped through CUDA-IPC and can be READ by gather plans / the fused FillPatch; kernels that write
+ * a set skip the boxes of other ranks.  owner == NULL: every box local. */
+int lbx_mf_create_dist(const lbx_box *valid, int nfabs, int ncomp, int ngrow, int dtype, const int *owner,
+                       lbx_mf **out);
 int lbx_mf_destroy(lbx_mf *mf);
 int lbx_mf_info(const lbx_mf *mf, int *nfabs, int *ncomp, int *ngrow, int *dtype, size_t *bytes);
 /* descriptor of fab i (usable with the single-fab kernels above), its valid box, and its

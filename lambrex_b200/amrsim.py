@@ -34,6 +34,8 @@ SYMBOLS = {
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
     "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]),
+    "lbx_sim_global_init_parallel": (_i, [_i, _i, _vp, _vp]), "lbx_sim_set_parallel_view": (_i, [_i, _i]),
+    "lbx_sim_owner": (_i, [_vp, _i, _i, ctypes.POINTER(_i)]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
     "lbx_sim_set_initial_density_view": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity_view": (_i, [_vp, _dp, _sz]),
     "lbx_sim_init_from_scratch": (_i, [_vp, _d]), "lbx_sim_regrid": (_i, [_vp, _i, _d]),
@@ -93,6 +95,38 @@ def lambrexInit():
     _check(lib().lbx_sim_global_init())
 
 
+_ALLGATHER_T = ctypes.CFUNCTYPE(_i, _vp, _sz, _vp, _vp)
+_par_keep = []
+
+
+def lambrexInitParallel(group=None):
+    """One process per GPU (torchrun): boxes of every level are owned by ranks, neighbours' boxes
+    are read over NVLink through CUDA-IPC.  torch.distributed (an initialised process group whose
+    CPU backend is gloo) is the host plumbing: it only carries IPC handles.  Collective."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allgather(send, nbytes, recv, _user):
+        try:
+            mine = torch.frombuffer(bytearray(ctypes.string_at(send, nbytes)), dtype=torch.uint8)
+            parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            ctypes.memmove(recv, torch.cat(parts).numpy().tobytes(), nbytes * world)
+            return 0
+        except Exception as exc:            # never unwind through the C frames
+            print("lambrex allgather failed:", exc, flush=True)
+            return 1
+
+    cb = _ALLGATHER_T(allgather)
+    _par_keep.append(cb)
+    _check(lib().lbx_sim_global_init_parallel(rank, world, cb, None))
+
+
+def setParallelView(rank, nranks):
+    _check(lib().lbx_sim_set_parallel_view(rank, nranks))
+
+
 def lambrexFinalise():
     _check(lib().lbx_sim_global_finalise())
 
@@ -135,6 +169,11 @@ class AmrSim:
 
     def SetUniformFastPath(self, on):
         _check(lib().lbx_sim_set_uniform_fast_path(self._h, int(on)))
+
+    def Owner(self, level, box):
+        r = _i()
+        _check(lib().lbx_sim_owner(self._h, level, box, ctypes.byref(r)))
+        return r.value
 
     def SetRohdeFusion(self, on):
         _check(lib().lbx_sim_set_rohde_fusion(self._h, int(on)))

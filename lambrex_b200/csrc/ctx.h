@@ -19,6 +19,14 @@ struct Ctx {
   cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev[NAUX] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t main_saved = nullptr;
+  // ranks of a distributed run (lbx_par_init): one process per GPU, peers reached through CUDA-IPC
+  int rank = 0, world = 1;
+  int (*allgather)(const void* send, size_t bytes, void* recv, void* user) = nullptr;
+  void* allgather_user = nullptr;
+  unsigned long long* bar_flags = nullptr;           // [world] slots written by the peers
+  unsigned long long** d_bar_peers = nullptr;        // device array [world]: every rank's flag array
+  unsigned long long bar_epoch = 0;
+  uint64_t barriers = 0;
   int conc_next = -1;              // >= 0: inside a concurrent section; index of the stream in use
   int conc_used = 0;
 };
@@ -32,6 +40,10 @@ cudaError_t arena_alloc(void** p, size_t bytes);
 void arena_free(void* p);
 void arena_release();                                    // cudaFree every cached block
 void arena_stats(size_t* in_use, size_t* cached, uint64_t* hits, uint64_t* misses);
+// distributed helpers (lbx_abi.cu)
+int par_barrier();                                       // device-side all-rank barrier on the current stream
+int par_allgather(const void* send, size_t bytes, void* recv);   // host, through the registered callback
+int ipc_open_cached(const unsigned char* handle, void** base);   // cudaIpcOpenMemHandle, once per handle
 int fail(const std::string& msg);            // records the message for lbx_last_error(); returns 1
 int after_launch(const char* what);          // counts the launch, reports launch errors
 }  // namespace lbx

@@ -276,10 +276,13 @@ __global__ void __launch_bounds__(BX) k_equilibrium(DFab f_, DFab rho_, DFab u_,
 // fastest) of the fab's operating region = valid box grown by `grow`.
 // ===========================================================================
 struct DFabT {
-  void* p;           // component 0 of the allocated box
+  void* p;           // component 0 of the allocated box (a CUDA-IPC peer pointer when !local)
   int lo[3], n[3];   // allocated box: lower corner, extents
   int vlo[3], vhi[3];  // valid box (inclusive)
+  int local;         // 1: this rank owns the box; 0: it lives in a peer's HBM (read-only here)
+  int pad;
 };
+static_assert(sizeof(DFabT) == 64, "DFabT is read as four 16-byte words");
 constexpr int MFT = 256;
 
 __device__ __forceinline__ int mf_fab_index() { return blockIdx.y + gridDim.y * blockIdx.z; }
@@ -313,6 +316,7 @@ __global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ st
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (!F.local) return;
   int i, j, k;
   if (!mf_cell(F, 0, i, j, k)) return;
   double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
@@ -476,6 +480,7 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT D = dt[b];
+  if (!D.local) return;                                   // a peer's box: its owner streams it
   const int tid = threadIdx.x;
   if ((int)blockIdx.x < valid_tiles) {
     // ---- valid source cells: collide, push ---------------------------------------------------
@@ -579,6 +584,7 @@ __global__ void __launch_bounds__(MFT) k_mf_moments(const DFabT* __restrict__ ft
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (!F.local) return;
   int i, j, k;
   if (!mf_cell(F, 0, i, j, k)) return;
   const double* fp = static_cast<const double*>(F.p) + mf_off(F, i, j, k);
@@ -604,6 +610,7 @@ __global__ void __launch_bounds__(MFT) k_mf_equilibrium(const DFabT* __restrict_
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (!F.local) return;
   int i, j, k;
   if (!mf_cell(F, 0, i, j, k)) return;
   const DFabT R = rt[b], U = ut[b];

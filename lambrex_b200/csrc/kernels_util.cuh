@@ -88,4 +88,30 @@ __global__ void k_peer_wait(const unsigned long long* flag_a, const unsigned lon
   }
 }
 
+// All-rank barrier on the device (distributed AMR path): thread r publishes `epoch` into slot
+// [my_rank] of rank r's flag array (CUDA-IPC peer pointer, release at system scope -- ordered after
+// every kernel queued before it on this stream), then spins until its own slot [r] shows that
+// rank r has arrived at the same barrier.  No host round trip; wall-clock timeout like k_peer_wait.
+__global__ void k_par_barrier(unsigned long long* const* __restrict__ peer_flags, const unsigned long long* my_flags,
+                              int my_rank, int world, unsigned long long epoch, unsigned long long timeout_ns, int* err) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + my_rank), "l"(epoch) : "memory");
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + r) : "memory");
+    if (v >= epoch) break;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) {
+      *err = 1;
+      __threadfence_system();
+      return;
+    }
+    __nanosleep(100);
+  }
+}
+
 }  // namespace lbx

@@ -4,8 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <string>
+#include <vector>
 #include <unordered_map>
 
 #include "../../include/lbx.h"
@@ -28,7 +30,9 @@ std::multimap<size_t, void*> a_cache;            // rounded size -> free block
 size_t a_in_use = 0, a_cached = 0;
 uint64_t a_hits = 0, a_misses = 0;
 size_t a_round(size_t b) {
-  const size_t g = b >= (size_t(2) << 20) ? (size_t(2) << 20) : 512;   // 2 MiB pages for big blocks
+  // 2 MiB pages for big blocks; in a distributed run EVERY block is a whole number of 2 MiB pages so
+  // that it is an allocation of its own that a CUDA-IPC handle maps at offset 0
+  const size_t g = (b >= (size_t(2) << 20) || g_ctx.world > 1) ? (size_t(2) << 20) : 512;
   return (b + g - 1) / g * g;
 }
 }  // namespace
@@ -69,6 +73,8 @@ void arena_free(void* p) {
   a_cache.emplace(rb, p);
   a_cached += rb;
   // keep at most half of the device's memory parked in the cache: evict the largest blocks first
+  // (not in a distributed run: peers may still have the block mapped)
+  if (g_ctx.world > 1) return;
   size_t fr = 0, tot = 0;
   if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return; }
   while (a_cached > tot / 2 && !a_cache.empty()) {
@@ -83,6 +89,43 @@ void arena_stats(size_t* in_use, size_t* cached, uint64_t* hits, uint64_t* misse
   if (cached) *cached = a_cached;
   if (hits) *hits = a_hits;
   if (misses) *misses = a_misses;
+}
+
+// ---- distributed helpers -------------------------------------------------------------------
+namespace {
+std::map<std::array<unsigned char, LBX_IPC_HANDLE_BYTES>, void*> ipc_opened;
+}
+int ipc_open_cached(const unsigned char* handle, void** base) {
+  std::array<unsigned char, LBX_IPC_HANDLE_BYTES> key;
+  memcpy(key.data(), handle, key.size());
+  auto it = ipc_opened.find(key);
+  if (it != ipc_opened.end()) { *base = it->second; return 0; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  ipc_opened[key] = *base;
+  return 0;
+}
+int par_allgather(const void* send, size_t bytes, void* recv) {
+  Ctx& g = g_ctx;
+  if (g.world == 1) { memcpy(recv, send, bytes); return 0; }
+  if (!g.allgather) return fail("lbx: distributed run without an allgather callback (lbx_par_init)");
+  if (g.allgather(send, bytes, recv, g.allgather_user) != 0) return fail("lbx: allgather callback failed");
+  return 0;
+}
+int par_barrier() {
+  Ctx& g = g_ctx;
+  if (g.world == 1) return 0;
+  int* derr = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&derr), g.peer_err, 0);
+  if (e != cudaSuccess) return fail("par_barrier: cudaHostGetDevicePointer");
+  ++g.bar_epoch;
+  ++g.barriers;
+  k_par_barrier<<<1, 32, 0, g.cur>>>(g.d_bar_peers, g.bar_flags, g.rank, g.world, g.bar_epoch, 30000000000ull, derr);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("par_barrier launch: ") + cudaGetErrorString(e));
+  return 0;
 }
 
 int after_launch(const char* what) {
@@ -230,6 +273,16 @@ int lbx_finalize(void) {
   if (!g.ready) return 0;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.own);
+  if (g.world > 1) {
+    // every rank stops using its peers' memory before anyone unmaps or frees it
+    lbx::par_barrier();
+    cudaStreamSynchronize(g.cur);
+    for (auto& kv : lbx::ipc_opened) cudaIpcCloseMemHandle(kv.second);
+    lbx::ipc_opened.clear();
+    unsigned char tok = 0;
+    std::vector<unsigned char> toks(g.world);
+    lbx::par_allgather(&tok, 1, toks.data());
+  }
   for (int a = 0; a < lbx::Ctx::NAUX; ++a) {
     if (g.aux[a]) { cudaStreamSynchronize(g.aux[a]); cudaStreamDestroy(g.aux[a]); }
     if (g.join_ev[a]) cudaEventDestroy(g.join_ev[a]);
@@ -245,6 +298,47 @@ int lbx_finalize(void) {
 }
 
 int lbx_initialized(void) { return g.ready ? 1 : 0; }
+
+/* One process per GPU.  `allgather(send, bytes, recv, user)` must gather `bytes` from every rank
+ * into recv (rank order) and return 0 -- the host plumbing (torch.distributed / MPI); it is used
+ * only to exchange CUDA-IPC handles when device fields are created.  Collective. */
+int lbx_par_init(int rank, int world, int (*allgather)(const void*, size_t, void*, void*), void* user) {
+  LBX_NEED_INIT();
+  if (world < 1 || rank < 0 || rank >= world || world > 32) return fail("lbx_par_init: bad rank/world (1..32 ranks)");
+  if (g.world > 1) return fail("lbx_par_init: already initialised");
+  if (world == 1) return 0;
+  if (!allgather) return fail("lbx_par_init: null allgather callback");
+  g.rank = rank; g.world = world; g.allgather = allgather; g.allgather_user = user;
+  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&g.bar_flags), sizeof(unsigned long long) * world));
+  LBX_CUDA(cudaMemset(g.bar_flags, 0, sizeof(unsigned long long) * world));
+  cudaIpcMemHandle_t mine;
+  LBX_CUDA(cudaIpcGetMemHandle(&mine, g.bar_flags));
+  std::vector<unsigned char> all((size_t)world * LBX_IPC_HANDLE_BYTES);
+  if (lbx::par_allgather(&mine, LBX_IPC_HANDLE_BYTES, all.data())) return 1;
+  std::vector<unsigned long long*> peers(world);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { peers[r] = g.bar_flags; continue; }
+    void* base = nullptr;
+    if (lbx::ipc_open_cached(all.data() + (size_t)r * LBX_IPC_HANDLE_BYTES, &base)) return 1;
+    peers[r] = static_cast<unsigned long long*>(base);
+  }
+  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&g.d_bar_peers), sizeof(void*) * world));
+  LBX_CUDA(cudaMemcpy(g.d_bar_peers, peers.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+  // nobody may signal before every rank has zeroed and published its flags
+  unsigned char tok = 0;
+  std::vector<unsigned char> toks(world);
+  return lbx::par_allgather(&tok, 1, toks.data());
+}
+int lbx_par_info(int* rank, int* world, uint64_t* barriers) {
+  if (rank) *rank = g.rank;
+  if (world) *world = g.world;
+  if (barriers) *barriers = g.barriers;
+  return 0;
+}
+int lbx_par_barrier(void) {
+  LBX_NEED_INIT();
+  return lbx::par_barrier();
+}
 
 int lbx_device_info(char* name, int name_cap, int* sm_count, size_t* total_bytes, size_t* free_bytes) {
   LBX_NEED_INIT();

@@ -14,11 +14,15 @@
 
 struct lbx_mf {
   int nfabs = 0, ncomp = 0, ngrow = 0, dtype = LBX_F64;
-  size_t bytes = 0;
-  char* base = nullptr;                 // one device allocation
+  size_t bytes = 0;                     // all fabs (host-mirror layout)
+  size_t local_bytes = 0;               // what this rank allocated
+  char* base = nullptr;                 // one device allocation: this rank's fabs
   lbx::DFabT* table = nullptr;          // device table [nfabs]
   std::vector<lbx::DFabT> host;         // same, host side
-  std::vector<size_t> offset;           // byte offset of fab i in `base`
+  std::vector<size_t> offset;           // byte offset of fab i in the host-mirror layout (all fabs, back to back)
+  std::vector<int> owner;               // rank that owns fab i (distributed runs; all 0 otherwise)
+  std::vector<size_t> own_off;          // byte offset of fab i inside ITS OWNER's allocation
+  bool dist = false;                    // some fabs live in peers' HBM
   long long max_valid = 0;              // largest valid-box cell count
   uint64_t geom = 0;                    // signature of (boxes, ngrow, ncomp, dtype)
   int max_extent(int dir) const {           // largest valid-box extent along dir
@@ -87,15 +91,20 @@ int need(const lbx_mf* f, int ncomp, int dtype, int ngrow_min, const char* what)
 
 extern "C" {
 
-int lbx_mf_create(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dtype, lbx_mf** out) {
+int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dtype, const int* owner, lbx_mf** out) {
   LBX_NEED_INIT();
   if (!valid || nfabs <= 0 || ncomp <= 0 || ngrow < 0 || !out) return fail("lbx_mf_create: bad arguments");
   if (dtype != LBX_F64 && dtype != LBX_I32) return fail("lbx_mf_create: unknown dtype");
+  const int world = g.world, rank = g.rank;
   auto* m = new lbx_mf;
   m->nfabs = nfabs; m->ncomp = ncomp; m->ngrow = ngrow; m->dtype = dtype;
+  m->dist = (world > 1 && owner != nullptr);
   const size_t item = dtype == LBX_F64 ? 8 : 4;
   m->host.resize(nfabs);
   m->offset.resize(nfabs);
+  m->owner.assign(nfabs, 0);
+  m->own_off.resize(nfabs);
+  std::vector<size_t> per_rank((size_t)world, 0);      // bytes each rank allocates (same arithmetic on every rank)
   size_t off = 0;
   uint64_t h = mix(mix(mix(0x1234, ncomp), ngrow), dtype);
   for (int i = 0; i < nfabs; ++i) {
@@ -109,27 +118,62 @@ int lbx_mf_create(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dty
       if (cells >= (size_t(1) << 31)) { delete m; return fail("lbx_mf_create: a fab exceeds 2^31 cells"); }
       h = mix(mix(h, (uint64_t)(uint32_t)f.vlo[d]), (uint64_t)(uint32_t)f.vhi[d]);
     }
+    const size_t fab_bytes = (cells * ncomp * item + 255) / 256 * 256;
     m->offset[i] = off;
-    off += (cells * ncomp * item + 255) / 256 * 256;
+    off += fab_bytes;
+    const int o = m->dist ? owner[i] : 0;
+    if (o < 0 || o >= world) { delete m; return fail("lbx_mf_create: owner rank out of range"); }
+    m->owner[i] = o;
+    m->own_off[i] = per_rank[o];
+    per_rank[o] += fab_bytes;
+    f.local = (!m->dist || o == rank) ? 1 : 0;
+    f.pad = 0;
+    if (m->dist) h = mix(h, (uint64_t)o);
   }
   m->bytes = off;
   m->geom = h;
   m->max_valid = m->max_cells(0);
-  cudaError_t e = lbx::arena_alloc(reinterpret_cast<void**>(&m->base), m->bytes);
+  const size_t mine = m->dist ? per_rank[rank] : off;
+  m->local_bytes = mine;
+  cudaError_t e = lbx::arena_alloc(reinterpret_cast<void**>(&m->base), mine ? mine : 256);
   if (e != cudaSuccess) { delete m; return fail(std::string("lbx_mf_create: cudaMalloc: ") + cudaGetErrorString(e)); }
-  for (int i = 0; i < nfabs; ++i) m->host[i].p = m->base + m->offset[i];
+  std::vector<char*> bases((size_t)world, nullptr);
+  bases[m->dist ? rank : 0] = m->base;
+  if (m->dist) {
+    // collective: every rank publishes the CUDA-IPC handle of its allocation and maps the others'
+    cudaIpcMemHandle_t hd;
+    e = cudaIpcGetMemHandle(&hd, m->base);
+    if (e != cudaSuccess) { lbx::arena_free(m->base); delete m; return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    std::vector<unsigned char> all((size_t)world * LBX_IPC_HANDLE_BYTES);
+    if (lbx::par_allgather(&hd, LBX_IPC_HANDLE_BYTES, all.data())) { lbx::arena_free(m->base); delete m; return 1; }
+    for (int r = 0; r < world; ++r) {
+      if (r == rank || per_rank[r] == 0) continue;
+      void* b = nullptr;
+      if (lbx::ipc_open_cached(all.data() + (size_t)r * LBX_IPC_HANDLE_BYTES, &b)) { lbx::arena_free(m->base); delete m; return 1; }
+      bases[r] = static_cast<char*>(b);
+    }
+  }
+  for (int i = 0; i < nfabs; ++i) m->host[i].p = bases[m->owner[i]] + m->own_off[i];
   e = lbx::arena_alloc(reinterpret_cast<void**>(&m->table), sizeof(lbx::DFabT) * nfabs);
   if (e != cudaSuccess) { lbx::arena_free(m->base); delete m; return fail("lbx_mf_create: cudaMalloc(table)"); }
   // pageable-host async copy: the driver stages it before returning, so `host` may change later
   LBX_CUDA(cudaMemcpyAsync(m->table, m->host.data(), sizeof(lbx::DFabT) * nfabs, cudaMemcpyHostToDevice, g.cur));
-  LBX_CUDA(cudaMemsetAsync(m->base, 0, m->bytes, g.cur));     // NEW_FAB_FILL = 0
+  if (mine) LBX_CUDA(cudaMemsetAsync(m->base, 0, mine, g.cur));     // NEW_FAB_FILL = 0
+  // a recycled arena block may still be read by a slow peer under its previous identity: nobody
+  // proceeds until every rank has got here (and has therefore finished what it queued before)
+  if (m->dist && lbx::par_barrier()) return 1;
   *out = m;
   return 0;
+}
+
+int lbx_mf_create(const lbx_box* valid, int nfabs, int ncomp, int ngrow, int dtype, lbx_mf** out) {
+  return lbx_mf_create_dist(valid, nfabs, ncomp, ngrow, dtype, nullptr, out);
 }
 
 int lbx_mf_destroy(lbx_mf* m) {
   if (!m) return 0;
   if (g.ready) {
+    if (m->dist) lbx::par_barrier();      // collective: no peer may still be reading these boxes
     cudaStreamSynchronize(g.cur);
     lbx::arena_free(m->base);
     lbx::arena_free(m->table);
@@ -163,17 +207,35 @@ int lbx_mf_fab(const lbx_mf* m, int i, lbx_fab* fab, lbx_box* valid, size_t* byt
   return 0;
 }
 
+// host mirrors hold ALL fabs back to back (lbx_mf_fab's byte_offset); a distributed set moves them
+// fab by fab: upload writes this rank's boxes, download also fetches the peers' (over NVLink)
 int lbx_mf_upload(lbx_mf* m, const void* host, size_t bytes) {
   LBX_NEED_INIT();
   if (!m || !host || bytes != m->bytes) return fail("lbx_mf_upload: size mismatch");
-  LBX_CUDA(cudaMemcpyAsync(m->base, host, bytes, cudaMemcpyHostToDevice, g.cur));
+  if (!m->dist) {
+    LBX_CUDA(cudaMemcpyAsync(m->base, host, bytes, cudaMemcpyHostToDevice, g.cur));
+    return 0;
+  }
+  for (int i = 0; i < m->nfabs; ++i) {
+    if (!m->host[i].local) continue;
+    const size_t n = (i + 1 < m->nfabs ? m->offset[i + 1] : m->bytes) - m->offset[i];
+    LBX_CUDA(cudaMemcpyAsync(m->host[i].p, static_cast<const char*>(host) + m->offset[i], n, cudaMemcpyHostToDevice, g.cur));
+  }
   return 0;
 }
 int lbx_mf_download(const lbx_mf* m, void* host, size_t bytes) {
   LBX_NEED_INIT();
   if (!m || !host || bytes != m->bytes) return fail("lbx_mf_download: size mismatch");
-  LBX_CUDA(cudaMemcpyAsync(host, m->base, bytes, cudaMemcpyDeviceToHost, g.cur));
-  return 0;
+  if (!m->dist) {
+    LBX_CUDA(cudaMemcpyAsync(host, m->base, bytes, cudaMemcpyDeviceToHost, g.cur));
+    return 0;
+  }
+  if (lbx::par_barrier()) return 1;
+  for (int i = 0; i < m->nfabs; ++i) {
+    const size_t n = (i + 1 < m->nfabs ? m->offset[i + 1] : m->bytes) - m->offset[i];
+    LBX_CUDA(cudaMemcpyAsync(static_cast<char*>(host) + m->offset[i], m->host[i].p, n, cudaMemcpyDeviceToHost, g.cur));
+  }
+  return lbx::par_barrier();
 }
 
 int lbx_mf_setval(lbx_mf* m, double value) {
@@ -317,11 +379,13 @@ int lbx_mf_from_user(lbx_mf* m, const double* user_dev, const lbx_box* dom, int 
 int lbx_mf_to_user(const lbx_mf* m, double* user_dev, const lbx_box* dom, int ncomp) {
   LBX_NEED_INIT();
   if (user_common(m, user_dev, dom, ncomp, "lbx_mf_to_user")) return 1;
+  if (m->dist && lbx::par_barrier()) return 1;          // reads every rank's boxes
   if (!user_tiled<false>(m, user_dev, dom, ncomp))
     lbx::k_mf_user<false><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
         m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
         dom->hi[2] - dom->lo[2] + 1, ncomp);
-  return lbx::after_launch("lbx_mf_to_user");
+  if (lbx::after_launch("lbx_mf_to_user")) return 1;
+  return m->dist ? lbx::par_barrier() : 0;
 }
 int lbx_fill_f64(double* dev, size_t n, double value) {
   LBX_NEED_INIT();
@@ -432,6 +496,8 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   if (op != LBX_OP_COPY && op != LBX_OP_ADD) return fail("lbx_plan_apply: unknown op");
   if (p->descs.empty()) return 0;
   if (validate_plan(p, dst, src0, src1)) return 1;
+  const bool remote = (src0 && src0->dist) || (src1 && src1->dist);   // sources may sit in peers' HBM
+  if (remote && lbx::par_barrier()) return 1;
   const dim3 grid = lbx::mf_grid(p->max_cells, (int)p->dsts.size());
   const lbx::DFabT* t0 = src0 ? src0->table : nullptr;
   const lbx::DFabT* t1 = src1 ? src1->table : nullptr;
@@ -451,7 +517,8 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
     else LBX_PLAN_LAUNCH(int, true, 0);
   }
 #undef LBX_PLAN_LAUNCH
-  return lbx::after_launch("lbx_plan_apply");
+  if (lbx::after_launch("lbx_plan_apply")) return 1;
+  return remote ? lbx::par_barrier() : 0;
 }
 
 int lbx_mf_collide_stream_fillpatch(const lbx_mf* src_valid, lbx_mf* dst, double omega_s, double omega_b, const lbx_mf* mask,
@@ -506,10 +573,13 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   } else if (src_ghost) {
     ghost_tiles = (dst->max_shell(2) + lbx::MFT - 1) / lbx::MFT;
   }
+  const bool remote = plan && ((src0 && src0->dist) || (src1 && src1->dist));
+  if (remote && lbx::par_barrier()) return 1;
   L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
                         mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
                         dst->max_extent(2), ghost_tiles, omega_s, omega_b, fine_val, zero_invalid);
-  return lbx::after_launch(what);
+  if (lbx::after_launch(what)) return 1;
+  return remote ? lbx::par_barrier() : 0;
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(MFT) k_mf_stream(const DFabT* __restrict__ st,
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT D = dt[b];
+  if (!D.local) return;
   int i, j, k;
   if (!mf_cell(D, grow_all, i, j, k)) return;
   double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(MFT) k_mf_zero_invalid(const DFabT* __restrict
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (!F.local) return;
   int i, j, k;
   if (!mf_cell(F, grow_all, i, j, k)) return;
   if (mf_in_valid(F, i, j, k)) return;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(MFT) k_mf_zero_ring(const DFabT* __restrict__ 
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (!F.local) return;
   int i, j, k;
   if (!mf_cell(F, grow_all, i, j, k)) return;
   const int g = grow_all - depth;   // cells inside valid grown by g are untouched
@@ -82,6 +85,7 @@ __global__ void __launch_bounds__(MFT) k_mf_average_down(const DFabT* __restrict
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT Cf = ct[b];
+  if (!Cf.local) return;
   int i, j, k;
   if (!mf_cell(Cf, cgrow, i, j, k)) return;
   const DFabT S = ft[b];
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(MFT) k_mf_user(const DFabT* __restrict__ ft, i
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (TO_FAB && !F.local) return;              // reading (to user) also takes peers' boxes, over NVLink
   int i, j, k;
   if (!mf_cell(F, 0, i, j, k)) return;
   double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
@@ -153,6 +158,7 @@ __global__ void __launch_bounds__(UT * 8) k_mf_user_tiled(const DFabT* __restric
                                                           int tiles_x, int d0, int d1, int d2, int ny, int nz) {
   __shared__ double tile[NC][UT][UT + 1];     // [n][z][x]
   const DFabT F = ft[blockIdx.z];
+  if (TO_FAB && !F.local) return;
   const int j = F.vlo[1] + blockIdx.y;
   const int i0 = F.vlo[0] + (blockIdx.x % tiles_x) * UT, k0 = F.vlo[2] + (blockIdx.x / tiles_x) * UT;
   if (j > F.vhi[1] || i0 > F.vhi[0] || k0 > F.vhi[2]) return;           // block-uniform
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(MFT) k_mf_setval(const DFabT* __restrict__ ft,
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
+  if (!F.local) return;
   int i, j, k;
   if (!mf_cell(F, grow_all, i, j, k)) return;
   T* fp = static_cast<T*>(F.p) + mf_off(F, i, j, k);
@@ -317,6 +324,7 @@ __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dst
   t /= nx;
   const int j = D.blo[1] + (int)(t % ny), k = D.blo[2] + (int)(t / ny);
   const DFabT F = dt[D.fab];
+  if (!F.local) return;                        // block-uniform: a peer's box is filled by its owner
   const long long dsc = mf_stride(F);
   T* dp = static_cast<T*>(F.p) + c0 * dsc + (active ? mf_off(F, i, j, k) : 0);
   const int nchunks = (D.count + PLAN_CHUNK - 1) / PLAN_CHUNK;

@@ -45,7 +45,12 @@ void DeviceFabArray<T, DTYPE>::define(const BoxArray& ba, const DistributionMapp
       for (int d = 0; d < 3; ++d) { vb[i].lo[d] = ba[i].smallEnd(d); vb[i].hi[d] = ba[i].bigEnd(d); }
   }
   st_ = std::make_shared<Storage>();
-  lbx_check(lbx_mf_create(vb.data(), (int)vb.size(), ncomp, sg, DTYPE, &st_->mf), "MultiFab::define");
+  // distributed run: box i lives on rank dm[i] (BOXES storage; FLAT is single-rank only)
+  const bool dist = DistributionMapping::NProcs() > 1 && lay == Layout::BOXES && dm.size() == ba.size();
+  if (DistributionMapping::NProcs() > 1 && lay == Layout::FLAT) Abort("FLAT storage is not available in a distributed run");
+  lbx_check(lbx_mf_create_dist(vb.data(), (int)vb.size(), ncomp, sg, DTYPE, dist ? dm.ProcessorMap().data() : nullptr,
+                               &st_->mf),
+            "MultiFab::define");
   size_t bytes = 0;
   lbx_check(lbx_mf_info(st_->mf, nullptr, nullptr, nullptr, nullptr, &bytes), "MultiFab::define");
   st_->elems = bytes / sizeof(T);
@@ -510,7 +515,8 @@ void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int nco
   const int r = ratio[0];
   if (fine.nGrow() % r != 0) Abort("sum_fine_to_coarse: fine.nGrow() must be a multiple of the ratio");
   const int cng = fine.nGrow() / r;
-  const std::string key = gkey(fine) + "|" + std::to_string(r);
+  const std::string key = gkey(fine) + "|" + std::to_string(r) + "|" + std::to_string(DistributionMapping::NProcs()) + "." +
+                          std::to_string(DistributionMapping::MyProc());
   if (!g_coarsened.count(key) && g_coarsened.size() >= 4) g_coarsened.clear();   // grids change at regrid: keep a few
   MultiFab& tmp = g_coarsened[key];
   if (tmp.empty()) {

@@ -79,6 +79,13 @@ extern "C" {
 const char* lbx_sim_last_error(void) { return g_msg.c_str(); }
 int lbx_sim_global_init(void) { return guarded([] { lambrexInit(); }); }
 int lbx_sim_global_finalise(void) { return guarded([] { lambrexFinalise(); }); }
+int lbx_sim_global_init_parallel(int rank, int nranks, int (*allgather)(const void*, size_t, void*, void*), void* user) {
+  return guarded([&] { lambrexInitParallel(rank, nranks, allgather, user); });
+}
+int lbx_sim_set_parallel_view(int rank, int nranks) { return guarded([&] { lambrexSetParallelView(rank, nranks); }); }
+int lbx_sim_owner(const lbx_sim* sim, int level, int box, int* rank) {
+  return guarded([&] { *rank = sim->s.DistributionMap(level)[box]; });
+}
 
 int lbx_sim_create(int nx, int ny, int nz, int max_level, const int per[3], double tau_s, double tau_b, lbx_sim** out) {
   return guarded([&] { *out = new lbx_sim(nx, ny, nz, max_level, {{per[0], per[1], per[2]}}, tau_s, tau_b); });

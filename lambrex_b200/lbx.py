@@ -65,6 +65,10 @@ SYMBOLS = {
     "lbx_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "lbx_free": (_i, [_vp]),
     "lbx_arena_release": (_i, []),
+    "lbx_par_init": (_i, [_i, _i, _vp, _vp]),
+    "lbx_par_info": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint64)]),
+    "lbx_par_barrier": (_i, []),
+    "lbx_mf_create_dist": (_i, [_vp, _i, _i, _i, _i, _vp, ctypes.POINTER(_vp)]),
     "lbx_concurrent_begin": (_i, []), "lbx_concurrent_end": (_i, []),
     "lbx_arena_info": (_i, [ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(ctypes.c_uint64),
                             ctypes.POINTER(ctypes.c_uint64)]),
@@ -160,6 +164,12 @@ def set_option(key, value):
 
 def launch_count():
     return int(lib().lbx_launch_count())
+
+
+def par_info():
+    r, w, b = _i(0), _i(1), ctypes.c_uint64(0)
+    check(lib().lbx_par_info(ctypes.byref(r), ctypes.byref(w), ctypes.byref(b)))
+    return {"rank": r.value, "world": w.value, "barriers": b.value}
 
 
 def device_info():

@@ -1,0 +1,126 @@
+"""torchrun entry (>= 2 GPUs): the DISTRIBUTED AMR path -- boxes of every level owned by ranks,
+neighbour boxes read over NVLink through CUDA-IPC, device-side all-rank barriers -- must reproduce
+the single-GPU AmrSim BIT FOR BIT: every cell (ghost rings included) of every box of every level,
+plus the clocks.  Each rank also runs the whole problem alone (all boxes local) as the reference.
+Prints AMR_DIST_CHECK_OK from rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lambrex_b200 import amrsim, lbx, workloads   # noqa: E402
+
+PER = (1, 1, 1)
+
+
+def build(nx, ny, nz, max_level, boxes, max_grid):
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    rho = rho * workloads.pulse_density(nx, ny, nz)
+    sim = amrsim.AmrSim(nx, ny, nz, max_level, PER, 0.3, 0.4)
+    sim.SetUniformFastPath(False)        # per-box storage with ghost cells on every path
+    sim.SetMaxGridSize(max_grid)
+    sim.SetInitialDensity(rho)
+    sim.SetInitialVelocity(u)
+    sim.InitFromScratch(0.0)
+    for lev, (lo, hi) in enumerate(boxes):
+        sim.SetStaticRefinement(lev, lo, hi)
+    return sim
+
+
+def snapshot(sim, max_level):
+    out = []
+    for lev in range(max_level + 1):
+        boxes = sim.FieldBoxes(lev, amrsim.DISTFN)
+        out.append((boxes, [sim.FieldFab(lev, amrsim.DISTFN, b, 2, 15) for b in range(len(boxes))],
+                    sim.GetTime(lev), sim.GetTimeStep(lev)))
+    rho = [sim.GetDensityField(lev) for lev in range(max_level + 1)]
+    return out, rho
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    amrsim.lambrexInitParallel()
+    ok = True
+    cases = [
+        ("1 level", (16, 12, 20), 0, [], 8, 3),
+        ("2 levels", (16, 12, 20), 1, [((3, 2, 4), (11, 9, 14))], 8, 3),
+        ("3 levels", (16, 16, 16), 2, [((3, 3, 3), (12, 12, 12)), ((10, 10, 10), (21, 21, 21))], 8, 2),
+    ]
+    for name, (nx, ny, nz), max_level, boxes, max_grid, steps in cases:
+        sim = build(nx, ny, nz, max_level, boxes, max_grid)
+        owners = [sorted({sim.Owner(lev, b) for b in range(len(sim.boxArray(lev)))}) for lev in range(max_level + 1)]
+        sim.Iterate(steps)
+        for lev in range(max_level + 1):
+            sim.CalcHydroVars(lev)
+        got, rho_got = snapshot(sim, max_level)
+        # regrid mid-run: move the finest static box, keep stepping
+        if boxes:
+            rlev = len(boxes) - 1
+            lo, hi = boxes[rlev]
+            sim.SetStaticRefinement(rlev, tuple(v + 1 for v in lo), tuple(v + 1 for v in hi))
+            sim.Iterate(1)
+            got2, _ = snapshot(sim, max_level)
+        sim.close()
+        dist.barrier()
+
+        amrsim.setParallelView(0, 1)            # the same problem, alone on this GPU
+        ref = build(nx, ny, nz, max_level, boxes, max_grid)
+        ref.Iterate(steps)
+        for lev in range(max_level + 1):
+            ref.CalcHydroVars(lev)
+        want, rho_want = snapshot(ref, max_level)
+        if boxes:
+            ref.SetStaticRefinement(rlev, tuple(v + 1 for v in lo), tuple(v + 1 for v in hi))
+            ref.Iterate(1)
+            want2, _ = snapshot(ref, max_level)
+        ref.close()
+        amrsim.setParallelView(rank, world)
+
+        def same(a, b):
+            good = True
+            for lv, ((ba, fa, ta, sa), (bb, fb, tb, sb)) in enumerate(zip(a, b)):
+                if not (ba == bb and ta == tb and sa == sb and len(fa) == len(fb)):
+                    firstdiff = [(x, y) for x, y in zip(ba, bb) if x != y][:2]
+                    print("[rank %d] %s level %d: metadata differs (%d vs %d boxes, t %s/%s, step %s/%s) first %s"
+                          % (rank, name, lv, len(ba), len(bb), ta, tb, sa, sb, firstdiff), flush=True)
+                    good = False
+                    continue
+                for bi, (x, y) in enumerate(zip(fa, fb)):
+                    if not np.array_equal(x, y):
+                        d = np.abs(x - y)
+                        dv = float(np.max(d[:, 2:-2, 2:-2, 2:-2]))
+                        if good:
+                            print("[rank %d] %s level %d box %d %s: max|diff| all %.3e valid %.3e, %d cells differ, nan got %d"
+                                  % (rank, name, lv, bi, ba[bi], float(np.nanmax(d)), dv, int(np.count_nonzero(d)),
+                                     int(np.isnan(x).sum())), flush=True)
+                        good = False
+            return good
+
+        good = same(got, want) and all(np.array_equal(x, y) for x, y in zip(rho_got, rho_want))
+        if boxes:
+            good = good and same(got2, want2)
+        flag = torch.tensor([1 if good else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("amr_dist_check %-8s world=%d owners per level=%s bit-equal=%s" % (name, world, owners, bool(flag.item())),
+                  flush=True)
+        ok = ok and bool(flag.item())
+    info = lbx.par_info()
+    if rank == 0:
+        print("device barriers executed: %d" % info["barriers"], flush=True)
+        if ok:
+            print("AMR_DIST_CHECK_OK", flush=True)
+    amrsim.lambrexFinalise()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
