@@ -85,6 +85,9 @@ int lbx_par_init(int rank, int world, int (*allgather)(const void *send, size_t 
                  void *user);
 int lbx_par_info(int *rank, int *world, uint64_t *barriers);
 int lbx_par_barrier(void);
+/* the registered allgather, for host metadata the ranks must agree on (regrid tag lists):
+ * recv holds `bytes` from every rank, rank order; a plain copy on a single rank */
+int lbx_par_allgather(const void *send, size_t bytes, void *recv);
 int lbx_sync(void);
 /* Concurrent section: the calls made between begin and end must be independent of one another
  * (they may read the same data but write disjoint data).  Each launch goes to its own auxiliary

@@ -335,6 +335,10 @@ int lbx_par_info(int* rank, int* world, uint64_t* barriers) {
   if (barriers) *barriers = g.barriers;
   return 0;
 }
+int lbx_par_allgather(const void* send, size_t bytes, void* recv) {
+  LBX_NEED_INIT();
+  return lbx::par_allgather(send, bytes, recv);
+}
 int lbx_par_barrier(void) {
   LBX_NEED_INIT();
   return lbx::par_barrier();

@@ -1,6 +1,9 @@
 // amrex-mini AmrMesh/AmrCore (see AMReX_AmrCore.H).  [AMReX, unverified] throughout: restated
 // from upstream semantics recorded in SURVEY.md appendix C, not from AMReX source.
 #include "AMReX_AmrCore.H"
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
 
 #include <iostream>
 #include <list>
@@ -43,44 +46,87 @@ int find_cut(const std::vector<int>& hist, CutStatus& status) {
   return cut;
 }
 
-Box min_box(const IntVect* p, size_t n) {
-  Box b(p[0], p[0]);
-  for (size_t i = 1; i < n; ++i) b.minBox(Box(p[i], p[i]));
+Box min_box(const std::vector<TagRun>& r) {
+  Box b(IntVect(r[0].i0, r[0].j, r[0].k), IntVect(r[0].i1, r[0].j, r[0].k));
+  for (const TagRun& t : r) b.minBox(Box(IntVect(t.i0, t.j, t.k), IntVect(t.i1, t.j, t.k)));
   return b;
+}
+long long cells_of(const std::vector<TagRun>& r) {
+  long long n = 0;
+  for (const TagRun& t : r) n += t.i1 - t.i0 + 1;
+  return n;
 }
 }  // namespace
 
-BoxList ClusterTags(std::vector<IntVect>& tags, Real eff) {
-  struct Cl { size_t first, count; Box box; };
+// Berger-Rigoutsos: split the minimal box of the tags at a hole / an inflection of the signature /
+// the middle until every box is filled to `eff` [AMReX ClusterList::chop, unverified].
+BoxList ClusterRuns(std::vector<TagRun> all, Real eff) {
+  struct Cl { std::vector<TagRun> r; long long count; Box box; };
   BoxList out;
-  if (tags.empty()) return out;
+  if (all.empty()) return out;
   std::list<Cl> lst;
-  lst.push_back({0, tags.size(), min_box(tags.data(), tags.size())});
+  {
+    Cl c;
+    c.r = std::move(all);
+    c.count = cells_of(c.r);
+    c.box = min_box(c.r);
+    lst.push_back(std::move(c));
+  }
   for (auto it = lst.begin(); it != lst.end();) {
     Cl& c = *it;
     if ((Real)c.count / (Real)c.box.numPts() >= eff) { ++it; continue; }
-    IntVect* p = tags.data() + c.first;
     CutStatus st[3], mincut = InvalidCut;
     int cut[3];
     for (int d = 0; d < 3; ++d) {
-      std::vector<int> hist(c.box.length(d), 0);
-      for (size_t q = 0; q < c.count; ++q) ++hist[p[q][d] - c.box.smallEnd(d)];
-      cut[d] = c.box.smallEnd(d) + find_cut(hist, st[d]);
+      const int lo = c.box.smallEnd(d), len = c.box.length(d);
+      std::vector<int> hist(len, 0);
+      if (d == 0) {
+        std::vector<int> diff(len + 1, 0);
+        for (const TagRun& t : c.r) { ++diff[t.i0 - lo]; --diff[t.i1 + 1 - lo]; }
+        int acc = 0;
+        for (int i = 0; i < len; ++i) { acc += diff[i]; hist[i] = acc; }
+      } else {
+        for (const TagRun& t : c.r) hist[(d == 1 ? t.j : t.k) - lo] += t.i1 - t.i0 + 1;
+      }
+      cut[d] = lo + find_cut(hist, st[d]);
       if (st[d] < mincut) mincut = st[d];
     }
     int dir = -1;
     for (int d = 0; d < 3; ++d)
       if (st[d] == mincut && (dir < 0 || c.box.length(d) > c.box.length(dir))) dir = d;
-    IntVect* mid = std::stable_partition(p, p + c.count, [&](const IntVect& v) { return v[dir] < cut[dir]; });
-    const size_t nlo = (size_t)(mid - p), nhi = c.count - nlo;
-    if (nlo == 0 || nhi == 0) { ++it; continue; }   // cannot split further
-    lst.push_back({c.first + nlo, nhi, min_box(mid, nhi)});
-    c.count = nlo;
-    c.box = min_box(p, nlo);
+    std::vector<TagRun> lo_r, hi_r;
+    for (const TagRun& t : c.r) {
+      if (dir == 0) {
+        if (t.i1 < cut[0]) lo_r.push_back(t);
+        else if (t.i0 >= cut[0]) hi_r.push_back(t);
+        else { lo_r.push_back({t.i0, cut[0] - 1, t.j, t.k}); hi_r.push_back({cut[0], t.i1, t.j, t.k}); }
+      } else {
+        ((dir == 1 ? t.j : t.k) < cut[dir] ? lo_r : hi_r).push_back(t);
+      }
+    }
+    if (lo_r.empty() || hi_r.empty()) { ++it; continue; }   // cannot split further
+    Cl h;
+    h.r = std::move(hi_r);
+    h.count = cells_of(h.r);
+    h.box = min_box(h.r);
+    lst.push_back(std::move(h));
+    c.r = std::move(lo_r);
+    c.count = cells_of(c.r);
+    c.box = min_box(c.r);
     // the low part is examined again before moving on
   }
   for (const Cl& c : lst) out.push_back(c.box);
   return out;
+}
+
+BoxList ClusterTags(std::vector<IntVect>& tags, Real eff) {
+  std::vector<TagRun> runs;
+  runs.reserve(tags.size());
+  for (const IntVect& p : tags) {              // consecutive cells of a row merge; any order is fine
+    if (!runs.empty() && runs.back().j == p[1] && runs.back().k == p[2] && runs.back().i1 + 1 == p[0]) ++runs.back().i1;
+    else runs.push_back({p[0], p[0], p[1], p[2]});
+  }
+  return ClusterRuns(std::move(runs), eff);
 }
 
 // ----------------------------------------------------------------------------- AmrMesh
@@ -156,9 +202,19 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
   for (int levc = max_crse; levc >= lbase; --levc) {
     const int levf = levc + 1;
     const int nbuf = n_error_buf[levc][0];
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!getenv("LBX_HOST_TIMING")) return;
+      auto T1 = std::chrono::steady_clock::now();
+      std::cerr << "  [regrid levc " << levc << "] " << what << " " << std::chrono::duration<double>(T1 - T0).count() << " s\n";
+      T0 = T1;
+    };
     TagBoxArray tags(grids[levc], dmap[levc], nbuf);
+    lap("alloc tags");
     ErrorEst(levc, tags, time, 0);
+    lap("ErrorEst");
     tags.buffer(nbuf);
+    lap("buffer");
     if (levf < new_finest) {
       // project the new grids two levels up down to levc so that the new levf contains them
       BoxList proj;
@@ -170,19 +226,15 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
       }
       tags.setVal(proj, TagBox::SET);
     }
-    std::vector<IntVect> tagvec;
-    tags.collate(tagvec, geom[levc].Domain(), geom[levc].isPeriodicArray());
-    if (!p_n_comp[levc].empty()) {             // remove cells outside the proper nesting domain
-      auto bad = [&](const IntVect& p) {
-        for (const Box& b : p_n_comp[levc])
-          if (b.contains(p)) return true;
-        return false;
-      };
-      tagvec.erase(std::remove_if(tagvec.begin(), tagvec.end(), bad), tagvec.end());
-    }
+    std::vector<TagRun> tagvec;
+    // cells outside the proper nesting domain are dropped while collating
+    tags.collate(tagvec, geom[levc].Domain(), geom[levc].isPeriodicArray(), p_n_comp[levc].empty() ? nullptr : &p_n_comp[levc]);
+    lap("collate");
+    lap("proper nesting filter");
     if (tagvec.empty()) continue;
     new_finest = std::max(new_finest, levf);
-    BoxList clusters = ClusterTags(tagvec, grid_eff);
+    BoxList clusters = ClusterRuns(std::move(tagvec), grid_eff);
+    lap("ClusterTags");
     BoxList clipped;                           // ClusterList::intersect(p_n)
     for (const Box& b : clusters) {
       bool whole = false;
@@ -200,6 +252,7 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
     maxSize(clipped, largest);
     for (Box& b : clipped) b.refine(ref_ratio[levc]);
     new_grids[levf].define(clipped);
+    lap("clip/simplify/maxSize");
   }
 }
 

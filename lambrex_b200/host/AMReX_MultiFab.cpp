@@ -139,7 +139,7 @@ template class DeviceFabArray<int, LBX_I32>;
 // ----------------------------------------------------------------------------- tags
 void TagBox::setVal(char v, const Box& region) {
   const Box r = region & box_;
-  if (!r.ok()) return;
+  if (!r.ok() || !allocated()) return;
   for (int k = r.smallEnd(2); k <= r.bigEnd(2); ++k)
     for (int j = r.smallEnd(1); j <= r.bigEnd(1); ++j) {
       char* row = &d_[index(IntVect(r.smallEnd(0), j, k))];
@@ -147,23 +147,43 @@ void TagBox::setVal(char v, const Box& region) {
     }
 }
 
+// Dilation of the SET cells inside `interior` by +-nbuf in every direction (a cube, so it is done
+// run by run: a row's run [i0, i1] of SET cells marks [i0 - nbuf, i1 + nbuf] in the (2 nbuf + 1)^2
+// neighbouring rows), CLEAR cells becoming BUF.  Same result as growing every SET cell on its own.
+// first index >= x in row[0..n) whose byte is not 0 (CLEAR), skipping eight cells at a time
+static inline int next_nonclear(const char* row, int x, int n) {
+  while (x < n && (reinterpret_cast<uintptr_t>(row + x) & 7) != 0) { if (row[x]) return x; ++x; }
+  while (x + 8 <= n && *reinterpret_cast<const uint64_t*>(row + x) == 0) x += 8;
+  while (x < n && !row[x]) ++x;
+  return x;
+}
+
 void TagBox::buffer(int nbuf, const Box& interior) {
-  if (nbuf <= 0) return;
+  if (nbuf <= 0 || !allocated()) return;
   const Box in = interior & box_;
   if (!in.ok()) return;
-  std::vector<IntVect> set;
+  struct Run { int i0, i1, j, k; };
+  std::vector<Run> runs;
   for (int k = in.smallEnd(2); k <= in.bigEnd(2); ++k)
-    for (int j = in.smallEnd(1); j <= in.bigEnd(1); ++j)
-      for (int i = in.smallEnd(0); i <= in.bigEnd(0); ++i)
-        if ((*this)(IntVect(i, j, k)) == SET) set.push_back(IntVect(i, j, k));
-  for (const IntVect& p : set) {
-    const Box nb = Box(p - IntVect(nbuf), p + IntVect(nbuf)) & box_;
-    for (int k = nb.smallEnd(2); k <= nb.bigEnd(2); ++k)
-      for (int j = nb.smallEnd(1); j <= nb.bigEnd(1); ++j)
-        for (int i = nb.smallEnd(0); i <= nb.bigEnd(0); ++i) {
-          char& t = (*this)(IntVect(i, j, k));
-          if (t == CLEAR) t = BUF;
-        }
+    for (int j = in.smallEnd(1); j <= in.bigEnd(1); ++j) {
+      const char* row = &d_[index(IntVect(in.smallEnd(0), j, k))];
+      const int n = in.length(0);
+      for (int x = next_nonclear(row, 0, n); x < n;) {
+        if (row[x] != SET) { x = next_nonclear(row, x + 1, n); continue; }
+        int y = x;
+        while (y + 1 < n && row[y + 1] == SET) ++y;
+        runs.push_back({in.smallEnd(0) + x, in.smallEnd(0) + y, j, k});
+        x = next_nonclear(row, y + 1, n);
+      }
+    }
+  for (const Run& r : runs) {
+    const int i0 = std::max(r.i0 - nbuf, box_.smallEnd(0)), i1 = std::min(r.i1 + nbuf, box_.bigEnd(0));
+    for (int k = std::max(r.k - nbuf, box_.smallEnd(2)); k <= std::min(r.k + nbuf, box_.bigEnd(2)); ++k)
+      for (int j = std::max(r.j - nbuf, box_.smallEnd(1)); j <= std::min(r.j + nbuf, box_.bigEnd(1)); ++j) {
+        char* row = &d_[index(IntVect(i0, j, k))];
+        for (int x = 0; x <= i1 - i0; ++x)
+          if (row[x] == CLEAR) row[x] = BUF;
+      }
   }
 }
 
@@ -173,7 +193,10 @@ TagBoxArray::TagBoxArray(const BoxArray& ba, const DistributionMapping& dm, int 
   ncomp_ = 1;
   ngrow_ = ngrow;
   fabs_.reserve(ba.size());
-  for (long i = 0; i < ba.size(); ++i) fabs_.emplace_back(amrex::grow(ba[i], ngrow));
+  // distributed run: a rank tags (and stores tags for) its own boxes only; collate() merges
+  const bool dist = DistributionMapping::NProcs() > 1 && dm.size() == ba.size();
+  for (long i = 0; i < ba.size(); ++i)
+    fabs_.emplace_back(amrex::grow(ba[i], ngrow), !dist || dm[i] == DistributionMapping::MyProc());
 }
 void TagBoxArray::setVal(const BoxArray& ba, TagBox::TagVal v) { setVal(ba.boxList(), v); }
 void TagBoxArray::setVal(const BoxList& bl, TagBox::TagVal v) {
@@ -183,26 +206,116 @@ void TagBoxArray::setVal(const BoxList& bl, TagBox::TagVal v) {
 void TagBoxArray::buffer(int nbuf) {
   for (long i = 0; i < size(); ++i) fabs_[i].buffer(nbuf, ba_[i]);
 }
-void TagBoxArray::collate(std::vector<IntVect>& out, const Box& domain, const std::array<int, 3>& is_per) const {
+// Every non-CLEAR cell mapped into `domain` through the periodic directions, minus the cells of
+// `remove`, as a sorted (z slowest), duplicate-free list.  Built on a bitmap over the bounding box
+// of the tagged rows: runs of tagged cells set bit ranges, `remove` boxes clear them, one scan emits
+// the points in order -- no per-cell sort, no per-cell box tests.
+void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std::array<int, 3>& is_per,
+                          const BoxList* remove) const {
   out.clear();
+  using Run = TagRun;
+  std::vector<Run> runs;
+  auto wrap1 = [&](int v, int d, bool& ok) {
+    const int len = domain.length(d), lo = domain.smallEnd(d);
+    if (v >= lo && v <= domain.bigEnd(d)) return v;
+    if (!is_per[d]) { ok = false; return v; }
+    return lo + (((v - lo) % len) + len) % len;
+  };
   for (const TagBox& t : fabs_) {
+    if (!t.allocated()) continue;
     const Box& b = t.box();
+    const int n = b.length(0);
     for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
-      for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j)
-        for (int i = b.smallEnd(0); i <= b.bigEnd(0); ++i) {
-          if (t(IntVect(i, j, k)) == TagBox::CLEAR) continue;
-          IntVect p(i, j, k);
-          bool inside = true;
-          for (int d = 0; d < 3; ++d) {
-            const int len = domain.length(d), lo = domain.smallEnd(d);
-            if (is_per[d]) p[d] = lo + (((p[d] - lo) % len) + len) % len;
-            else if (p[d] < lo || p[d] > domain.bigEnd(d)) inside = false;
+      for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j) {
+        bool ok = true;
+        const int jj = wrap1(j, 1, ok), kk = wrap1(k, 2, ok);
+        if (!ok) continue;
+        const char* row = &t(IntVect(b.smallEnd(0), j, k));
+        for (int x = next_nonclear(row, 0, n); x < n;) {
+          int y = x;
+          while (y + 1 < n && row[y + 1] != TagBox::CLEAR) ++y;
+          // the run [x, y] in index space, cut at the domain faces and wrapped piece by piece
+          int a = b.smallEnd(0) + x;
+          const int e = b.smallEnd(0) + y;
+          while (a <= e) {
+            const int lo = domain.smallEnd(0), len = domain.length(0);
+            const int cell0 = lo + (((a - lo) % len) + len) % len;         // image of a
+            const int room = domain.bigEnd(0) - cell0;                     // cells up to the face
+            const int piece = std::min(e - a, room);
+            const bool inside = a >= lo && a <= domain.bigEnd(0);
+            if (inside || is_per[0]) runs.push_back({cell0, cell0 + piece, jj, kk});
+            a += piece + 1;
           }
-          if (inside) out.push_back(p);
+          x = next_nonclear(row, y + 1, n);
         }
+      }
   }
-  std::sort(out.begin(), out.end());
-  out.erase(std::unique(out.begin(), out.end()), out.end());
+  if (DistributionMapping::NProcs() > 1) {
+    // every rank contributes the runs of its own boxes: sizes first, then the padded lists
+    const int np = DistributionMapping::NProcs();
+    long long mine = (long long)runs.size();
+    std::vector<long long> counts(np);
+    lbx_check(lbx_par_allgather(&mine, sizeof(mine), counts.data()), "TagBoxArray::collate");
+    long long most = 0;
+    for (long long c : counts) most = std::max(most, c);
+    if (most == 0) return;
+    std::vector<Run> send((size_t)most, Run{0, -1, 0, 0}), all((size_t)most * np);
+    std::copy(runs.begin(), runs.end(), send.begin());
+    lbx_check(lbx_par_allgather(send.data(), sizeof(Run) * (size_t)most, all.data()), "TagBoxArray::collate");
+    runs.clear();
+    for (int r = 0; r < np; ++r) runs.insert(runs.end(), all.begin() + (size_t)r * most, all.begin() + (size_t)r * most + counts[r]);
+  }
+  if (runs.empty()) return;
+  IntVect blo(runs[0].i0, runs[0].j, runs[0].k), bhi(runs[0].i1, runs[0].j, runs[0].k);
+  for (const Run& r : runs) {
+    blo[0] = std::min(blo[0], r.i0); bhi[0] = std::max(bhi[0], r.i1);
+    blo[1] = std::min(blo[1], r.j);  bhi[1] = std::max(bhi[1], r.j);
+    blo[2] = std::min(blo[2], r.k);  bhi[2] = std::max(bhi[2], r.k);
+  }
+  const Box bb(blo, bhi);
+  const size_t wpr = ((size_t)bb.length(0) + 63) / 64, ny = (size_t)bb.length(1), nz = (size_t)bb.length(2);
+  std::vector<uint64_t> bits(wpr * ny * nz, 0);
+  auto range = [&](int i0, int i1, int j, int k, bool set) {          // [i0, i1] relative to blo[0]
+    uint64_t* row = &bits[wpr * ((size_t)(j - blo[1]) + ny * (size_t)(k - blo[2]))];
+    const size_t w0 = (size_t)i0 / 64, w1 = (size_t)i1 / 64;
+    for (size_t w = w0; w <= w1; ++w) {
+      uint64_t m = ~uint64_t(0);
+      if (w == w0) m &= ~uint64_t(0) << (i0 % 64);
+      if (w == w1) m &= ~uint64_t(0) >> (63 - (i1 % 64));
+      if (set) row[w] |= m; else row[w] &= ~m;
+    }
+  };
+  for (const Run& r : runs) range(r.i0 - blo[0], r.i1 - blo[0], r.j, r.k, true);
+  if (remove)
+    for (const Box& q : *remove) {
+      const Box r = q & bb;
+      if (!r.ok()) continue;
+      for (int k = r.smallEnd(2); k <= r.bigEnd(2); ++k)
+        for (int j = r.smallEnd(1); j <= r.bigEnd(1); ++j) range(r.smallEnd(0) - blo[0], r.bigEnd(0) - blo[0], j, k, false);
+    }
+  for (size_t k = 0; k < nz; ++k)
+    for (size_t j = 0; j < ny; ++j) {
+      const uint64_t* row = &bits[wpr * (j + ny * k)];
+      const int nbits = bb.length(0);
+      int x = 0;
+      while (x < nbits) {
+        const uint64_t rest = row[x / 64] >> (x % 64);
+        if (!rest) { x = (x / 64 + 1) * 64; continue; }
+        x += __builtin_ctzll(rest);                               // first set bit at or after x
+        int y = x;                                                // extend over the run of set bits
+        for (;;) {
+          const uint64_t inv = ~(row[y / 64] >> (y % 64));        // zero bits from y on (shifted-in bits count as zero)
+          const int room = 64 - (y % 64);
+          const int ones = inv ? __builtin_ctzll(inv) : 64;
+          if (ones < room) { y += ones; break; }
+          y += room;
+          if (y >= nbits) break;
+        }
+        if (y > nbits) y = nbits;
+        out.push_back({blo[0] + x, blo[0] + y - 1, blo[1] + (int)j, blo[2] + (int)k});
+        x = y;
+      }
+    }
 }
 
 // ----------------------------------------------------------------------------- gather plans

@@ -68,6 +68,7 @@ SYMBOLS = {
     "lbx_par_init": (_i, [_i, _i, _vp, _vp]),
     "lbx_par_info": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint64)]),
     "lbx_par_barrier": (_i, []),
+    "lbx_par_allgather": (_i, [_vp, _sz, _vp]),
     "lbx_mf_create_dist": (_i, [_vp, _i, _i, _i, _i, _vp, ctypes.POINTER(_vp)]),
     "lbx_concurrent_begin": (_i, []), "lbx_concurrent_end": (_i, []),
     "lbx_arena_info": (_i, [ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(ctypes.c_uint64),

@@ -53,6 +53,10 @@ def main():
         ("2 levels", (16, 12, 20), 1, [((3, 2, 4), (11, 9, 14))], 8, 3),
         ("3 levels", (16, 16, 16), 2, [((3, 3, 3), (12, 12, 12)), ((10, 10, 10), (21, 21, 21))], 8, 2),
     ]
+    if "--big" in sys.argv:
+        cases = [("64^3 L2", (64, 64, 64), 1, [((16, 16, 16), (47, 47, 47))], 16, 3),
+                 ("128^3 L2", (128, 128, 128), 1, [((32, 32, 32), (95, 95, 95))], 32, 3),
+                 ("128^3 L3", (128, 128, 128), 2, [((32, 32, 32), (95, 95, 95)), ((96, 96, 96), (159, 159, 159))], 32, 2)]
     for name, (nx, ny, nz), max_level, boxes, max_grid, steps in cases:
         sim = build(nx, ny, nz, max_level, boxes, max_grid)
         owners = [sorted({sim.Owner(lev, b) for b in range(len(sim.boxArray(lev)))}) for lev in range(max_level + 1)]
