@@ -359,7 +359,18 @@ def run_single_raw(args):
     lbx.check(L.lbx_host_free(hp))
 
 
+def json_only_stdout():
+    """The host library keeps the reference's own stdout chatter ("NX: .. NY: .. NZ: ..",
+    src/AmrSim.cpp:776, grid summaries).  The bench contract is ONE JSON line on stdout: move
+    file descriptor 1 to stderr for everything native and keep the real stdout for print()."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w")
+
+
 def main():
+    json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
