@@ -390,6 +390,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference" or args.gpus == 1:
+        # the CPU arm uses every host core it can: torchrun exports OMP_NUM_THREADS=1 to its workers,
+        # which would time the OpenMP oracle on one thread (set before libgomp is loaded)
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("LBX_BENCH_THREADS") or str(len(os.sched_getaffinity(0)))
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus == 1:

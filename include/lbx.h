@@ -213,6 +213,11 @@ int lbx_mf_collide_stream(const lbx_mf *src_valid, const lbx_mf *src_ghost, lbx_
  * coarse box (fine ghosts = ratio x coarse ghosts).  The ADD into the coarse level is then a COPY-kind
  * plan applied with LBX_OP_ADD over these patches. */
 int lbx_mf_average_down(const lbx_mf *fine, lbx_mf *crse, int ratio);
+/* dst = a * x + b * y on the valid cells of every box (MultiFab::LinComb; the time interpolation of
+ * FillPatchTwoLevels between two coarse states, used by the conventional subcycling driver -- the
+ * reference's DistFnFillPatch :359-391 passes one state and so never interpolates).  Products and sum
+ * are rounded separately.  The three sets hold the same boxes and component count; dst may alias. */
+int lbx_mf_lincomb(lbx_mf *dst, double a, const lbx_mf *x, double b, const lbx_mf *y);
 /* ZeroInvalidComponents :604-617: in the ghost shell, f_m = 0 unless pos - 2 c_m is valid */
 int lbx_mf_zero_invalid(lbx_mf *f);
 /* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */

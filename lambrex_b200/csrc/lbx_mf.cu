@@ -321,6 +321,17 @@ int lbx_mf_average_down(const lbx_mf* fine, lbx_mf* crse, int ratio) {
   return lbx::after_launch("lbx_mf_average_down");
 }
 
+int lbx_mf_lincomb(lbx_mf* dst, double a, const lbx_mf* x, double b, const lbx_mf* y) {
+  LBX_NEED_INIT();
+  if (need(dst, 1, LBX_F64, 0, "lbx_mf_lincomb dst") || need(x, 1, LBX_F64, 0, "lbx_mf_lincomb x") ||
+      need(y, 1, LBX_F64, 0, "lbx_mf_lincomb y") || same_boxes(dst, x, "lbx_mf_lincomb") || same_boxes(dst, y, "lbx_mf_lincomb"))
+    return 1;
+  if (x->ncomp != dst->ncomp || y->ncomp != dst->ncomp) return fail("lbx_mf_lincomb: component counts differ");
+  lbx::k_mf_lincomb<<<lbx::mf_grid(dst->max_valid, dst->nfabs), lbx::MFT, 0, g.cur>>>(dst->table, x->table, y->table, dst->nfabs,
+                                                                                     dst->ncomp, a, b);
+  return lbx::after_launch("lbx_mf_lincomb");
+}
+
 int lbx_mf_zero_invalid(lbx_mf* f) {
   LBX_NEED_INIT();
   if (need(f, LBX_NV, LBX_F64, 1, "lbx_mf_zero_invalid")) return 1;

@@ -127,6 +127,33 @@ __global__ void __launch_bounds__(MFT) k_mf_average_down(const DFabT* __restrict
   }
 }
 
+// dst = a * x + b * y on the valid cells of every box, `ncomp` components (MultiFab::LinComb --
+// the time interpolation of FillPatchTwoLevels between two coarse states [AMReX]).  Products
+// and sum are rounded separately (no FMA contraction): bit-identical to the CPU statement.
+__global__ void __launch_bounds__(MFT) k_mf_lincomb(const DFabT* __restrict__ dt, const DFabT* __restrict__ xt,
+                                                    const DFabT* __restrict__ yt, int nfabs, int ncomp, double a, double b) {
+  const int q = mf_fab_index();
+  if (q >= nfabs) return;
+  const DFabT D = dt[q];
+  if (!D.local) return;
+  int i, j, k;
+  if (!mf_cell(D, 0, i, j, k)) return;
+  const DFabT X = xt[q], Y = yt[q];
+  const double* xp = static_cast<const double*>(X.p) + mf_off(X, i, j, k);
+  const double* yp = static_cast<const double*>(Y.p) + mf_off(Y, i, j, k);
+  double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
+  const long long xs = mf_stride(X), ys = mf_stride(Y), ds = mf_stride(D);
+  for (int c0 = 0; c0 < ncomp; c0 += 5) {          // 10 loads in flight per thread
+    double v[5], w[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+      if (c0 + c < ncomp) { v[c] = __ldcs(xp + (c0 + c) * xs); w[c] = __ldcs(yp + (c0 + c) * ys); }
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+      if (c0 + c < ncomp) dp[(c0 + c) * ds] = __dadd_rn(__dmul_rn(a, v[c]), __dmul_rn(b, w[c]));
+  }
+}
+
 // User arrays of the reference's API are C-ordered, i slowest, component fastest
 // (CLindex, include/AmrSim.h:79-83): user[(((i-d0)*NY + (j-d1))*NZ + (k-d2))*ncomp + n].
 // TO_FAB: valid cells of every fab <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);

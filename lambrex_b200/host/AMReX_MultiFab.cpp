@@ -646,6 +646,45 @@ void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int nco
   ParallelCopy(crse, tmp, cng, 0, cgeom.periodicity(), true);
 }
 
+// One AVG plan: coarse box k, region coarsen(fine box i) n (valid box k) <- mean of the fine cells above
+// it.  Fine valid boxes are disjoint, so every coarse cell has at most one source.
+void average_down(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, const IntVect& ratio) {
+  if (fine.empty() || crse.empty()) return;
+  if (scomp != 0 || ncomp != crse.nComp() || ncomp != fine.nComp()) Abort("average_down: only all components are supported");
+  if (fine.isFlat() || crse.isFlat()) Abort("average_down: both levels must use BOXES storage");
+  if (ratio[0] != ratio[1] || ratio[0] != ratio[2]) Abort("anisotropic refinement ratios are not supported");
+  const int r = ratio[0];
+  const std::string key = "AD|" + gkey(crse) + "|" + gkey(fine) + "|" + std::to_string(r);
+  lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
+    std::vector<Box> cf(fine.size());
+    for (long i = 0; i < fine.size(); ++i) {
+      cf[i] = amrex::coarsen(fine.box((int)i), r);
+      if (amrex::refine(cf[i], r) != fine.box((int)i)) Abort("average_down: fine box not aligned to the coarse grid");
+    }
+    const BoxHash fh(cf);
+    for (int k = 0; k < (int)crse.size(); ++k) {
+      const Box want = crse.box(k);
+      const size_t from = d.size();
+      for (int i : fh.query(want)) {
+        const Box reg = cf[i] & want;
+        if (reg.ok()) d.push_back(make_desc(k, 0, i, LBX_G_AVG, r, IntVect(0), reg));
+      }
+      by_volume(d, from);
+    }
+  });
+  lbx_check(lbx_plan_apply(p, crse.mf(), fine.mf(), nullptr, LBX_OP_COPY), "average_down");
+  crse.touch();
+}
+
+void LinComb(MultiFab& dst, double a, const MultiFab& x, double b, const MultiFab& y) {
+  if (dst.empty()) return;
+  if (dst.boxArray() != x.boxArray() || dst.boxArray() != y.boxArray() || dst.layout() != x.layout() ||
+      dst.layout() != y.layout())
+    Abort("LinComb: the three MultiFabs must share boxes and layout");
+  lbx_check(lbx_mf_lincomb(dst.mf(), a, x.mf(), b, y.mf()), "LinComb");
+  dst.touch();
+}
+
 iMultiFab makeFineMask(const MultiFab& cmf, const BoxArray& fba, const IntVect& ratio, int crse_value, int fine_value) {
   iMultiFab mask(cmf.boxArray(), cmf.DistributionMap(), 1, cmf.nGrow());
   if (mask.empty()) return mask;
