@@ -41,6 +41,12 @@ int lbx_sim_set_max_grid_size(lbx_sim *sim, int n);
 int lbx_sim_set_uniform_fast_path(lbx_sim *sim, int on);
 /* 0: Rohde cycle as the reference's literal pass sequence; 1 (default): collide+Stream fused per level */
 int lbx_sim_set_rohde_fusion(lbx_sim *sim, int on);
+/* addition: how Iterate couples refined levels.  ROHDE (default) = the reference's live
+ * RohdeCycle (src/AmrSim.cpp:430-469); SUBCYCLE = the conventional driver its dead SubCycle (:335-344)
+ * sketches: per-level FillPatch (time-interpolated coarse data) + collide + FillBoundary + Stream,
+ * `ratio` fine steps per coarse step, then average_down of the populations. */
+enum { LBX_COUPLING_ROHDE = 0, LBX_COUPLING_SUBCYCLE = 1 };
+int lbx_sim_set_coupling(lbx_sim *sim, int coupling);
 
 /* SetInitialDensity / SetInitialVelocity (:141-144); n == 1 selects the scalar overloads */
 int lbx_sim_set_initial_density(lbx_sim *sim, const double *rho, size_t n);

@@ -20,6 +20,9 @@ DISTFN, DENSITY, VELOCITY, DISTFN_NEXT, FINE_MASK = range(5)
 TAG_CLEAR, TAG_BUF, TAG_SET = 0, 1, 2
 
 
+ROHDE, SUBCYCLE = 0, 1      # AmrSim::Coupling (include/lambrex_c.h)
+
+
 class LambrexError(RuntimeError):
     pass
 
@@ -33,7 +36,7 @@ SYMBOLS = {
     "lbx_sim_create": (_i, [_i, _i, _i, _i, _ip, _d, _d, ctypes.POINTER(_vp)]),
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
-    "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]),
+    "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]), "lbx_sim_set_coupling": (_i, [_vp, _i]),
     "lbx_sim_global_init_parallel": (_i, [_i, _i, _vp, _vp]), "lbx_sim_set_parallel_view": (_i, [_i, _i]),
     "lbx_sim_owner": (_i, [_vp, _i, _i, ctypes.POINTER(_i)]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
@@ -177,6 +180,11 @@ class AmrSim:
 
     def SetRohdeFusion(self, on):
         _check(lib().lbx_sim_set_rohde_fusion(self._h, int(on)))
+
+    def SetCoupling(self, coupling):
+        """ROHDE (default, the reference's live path) or SUBCYCLE (conventional subcycling with
+        time-interpolated FillPatch and average_down)."""
+        _check(lib().lbx_sim_set_coupling(self._h, int(coupling)))
 
     def _set(self, fn, v):
         a = np.ascontiguousarray(np.atleast_1d(np.asarray(v, dtype=np.float64)).reshape(-1))

@@ -1,6 +1,7 @@
 // AmrSim on the GPU: host control flow of the reference's time stepping
 // (/root/reference/src/AmrSim.cpp), every field operation a kernel launch through
 // include/lbx.h.  Reference lines are cited per member.
+#include <cmath>
 #include "AmrSim.h"
 
 #include <iostream>
@@ -216,9 +217,16 @@ void AmrSim::CollideLevel(int const level) {
   const double omega_b = 1.0 / (tau_b.at(level) + 0.5);
   MultiFab& f_pc = levels.at(level).next.get<DistFn>();
   const MultiFab& f_now = levels.at(level).now.get<DistFn>();
-  if (level == 0 && f_pc.boxArray() == f_now.boxArray() && f_pc.layout() == f_now.layout()) {
+  const bool same_boxes = f_pc.boxArray() == f_now.boxArray() && f_pc.layout() == f_now.layout();
+  if (level == 0 && same_boxes) {
     // FillPatch's valid-cell copy fused into the collision (next <- collide(now)); its ghost
     // fill is dead work here because the FillBoundary below rewrites every ghost cell
+    lbx_check(lbx_mf_collide2(f_now.mf(), f_pc.mf(), omega_s, omega_b, nullptr, FINE_VAL), "CollideLevel");
+    f_pc.touch();
+  } else if (same_boxes && !f_now.isFlat()) {
+    // finer level: FillPatch writes the ghost cells only (the coarse-fine ones survive the
+    // FillBoundary below), the valid-cell copy is again fused into the collision
+    FillPatchImpl(level, f_pc, true);
     lbx_check(lbx_mf_collide2(f_now.mf(), f_pc.mf(), omega_s, omega_b, nullptr, FINE_VAL), "CollideLevel");
     f_pc.touch();
   } else {
@@ -296,8 +304,50 @@ void AmrSim::FillPatchImpl(int const level, MultiFab& dest, bool ghosts_only, co
   if (!level) {
     amrex::FillPatchSingleLevel(dest, levels[level].now.get<DistFn>(), geom[level], ghosts_only, push);
   } else {
-    amrex::FillPatchTwoLevels(dest, levels[level - 1].now.get<DistFn>(), levels[level].now.get<DistFn>(), geom[level - 1],
-                              geom[level], refRatio(level - 1), ghosts_only, push);
+    amrex::FillPatchTwoLevels(dest, CoarseStateAt(level - 1, levels[level].time.current), levels[level].now.get<DistFn>(),
+                              geom[level - 1], geom[level], refRatio(level - 1), ghosts_only, push);
+  }
+}
+
+// The reference hands FillPatchTwoLevels ONE coarse state, NOW, whatever its time (src/AmrSim.cpp:373-389).
+// The conventional driver advances the coarse level first, so at fine time t the coarse level holds
+// two states -- NOW at t1 and, in NEXT since UpdateNow's swap, the old one at t0 = t1 - dt -- and
+// FillPatchTwoLevels interpolates between them [AMReX: state 0 or 1 when t is within 1e-3 dt of its
+// time, else LinComb((t1-t)/(t1-t0), old, (t-t0)/(t1-t0), new)].
+const MultiFab& AmrSim::CoarseStateAt(int const coarse_level, double const t) {
+  auto& crse = levels.at(coarse_level);
+  const MultiFab& f_new = crse.now.get<DistFn>();
+  if (coupling != Coupling::SUBCYCLE) return f_new;
+  const double t1 = crse.time.current, dt = crse.time.delta, t0 = t1 - dt, eps = 1e-3 * dt;
+  if (std::abs(t - t1) < eps || crse.time.step == 0) return f_new;
+  const MultiFab& f_old = crse.next.get<DistFn>();
+  if (f_old.empty() || f_old.boxArray() != f_new.boxArray() || f_old.layout() != f_new.layout())
+    amrex::Abort("CoarseStateAt: the coarse level's old state is not available");
+  if (std::abs(t - t0) < eps) return f_old;
+  if (t < t0 - eps || t > t1 + eps) amrex::Abort("CoarseStateAt: fine time outside the coarse step");
+  if (coarse_interp.size() < levels.size()) coarse_interp.resize(levels.size());
+  MultiFab& tmp = coarse_interp[coarse_level];
+  if (tmp.empty() || tmp.boxArray() != f_new.boxArray() || tmp.layout() != f_new.layout())
+    tmp = field_traits<DistFn>::MakeLevelData(f_new.boxArray(), f_new.DistributionMap(), f_new.layout());
+  amrex::LinComb(tmp, (t1 - t) / (t1 - t0), f_old, (t - t0) / (t1 - t0), f_new);
+  return tmp;
+}
+
+// amrex::average_down of the populations: coarse NOW valid cells under fine valid cells <- mean of
+// the ratio^3 fine NOW cells.
+void AmrSim::AverageDown(int const coarse_level) {
+  amrex::average_down(levels.at(coarse_level + 1).now.get<DistFn>(), levels.at(coarse_level).now.get<DistFn>(), 0, NMODES,
+                      refRatio(coarse_level));
+}
+
+// Coupling::SUBCYCLE.  Unlike the reference's dead SubCycle (above), an intermediate level takes
+// `ratio` steps per step of its parent, and each group of fine steps ends with an average_down.
+void AmrSim::SubCycleAdvance(int const level) {
+  IterateLevel(level);
+  if (level < finest_level) {
+    const int r = refRatio(level)[0];
+    for (int iter = 0; iter < r; ++iter) SubCycleAdvance(level + 1);
+    AverageDown(level);
   }
 }
 
@@ -500,6 +550,10 @@ void AmrSim::Iterate(int const nsteps) {
     for (int t = 0; t < nsteps; ++t) IterateLevel(0);
   } else {
     for (int l = 0; l <= finest_level; ++l) SetLevelLayout(l, Layout::BOXES);
+    if (coupling == Coupling::SUBCYCLE) {
+      for (int t = 0; t < nsteps; ++t) SubCycleAdvance(0);
+      return;
+    }
     for (int t = 0; t < nsteps; ++t) {
       defer_boundaries = (t + 1 < nsteps);
       RohdeCycle(0);

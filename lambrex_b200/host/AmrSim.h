@@ -74,6 +74,15 @@ class AmrSim : public amrex::AmrCore {
   // false: run the Rohde cycle as the reference's literal sequence of passes (collide, Stream and
   // ZeroInvalidComponents as separate launches).  Default true: one fused pass per collide+Stream.
   void SetRohdeFusion(bool on) { rohde_fused = on; }
+  // How Iterate couples the levels of a refined hierarchy.
+  //   ROHDE    (default): the reference's live path, RohdeCycle (src/AmrSim.cpp:430-469), bug for bug.
+  //   SUBCYCLE : the conventional AMR driver the reference sketches in its dead SubCycle (:335-344):
+  //              per level FillPatch (coarse ghost data interpolated in TIME between the coarse
+  //              level's old and new states, piecewise constant in space) + collide + FillBoundary +
+  //              Stream, `ratio` fine steps per coarse step, then average_down of the populations.
+  enum class Coupling { ROHDE = 0, SUBCYCLE = 1 };
+  void SetCoupling(Coupling c) { coupling = c; }
+  Coupling GetCoupling() const { return coupling; }
 
  protected:
   const int NX, NY, NZ, NUMEL, COORD_SYS;
@@ -109,6 +118,10 @@ class AmrSim : public amrex::AmrCore {
   void CollideAndStream(int const level);
   void IterateLevel(int const level);
   void SubCycle(int const base_level, int const num_steps);
+  // conventional subcycling (Coupling::SUBCYCLE): one step of `level`, then ratio x the finer
+  // levels, then AverageDown(level)
+  void SubCycleAdvance(int const level);
+  void AverageDown(int const coarse_level);
 
   // set-up
   void InitDensity(int const level);
@@ -153,6 +166,11 @@ class AmrSim : public amrex::AmrCore {
   void RohdeCycleFused(int const coarse_level);
   void CollideStreamFused(int const level, bool masked, bool zero_invalid, bool from_fillpatch);
   bool defer_boundaries = false;
+  Coupling coupling = Coupling::ROHDE;
+  // the coarse populations FillPatchTwoLevels reads when filling `fine_level` at time t: NOW in the
+  // reference's coupling; under SUBCYCLE the coarse state at t (old, new, or their LinComb)
+  const amrex::MultiFab& CoarseStateAt(int const coarse_level, double const t);
+  std::vector<amrex::MultiFab> coarse_interp;    // LinComb scratch per coarse level (SUBCYCLE)
   void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp);
   const double* density_view = nullptr;
   const double* velocity_view = nullptr;

@@ -96,6 +96,13 @@ int lbx_sim_set_uniform_fast_path(lbx_sim* sim, int on) { return guarded([&] { s
 
 int lbx_sim_set_rohde_fusion(lbx_sim* sim, int on) { return guarded([&] { sim->s.SetRohdeFusion(on != 0); }); }
 
+int lbx_sim_set_coupling(lbx_sim* sim, int coupling) {
+  return guarded([&] {
+    if (coupling != LBX_COUPLING_ROHDE && coupling != LBX_COUPLING_SUBCYCLE) amrex::Abort("unknown coupling");
+    sim->s.SetCoupling(coupling == LBX_COUPLING_SUBCYCLE ? AmrSim::Coupling::SUBCYCLE : AmrSim::Coupling::ROHDE);
+  });
+}
+
 int lbx_sim_set_initial_density(lbx_sim* sim, const double* rho, size_t n) {
   return guarded([&] {
     if (n == 1) sim->s.SetInitialDensity(rho[0]);

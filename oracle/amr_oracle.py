@@ -289,6 +289,29 @@ def sum_fine_to_coarse(fine, crse, cperiod, ratio=REF_RATIO):
     parallel_copy(crse, tmp, tmp.ng, 0, cperiod, add=True)
 
 
+def average_down(fine, crse, ratio=REF_RATIO):
+    """amrex::average_down [AMReX, unverified]: every coarse VALID cell under fine VALID cells <- mean
+    of its ratio^3 fine cells (amrex_avgdown order: iref fastest), overwriting; no ghost cells, no
+    periodic images.  Used by the conventional subcycling driver, not by the
+    reference's live path."""
+    for i, fb in enumerate(fine.boxes):
+        cb = coarsen(fb, ratio)
+        assert refine(cb, ratio) == fb, "fine box not aligned to the coarse grid"
+        f = fine.valid(i)
+        acc = np.zeros((fine.ncomp,) + tuple(s // ratio for s in f.shape[1:]))
+        for kr in range(ratio):
+            for jr in range(ratio):
+                for ir in range(ratio):
+                    acc = acc + f[:, kr::ratio, jr::ratio, ir::ratio]
+        acc = acc * (1.0 / ratio ** 3)
+        for k, kb in enumerate(crse.boxes):
+            r = isect(cb, kb)
+            if r is None:
+                continue
+            sl = tuple(slice(r[0][d] - cb[0][d], r[1][d] - cb[0][d] + 1) for d in (2, 1, 0))
+            crse.view(k, r)[...] = acc[(slice(None),) + sl]
+
+
 def make_fine_mask(cmf_boxes, ng, fba, ratio=REF_RATIO):
     """amrex::makeFineMask(cmf, fba, ratio, crse, fine) [AMReX, unverified]: int mask on the coarse
     boxes (with cmf's ghosts), FINE_VAL on coarsen(fba) n grown fab box, no periodic images."""
@@ -399,6 +422,7 @@ class AmrSimOracle:
         self.grids = [[] for _ in range(max_level + 1)]
         self.co = coracle or lo.COracle()
         self.initial_density = self.initial_velocity = None
+        self.coupling = "rohde"      # or "subcycle": conventional driver, see subcycle_advance
 
     # -- geometry
     def domain(self, level):
@@ -500,8 +524,40 @@ class AmrSimOracle:
         if level == 0:
             fillpatch_single(dest, self.levels[0].now_f, self.period(0))
         else:
-            fillpatch_two(dest, self.levels[level - 1].now_f, self.levels[level].now_f,
-                          self.period(level - 1), self.period(level))
+            fillpatch_two(dest, self.coarse_state_at(level - 1, self.levels[level].time),
+                          self.levels[level].now_f, self.period(level - 1), self.period(level))
+
+    def coarse_state_at(self, clev, t):
+        """The coarse populations FillPatchTwoLevels interpolates from.  Reference coupling: NOW,
+        whatever its time (src/AmrSim.cpp:373-389 passes one state).  "subcycle": the coarse level
+        has already advanced, NOW is at t1 and NEXT holds the old state at t0 = t1 - dt (UpdateNow
+        swapped them): state 0 / 1 when t is within 1e-3 dt of its time, else the linear
+        combination (t1-t)/(t1-t0) old + (t-t0)/(t1-t0) new [AMReX FillPatchTwoLevels, unverified]."""
+        Lc = self.levels[clev]
+        if self.coupling != "subcycle":
+            return Lc.now_f
+        t1, dt = Lc.time, Lc.delta
+        t0, eps = t1 - dt, 1e-3 * dt
+        if abs(t - t1) < eps or Lc.step == 0:
+            return Lc.now_f
+        assert Lc.next_f.boxes == Lc.now_f.boxes
+        if abs(t - t0) < eps:
+            return Lc.next_f
+        assert t0 - eps <= t <= t1 + eps
+        a, b = (t1 - t) / (t1 - t0), (t - t0) / (t1 - t0)
+        tmp = MultiFab(Lc.now_f.boxes, NV, HALO)
+        for i in range(len(tmp.boxes)):
+            tmp.valid(i)[...] = a * Lc.next_f.valid(i) + b * Lc.now_f.valid(i)
+        return tmp
+
+    def subcycle_advance(self, level):
+        """Conventional subcycling (the corrected form of the reference's dead SubCycle,
+        src/AmrSim.cpp:335-344): one step of `level`, `ratio` x the finer levels, average_down."""
+        self.iterate_level(level)
+        if level < self.finest_level:
+            for _ in range(REF_RATIO):
+                self.subcycle_advance(level + 1)
+            average_down(self.levels[level + 1].now_f, self.levels[level].now_f)
 
     def update_boundaries(self, level):
         """src/AmrSim.cpp:19-23: FillBoundary on NEXT."""
@@ -620,6 +676,8 @@ class AmrSimOracle:
         for _ in range(nsteps):
             if self.finest_level == 0:
                 self.iterate_level(0)
+            elif self.coupling == "subcycle":
+                self.subcycle_advance(0)
             else:
                 self.rohde_cycle(0)
 

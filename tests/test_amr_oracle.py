@@ -129,3 +129,64 @@ def test_two_level_pulse_runs_and_clocks_advance(coracle):
     assert (sim.levels[0].time, sim.levels[0].step) == (3.0, 3)
     assert (sim.levels[1].time, sim.levels[1].step) == (3.0, 6)
     assert np.isfinite(sim.gather_valid(0, "f")).all()
+
+
+# ------------------------------------------------------------------ conventional subcycling
+def test_average_down_inverts_piecewise_constant_interpolation(coracle):
+    rng = np.random.default_rng(5)
+    cboxes = [((0, 0, 0), (7, 7, 3)), ((0, 0, 4), (7, 7, 7))]
+    crse = ao.MultiFab(cboxes, ao.NV, ao.HALO)
+    for i in range(len(cboxes)):
+        crse.valid(i)[...] = rng.random(crse.valid(i).shape)
+    fboxes = [((4, 4, 4), (11, 11, 11)), ((4, 4, 2), (11, 11, 3))]
+    fine = ao.MultiFab(fboxes, ao.NV, ao.HALO)
+    ao.pc_interp_fill(fine, crse, (8, 8, 8))
+    out = ao.MultiFab(cboxes, ao.NV, ao.HALO, fill=-7.0)
+    ao.average_down(fine, out)
+    covered = 0
+    for i, b in enumerate(cboxes):
+        for fb in fboxes:
+            r = ao.isect(ao.coarsen(fb, 2), b)
+            if r is not None:
+                # sequential sum of 8 equal values rounds at 3x, 5x, 6x(exact), 7x: a few ulp
+                assert np.max(np.abs(out.view(i, r) - crse.view(i, r))) <= 4e-16
+                covered += ao.numpts(r)
+    assert covered == (8 * 8 * 8 + 8 * 8 * 2) // 8
+    assert sum(int((out.valid(i)[0] != -7.0).sum()) for i in range(2)) == covered     # nothing else written
+
+
+def test_subcycle_uniform_state_is_a_fixed_point_and_clocks(coracle):
+    sim = ao.AmrSimOracle(48, 24, 12, 1, 0.3, 0.3, coracle=coracle)
+    sim.set_initial_density(0.8)
+    sim.set_initial_velocity(0.0)      # at rest the initial equilibrium is a fixed point of the collision
+    sim.init_from_scratch(0.0)
+    sim.coupling = "subcycle"
+    sim.set_static_refinement(0, (12, 6, 3), (35, 17, 8))
+    assert sim.finest_level == 1
+    ref = sim.levels[1].now_f.valid(0).copy()
+    sim.iterate(2)
+    assert (sim.levels[0].time, sim.levels[0].step) == (2.0, 2)
+    assert (sim.levels[1].time, sim.levels[1].step) == (2.0, 4)
+    for lev in (0, 1):
+        L = sim.levels[lev]
+        for i in range(len(L.boxes)):
+            assert np.max(np.abs(L.now_f.valid(i) - ref[:, :1, :1, :1])) < 1e-15
+
+
+def test_subcycle_time_interpolation_of_coarse_ghost_data(coracle):
+    """coarse_state_at: old state at the first fine substep, the half-half LinComb at the second."""
+    nx, ny, nz = 16, 8, 8
+    sim = ao.AmrSimOracle(nx, ny, nz, 1, 0.4, 0.4, coracle=coracle)
+    sim.coupling = "subcycle"
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    sim.set_initial_density(rho)
+    sim.set_initial_velocity(u)
+    sim.init_from_scratch(0.0)
+    sim.set_static_refinement(0, (4, 2, 2), (11, 5, 5))
+    sim.iterate_level(0)
+    L0 = sim.levels[0]
+    assert sim.coarse_state_at(0, 0.0) is L0.next_f and sim.coarse_state_at(0, 1.0) is L0.now_f
+    mid = sim.coarse_state_at(0, 0.5)
+    assert np.array_equal(mid.valid(0), 0.5 * L0.next_f.valid(0) + 0.5 * L0.now_f.valid(0))
+    sim.coupling = "rohde"
+    assert sim.coarse_state_at(0, 0.5) is L0.now_f          # the reference: NOW, whatever its time

@@ -353,3 +353,62 @@ def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level):
             assert sims[0].GetTime(lev) == sims[1].GetTime(lev) and sims[0].GetTimeStep(lev) == sims[1].GetTimeStep(lev)
     for sim in sims:
         sim.close()
+
+
+# ------------------------------------------------------------------ conventional subcycling
+@pytest.mark.parametrize("max_level", [1, 2])
+def test_subcycle_coupling_matches_oracle(coracle, max_level):
+    """Coupling SUBCYCLE: per-level FillPatch with TIME-interpolated coarse data, collide,
+    FillBoundary, Stream, `ratio` fine steps per coarse step, average_down -- every valid cell of
+    every level after each coarse step, and the clocks (level l takes 2^l steps)."""
+    nx, ny, nz = 16, 16, 32
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    rho = rho * workloads.pulse_density(nx, ny, nz)
+    # tau = 0.5 is the fixed point of the reference's tau ladder (SURVEY B-7); 0.3 gives tau_1 = 0.1 but
+    # tau_2 = -0.3 (omega = 5: rounding differences are amplified beyond any tolerance)
+    sim, o = make_pair(nx, ny, nz, max_level, 0.3 if max_level == 1 else 0.5, coracle, rho=rho, u=u)
+    sim.SetCoupling(amrsim.SUBCYCLE)
+    o.coupling = "subcycle"
+    for setf in (sim.SetStaticRefinement, o.set_static_refinement):
+        setf(0, (4, 4, 8), (11, 11, 23))
+        if max_level == 2:
+            setf(1, (12, 12, 24), (19, 19, 39))
+    assert sim.finestLevel() == max_level == o.finest_level
+    levels = tuple(range(max_level + 1))
+    for step in range(3):
+        sim.Iterate(1)
+        o.iterate(1)
+        compare_levels(sim, o, levels)
+    for lev in levels:
+        assert sim.GetTimeStep(lev) == 3 * 2 ** lev and sim.GetTime(lev) == 3.0
+    # regrid in the middle of a run (levels are synchronised between Iterate calls), then on
+    for setf in (sim.SetStaticRefinement, o.set_static_refinement):
+        setf(0, (5, 4, 6), (12, 11, 21))
+    assert sim.boxArray(1) == o.grids[1]
+    sim.Iterate(2)
+    o.iterate(2)
+    compare_levels(sim, o, levels)
+    sim.close()
+
+
+def test_subcycle_coupling_is_stable_and_close_to_single_level(coracle):
+    """The property the reference's ml_pulse test is after (tests/catch2RegressionTests.cpp:95-196):
+    a refined run stays close to the single-level solution.  The bug-compatible Rohde cycle cannot
+    (SURVEY B-1: mass is double counted and the run diverges); conventional subcycling does."""
+    nx, ny, nz = 16, 16, 32
+    rho0 = workloads.pulse_density(nx, ny, nz)
+    out = []
+    for max_level in (0, 1):
+        sim = AmrSim(nx, ny, nz, max_level, PER, 0.5, 0.5)
+        sim.SetCoupling(amrsim.SUBCYCLE)
+        sim.SetInitialDensity(rho0)
+        sim.SetInitialVelocity(0.0)
+        sim.InitFromScratch(0.0)
+        if max_level:
+            sim.SetStaticRefinement(0, (4, 4, 8), (11, 11, 23))
+        sim.Iterate(20)
+        sim.CalcHydroVars(0)
+        out.append(sim.GetDensityField(0))
+        sim.close()
+    assert abs(out[1].mean() - 1.0) < 1e-4
+    assert np.max(np.abs(out[1] - out[0])) < 0.5 * (rho0.max() - rho0.min())
