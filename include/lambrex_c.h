@@ -47,6 +47,14 @@ int lbx_sim_set_rohde_fusion(lbx_sim *sim, int on);
  * `ratio` fine steps per coarse step, then average_down of the populations. */
 enum { LBX_COUPLING_ROHDE = 0, LBX_COUPLING_SUBCYCLE = 1 };
 int lbx_sim_set_coupling(lbx_sim *sim, int coupling);
+/* addition: dynamic refinement.  Gradient criterion: ErrorEst also tags valid cells of
+ * `level` where the central-difference |grad rho| > threshold (device kernel); set/unset regrid at
+ * once like Set/UnsetStaticRefinement.  Regrid interval n > 0: Iterate calls regrid(0, t) after every
+ * n-th coarse step (0, the default and the reference's behaviour: only on request). */
+int lbx_sim_set_gradient_refinement(lbx_sim *sim, int level, double threshold);
+int lbx_sim_unset_gradient_refinement(lbx_sim *sim, int level);
+int lbx_sim_set_regrid_interval(lbx_sim *sim, int n);
+int lbx_sim_num_regrids(const lbx_sim *sim);
 
 /* SetInitialDensity / SetInitialVelocity (:141-144); n == 1 selects the scalar overloads */
 int lbx_sim_set_initial_density(lbx_sim *sim, const double *rho, size_t n);

@@ -218,6 +218,10 @@ int lbx_mf_average_down(const lbx_mf *fine, lbx_mf *crse, int ratio);
  * reference's DistFnFillPatch :359-391 passes one state and so never interpolates).  Products and sum
  * are rounded separately.  The three sets hold the same boxes and component count; dst may alias. */
 int lbx_mf_lincomb(lbx_mf *dst, double a, const lbx_mf *x, double b, const lbx_mf *y);
+/* Gradient refinement criterion, the device side of an ErrorEst (:633-663 tags a static box only):
+ * tags(x) = set_val on valid cells where sum_d (rho(x+e_d) - rho(x-e_d))^2 / 4 > threshold^2; other
+ * cells keep their value.  rho: 1 component, >= 1 filled ghost cell; tags: int32, same boxes. */
+int lbx_mf_tag_gradient(const lbx_mf *rho, double threshold, lbx_mf *tags, int set_val);
 /* ZeroInvalidComponents :604-617: in the ghost shell, f_m = 0 unless pos - 2 c_m is valid */
 int lbx_mf_zero_invalid(lbx_mf *f);
 /* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */

@@ -37,6 +37,8 @@ SYMBOLS = {
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
     "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]), "lbx_sim_set_coupling": (_i, [_vp, _i]),
+    "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
+    "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
     "lbx_sim_global_init_parallel": (_i, [_i, _i, _vp, _vp]), "lbx_sim_set_parallel_view": (_i, [_i, _i]),
     "lbx_sim_owner": (_i, [_vp, _i, _i, ctypes.POINTER(_i)]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
@@ -185,6 +187,18 @@ class AmrSim:
         """ROHDE (default, the reference's live path) or SUBCYCLE (conventional subcycling with
         time-interpolated FillPatch and average_down)."""
         _check(lib().lbx_sim_set_coupling(self._h, int(coupling)))
+
+    def SetGradientRefinement(self, level, threshold):
+        _check(lib().lbx_sim_set_gradient_refinement(self._h, level, float(threshold)))
+
+    def UnsetGradientRefinement(self, level):
+        _check(lib().lbx_sim_unset_gradient_refinement(self._h, level))
+
+    def SetRegridInterval(self, n):
+        _check(lib().lbx_sim_set_regrid_interval(self._h, int(n)))
+
+    def NumRegrids(self):
+        return int(lib().lbx_sim_num_regrids(self._h))
 
     def _set(self, fn, v):
         a = np.ascontiguousarray(np.atleast_1d(np.asarray(v, dtype=np.float64)).reshape(-1))

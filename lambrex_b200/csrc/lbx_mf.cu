@@ -332,6 +332,17 @@ int lbx_mf_lincomb(lbx_mf* dst, double a, const lbx_mf* x, double b, const lbx_m
   return lbx::after_launch("lbx_mf_lincomb");
 }
 
+int lbx_mf_tag_gradient(const lbx_mf* rho, double threshold, lbx_mf* tags, int set_val) {
+  LBX_NEED_INIT();
+  if (need(rho, 1, LBX_F64, 1, "lbx_mf_tag_gradient rho") || need(tags, 1, LBX_I32, 0, "lbx_mf_tag_gradient tags") ||
+      same_boxes(rho, tags, "lbx_mf_tag_gradient"))
+    return 1;
+  if (!(threshold >= 0.0)) return fail("lbx_mf_tag_gradient: threshold must be >= 0");
+  lbx::k_mf_tag_gradient<<<lbx::mf_grid(tags->max_valid, tags->nfabs), lbx::MFT, 0, g.cur>>>(rho->table, tags->table, tags->nfabs,
+                                                                                            threshold * threshold, set_val);
+  return lbx::after_launch("lbx_mf_tag_gradient");
+}
+
 int lbx_mf_zero_invalid(lbx_mf* f) {
   LBX_NEED_INIT();
   if (need(f, LBX_NV, LBX_F64, 1, "lbx_mf_zero_invalid")) return 1;

@@ -154,6 +154,27 @@ __global__ void __launch_bounds__(MFT) k_mf_lincomb(const DFabT* __restrict__ dt
   }
 }
 
+// Refinement criterion on the device (replaces the host loop of ErrorEst, src/AmrSim.cpp:633-663, for
+// the gradient criterion of SURVEY.md 8f-2): a valid cell is tagged when the squared central
+// difference of the density, (|rho(x+e_d) - rho(x-e_d)|^2 summed over d) / 4, exceeds thr2.  rho has at
+// least one FILLED ghost cell.  Tagged cells get `set_val`; others are left alone.  Every
+// operation is rounded separately, in a fixed order: the tag set is bit-reproducible on the CPU.
+__global__ void __launch_bounds__(MFT) k_mf_tag_gradient(const DFabT* __restrict__ rt, const DFabT* __restrict__ tt, int nfabs,
+                                                         double thr2, int set_val) {
+  const int q = mf_fab_index();
+  if (q >= nfabs) return;
+  const DFabT T = tt[q];
+  if (!T.local) return;
+  int i, j, k;
+  if (!mf_cell(T, 0, i, j, k)) return;
+  const DFabT R = rt[q];
+  const double* rp = static_cast<const double*>(R.p) + mf_off(R, i, j, k);
+  const long long sy = R.n[0], sz = (long long)R.n[0] * R.n[1];
+  const double gx = __dsub_rn(rp[1], rp[-1]), gy = __dsub_rn(rp[sy], rp[-sy]), gz = __dsub_rn(rp[sz], rp[-sz]);
+  const double g2 = __dmul_rn(0.25, __dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+  if (g2 > thr2) static_cast<int*>(T.p)[mf_off(T, i, j, k)] = set_val;
+}
+
 // User arrays of the reference's API are C-ordered, i slowest, component fastest
 // (CLindex, include/AmrSim.h:79-83): user[(((i-d0)*NY + (j-d1))*NZ + (k-d2))*ncomp + n].
 // TO_FAB: valid cells of every fab <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);

@@ -49,6 +49,7 @@ AmrSim::AmrSim(int const nx, int const ny, int const nz, int const max_ref_level
   tau_b.resize(num_levels);
   mass.resize(num_levels);
   static_tags.resize(num_levels);
+  gradient_threshold.assign(num_levels, 0.0);
   fine_masks.resize(num_levels);
   for (int d = 0; d < NDIMS; ++d)
     if (!PERIODICITY[d]) amrex::Abort("Currently only periodic boundary conditions allowed.");
@@ -543,23 +544,35 @@ void AmrSim::UpdateDistribution(int const level) {
   std::swap(lvl.now.get<DistFn>(), lvl.next.get<DistFn>());
 }
 
-// src/AmrSim.cpp:981-993
+// src/AmrSim.cpp:981-993 (+ the regrid_int hook)
 void AmrSim::Iterate(int const nsteps) {
-  if (!finest_level) {
-    SetLevelLayout(0, PreferredLayout(0));
-    for (int t = 0; t < nsteps; ++t) IterateLevel(0);
-  } else {
-    for (int l = 0; l <= finest_level; ++l) SetLevelLayout(l, Layout::BOXES);
-    if (coupling == Coupling::SUBCYCLE) {
-      for (int t = 0; t < nsteps; ++t) SubCycleAdvance(0);
-      return;
+  for (int t = 0; t < nsteps; ++t) {
+    if (!finest_level) {
+      SetLevelLayout(0, PreferredLayout(0));
+      IterateLevel(0);
+    } else {
+      for (int l = 0; l <= finest_level; ++l) SetLevelLayout(l, Layout::BOXES);
+      if (coupling == Coupling::SUBCYCLE) {
+        SubCycleAdvance(0);
+      } else {
+        defer_boundaries = (t + 1 < nsteps);
+        RohdeCycle(0);
+        defer_boundaries = false;
+      }
     }
-    for (int t = 0; t < nsteps; ++t) {
-      defer_boundaries = (t + 1 < nsteps);
-      RohdeCycle(0);
-    }
-    defer_boundaries = false;
+    RegridIfDue();
   }
+}
+
+// AMReX's regrid_int: after every regrid_int-th coarse step, regrid from level 0 up (tags from
+// ErrorEst: static boxes and/or the gradient criterion); the fine masks follow the new grids.
+void AmrSim::RegridIfDue() {
+  if (regrid_int <= 0 || max_level == 0) return;
+  if (++steps_since_regrid < regrid_int) return;
+  steps_since_regrid = 0;
+  ++num_regrids;
+  regrid(0, GetTime(0));
+  for (int l = 0; l < finest_level; ++l) MakeFineMask(l);
 }
 
 // ----------------------------------------------------------------------------- regrid hooks
@@ -571,6 +584,38 @@ void AmrSim::ErrorEst(int level, amrex::TagBoxArray& tba, double /*time*/, int /
     amrex::TagBox& tagfab = tba[mfi];
     tagfab.setVal(amrex::TagBox::CLEAR, box);
     for (const auto& hit : static_tags.at(level).intersections(box)) tagfab.setVal(amrex::TagBox::SET, hit.second);
+  }
+  if (gradient_threshold.at(level) > 0.0) GradientTags(level, tba);
+}
+
+// Gradient criterion: rho of the level's NOW with one ghost cell filled the way DistFnFillPatch fills
+// the populations (same level + periodic images, else piecewise constant from the coarse level),
+// one tagging launch, one device->host copy of the int tags.
+void AmrSim::GradientTags(int const level, amrex::TagBoxArray& tba) {
+  CalcHydroVars(level);
+  const MultiFab& rho = levels[level].now.get<Density>();
+  MultiFab rho_g(rho.boxArray(), rho.DistributionMap(), 1, 1);
+  if (level == 0) {
+    amrex::FillPatchSingleLevel(rho_g, rho, geom[0]);
+  } else {
+    CalcHydroVars(level - 1);
+    amrex::FillPatchTwoLevels(rho_g, levels[level - 1].now.get<Density>(), rho, geom[level - 1], geom[level],
+                              refRatio(level - 1));
+  }
+  amrex::iMultiFab tg(rho.boxArray(), rho.DistributionMap(), 1, 0);
+  tg.setVal(0);
+  lbx_check(lbx_mf_tag_gradient(rho_g.mf(), gradient_threshold[level], tg.mf(), 1), "ErrorEst (gradient)");
+  tg.touch();
+  const std::vector<int>& m = tg.hostMirror();
+  for (amrex::MFIter mfi(tg); mfi.isValid(); ++mfi) {
+    amrex::TagBox& tagfab = tba[mfi];
+    if (!tagfab.allocated()) continue;           // another rank's box: its owner tags it
+    const Box box = mfi.validbox();
+    const int* t = m.data() + tg.storageOffset(mfi.index());
+    for (int k = box.smallEnd(2); k <= box.bigEnd(2); ++k)
+      for (int j = box.smallEnd(1); j <= box.bigEnd(1); ++j)
+        for (int i = box.smallEnd(0); i <= box.bigEnd(0); ++i)
+          if (*t++) tagfab(IntVect(i, j, k)) = amrex::TagBox::SET;
   }
 }
 
@@ -645,6 +690,19 @@ void AmrSim::SetStaticRefinement(int const level, const std::array<int, NDIMS>& 
 // src/AmrSim.cpp:1011-1017
 void AmrSim::UnsetStaticRefinement(int const level) {
   static_tags.at(level).clear();
+  regrid(level, GetTime(level));
+  MakeFineMask(level);
+}
+
+void AmrSim::SetGradientRefinement(int const level, double const threshold) {
+  if (!(threshold > 0.0)) amrex::Abort("SetGradientRefinement: threshold must be positive");
+  gradient_threshold.at(level) = threshold;
+  regrid(level, GetTime(level));
+  MakeFineMask(level);
+}
+
+void AmrSim::UnsetGradientRefinement(int const level) {
+  gradient_threshold.at(level) = 0.0;
   regrid(level, GetTime(level));
   MakeFineMask(level);
 }

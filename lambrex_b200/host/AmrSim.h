@@ -80,6 +80,15 @@ class AmrSim : public amrex::AmrCore {
   //              per level FillPatch (coarse ghost data interpolated in TIME between the coarse
   //              level's old and new states, piecewise constant in space) + collide + FillBoundary +
   //              Stream, `ratio` fine steps per coarse step, then average_down of the populations.
+  // Dynamic refinement (the reference tags one static box per level, TagCell :413-417).
+  // SetGradientRefinement: ErrorEst also tags the valid cells of `level` where the central-difference
+  // density gradient |grad rho| exceeds `threshold` (evaluated on the device); like
+  // SetStaticRefinement it regrids at once.  SetRegridInterval(n > 0): Iterate calls regrid(0, t)
+  // after every n-th coarse step (AMReX's regrid_int); 0 = only on request (the reference).
+  void SetGradientRefinement(int const level, double const threshold);
+  void UnsetGradientRefinement(int const level);
+  void SetRegridInterval(int const n) { regrid_int = n; }
+  int NumRegrids() const { return num_regrids; }
   enum class Coupling { ROHDE = 0, SUBCYCLE = 1 };
   void SetCoupling(Coupling c) { coupling = c; }
   Coupling GetCoupling() const { return coupling; }
@@ -167,6 +176,10 @@ class AmrSim : public amrex::AmrCore {
   void CollideStreamFused(int const level, bool masked, bool zero_invalid, bool from_fillpatch);
   bool defer_boundaries = false;
   Coupling coupling = Coupling::ROHDE;
+  std::vector<double> gradient_threshold;        // per level; <= 0: criterion off
+  int regrid_int = 0, steps_since_regrid = 0, num_regrids = 0;
+  void GradientTags(int const level, amrex::TagBoxArray& tags);
+  void RegridIfDue();
   // the coarse populations FillPatchTwoLevels reads when filling `fine_level` at time t: NOW in the
   // reference's coupling; under SUBCYCLE the coarse state at t (old, new, or their LinComb)
   const amrex::MultiFab& CoarseStateAt(int const coarse_level, double const t);

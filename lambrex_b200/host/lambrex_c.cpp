@@ -96,6 +96,13 @@ int lbx_sim_set_uniform_fast_path(lbx_sim* sim, int on) { return guarded([&] { s
 
 int lbx_sim_set_rohde_fusion(lbx_sim* sim, int on) { return guarded([&] { sim->s.SetRohdeFusion(on != 0); }); }
 
+int lbx_sim_set_gradient_refinement(lbx_sim* sim, int level, double threshold) {
+  return guarded([&] { sim->s.SetGradientRefinement(level, threshold); });
+}
+int lbx_sim_unset_gradient_refinement(lbx_sim* sim, int level) { return guarded([&] { sim->s.UnsetGradientRefinement(level); }); }
+int lbx_sim_set_regrid_interval(lbx_sim* sim, int n) { return guarded([&] { sim->s.SetRegridInterval(n); }); }
+int lbx_sim_num_regrids(const lbx_sim* sim) { return sim->s.NumRegrids(); }
+
 int lbx_sim_set_coupling(lbx_sim* sim, int coupling) {
   return guarded([&] {
     if (coupling != LBX_COUPLING_ROHDE && coupling != LBX_COUPLING_SUBCYCLE) amrex::Abort("unknown coupling");

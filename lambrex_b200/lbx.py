@@ -114,6 +114,7 @@ SYMBOLS = {
     "lbx_mf_zero_invalid": (_i, [_vp]),
     "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
     "lbx_mf_lincomb": (_i, [_vp, _d, _vp, _d, _vp]),
+    "lbx_mf_tag_gradient": (_i, [_vp, _d, _vp, _i]),
     "lbx_mf_from_user": (_i, [_vp, _vp, _bp, _i]),
     "lbx_mf_to_user": (_i, [_vp, _vp, _bp, _i]),
     "lbx_fill_f64": (_i, [_vp, _sz, _d]),

@@ -423,6 +423,10 @@ class AmrSimOracle:
         self.co = coracle or lo.COracle()
         self.initial_density = self.initial_velocity = None
         self.coupling = "rohde"      # or "subcycle": conventional driver, see subcycle_advance
+        # dynamic refinement (not in the reference): gradient criterion per level
+        # and AMReX-style regrid interval in coarse steps
+        self.gradient_threshold = [0.0] * (max_level + 1)
+        self.regrid_int, self.steps_since_regrid, self.num_regrids = 0, 0, 0
 
     # -- geometry
     def domain(self, level):
@@ -680,6 +684,14 @@ class AmrSimOracle:
                 self.subcycle_advance(0)
             else:
                 self.rohde_cycle(0)
+            if self.regrid_int > 0 and self.max_level > 0:
+                self.steps_since_regrid += 1
+                if self.steps_since_regrid >= self.regrid_int:
+                    self.steps_since_regrid = 0
+                    self.num_regrids += 1
+                    self.regrid(0, self.levels[0].time)
+                    for l in range(self.finest_level):
+                        self.make_fine_mask(l)
 
     # -- tagging and regrid
     def error_est(self, level, tags):
@@ -695,6 +707,34 @@ class AmrSimOracle:
             if r is not None:
                 core[r[0][2] - b[0][2]:r[1][2] - b[0][2] + 1, r[0][1] - b[0][1]:r[1][1] - b[0][1] + 1,
                      r[0][0] - b[0][0]:r[1][0] - b[0][0] + 1] = TAG_SET
+        if self.gradient_threshold[level] > 0.0:
+            self._gradient_tags(level, tags)
+
+    def _gradient_tags(self, level, tags):
+        """Gradient criterion (addition): rho of NOW with one ghost cell, filled like DistFnFillPatch
+        fills populations (same level + periodic images, else PC from the coarse level); a valid cell
+        is SET when 0.25 * ((rho(x+ex)-rho(x-ex))^2 + (..y..)^2 + (..z..)^2) > threshold^2, every
+        operation rounded separately in this order."""
+        ng = tags["ng"]
+        L = self.levels[level]
+        self.calc_hydro_vars(level)
+        rho_g = MultiFab(L.now_rho.boxes, 1, 1)
+        if level == 0:
+            parallel_copy(rho_g, L.now_rho, 0, 1, self.period(0))
+        else:
+            self.calc_hydro_vars(level - 1)
+            pc_interp_fill(rho_g, self.levels[level - 1].now_rho, self.period(level - 1))
+            parallel_copy(rho_g, L.now_rho, 0, 1, self.period(level))
+        thr2 = self.gradient_threshold[level] * self.gradient_threshold[level]
+        for i in range(len(L.now_rho.boxes)):
+            r = rho_g.fabs[i][0]
+            gx = r[1:-1, 1:-1, 2:] - r[1:-1, 1:-1, :-2]
+            gy = r[1:-1, 2:, 1:-1] - r[1:-1, :-2, 1:-1]
+            gz = r[2:, 1:-1, 1:-1] - r[:-2, 1:-1, 1:-1]
+            g2 = 0.25 * ((gx * gx + gy * gy) + gz * gz)
+            t = tags["fabs"][i]
+            core = t[ng:t.shape[0] - ng, ng:t.shape[1] - ng, ng:t.shape[2] - ng]
+            core[g2 > thr2] = TAG_SET
 
     def _tag_points(self, levc, extra_boxes):
         """Tagged cells of level levc after ErrorEst, buffering, projection of finer grids and
@@ -834,6 +874,17 @@ class AmrSimOracle:
     def unset_static_refinement(self, level):
         """src/AmrSim.cpp:1011-1017."""
         self.static_tags[level] = None
+        self.regrid(level, self.levels[level].time)
+        self.make_fine_mask(level)
+
+    def set_gradient_refinement(self, level, threshold):
+        assert threshold > 0.0
+        self.gradient_threshold[level] = threshold
+        self.regrid(level, self.levels[level].time)
+        self.make_fine_mask(level)
+
+    def unset_gradient_refinement(self, level):
+        self.gradient_threshold[level] = 0.0
         self.regrid(level, self.levels[level].time)
         self.make_fine_mask(level)
 

@@ -190,3 +190,32 @@ def test_subcycle_time_interpolation_of_coarse_ghost_data(coracle):
     assert np.array_equal(mid.valid(0), 0.5 * L0.next_f.valid(0) + 0.5 * L0.now_f.valid(0))
     sim.coupling = "rohde"
     assert sim.coarse_state_at(0, 0.5) is L0.now_f          # the reference: NOW, whatever its time
+
+
+# ------------------------------------------------------------------ dynamic refinement
+def test_gradient_refinement_follows_the_pulse(coracle):
+    nx, ny, nz = 8, 8, 48
+    sim = ao.AmrSimOracle(nx, ny, nz, 1, 0.5, 0.5, max_grid_size=16, coracle=coracle)
+    sim.coupling = "subcycle"
+    sim.set_initial_density(workloads.pulse_density(nx, ny, nz))
+    sim.set_initial_velocity(0.0)
+    sim.init_from_scratch(0.0)
+    sim.set_gradient_refinement(0, 2e-4)
+    assert sim.finest_level == 1
+    # the planar pulse sits at k = nz/2 - 1: only planes next to it are tagged, over the whole x-y extent
+    zs = sorted({(b[0][2], b[1][2]) for b in sim.grids[1]})
+    assert zs == [(2 * (nz // 2 - 3), 2 * (nz // 2 + 1) + 1)]
+    assert sum(ao.numpts(b) for b in sim.grids[1]) == (2 * nx) * (2 * ny) * (zs[0][1] - zs[0][0] + 1)
+    sim.regrid_int = 4
+    sim.iterate(8)
+    assert sim.num_regrids == 2 and sim.finest_level == 1
+    z2 = sorted({(b[0][2], b[1][2]) for b in sim.grids[1]})
+    assert z2 != zs and min(z[0] for z in z2) < zs[0][0] and max(z[1] for z in z2) > zs[0][1]   # two pulses moving apart
+    sim.calc_hydro_vars(0)
+    assert abs(sim.gather_valid(0, "rho")[0].mean() - 1.0) < 1e-4
+    # threshold above every gradient: the fine level disappears at the next regrid
+    sim.gradient_threshold[0] = 1.0
+    sim.iterate(4)
+    assert sim.finest_level == 0 and sim.levels[1].now_f is None
+    sim.iterate(2)                               # and the run continues on one level
+    assert sim.levels[0].step == 14

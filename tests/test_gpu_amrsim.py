@@ -412,3 +412,55 @@ def test_subcycle_coupling_is_stable_and_close_to_single_level(coracle):
         sim.close()
     assert abs(out[1].mean() - 1.0) < 1e-4
     assert np.max(np.abs(out[1] - out[0])) < 0.5 * (rho0.max() - rho0.min())
+
+
+# ------------------------------------------------------------------ dynamic refinement
+def test_gradient_refinement_and_regrid_interval_match_oracle(coracle):
+    """Device-side gradient tagging (lbx_mf_tag_gradient) and AMReX-style regrid_int inside Iterate:
+    tag sets, box lists after every regrid and all populations agree with the oracle.  Literal
+    collision arithmetic: the densities, and hence the threshold comparisons, are bit-identical."""
+    from lambrex_b200 import lbx
+    lbx.set_option(lbx.OPT_COLLIDE_LITERAL, 1)
+    try:
+        nx, ny, nz = 16, 16, 48
+        sim = AmrSim(nx, ny, nz, 1, PER, 0.5, 0.5)
+        o = ao.AmrSimOracle(nx, ny, nz, 1, 0.5, 0.5, max_grid_size=16, coracle=coracle)
+        sim.SetMaxGridSize(16)
+        sim.SetCoupling(amrsim.SUBCYCLE)
+        o.coupling = "subcycle"
+        rho = workloads.pulse_density(nx, ny, nz)
+        for den, vel, init in ((sim.SetInitialDensity, sim.SetInitialVelocity, sim.InitFromScratch),
+                               (o.set_initial_density, o.set_initial_velocity, o.init_from_scratch)):
+            den(rho)
+            vel(0.0)
+            init(0.0)
+        thr = 2e-4
+        sim.SetGradientRefinement(0, thr)
+        o.set_gradient_refinement(0, thr)
+        assert sim.finestLevel() == 1 == o.finest_level and sim.boxArray(1) == o.grids[1]
+        # the tag set itself, cell by cell
+        ba = sim.boxArray(0)
+        tags = {"ng": 0, "fabs": [np.zeros(tuple(h - l + 1 for l, h in zip(*b))[::-1], dtype=np.uint8) for b in ba]}
+        o.error_est(0, tags)
+        got = sim.CallErrorEst(0, ba, amrsim.TAG_CLEAR)
+        assert sum(int((t == amrsim.TAG_SET).sum()) for t in got) > 0
+        for t, w in zip(got, tags["fabs"]):
+            assert np.array_equal(np.asarray(t).reshape(w.shape), w)
+        sim.SetRegridInterval(4)
+        o.regrid_int = 4
+        seen = set()
+        for chunk in range(3):
+            sim.Iterate(4)
+            o.iterate(4)
+            assert sim.NumRegrids() == o.num_regrids == chunk + 1
+            assert sim.finestLevel() == o.finest_level == 1
+            assert sim.boxArray(1) == o.grids[1]
+            seen.add(tuple(o.grids[1]))
+            compare_levels(sim, o, (0, 1))
+        assert len(seen) == 3                     # the refined region follows the two sound pulses
+        sim.UnsetGradientRefinement(0)
+        o.unset_gradient_refinement(0)
+        assert sim.finestLevel() == 0 == o.finest_level
+        sim.close()
+    finally:
+        lbx.set_option(lbx.OPT_COLLIDE_LITERAL, 0)
