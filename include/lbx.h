@@ -56,6 +56,10 @@ enum {
                                   non-FMA CPU build); 0 (default): fast structured form */
   LBX_OPT_SMEM_PAD = 2,        /* bytes of dynamic shared memory added to the fused kernels' launches to
                                   cap resident CTAs per SM (tuning knob; 0 = uncapped, max 49152) */
+  LBX_OPT_VALID_TILING = 3,    /* valid-cell tiles of lbx_mf_collide_stream*: 0 = a warp per box row,
+                                  1 = 256 consecutive cells of the box (every lane busy)            */
+  LBX_OPT_DEBUG_SKIP = 4,      /* PROFILING ONLY (results are wrong): bit 0 skips the valid-cell work of
+                                  lbx_mf_collide_stream*, bit 1 the ghost-cell work                  */
 };
 /* fused step schemes for lbx_collide_stream */
 enum {

@@ -470,30 +470,52 @@ struct CSPlan {                    // ghosts-only FillPatch plan of the level be
 constexpr int CSX = 32, CSY = 8;
 static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
 
-template <class C>
+// LINEAR (valid tiles): false = CSY rows of one z-plane per CTA, a warp per row (no per-thread
+// division, but lanes beyond the row end and rows beyond the box idle: a 26^3 box uses 66 % of
+// the lanes); true = MFT consecutive cells of the box's valid region in x-fastest order (two
+// integer divisions per thread, every lane busy; a warp's plane access is 1-3 row segments).
+// flags: bit 0 = zero_invalid; bits 8 / 9 (profiling only) skip the valid / ghost tiles' work.
+template <class C, bool LINEAR>
 __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
                                                            const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
                                                            const DFabT* __restrict__ gt, CSPlan plan, int nfabs,
                                                            int ytiles, int valid_tiles, double omega_s, double omega_b,
-                                                           int fine_val, int zero_invalid) {
+                                                           int fine_val, int flags) {
   __shared__ GDesc sd[PLAN_CHUNK];
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT D = dt[b];
   if (!D.local) return;                                   // a peer's box: its owner streams it
   const int tid = threadIdx.x;
+  const int zero_invalid = flags & 1;
   if ((int)blockIdx.x < valid_tiles) {
+    if (flags & 0x100) return;
     // ---- valid source cells: collide, push ---------------------------------------------------
-    const int ty = tid / CSX, tx = tid % CSX;
-    const int j = D.vlo[1] + ((int)blockIdx.x % ytiles) * CSY + ty, k = D.vlo[2] + (int)blockIdx.x / ytiles;
-    if (j > D.vhi[1] || k > D.vhi[2]) return;
+    int i0, j, k, istep;
+    if (LINEAR) {
+      const unsigned nx = D.vhi[0] - D.vlo[0] + 1, ny = D.vhi[1] - D.vlo[1] + 1, nz = D.vhi[2] - D.vlo[2] + 1;
+      unsigned t = blockIdx.x * MFT + tid;
+      if (t >= nx * ny * nz) return;
+      i0 = D.vlo[0] + (int)(t % nx);
+      t /= nx;
+      j = D.vlo[1] + (int)(t % ny);
+      k = D.vlo[2] + (int)(t / ny);
+      istep = 1 << 30;                                    // one cell per thread
+    } else {
+      const int ty = tid / CSX, tx = tid % CSX;
+      j = D.vlo[1] + ((int)blockIdx.x % ytiles) * CSY + ty;
+      k = D.vlo[2] + (int)blockIdx.x / ytiles;
+      if (j > D.vhi[1] || k > D.vhi[2]) return;
+      i0 = D.vlo[0] + tx;
+      istep = CSX;
+    }
     const int* mp = mt ? static_cast<const int*>(mt[b].p) : nullptr;   // mask: same boxes and ghosts, 1 comp
     const long long sc = mf_stride(D), dy = D.n[0], dz = (long long)D.n[0] * D.n[1];
     const long long row = mf_off(D, D.lo[0], j, k);                 // offset of x = lo[0] in this row
     double* drow = static_cast<double*>(D.p) + row;
     const double* srow = vbase + (static_cast<double*>(D.p) - dbase) + row;
     const bool rim_jk = j == D.vlo[1] || j == D.vhi[1] || k == D.vlo[2] || k == D.vhi[2];
-    for (int i = D.vlo[0] + tx; i <= D.vhi[0]; i += CSX) {
+    for (int i = i0; i <= D.vhi[0]; i += istep) {
       const int x = i - D.lo[0];
       double f[NV];
       if (mp && mp[row + x] == fine_val) {
@@ -517,6 +539,7 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
     }
     return;
   }
+  if (flags & 0x200) return;
   const unsigned gtile = blockIdx.x - valid_tiles;
   int i, j, k;
   if (!plan.dsts) {

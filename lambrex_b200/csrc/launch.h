@@ -7,6 +7,10 @@ namespace lbx {
 // dynamic shared memory added to the fused kernels' launches purely to cap resident CTAs/SM
 // (occupancy tuning knob, LBX_OPT_SMEM_PAD); 0 = no cap
 extern int g_smem_pad;
+// valid tiles of k_mf_collide_stream: 1 = MFT consecutive cells (default), 0 = a warp per row (LBX_OPT_VALID_TILING)
+extern int g_valid_linear;
+// profiling only (LBX_OPT_DEBUG_SKIP): bit 0 skips the valid tiles' work, bit 1 the ghost tiles' (results are wrong)
+extern int g_debug_skip;
 struct Launchers {
   void (*equilibrium)(cudaStream_t, DFab f, DFab rho, DFab u, DBox box);
   void (*moments)(cudaStream_t, DFab f, DFab rho, DFab u, DBox box);
@@ -18,8 +22,8 @@ struct Launchers {
   void (*mf_collide)(cudaStream_t, const DFabT* src, const DFabT* f, const DFabT* mask, int nfabs, long long max_cells, double ws,
                      double wb, int fine_val);
   void (*mf_collide_stream)(cudaStream_t, const double* vbase, double* dbase, const DFabT* dst, const DFabT* mask,
-                            const DFabT* gsrc, CSPlan plan, int nfabs, int max_ny, int max_nz, long long ghost_tiles, double ws,
-                            double wb, int fine_val, int zero_invalid);
+                            const DFabT* gsrc, CSPlan plan, int nfabs, int max_ny, int max_nz, long long max_valid,
+                            long long ghost_tiles, double ws, double wb, int fine_val, int zero_invalid);
   void (*mf_moments)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs, long long max_cells);
   void (*mf_equilibrium)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs,
                          long long max_cells);

@@ -599,7 +599,7 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   if (remote && lbx::par_barrier()) return 1;
   L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
                         mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
-                        dst->max_extent(2), ghost_tiles, omega_s, omega_b, fine_val, zero_invalid);
+                        dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val, zero_invalid);
   if (lbx::after_launch(what)) return 1;
   return remote ? lbx::par_barrier() : 0;
 }

@@ -321,10 +321,13 @@ def test_three_level_shear_matches_oracle(coracle):
     assert (sim.GetTime(2), sim.GetTimeStep(2)) == (o.levels[2].time, o.levels[2].step)
 
 
+@pytest.mark.parametrize("tiling", [0, 1])
 @pytest.mark.parametrize("max_level", [1, 2])
-def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level):
+def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level, tiling):
     """The fused collide+Stream(+ZeroInvalidComponents) passes reproduce the reference's literal
     sequence of passes bit for bit: every cell of NOW (ghost rings included) on every level."""
+    from lambrex_b200 import lbx
+    lbx.set_option(lbx.OPT_VALID_TILING, tiling)     # valid tiles: a warp per row / 256 consecutive cells
     nx, ny, nz = 16, 12, 20
     rho, u = workloads.shear_wave(nx, ny, nz)
     rho = rho * workloads.pulse_density(nx, ny, nz)
@@ -353,6 +356,7 @@ def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level):
             assert sims[0].GetTime(lev) == sims[1].GetTime(lev) and sims[0].GetTimeStep(lev) == sims[1].GetTimeStep(lev)
     for sim in sims:
         sim.close()
+    lbx.set_option(lbx.OPT_VALID_TILING, lbx.DEFAULT_VALID_TILING)
 
 
 # ------------------------------------------------------------------ conventional subcycling

@@ -35,6 +35,14 @@ def main():
     ap.add_argument("--max-grid", type=int, default=32)
     ap.add_argument("--regrid-every", type=int, default=0, help="coarse steps between regrids (0: never)")
     ap.add_argument("--no-fusion", action="store_true", help="Rohde cycle as the literal pass sequence")
+    ap.add_argument("--valid-tiling", default=None, choices=["rows", "linear"], help="valid-cell tiles of the fused pass")
+    ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 skip valid tiles, 2 skip ghost tiles")
+    ap.add_argument("--coupling", default="rohde", choices=["rohde", "subcycle"],
+                    help="rohde: the reference's live RohdeCycle; subcycle: conventional subcycling (FillPatch with "
+                         "time interpolation, average_down)")
+    ap.add_argument("--gradient", type=float, default=0.0,
+                    help="> 0: refine level 0 by the density-gradient criterion with this threshold (device tagging) "
+                         "instead of static boxes; regrids happen inside Iterate every --regrid-every steps")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -47,16 +55,25 @@ def main():
         amrsim.lambrexInitParallel()
     else:
         amrsim.lambrexInit()
+    if args.valid_tiling:
+        lbx.set_option(lbx.OPT_VALID_TILING, 1 if args.valid_tiling == "linear" else 0)
     n = args.grid
     sim = amrsim.AmrSim(n, n, n, args.levels - 1, (1, 1, 1), 0.5, 0.5)
     sim.SetMaxGridSize(args.max_grid)
     sim.SetRohdeFusion(not args.no_fusion)
+    sim.SetCoupling(amrsim.SUBCYCLE if args.coupling == "subcycle" else amrsim.ROHDE)
     sim.SetInitialDensity(workloads.pulse_density(n, n, n))
     sim.SetInitialVelocity(0.0)
     sim.InitFromScratch(0.0)
     t0 = time.perf_counter()
-    for lev, (lo, hi) in enumerate(static_boxes(n, args.levels)):
-        sim.SetStaticRefinement(lev, lo, hi)
+    if args.gradient > 0:
+        sim.SetGradientRefinement(0, args.gradient)
+        for lev, (lo, hi) in list(enumerate(static_boxes(n, args.levels)))[1:]:
+            sim.SetStaticRefinement(lev, lo, hi)
+        sim.SetRegridInterval(args.regrid_every)
+    else:
+        for lev, (lo, hi) in enumerate(static_boxes(n, args.levels)):
+            sim.SetStaticRefinement(lev, lo, hi)
     lbx.sync()
     regrid_s = time.perf_counter() - t0
     cells = [sum(int(np.prod([h - l + 1 for l, h in zip(*b)])) for b in sim.boxArray(l)) for l in range(args.levels)]
@@ -69,10 +86,14 @@ def main():
     first_s = time.perf_counter() - t0
     if dist:
         dist.barrier()
+    lbx.set_option(lbx.OPT_DEBUG_SKIP, args.debug_skip)
     l0 = lbx.launch_count()
     regrids, regrid_in_loop_s = 0, 0.0
     with lbx.Timer() as t:
-        if args.regrid_every > 0:
+        if args.gradient > 0:
+            sim.Iterate(args.steps)          # regrid_int inside Iterate
+            regrids = sim.NumRegrids()
+        elif args.regrid_every > 0:
             done = 0
             while done < args.steps:
                 k = min(args.regrid_every, args.steps - done)
@@ -93,12 +114,15 @@ def main():
         tt = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    work = sum(c * s for c, s in zip(cells, substeps))
+    work = sum(c * s for c, s in zip(cells, substeps))      # (cells of the INITIAL grids; regrids change them little)
+    cells_end = [sum(int(np.prod([h - l + 1 for l, h in zip(*b)])) for b in sim.boxArray(l)) for l in range(sim.finestLevel() + 1)]
     sim.CalcHydroVars(0)
     rho = sim.GetDensityField(0)
     if rank == 0:
         print(json.dumps({"metric": "MLUPS (fp64 D3Q15, Rohde cycle)", "value": work * args.steps / (ms * 1e-3) / 1e6,
                           "n_gpus": world, "ms_per_coarse_step": ms / args.steps, "levels": args.levels,
+                          "coupling": args.coupling, "gradient_threshold": args.gradient, "cells_per_level_at_end": cells_end,
+                          "valid_tiling": args.valid_tiling, "debug_skip": args.debug_skip,
                           "fused": not args.no_fusion, "max_grid": args.max_grid, "base_grid": [n, n, n],
                           "cells_per_level": cells, "boxes_per_level": nbox, "boxes_of_rank0": mine, "substeps": substeps,
                           "launches_per_coarse_step": launches / args.steps, "regrid_seconds": regrid_s,

@@ -22,12 +22,17 @@ def build(nx, ny, nz, max_level, boxes, max_grid):
     rho = rho * workloads.pulse_density(nx, ny, nz)
     sim = amrsim.AmrSim(nx, ny, nz, max_level, PER, 0.3, 0.4)
     sim.SetUniformFastPath(False)        # per-box storage with ghost cells on every path
+    if "--subcycle" in sys.argv:         # conventional subcycling + gradient tagging + regrid_int
+        sim.SetCoupling(amrsim.SUBCYCLE)
     sim.SetMaxGridSize(max_grid)
     sim.SetInitialDensity(rho)
     sim.SetInitialVelocity(u)
     sim.InitFromScratch(0.0)
     for lev, (lo, hi) in enumerate(boxes):
         sim.SetStaticRefinement(lev, lo, hi)
+    if "--subcycle" in sys.argv and boxes:
+        sim.SetGradientRefinement(0, 2e-3)
+        sim.SetRegridInterval(2)
     return sim
 
 
