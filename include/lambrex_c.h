@@ -76,6 +76,12 @@ int lbx_sim_get_velocity(const lbx_sim *sim, int i, int j, int k, int n, int lev
 /* bulk output (addition): dense over the level's domain, C-ordered [i][j][k]([n]) */
 int lbx_sim_get_density_field(const lbx_sim *sim, int level, double *out, size_t n);
 int lbx_sim_get_velocity_field(const lbx_sim *sim, int level, double *out, size_t n);
+/* addition: generic derived variable = linear moment of the populations
+ * (include/derived_var.h:55-91; d3q15_bgk.h:34-55): out[..][c] = sum_p weights[c*15+p] f_p, c < ncomp <= 10,
+ * divided by rho when per_unit_density; dense over the level's domain, C-ordered [i][j][k][c], cells the
+ * level does not hold = sentinel. */
+int lbx_sim_get_linear_moment_field(const lbx_sim *sim, int level, const double *weights, int ncomp,
+                                    int per_unit_density, double sentinel, double *out, size_t n);
 /* GetTime, GetTimeStep, GetDims, GetExtent (:130-139, 154) */
 int lbx_sim_get_time(const lbx_sim *sim, int level, double *out);
 int lbx_sim_get_time_step(const lbx_sim *sim, int level, int *out);

@@ -226,6 +226,12 @@ int lbx_mf_lincomb(lbx_mf *dst, double a, const lbx_mf *x, double b, const lbx_m
  * tags(x) = set_val on valid cells where sum_d (rho(x+e_d) - rho(x-e_d))^2 / 4 > threshold^2; other
  * cells keep their value.  rho: 1 component, >= 1 filled ghost cell; tags: int32, same boxes. */
 int lbx_mf_tag_gradient(const lbx_mf *rho, double threshold, lbx_mf *tags, int set_val);
+/* Generic derived variable (include/derived_var.h:55-91): out_c = sum_p weights[c*15 + p] * f_p on the valid
+ * cells, c < ncomp <= 10, accumulated from 0.0 in increasing p (multiply and add rounded separately);
+ * normalise != 0 divides every component by rho = sum_p f_p.  Density = one row of ones, momentum density =
+ * the rows c_x, c_y, c_z (d3q15_bgk.h:43-55), velocity = the same normalised, stress = the rows Q_ab.
+ * `weights` is HOST memory (copied into the launch parameters). */
+int lbx_mf_linear_moments(const lbx_mf *f, lbx_mf *out, const double *weights, int ncomp, int normalise);
 /* ZeroInvalidComponents :604-617: in the ghost shell, f_m = 0 unless pos - 2 c_m is valid */
 int lbx_mf_zero_invalid(lbx_mf *f);
 /* InitPostCollision :477-482: `comp` = 0 on the outermost `depth` rings of every fab box */

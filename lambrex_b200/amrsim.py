@@ -37,6 +37,7 @@ SYMBOLS = {
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
     "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]), "lbx_sim_set_coupling": (_i, [_vp, _i]),
+    "lbx_sim_get_linear_moment_field": (_i, [_vp, _i, _dp, _i, _i, _d, _dp, _sz]),
     "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
     "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
     "lbx_sim_global_init_parallel": (_i, [_i, _i, _vp, _vp]), "lbx_sim_set_parallel_view": (_i, [_i, _i]),
@@ -262,6 +263,16 @@ class AmrSim:
             out = np.empty(self._level_dims(level) + (3,))
         _check(lib().lbx_sim_get_velocity_field(self._h, level, out.ctypes.data_as(_dp), out.size))
         return out.reshape(self._level_dims(level) + (3,))
+
+    def GetLinearMomentField(self, level, weights, per_unit_density=False, sentinel=-3e8):
+        """Generic derived variable: rows of `weights` ([ncomp, 15]) applied to the populations of
+        every valid cell; dense [nx, ny, nz, ncomp] over the level's domain."""
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64).reshape(-1, 15))
+        dims = self._level_dims(level)
+        out = np.empty(tuple(dims) + (w.shape[0],))
+        _check(lib().lbx_sim_get_linear_moment_field(self._h, level, w.ctypes.data_as(_dp), w.shape[0], int(per_unit_density),
+                                                     float(sentinel), out.ctypes.data_as(_dp), out.size))
+        return out
 
     def GetTime(self, level):
         v = _d()

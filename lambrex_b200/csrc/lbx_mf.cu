@@ -343,6 +343,21 @@ int lbx_mf_tag_gradient(const lbx_mf* rho, double threshold, lbx_mf* tags, int s
   return lbx::after_launch("lbx_mf_tag_gradient");
 }
 
+int lbx_mf_linear_moments(const lbx_mf* f, lbx_mf* out, const double* weights, int ncomp, int normalise) {
+  LBX_NEED_INIT();
+  if (need(f, LBX_NV, LBX_F64, 0, "lbx_mf_linear_moments f") || need(out, 1, LBX_F64, 0, "lbx_mf_linear_moments out") ||
+      same_boxes(f, out, "lbx_mf_linear_moments"))
+    return 1;
+  if (!weights || ncomp < 1 || ncomp > lbx::LM_MAX || out->ncomp < ncomp)
+    return fail("lbx_mf_linear_moments: 1..10 weight rows, at most the output's component count");
+  lbx::LMWeights W;
+  memset(&W, 0, sizeof(W));
+  memcpy(W.w, weights, sizeof(double) * (size_t)ncomp * LBX_NV);
+  lbx::k_mf_linear_moments<<<lbx::mf_grid(out->max_valid, out->nfabs), lbx::MFT, 0, g.cur>>>(f->table, out->table, out->nfabs,
+                                                                                            ncomp, normalise ? 1 : 0, W);
+  return lbx::after_launch("lbx_mf_linear_moments");
+}
+
 int lbx_mf_zero_invalid(lbx_mf* f) {
   LBX_NEED_INIT();
   if (need(f, LBX_NV, LBX_F64, 1, "lbx_mf_zero_invalid")) return 1;

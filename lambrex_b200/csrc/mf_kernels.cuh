@@ -175,6 +175,44 @@ __global__ void __launch_bounds__(MFT) k_mf_tag_gradient(const DFabT* __restrict
   if (g2 > thr2) static_cast<int*>(T.p)[mf_off(T, i, j, k)] = set_val;
 }
 
+// Generic derived variable (include/derived_var.h:55-91 fill_box + a per-cell `calculate`): every
+// derived variable the reference defines or sketches -- density (d3q15_bgk.h:34-41), momentum
+// density and stress (:43-55, commented out) -- is a LINEAR moment of the populations,
+//   out_c(x) = sum_p W[c][p] f_p(x),   optionally divided by rho(x) = sum_p f_p(x),
+// so one kernel with the weight rows as a launch parameter serves them all.  Accumulated from 0.0
+// in increasing p with separately rounded multiply and add (the order of `calculate`'s loop).
+constexpr int LM_MAX = 10;
+struct LMWeights { double w[LM_MAX][NV]; };
+__global__ void __launch_bounds__(MFT) k_mf_linear_moments(const DFabT* __restrict__ ft, const DFabT* __restrict__ ot, int nfabs,
+                                                           int ncomp, int normalise, const __grid_constant__ LMWeights W) {
+  const int q = mf_fab_index();
+  if (q >= nfabs) return;
+  const DFabT O = ot[q];
+  if (!O.local) return;
+  int i, j, k;
+  if (!mf_cell(O, 0, i, j, k)) return;
+  const DFabT F = ft[q];
+  const double* fp = static_cast<const double*>(F.p) + mf_off(F, i, j, k);
+  const long long fs = mf_stride(F), os = mf_stride(O);
+  double f[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) f[p] = __ldcs(fp + p * fs);
+  double inv = 1.0;
+  if (normalise) {
+    double rho = 0.0;
+#pragma unroll
+    for (int p = 0; p < NV; ++p) rho = __dadd_rn(rho, f[p]);
+    inv = rho;
+  }
+  double* op = static_cast<double*>(O.p) + mf_off(O, i, j, k);
+  for (int c = 0; c < ncomp; ++c) {
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < NV; ++p) acc = __dadd_rn(acc, __dmul_rn(f[p], W.w[c][p]));
+    op[c * os] = normalise ? __ddiv_rn(acc, inv) : acc;
+  }
+}
+
 // User arrays of the reference's API are C-ordered, i slowest, component fastest
 // (CLindex, include/AmrSim.h:79-83): user[(((i-d0)*NY + (j-d1))*NZ + (k-d2))*ncomp + n].
 // TO_FAB: valid cells of every fab <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);

@@ -136,6 +136,15 @@ void AmrSim::GetDensityField(int const level, double* out, size_t n) const {
 void AmrSim::GetVelocityField(int const level, double* out, size_t n) const {
   dense_field_into(velocity.at(level), level, NL_VELOCITY, out, n);
 }
+void AmrSim::GetLinearMomentField(int const level, const double* weights, int const ncomp, bool const per_unit_density,
+                                  double const sentinel, double* out, size_t n) const {
+  const MultiFab& f = levels.at(level).now.get<DistFn>();
+  if (f.empty()) amrex::Abort("GetLinearMomentField: empty level");
+  MultiFab dv(f.boxArray(), f.DistributionMap(), ncomp, 0, f.layout());
+  lbx_check(lbx_mf_linear_moments(f.mf(), dv.mf(), weights, ncomp, per_unit_density ? 1 : 0), "GetLinearMomentField");
+  dv.touch();
+  dense_field_into(dv, level, sentinel, out, n);
+}
 std::vector<double> AmrSim::GetDensityField(int const level) const {
   std::vector<double> out((size_t)geom.at(level).Domain().numPts());
   GetDensityField(level, out.data(), out.size());

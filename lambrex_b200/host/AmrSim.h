@@ -64,6 +64,19 @@ class AmrSim : public amrex::AmrCore {
   std::vector<double> GetVelocityField(int const level) const;
   void GetDensityField(int const level, double* out, size_t n) const;    // into caller memory
   void GetVelocityField(int const level, double* out, size_t n) const;
+  // generic derived variables (include/derived_var.h LinearMoment): DV::fill on the
+  // level's NOW populations, `out` (re)defined on the level's boxes when needed ...
+  template <class DV>
+  void CalcDerived(int const level, amrex::MultiFab& out) {
+    const amrex::MultiFab& f = levels.at(level).now.get<DistFn>();
+    if (out.empty() || out.boxArray() != f.boxArray() || out.layout() != f.layout() || out.nComp() != (int)DV::NELEM)
+      out.define(f.boxArray(), f.DistributionMap(), (int)DV::NELEM, 0, f.layout());
+    DV::fill(out, f);
+  }
+  // ... and its run-time form: `ncomp` (<= 10) weight rows over the 15 populations, result dense over
+  // the level's domain, C-ordered [i][j][k][c]; cells the level does not hold carry `sentinel`
+  void GetLinearMomentField(int const level, const double* weights, int const ncomp, bool const per_unit_density,
+                            double const sentinel, double* out, size_t n) const;
   // zero-copy inputs: the arrays (same C ordering) are read at InitFromScratch directly from
   // caller memory -- pinned memory makes that one DMA -- and must stay valid until it returns.
   void SetInitialDensityView(const double* rho_init, size_t n) { density_view = rho_init; density_view_n = n; }

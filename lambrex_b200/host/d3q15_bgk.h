@@ -30,6 +30,31 @@ struct Density : DerivedVar<Density, 1, DistFn> {
   }
 };
 
+// The derived variables the reference sketches but leaves commented out
+// (/root/reference/include/d3q15_bgk.h:43-55), as linear moments on the generic device path.
+struct MomentumDensity : LinearMoment<MomentumDensity, 3, DistFn> {      // rho u_a = sum_i f_i c_ia
+  static constexpr bool PER_UNIT_DENSITY = false;
+  static constexpr double WEIGHTS[3][15] = {{0, 1, -1, 0, 0, 0, 0, 1, 1, 1, 1, -1, -1, -1, -1},
+                                            {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1},
+                                            {0, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1}};
+};
+struct Velocity : LinearMoment<Velocity, 3, DistFn> {                    // u_a = sum_i f_i c_ia / rho
+  static constexpr bool PER_UNIT_DENSITY = true;
+  static constexpr double WEIGHTS[3][15] = {{0, 1, -1, 0, 0, 0, 0, 1, 1, 1, 1, -1, -1, -1, -1},
+                                            {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1},
+                                            {0, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1}};
+};
+// second moment sum_i f_i c_ia c_ib, components xx, xy, xz, yy, yz, zz
+struct MomentumFlux : LinearMoment<MomentumFlux, 6, DistFn> {
+  static constexpr bool PER_UNIT_DENSITY = false;
+  static constexpr double WEIGHTS[6][15] = {{0, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1},
+                                            {0, 0, 0, 0, 0, 0, 0, 1, 1, -1, -1, -1, -1, 1, 1},
+                                            {0, 0, 0, 0, 0, 0, 0, 1, -1, 1, -1, -1, 1, -1, 1},
+                                            {0, 0, 0, 1, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1},
+                                            {0, 0, 0, 0, 0, 0, 0, 1, -1, -1, 1, 1, -1, -1, 1},
+                                            {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}};
+};
+
 using SimState = State<DistFn, Density>;
 using SimLevelData = LevelData<SimState>;
 #endif

@@ -8,6 +8,8 @@
 #include <cstddef>
 #include <tuple>
 
+#include "AMReX_MultiFab.H"
+
 struct ScalarTag {};
 
 template <typename Impl, std::size_t DIM, typename... Deps>
@@ -15,5 +17,25 @@ struct DerivedVar {
   static constexpr std::size_t NELEM = DIM;
   using dependencies = std::tuple<Deps...>;
   static constexpr bool is_derived_var = true;
+};
+
+// Generic device path for derived variables that are linear moments of a distribution function
+// (SURVEY.md 8f-3): where the reference's DerivedVar::fill_box (:80-90) loops over the cells of a
+// box calling Impl::calculate, an implementation here states its per-cell rule as NELEM weight
+// rows over the NV populations,
+//     static constexpr double WEIGHTS[NELEM][NV];   static constexpr bool PER_UNIT_DENSITY;
+// and fill() evaluates out_c = sum_p WEIGHTS[c][p] f_p (divided by rho when PER_UNIT_DENSITY) for
+// every valid cell of the level in one launch (lbx_mf_linear_moments) -- a new moment needs no
+// new kernel.  Density, MomentumDensity, Velocity and Stress in d3q15_bgk.h are such moments.
+template <typename Impl, std::size_t DIM, typename DistT>
+struct LinearMoment : DerivedVar<Impl, DIM, DistT> {
+  static void fill(amrex::MultiFab& out, const amrex::MultiFab& f) {
+    static_assert(DIM >= 1 && DIM <= 10, "lbx_mf_linear_moments takes 1..10 weight rows");
+    if (out.boxArray() != f.boxArray() || out.layout() != f.layout() || out.nComp() < (int)DIM)
+      amrex::Abort("LinearMoment::fill: output and source must share boxes and layout");
+    amrex::lbx_check(lbx_mf_linear_moments(f.mf(), out.mf(), &Impl::WEIGHTS[0][0], (int)DIM, Impl::PER_UNIT_DENSITY ? 1 : 0),
+                     "LinearMoment::fill");
+    out.touch();
+  }
 };
 #endif

@@ -103,6 +103,11 @@ int lbx_sim_unset_gradient_refinement(lbx_sim* sim, int level) { return guarded(
 int lbx_sim_set_regrid_interval(lbx_sim* sim, int n) { return guarded([&] { sim->s.SetRegridInterval(n); }); }
 int lbx_sim_num_regrids(const lbx_sim* sim) { return sim->s.NumRegrids(); }
 
+int lbx_sim_get_linear_moment_field(const lbx_sim* sim, int level, const double* weights, int ncomp, int per_unit_density,
+                                    double sentinel, double* out, size_t n) {
+  return guarded([&] { sim->s.GetLinearMomentField(level, weights, ncomp, per_unit_density != 0, sentinel, out, n); });
+}
+
 int lbx_sim_set_coupling(lbx_sim* sim, int coupling) {
   return guarded([&] {
     if (coupling != LBX_COUPLING_ROHDE && coupling != LBX_COUPLING_SUBCYCLE) amrex::Abort("unknown coupling");

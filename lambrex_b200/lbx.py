@@ -116,6 +116,7 @@ SYMBOLS = {
     "lbx_mf_zero_invalid": (_i, [_vp]),
     "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
     "lbx_mf_lincomb": (_i, [_vp, _d, _vp, _d, _vp]),
+    "lbx_mf_linear_moments": (_i, [_vp, _vp, _vp, _i, _i]),
     "lbx_mf_tag_gradient": (_i, [_vp, _d, _vp, _i]),
     "lbx_mf_from_user": (_i, [_vp, _vp, _bp, _i]),
     "lbx_mf_to_user": (_i, [_vp, _vp, _bp, _i]),
@@ -455,6 +456,19 @@ def mf_collide_stream(src_valid, src_ghost, dst, omega_s, omega_b, mask=None, fi
 
 def mf_stream(src, dst):
     check(lib().lbx_mf_stream(src.h, dst.h))
+
+
+def mf_lincomb(dst, a, x, b, y):
+    check(lib().lbx_mf_lincomb(dst.h, float(a), x.h, float(b), y.h))
+
+
+def mf_tag_gradient(rho, threshold, tags, set_val=1):
+    check(lib().lbx_mf_tag_gradient(rho.h, float(threshold), tags.h, int(set_val)))
+
+
+def mf_linear_moments(f, out, weights, per_unit_density=False):
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64).reshape(-1, 15))
+    check(lib().lbx_mf_linear_moments(f.h, out.h, w.ctypes.data_as(ctypes.c_void_p), w.shape[0], 1 if per_unit_density else 0))
 
 
 def mf_zero_invalid(f):

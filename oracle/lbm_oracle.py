@@ -167,6 +167,27 @@ def _ptr(a):
     return a.ctypes.data_as(_dp)
 
 
+
+def linear_moments(f, weights, per_unit_density=False):
+    """Generic derived variable (include/derived_var.h:55-91 fill_box over a `calculate` that is a
+    linear moment, include/d3q15_bgk.h:34-55): out[c] = sum_p weights[c][p] * f[p], accumulated from
+    0.0 in increasing p, multiply and add rounded separately; divided by rho = sum_p f[p] (same
+    order) when per_unit_density.  f is [15, ...]; returns [ncomp, ...]."""
+    w = np.asarray(weights, dtype=np.float64).reshape(-1, NV)
+    out = np.zeros((w.shape[0],) + f.shape[1:])
+    for c in range(w.shape[0]):
+        acc = np.zeros(f.shape[1:])
+        for p in range(NV):
+            acc = acc + f[p] * w[c, p]
+        out[c] = acc
+    if per_unit_density:
+        rho = np.zeros(f.shape[1:])
+        for p in range(NV):
+            rho = rho + f[p]
+        out = out / rho
+    return out
+
+
 class COracle:
     def __init__(self):
         if not os.path.exists(_SO):

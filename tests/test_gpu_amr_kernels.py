@@ -178,3 +178,53 @@ def test_plan_validation_is_loud():
         lbx.Plan([dict(dst_fab=0, kind=lbx.G_COPY, shift=(5, 0, 0), lo=(4, 0, 0), hi=(8, 0, 0))]).apply(A, B)
     with pytest.raises(lbx.LbxError):      # missing source set
         lbx.Plan([dict(dst_fab=0, kind=lbx.G_COPY, lo=(0, 0, 0), hi=(1, 1, 1))]).apply(A)
+
+
+# ------------------------------------------------------------------ kernels of the section-8f additions
+def test_mf_linear_moments_generic_derived_variables(coracle):
+    """lbx_mf_linear_moments: one kernel for every linear-moment derived variable
+    (include/derived_var.h:55-91, d3q15_bgk.h:34-55).  Separately rounded, fixed order: bit-identical
+    to the numpy statement; density / velocity rows agree with the dedicated moments kernel."""
+    f = rand_mf(BOXES, 15, 2, 11)
+    F = to_dev(f)
+    M, _, c, _ = lbx.tables()
+    cases = [("density", np.ones((1, 15)), False), ("momentum", np.asarray(c, dtype=np.float64).T, False),
+             ("velocity", np.asarray(c, dtype=np.float64).T, True), ("modes 0-9", np.asarray(M)[:10], False)]
+    for name, w, norm in cases:
+        out = lbx.MF(BOXES, w.shape[0], 0)
+        lbx.mf_linear_moments(F, out, w, norm)
+        got = out.download()
+        for i in range(len(BOXES)):
+            want = orc.linear_moments(f.fabs[i][:, 2:-2, 2:-2, 2:-2], w, norm)
+            assert np.array_equal(got[i], want), name
+    # the dedicated kernel (CalcHydroVars) and the generic path agree to rounding
+    R, U = lbx.MF(BOXES, 1, 0), lbx.MF(BOXES, 3, 0)
+    lbx.mf_moments(F, R, U)
+    V = lbx.MF(BOXES, 3, 0)
+    lbx.mf_linear_moments(F, V, np.asarray(c, dtype=np.float64).T, True)
+    for a, b in zip(U.download(), V.download()):
+        assert np.max(np.abs(a - b)) < 1e-14
+    with pytest.raises(lbx.LbxError):
+        lbx.mf_linear_moments(F, lbx.MF(BOXES, 2, 0), np.ones((3, 15)))      # more rows than output components
+
+
+def test_mf_lincomb_and_tag_gradient():
+    x, y = rand_mf(BOXES, 15, 2, 21), rand_mf(BOXES, 15, 2, 22)
+    X, Y, D = to_dev(x), to_dev(y), lbx.MF(BOXES, 15, 2)
+    lbx.mf_lincomb(D, 0.25, X, 0.75, Y)
+    for i, got in enumerate(D.download()):
+        want = np.zeros_like(got)                                            # ghost cells are not written
+        want[:, 2:-2, 2:-2, 2:-2] = 0.25 * x.fabs[i][:, 2:-2, 2:-2, 2:-2] + 0.75 * y.fabs[i][:, 2:-2, 2:-2, 2:-2]
+        assert np.array_equal(got, want)
+    rho = rand_mf(BOXES, 1, 1, 23)
+    R, T = to_dev(rho), lbx.MF(BOXES, 1, 0, lbx.I32)
+    thr = 0.35
+    lbx.mf_tag_gradient(R, thr, T, 2)
+    ntag = 0
+    for i, got in enumerate(T.download()):
+        r = rho.fabs[i][0]
+        gx, gy, gz = r[1:-1, 1:-1, 2:] - r[1:-1, 1:-1, :-2], r[1:-1, 2:, 1:-1] - r[1:-1, :-2, 1:-1], r[2:, 1:-1, 1:-1] - r[:-2, 1:-1, 1:-1]
+        want = np.where(0.25 * ((gx * gx + gy * gy) + gz * gz) > thr * thr, 2, 0)
+        assert np.array_equal(got[0], want)
+        ntag += int((want == 2).sum())
+    assert 0 < ntag < sum(ao.numpts(b) for b in BOXES)

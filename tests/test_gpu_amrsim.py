@@ -468,3 +468,35 @@ def test_gradient_refinement_and_regrid_interval_match_oracle(coracle):
         sim.close()
     finally:
         lbx.set_option(lbx.OPT_COLLIDE_LITERAL, 0)
+
+
+# ------------------------------------------------------------------ generic derived variables
+def test_linear_moment_fields_through_amrsim(coracle):
+    """AmrSim::GetLinearMomentField: momentum density / velocity / density as weight rows; consistent
+    with CalcHydroVars + the getters, sentinel off-level."""
+    from lambrex_b200 import lbx
+    nx, ny, nz = 16, 12, 20
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    sim = AmrSim(nx, ny, nz, 1, PER, 0.5, 0.5)
+    sim.SetInitialDensity(rho)
+    sim.SetInitialVelocity(u)
+    sim.InitFromScratch(0.0)
+    sim.SetStaticRefinement(0, (3, 2, 4), (11, 9, 14))
+    sim.SetCoupling(amrsim.SUBCYCLE)
+    sim.Iterate(3)
+    _, _, c, _ = lbx.tables()
+    cw = np.asarray(c, dtype=np.float64).T
+    for lev in (0, 1):
+        sim.CalcHydroVars(lev)
+        r, v = sim.GetDensityField(lev), sim.GetVelocityField(lev).reshape(sim.GetDensityField(lev).shape + (3,))
+        own = r != amrsim.NL_DENSITY
+        dens = sim.GetLinearMomentField(lev, np.ones((1, 15)), sentinel=amrsim.NL_DENSITY)[..., 0]
+        vel = sim.GetLinearMomentField(lev, cw, per_unit_density=True)
+        mom = sim.GetLinearMomentField(lev, cw)
+        assert np.array_equal(dens != amrsim.NL_DENSITY, own)
+        assert np.max(np.abs(dens[own] - r[own])) < 1e-14
+        assert np.max(np.abs(vel[own] - v[own])) < 1e-14
+        assert np.max(np.abs(mom[own] - v[own] * r[own][:, None])) < 1e-14
+        if lev == 1:
+            assert np.all(vel[~own] == -3e8) and (~own).any()
+    sim.close()

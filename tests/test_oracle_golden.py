@@ -126,3 +126,15 @@ def test_reference_pass_structure_equals_periodic_step(coracle):
         got, secs = coracle.ref_passes(f, 1.1, 0.8, 3, edges, loop_order=order)
         assert np.array_equal(got, want)
         assert secs >= 0.0
+
+
+def test_linear_moments_restate_the_mode_matrix_rows(coracle):
+    """oracle.linear_moments (generic derived variables, include/derived_var.h:55-91): rows of the
+    mode matrix reproduce the oracle's own density / velocity (src/AmrSim.cpp:957-971)."""
+    rng = np.random.default_rng(3)
+    f = rng.random((15, 4, 5, 6)) + 0.5
+    M, _, c = coracle.tables()
+    rho, u = coracle.moments(f)
+    assert np.max(np.abs(orc.linear_moments(f, M[:1])[0] - rho)) < 1e-14
+    assert np.max(np.abs(orc.linear_moments(f, M[1:4], per_unit_density=True) - u)) < 1e-14
+    assert np.array_equal(orc.linear_moments(f, np.asarray(c, dtype=np.float64).T), orc.linear_moments(f, M[1:4]))
