@@ -294,7 +294,15 @@ void AmrCore::regrid(int lbase, Real time, bool) {
   if (lbase >= max_level) return;
   int new_finest;
   Vector<BoxArray> new_grids(finest_level + 2);
+  auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what, int lev) {
+    if (!getenv("LBX_HOST_TIMING")) return;
+    auto T1 = std::chrono::steady_clock::now();
+    std::cerr << "  [regrid lbase " << lbase << "] " << what << " " << lev << ": " << std::chrono::duration<double>(T1 - T0).count() << " s\n";
+    T0 = T1;
+  };
   MakeNewGrids(lbase, time, new_finest, new_grids);
+  lap("MakeNewGrids", lbase);
   bool coarse_ba_changed = false;
   for (int lev = lbase + 1; lev <= new_finest; ++lev) {
     if (lev <= finest_level) {                 // an existing level
@@ -307,6 +315,7 @@ void AmrCore::regrid(int lbase, Real time, bool) {
           level_dmap = DistributionMapping(level_grids);
         }
         RemakeLevel(lev, time, level_grids, level_dmap);
+        lap("RemakeLevel", lev);
         SetBoxArray(lev, level_grids);
         SetDistributionMap(lev, level_dmap);
       }
@@ -314,6 +323,7 @@ void AmrCore::regrid(int lbase, Real time, bool) {
     } else {                                   // a new level
       const DistributionMapping new_dmap(new_grids[lev]);
       MakeNewLevelFromCoarse(lev, time, new_grids[lev], new_dmap);
+      lap("MakeNewLevelFromCoarse", lev);
       SetBoxArray(lev, new_grids[lev]);
       SetDistributionMap(lev, new_dmap);
     }

@@ -1,5 +1,8 @@
 // amrex-mini: device field containers, host tag boxes, and the gather-plan builders that stand
 // in for AMReX's ParallelCopy family (see AMReX_MultiFab.H, AMReX_FillPatch.H).
+#include <chrono>
+#include <iostream>
+#include <cstdlib>
 #include "AMReX_MultiFab.H"
 
 #include <cstring>
@@ -181,8 +184,12 @@ void TagBox::buffer(int nbuf, const Box& interior) {
     for (int k = std::max(r.k - nbuf, box_.smallEnd(2)); k <= std::min(r.k + nbuf, box_.bigEnd(2)); ++k)
       for (int j = std::max(r.j - nbuf, box_.smallEnd(1)); j <= std::min(r.j + nbuf, box_.bigEnd(1)); ++j) {
         char* row = &d_[index(IntVect(i0, j, k))];
-        for (int x = 0; x <= i1 - i0; ++x)
-          if (row[x] == CLEAR) row[x] = BUF;
+        const int len = i1 - i0 + 1;
+        // inside a solid tagged region the neighbouring rows hold no CLEAR cell at all: libc's
+        // vectorised scan finds that out an order of magnitude faster than the byte loop
+        char* z = static_cast<char*>(std::memchr(row, CLEAR, (size_t)len));
+        if (!z) continue;
+        for (int x = (int)(z - row); x < len; ++x) row[x] = row[x] == CLEAR ? (char)BUF : row[x];
       }
   }
 }
@@ -420,9 +427,15 @@ lbx_plan* cached(const std::string& key, const std::function<void(std::vector<lb
   auto it = g_plans.find(key);
   if (it != g_plans.end()) return it->second.get();
   std::vector<lbx_gather> descs;
+  const auto T0 = std::chrono::steady_clock::now();
   build(descs);
+  const auto T1 = std::chrono::steady_clock::now();
   lbx_plan* p = nullptr;
   lbx_check(lbx_plan_create(descs.data(), (int)descs.size(), &p), "gather plan");
+  if (getenv("LBX_HOST_TIMING"))
+    std::cerr << "  [plan " << key.substr(0, 3) << "] " << descs.size() << " descriptors: intersections "
+              << std::chrono::duration<double>(T1 - T0).count() << " s, upload "
+              << std::chrono::duration<double>(std::chrono::steady_clock::now() - T1).count() << " s\n";
   g_plans[key].reset(p);
   return p;
 }

@@ -1,7 +1,9 @@
 // AmrSim on the GPU: host control flow of the reference's time stepping
 // (/root/reference/src/AmrSim.cpp), every field operation a kernel launch through
 // include/lbx.h.  Reference lines are cited per member.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include "AmrSim.h"
 
 #include <iostream>
@@ -692,8 +694,13 @@ void AmrSim::ClearLevel(int level) {
 void AmrSim::SetStaticRefinement(int const level, const std::array<int, NDIMS>& lo_corner,
                                  const std::array<int, NDIMS>& hi_corner) {
   static_tags.at(level).define(Box(IntVect(lo_corner), IntVect(hi_corner)));
+  const auto T0 = std::chrono::steady_clock::now();
   regrid(level, GetTime(level));
+  const auto T1 = std::chrono::steady_clock::now();
   MakeFineMask(level);
+  if (getenv("LBX_HOST_TIMING"))
+    std::cerr << "[SetStaticRefinement " << level << "] regrid " << std::chrono::duration<double>(T1 - T0).count()
+              << " s, MakeFineMask " << std::chrono::duration<double>(std::chrono::steady_clock::now() - T1).count() << " s\n";
 }
 
 // src/AmrSim.cpp:1011-1017

@@ -84,6 +84,13 @@ def main():
     sim.Iterate(args.warmup)        # includes the FLAT -> BOXES re-layout and plan building
     lbx.sync()
     first_s = time.perf_counter() - t0
+    if args.regrid_every > 0 and args.gradient <= 0:
+        # one untimed regrid: the steady state of a periodically regridding run reuses the device blocks
+        # (and, distributed, the CUDA-IPC mappings) the previous regrid released
+        for lev, (lo, hi) in enumerate(static_boxes(n, args.levels, shift=2)):
+            sim.SetStaticRefinement(lev, lo, hi)
+        sim.Iterate(1)
+        lbx.sync()
     if dist:
         dist.barrier()
     lbx.set_option(lbx.OPT_DEBUG_SKIP, args.debug_skip)
