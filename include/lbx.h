@@ -58,6 +58,10 @@ enum {
                                   cap resident CTAs per SM (tuning knob; 0 = uncapped, max 49152) */
   LBX_OPT_VALID_TILING = 3,    /* valid-cell tiles of lbx_mf_collide_stream*: 0 = a warp per box row,
                                   1 = 256 consecutive cells of the box (every lane busy)            */
+  LBX_OPT_ALIGN_ROWS = 5,      /* fab sets created from now on: 1 = fp64 fabs with ghost cells get sector-
+                                  aligned valid rows (x extent padded, see lbx_mf_fab); 0 (default) = tight.
+                                  Measured (profiles/r01_alignment.md): 1.5x on kernels that write valid
+                                  cells only, 0.7x on the passes that also write ghost cells            */
   LBX_OPT_DEBUG_SKIP = 4,      /* PROFILING ONLY (results are wrong): bit 0 skips the valid-cell work of
                                   lbx_mf_collide_stream*, bit 1 the ghost-cell work                  */
 };
@@ -185,7 +189,8 @@ int lbx_mf_create_dist(const lbx_box *valid, int nfabs, int ncomp, int ngrow, in
 int lbx_mf_destroy(lbx_mf *mf);
 int lbx_mf_info(const lbx_mf *mf, int *nfabs, int *ncomp, int *ngrow, int *dtype, size_t *bytes);
 /* descriptor of fab i (usable with the single-fab kernels above), its valid box, and its
- * byte offset inside the allocation (host mirrors: fab after fab, [comp][z][y][x]) */
+ * byte offset inside the allocation (host mirrors: fab after fab, [comp][z][y][x] over the ALLOCATED
+ * box fab->lo, fab->n -- which in x may be wider than valid + ghosts: unused alignment cells) */
 int lbx_mf_fab(const lbx_mf *mf, int i, lbx_fab *fab, lbx_box *valid, size_t *byte_offset);
 int lbx_mf_upload(lbx_mf *mf, const void *host, size_t bytes);
 int lbx_mf_download(const lbx_mf *mf, void *host, size_t bytes);
@@ -284,6 +289,18 @@ int lbx_plan_apply(lbx_plan *plan, lbx_mf *dst, const lbx_mf *src0, const lbx_mf
 int lbx_mf_collide_stream_fillpatch(const lbx_mf *src_valid, lbx_mf *dst, double omega_s, double omega_b,
                                     const lbx_mf *mask, int fine_val, int zero_invalid, lbx_plan *ghost_plan,
                                     const lbx_mf *src0, const lbx_mf *src1, const lbx_mf *fallback);
+/* One CONVENTIONAL level step in one pass -- CollideLevel (DistFnFillPatch, Collide, FillBoundary) :124-135
+ * followed by Stream :109-122, as IterateLevel :324-333 runs it (the subcycling driver):
+ *   valid cells : dst(x + c_p, p) = collide(now(x))_p;
+ *   ghost cells : looked up in `ghost_plan` (a ghosts-only FillPatch plan, as above).  A cell FillPatch copies
+ *                 from a same-level valid cell (src0, periodic images included) pushes that cell's COLLIDED
+ *                 populations -- what FillBoundary leaves there after Collide; a cell under the coarse level
+ *                 pushes wa * crse_a (+ wb * crse_b when crse_b != NULL) UNcollided: FillPatchTwoLevels'
+ *                 piecewise-constant interpolation of the coarse state, linear in time between two states;
+ *   ghost ring 2 of dst = 0 (fresh fab). */
+int lbx_mf_collide_stream_level(const lbx_mf *now, lbx_mf *dst, double omega_s, double omega_b, lbx_plan *ghost_plan,
+                                const lbx_mf *src0, const lbx_mf *crse_a, double wa, const lbx_mf *crse_b, double wb,
+                                const lbx_mf *fallback);
 int lbx_plan_destroy(lbx_plan *plan);
 
 /* lattice constants and moment basis the kernels use (host-side query; no GPU needed):

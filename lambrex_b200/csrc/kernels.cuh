@@ -425,6 +425,49 @@ __device__ __forceinline__ void ghost_push(const DFabT& D, int i, int j, int k, 
   }
 }
 
+// Ghost push of the conventional level step: as ghost_push, but the source populations are
+//   collide_src : collide(sp[.]) -- all 15 loaded, collided, then the ones with a destination stored;
+//   else        : sp[p] or, with a second source, wa * sp[p] + wb * spb[p] (separately rounded, like
+//                 k_mf_lincomb followed by a copy).
+template <class C>
+__device__ __forceinline__ void ghost_push_level(const DFabT& D, int i, int j, int k, const double* __restrict__ sp,
+                                                 long long ssc, const double* __restrict__ spb, double wa, double wb,
+                                                 bool collide_src, double omega_s, double omega_b) {
+  double* dp = static_cast<double*>(D.p) + mf_off(D, i, j, k);
+  const long long dsc = mf_stride(D), dy = D.n[0], dz = (long long)D.n[0] * D.n[1];
+  const int ex = i < D.vlo[0] ? i - D.vlo[0] : i > D.vhi[0] ? i - D.vhi[0] : 0;
+  const int ey = j < D.vlo[1] ? j - D.vlo[1] : j > D.vhi[1] ? j - D.vhi[1] : 0;
+  const int ez = k < D.vlo[2] ? k - D.vlo[2] : k > D.vhi[2] ? k - D.vhi[2] : 0;
+  double f[NV];
+  bool go[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) {
+    const int rx = ex == 0 ? 0 : (ex > 0 ? ex + cx(p) : -(ex + cx(p)));
+    const int ry = ey == 0 ? 0 : (ey > 0 ? ey + cy(p) : -(ey + cy(p)));
+    const int rz = ez == 0 ? 0 : (ez > 0 ? ez + cz(p) : -(ez + cz(p)));
+    go[p] = rx <= 1 && ry <= 1 && rz <= 1;
+  }
+  if (collide_src) {
+#pragma unroll
+    for (int p = 0; p < NV; ++p) f[p] = __ldcs(sp + p * ssc);
+    C::collide(f, omega_s, omega_b);
+  } else {
+#pragma unroll
+    for (int p = 0; p < NV; ++p) {
+      if (!go[p] || !sp) f[p] = 0.0;
+      else if (spb) f[p] = __dadd_rn(__dmul_rn(wa, __ldcs(sp + p * ssc)), __dmul_rn(wb, __ldcs(spb + p * ssc)));
+      else f[p] = __ldcs(sp + p * ssc);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NV; ++p)
+    if (go[p]) __stcs(dp + p * dsc + cx(p) + cy(p) * dy + cz(p) * dz, f[p]);
+  if (ex < -1 || ex > 1 || ey < -1 || ey > 1 || ez < -1 || ez > 1) {   // own cell is in ring 2
+#pragma unroll
+    for (int p = 0; p < NV; ++p) dp[p * dsc] = 0.0;
+  }
+}
+
 // ---- gather-plan records (built by lbx_plan_create, see mf_kernels.cuh for the semantics) ------
 enum { G_COPY = 0, G_PC = 1, G_AVG = 2, G_CONST = 3, G_NONE = 4 };
 struct alignas(16) GDesc {   // 64 bytes
@@ -466,6 +509,12 @@ struct CSPlan {                    // ghosts-only FillPatch plan of the level be
   const DFabT* s1;                 // coarse source set (NOW of level - 1)
   const DFabT* fb;                 // fallback: the fab FillPatch would have filled
   int tiles_per_group;
+  // conventional level step (k_mf_collide_stream<.., LEVELSTEP = true>): ghost cells FillPatch takes
+  // from a same-level valid cell push that cell's COLLIDED populations (CollideLevel's FillBoundary,
+  // src/AmrSim.cpp:132, runs after its Collide); ghost cells under the coarse level push
+  // wa * s1 (+ wb * s1b): FillPatchTwoLevels' interpolation in time between two coarse states
+  const DFabT* s1b;                // second coarse set (same boxes as s1) or null
+  double wa, wb;
 };
 constexpr int CSX = 32, CSY = 8;
 static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
@@ -475,7 +524,9 @@ static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
 // the lanes); true = MFT consecutive cells of the box's valid region in x-fastest order (two
 // integer divisions per thread, every lane busy; a warp's plane access is 1-3 row segments).
 // flags: bit 0 = zero_invalid; bits 8 / 9 (profiling only) skip the valid / ghost tiles' work.
-template <class C, bool LINEAR>
+// LEVELSTEP: the conventional level step (CollideLevel + Stream, src/AmrSim.cpp:124-135, 109-122) instead
+// of the Rohde pair: needs a plan; see CSPlan and ghost_push_level.
+template <class C, bool LINEAR, bool LEVELSTEP = false>
 __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
                                                            const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
                                                            const DFabT* __restrict__ gt, CSPlan plan, int nfabs,
@@ -565,6 +616,8 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
   const bool ghost = in_box && !mf_in_valid(D, i, j, k);   // these plans tile ghost slabs only
   bool searching = ghost;
   const double* sp = nullptr;
+  const double* spb = nullptr;         // LEVELSTEP: the second coarse state of a PC source
+  bool collide_src = false;            // LEVELSTEP: the source is a same-level valid cell
   long long ssc = 0;
   const int nchunks = (G.count + PLAN_CHUNK - 1) / PLAN_CHUNK;
   for (int ch = 0; ch < nchunks; ++ch) {                   // backwards: the last matching descriptor wins
@@ -583,8 +636,13 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
           const DFabT S = (g.src_set ? plan.s1 : plan.s0)[g.src_fab];
           int si = i, sj = j, sk = k;
           if (g.kind == G_PC) { si = fdiv(i, g.ratio); sj = fdiv(j, g.ratio); sk = fdiv(k, g.ratio); }
-          sp = static_cast<const double*>(S.p) + mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
+          const long long so = mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
+          sp = static_cast<const double*>(S.p) + so;
           ssc = mf_stride(S);
+          if (LEVELSTEP) {
+            collide_src = g.kind == G_COPY;
+            if (g.kind == G_PC && plan.s1b) spb = static_cast<const double*>(plan.s1b[g.src_fab].p) + so;
+          }
         }
         searching = false;                                  // a G_NONE hit ends the search too: no source
         break;
@@ -598,7 +656,12 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
     sp = static_cast<const double*>(B.p) + mf_off(B, i, j, k);
     ssc = mf_stride(B);
   }
-  ghost_push(D, i, j, k, sp, ssc, zero_invalid);
+  if (LEVELSTEP) {
+    const bool lerp = spb != nullptr;
+    ghost_push_level<C>(D, i, j, k, sp, ssc, spb, lerp ? plan.wa : 1.0, lerp ? plan.wb : 0.0, collide_src, omega_s, omega_b);
+  } else {
+    ghost_push(D, i, j, k, sp, ssc, zero_invalid);
+  }
 }
 
 template <class C>

@@ -9,6 +9,8 @@ namespace lbx {
 extern int g_smem_pad;
 // valid tiles of k_mf_collide_stream: 1 = MFT consecutive cells (default), 0 = a warp per row (LBX_OPT_VALID_TILING)
 extern int g_valid_linear;
+// 1: fabs with ghost cells are allocated with sector-aligned valid rows (LBX_OPT_ALIGN_ROWS); default 0
+extern int g_align_rows;
 // profiling only (LBX_OPT_DEBUG_SKIP): bit 0 skips the valid tiles' work, bit 1 the ghost tiles' (results are wrong)
 extern int g_debug_skip;
 struct Launchers {

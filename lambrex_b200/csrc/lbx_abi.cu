@@ -18,6 +18,7 @@
 namespace lbx {
 int g_smem_pad = 0;
 int g_valid_linear = 0;
+int g_align_rows = 0;
 int g_debug_skip = 0;
 Ctx g_ctx;
 thread_local std::string g_err;
@@ -370,6 +371,7 @@ int lbx_set_option(int key, int value) {
       if (value < 0 || value > 48 * 1024) return fail("lbx_set_option: LBX_OPT_SMEM_PAD must be 0..49152");
       lbx::g_smem_pad = value;
       return 0;
+    case LBX_OPT_ALIGN_ROWS: lbx::g_align_rows = (value != 0); return 0;
     case LBX_OPT_VALID_TILING: lbx::g_valid_linear = (value != 0); return 0;
     case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 3; return 0;
     default: return fail("lbx_set_option: unknown key");

@@ -114,6 +114,15 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
       if (valid[i].hi[d] < valid[i].lo[d]) { delete m; return fail("lbx_mf_create: empty box"); }
       f.vlo[d] = valid[i].lo[d]; f.vhi[d] = valid[i].hi[d];
       f.lo[d] = f.vlo[d] - ngrow; f.n[d] = f.vhi[d] - f.vlo[d] + 1 + 2 * ngrow;
+      if (d == 0 && dtype == LBX_F64 && ngrow > 0 && lbx::g_align_rows) {
+        // 32-byte sector alignment of the VALID rows (profiles/r01_alignment.md): unused lead-in cells
+        // put the first valid cell of every row on a sector boundary and the row pitch is a whole
+        // number of sectors, so out-of-place row stores are whole sectors instead of partial ones
+        // that the L2 has to complete from DRAM (measured: 1.5x on the out-of-place collision).
+        const int A = 4, lead = (A - ngrow % A) % A;
+        f.lo[0] -= lead;
+        f.n[0] = (f.n[0] + lead + A - 1) / A * A;
+      }
       cells *= (size_t)f.n[d];
       if (cells >= (size_t(1) << 31)) { delete m; return fail("lbx_mf_create: a fab exceeds 2^31 cells"); }
       h = mix(mix(h, (uint64_t)(uint32_t)f.vlo[d]), (uint64_t)(uint32_t)f.vhi[d]);
@@ -285,7 +294,8 @@ int lbx_mf_collide(lbx_mf* f, double omega_s, double omega_b, const lbx_mf* mask
 
 static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
                                  const lbx_mf* mask, int fine_val, int zero_invalid, lbx_plan* plan, const lbx_mf* src0,
-                                 const lbx_mf* src1, const lbx_mf* fallback);
+                                 const lbx_mf* src1, const lbx_mf* fallback, bool level_step = false,
+                                 const lbx_mf* src1b = nullptr, double wa = 1.0, double wb = 0.0);
 
 int lbx_mf_collide_stream(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
                           const lbx_mf* mask, int fine_val, int zero_invalid) {
@@ -312,8 +322,9 @@ int lbx_mf_average_down(const lbx_mf* fine, lbx_mf* crse, int ratio) {
   for (int i = 0; i < fine->nfabs; ++i)
     for (int d = 0; d < 3; ++d) {
       const lbx::DFabT &f = fine->host[i], &c = crse->host[i];
-      // allocated fine box = refine(allocated coarse box)
-      if (f.lo[d] != c.lo[d] * ratio || f.n[d] != c.n[d] * ratio)
+      // fine box with its ghosts = refine(coarse box with its ghosts)
+      if (f.vlo[d] - fine->ngrow != (c.vlo[d] - crse->ngrow) * ratio ||
+          f.vhi[d] + fine->ngrow != (c.vhi[d] + crse->ngrow) * ratio + ratio - 1)
         return fail("lbx_mf_average_down: fine box (with ghosts) is not the refinement of the coarse box (with ghosts)");
     }
   lbx::k_mf_average_down<<<lbx::mf_grid(crse->max_cells(crse->ngrow), crse->nfabs), lbx::MFT, 0, g.cur>>>(
@@ -498,16 +509,17 @@ int lbx_plan_destroy(lbx_plan* p) {
 static int validate_plan(lbx_plan* p, const lbx_mf* dst, const lbx_mf* s0, const lbx_mf* s1) {
   const auto key = std::make_tuple(dst->geom, s0 ? s0->geom : 0, s1 ? s1->geom : 0);
   if (p->validated.count(key)) return 0;
-  auto inside = [](const lbx::DFabT& f, const int* lo, const int* hi) {
+  // inside valid + ghosts (the allocated box may be wider in x: alignment cells are nobody's data)
+  auto inside = [](const lbx::DFabT& f, int ngrow, const int* lo, const int* hi) {
     for (int d = 0; d < 3; ++d)
-      if (lo[d] < f.lo[d] || hi[d] > f.lo[d] + f.n[d] - 1) return false;
+      if (lo[d] < f.vlo[d] - ngrow || hi[d] > f.vhi[d] + ngrow) return false;
     return true;
   };
   for (const auto& t : p->dsts) {
     if (t.fab < 0 || t.fab >= dst->nfabs) return fail("lbx_plan_apply: destination fab index out of range");
     for (int q = t.first; q < t.first + t.count; ++q) {
       const lbx::GDesc& d = p->descs[q];
-      if (!inside(dst->host[t.fab], d.lo, d.hi)) return fail("lbx_plan_apply: region outside the destination fab");
+      if (!inside(dst->host[t.fab], dst->ngrow, d.lo, d.hi)) return fail("lbx_plan_apply: region outside the destination fab");
       if (d.kind == lbx::G_CONST || d.kind == lbx::G_NONE) continue;
       const lbx_mf* s = d.src_set ? s1 : s0;
       if (!s) return fail("lbx_plan_apply: plan needs a source set that was not given");
@@ -520,7 +532,7 @@ static int validate_plan(lbx_plan* p, const lbx_mf* dst, const lbx_mf* s0, const
         else if (d.kind == lbx::G_PC) { lo[k] = fd(d.lo[k], d.ratio) + d.shift[k]; hi[k] = fd(d.hi[k], d.ratio) + d.shift[k]; }
         else { lo[k] = d.lo[k] * d.ratio + d.shift[k]; hi[k] = d.hi[k] * d.ratio + d.shift[k] + d.ratio - 1; }
       }
-      if (!inside(s->host[d.src_fab], lo, hi)) return fail("lbx_plan_apply: mapped source region outside the source fab");
+      if (!inside(s->host[d.src_fab], s->ngrow, lo, hi)) return fail("lbx_plan_apply: mapped source region outside the source fab");
     }
   }
   p->validated.insert(key);
@@ -566,9 +578,20 @@ int lbx_mf_collide_stream_fillpatch(const lbx_mf* src_valid, lbx_mf* dst, double
                                fallback);
 }
 
+int lbx_mf_collide_stream_level(const lbx_mf* now, lbx_mf* dst, double omega_s, double omega_b, lbx_plan* ghost_plan,
+                                const lbx_mf* src0, const lbx_mf* crse_a, double wa, const lbx_mf* crse_b, double wb,
+                                const lbx_mf* fallback) {
+  if (!ghost_plan) return fail("lbx_mf_collide_stream_level: null plan");
+  if (crse_b && (!crse_a || crse_a->geom != crse_b->geom))
+    return fail("lbx_mf_collide_stream_level: the two coarse states must hold the same boxes");
+  return collide_stream_common(now, nullptr, dst, omega_s, omega_b, nullptr, 0, 0, ghost_plan, src0, crse_a, fallback, true, crse_b,
+                               wa, wb);
+}
+
 static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
                                  const lbx_mf* mask, int fine_val, int zero_invalid, lbx_plan* plan, const lbx_mf* src0,
-                                 const lbx_mf* src1, const lbx_mf* fallback) {
+                                 const lbx_mf* src1, const lbx_mf* fallback, bool level_step, const lbx_mf* src1b, double wa,
+                                 double wb) {
   LBX_NEED_INIT();
   const char* what = "lbx_mf_collide_stream";
   if (need(src_valid, LBX_NV, LBX_F64, 2, what) || need(dst, LBX_NV, LBX_F64, 2, what)) return 1;
@@ -576,7 +599,7 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
     return fail("lbx_mf_collide_stream: src_valid and dst must hold the same boxes, 15 components, 2 ghost cells");
   for (const lbx_mf* s : {src_ghost, fallback})
     if (s && s->geom != dst->geom) return fail("lbx_mf_collide_stream: ghost source and dst differ in geometry");
-  for (const lbx_mf* s : {src_valid, src_ghost, src0, src1, fallback})
+  for (const lbx_mf* s : {src_valid, src_ghost, src0, src1, src1b, fallback})
     if (s && s->base == dst->base) return fail("lbx_mf_collide_stream: dst aliases a source");
   if (mask && (need(mask, 1, LBX_I32, 2, what) || mask->ngrow != 2 || mask->ncomp != 1 || same_boxes(dst, mask, what))) return 1;
   if (dst->max_extent(2) > 65535) return fail("lbx_mf_collide_stream: box extents exceed the launch grid");
@@ -605,16 +628,20 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
     cp.s0 = src0 ? src0->table : nullptr;
     cp.s1 = src1 ? src1->table : nullptr;
     cp.fb = fallback ? fallback->table : nullptr;
+    cp.s1b = src1b ? src1b->table : nullptr;
+    cp.wa = wa;
+    cp.wb = wb;
     cp.tiles_per_group = (int)((plan->max_cells + lbx::MFT - 1) / lbx::MFT);
     ghost_tiles = (long long)cp.tiles_per_group * plan->max_groups;
   } else if (src_ghost) {
     ghost_tiles = (dst->max_shell(2) + lbx::MFT - 1) / lbx::MFT;
   }
-  const bool remote = plan && ((src0 && src0->dist) || (src1 && src1->dist));
+  const bool remote = plan && ((src0 && src0->dist) || (src1 && src1->dist) || (src1b && src1b->dist));
   if (remote && lbx::par_barrier()) return 1;
   L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
                         mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
-                        dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val, zero_invalid);
+                        dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val,
+                        (zero_invalid ? 1 : 0) | (level_step ? 2 : 0));
   if (lbx::after_launch(what)) return 1;
   return remote ? lbx::par_barrier() : 0;
 }

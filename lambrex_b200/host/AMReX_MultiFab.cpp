@@ -115,10 +115,12 @@ template <class T, int DTYPE>
 T DeviceFabArray<T, DTYPE>::hostValue(int bi, const IntVect& p, int comp) const {
   const std::vector<T>& m = hostMirror();
   const int s = isFlat() ? 0 : bi;
-  const Box a = storageBox(s);
-  if (!a.contains(p)) Abort("MultiFab::hostValue: cell outside the fab");
-  const size_t nx = a.length(0), ny = a.length(1), nz = a.length(2);
-  const size_t c = (size_t)(p[0] - a.smallEnd(0)) + nx * ((size_t)(p[1] - a.smallEnd(1)) + ny * (size_t)(p[2] - a.smallEnd(2)));
+  if (!storageBox(s).contains(p)) Abort("MultiFab::hostValue: cell outside the fab");
+  // the ALLOCATED fab may be wider in x than valid + ghosts (sector alignment, lbx_mf_fab)
+  lbx_fab fd;
+  lbx_check(lbx_mf_fab(st_->mf, s, &fd, nullptr, nullptr), "MultiFab::hostValue");
+  const size_t nx = fd.n[0], ny = fd.n[1], nz = fd.n[2];
+  const size_t c = (size_t)(p[0] - fd.lo[0]) + nx * ((size_t)(p[1] - fd.lo[1]) + ny * (size_t)(p[2] - fd.lo[2]));
   return m[st_->offset[s] + (size_t)comp * nx * ny * nz + c];
 }
 
@@ -513,7 +515,12 @@ void whole_region(std::vector<lbx_gather>& d, int k, const Box& reg) {
 }
 void run_plan(lbx_plan* p, MultiFab& dst, const lbx_mf* s0, const lbx_mf* s1, int op, const GhostPush* push,
               const char* what) {
-  if (push)
+  if (push && push->level_step)
+    lbx_check(lbx_mf_collide_stream_level(push->src_valid->mf(), dst.mf(), push->omega_s, push->omega_b, p, s0, s1, push->wa,
+                                          push->crse_b ? push->crse_b->mf() : nullptr, push->wb,
+                                          push->fallback ? push->fallback->mf() : nullptr),
+              what);
+  else if (push)
     lbx_check(lbx_mf_collide_stream_fillpatch(push->src_valid->mf(), dst.mf(), push->omega_s, push->omega_b,
                                               push->mask ? push->mask->mf() : nullptr, push->fine_val,
                                               push->zero_invalid ? 1 : 0, p, s0, s1,

@@ -268,11 +268,46 @@ void AmrSim::CollideAndStream(int const level) {
                                  LBX_PUSH),
               "CollideAndStream");
     next_f.touch();
+  } else if (rohde_fused && CanFuseLevelStep(level)) {
+    LevelStepFused(level);
   } else {
     CollideLevel(level);
     Stream(level);
   }
   lvl.UpdateNow();
+}
+
+// CollideLevel + Stream in one pass over the level (per-box storage, any level).  Same values per
+// cell as the literal sequence: valid cells collide(NOW) pushed; ghost cells FillPatch would take from
+// same-level valid cells push those cells' collided values (what FillBoundary leaves after Collide),
+// ghost cells under the coarse level push the coarse state, interpolated in time under SUBCYCLE.
+bool AmrSim::CanFuseLevelStep(int const level) const {
+  const MultiFab& a = levels[level].now.get<DistFn>();
+  const MultiFab& b = levels[level].next.get<DistFn>();
+  return !(a.empty() || b.empty() || a.isFlat() || b.isFlat() || a.nGrow() != 2 || b.nGrow() != 2 ||
+           a.boxArray() != b.boxArray());
+}
+
+void AmrSim::LevelStepFused(int const level) {
+  MultiFab& f_nxt = levels[level].next.get<DistFn>();
+  const MultiFab& f_now = levels[level].now.get<DistFn>();
+  MultiFab& f_prop = stream_scratch.at(level);
+  if (f_prop.empty() || f_prop.boxArray() != f_nxt.boxArray() || f_prop.layout() != f_nxt.layout())
+    f_prop = field_traits<DistFn>::MakeLevelData(f_nxt.boxArray(), f_nxt.DistributionMap(), f_nxt.layout());
+  amrex::GhostPush push;
+  push.src_valid = &f_now;
+  push.fallback = &f_nxt;
+  push.omega_s = 1.0 / (tau_s.at(level) + 0.5);
+  push.omega_b = 1.0 / (tau_b.at(level) + 0.5);
+  push.level_step = true;
+  if (!level) {
+    amrex::FillPatchSingleLevel(f_prop, f_now, geom[level], true, &push);
+  } else {
+    const MultiFab* ca = nullptr;
+    CoarseStatesAt(level - 1, levels[level].time.current, ca, push.wa, push.crse_b, push.wb);
+    amrex::FillPatchTwoLevels(f_prop, *ca, f_now, geom[level - 1], geom[level], refRatio(level - 1), true, &push);
+  }
+  std::swap(f_nxt, f_prop);          // NEXT = the streamed state, as after the reference's Stream
 }
 
 // src/AmrSim.cpp:324-333
@@ -326,6 +361,25 @@ void AmrSim::FillPatchImpl(int const level, MultiFab& dest, bool ghosts_only, co
 // two states -- NOW at t1 and, in NEXT since UpdateNow's swap, the old one at t0 = t1 - dt -- and
 // FillPatchTwoLevels interpolates between them [AMReX: state 0 or 1 when t is within 1e-3 dt of its
 // time, else LinComb((t1-t)/(t1-t0), old, (t-t0)/(t1-t0), new)].
+void AmrSim::CoarseStatesAt(int const coarse_level, double const t, const MultiFab*& a, double& wa, const MultiFab*& b,
+                            double& wb) {
+  auto& crse = levels.at(coarse_level);
+  const MultiFab& f_new = crse.now.get<DistFn>();
+  a = &f_new; wa = 1.0; b = nullptr; wb = 0.0;
+  if (coupling != Coupling::SUBCYCLE) return;
+  const double t1 = crse.time.current, dt = crse.time.delta, t0 = t1 - dt, eps = 1e-3 * dt;
+  if (std::abs(t - t1) < eps || crse.time.step == 0) return;
+  const MultiFab& f_old = crse.next.get<DistFn>();
+  if (f_old.empty() || f_old.boxArray() != f_new.boxArray() || f_old.layout() != f_new.layout())
+    amrex::Abort("CoarseStateAt: the coarse level's old state is not available");
+  a = &f_old;
+  if (std::abs(t - t0) < eps) return;
+  if (t < t0 - eps || t > t1 + eps) amrex::Abort("CoarseStateAt: fine time outside the coarse step");
+  wa = (t1 - t) / (t1 - t0);
+  b = &f_new;
+  wb = (t - t0) / (t1 - t0);
+}
+
 const MultiFab& AmrSim::CoarseStateAt(int const coarse_level, double const t) {
   auto& crse = levels.at(coarse_level);
   const MultiFab& f_new = crse.now.get<DistFn>();

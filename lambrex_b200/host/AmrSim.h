@@ -187,6 +187,9 @@ class AmrSim : public amrex::AmrCore {
   bool CanFuseRohde(int const level) const;
   void RohdeCycleFused(int const coarse_level);
   void CollideStreamFused(int const level, bool masked, bool zero_invalid, bool from_fillpatch);
+  // CollideLevel + Stream of a level on per-box storage as ONE launch (lbx_mf_collide_stream_level)
+  bool CanFuseLevelStep(int const level) const;
+  void LevelStepFused(int const level);
   bool defer_boundaries = false;
   Coupling coupling = Coupling::ROHDE;
   std::vector<double> gradient_threshold;        // per level; <= 0: criterion off
@@ -196,6 +199,9 @@ class AmrSim : public amrex::AmrCore {
   // the coarse populations FillPatchTwoLevels reads when filling `fine_level` at time t: NOW in the
   // reference's coupling; under SUBCYCLE the coarse state at t (old, new, or their LinComb)
   const amrex::MultiFab& CoarseStateAt(int const coarse_level, double const t);
+  // the same choice without materialising the LinComb: state a with weight wa (+ state b with wb)
+  void CoarseStatesAt(int const coarse_level, double const t, const amrex::MultiFab*& a, double& wa,
+                      const amrex::MultiFab*& b, double& wb);
   std::vector<amrex::MultiFab> coarse_interp;    // LinComb scratch per coarse level (SUBCYCLE)
   void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp);
   const double* density_view = nullptr;

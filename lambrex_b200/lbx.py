@@ -14,7 +14,7 @@ NV, ND, HALO = 15, 3, 2
 F64, I32 = 0, 1
 PUSH, PULL = 0, 1
 OPT_COLLIDE_LITERAL = 1
-OPT_VALID_TILING, OPT_DEBUG_SKIP = 3, 4
+OPT_VALID_TILING, OPT_DEBUG_SKIP, OPT_ALIGN_ROWS = 3, 4, 5
 DEFAULT_VALID_TILING = 0      # lbx_abi.cu g_valid_linear
 OPT_SMEM_PAD = 2
 IPC_HANDLE_BYTES = 64
@@ -116,6 +116,7 @@ SYMBOLS = {
     "lbx_mf_zero_invalid": (_i, [_vp]),
     "lbx_mf_zero_ring": (_i, [_vp, _i, _i]),
     "lbx_mf_lincomb": (_i, [_vp, _d, _vp, _d, _vp]),
+    "lbx_mf_collide_stream_level": (_i, [_vp, _vp, _d, _d, _vp, _vp, _vp, _d, _vp, _d, _vp]),
     "lbx_mf_linear_moments": (_i, [_vp, _vp, _vp, _i, _i]),
     "lbx_mf_tag_gradient": (_i, [_vp, _d, _vp, _i]),
     "lbx_mf_from_user": (_i, [_vp, _vp, _bp, _i]),
@@ -389,12 +390,16 @@ class MF:
         self.nbytes = nb.value
         self.item = 8 if dtype == F64 else 4
         self.npdtype = np.float64 if dtype == F64 else np.int32
-        self.offsets, self.shapes = [], []
-        for i in range(len(self.boxes)):
+        # shapes: the LOGICAL fab (valid + ghosts) the caller sees; alloc / xoff: the allocated fab, which
+        # may carry unused alignment cells in x (lbx_mf_fab)
+        self.offsets, self.shapes, self.alloc, self.xoff = [], [], [], []
+        for i, (lo, hi) in enumerate(self.boxes):
             f, off = lbx_fab(), _sz(0)
             check(lib().lbx_mf_fab(self.h, i, ctypes.byref(f), None, ctypes.byref(off)))
             self.offsets.append(off.value)
-            self.shapes.append((self.ncomp, f.n[2], f.n[1], f.n[0]))
+            self.alloc.append((self.ncomp, f.n[2], f.n[1], f.n[0]))
+            self.xoff.append(lo[0] - self.ngrow - f.lo[0])
+            self.shapes.append((self.ncomp,) + tuple(hi[d] - lo[d] + 1 + 2 * self.ngrow for d in (2, 1, 0)))
 
     def fab(self, i):
         f = lbx_fab()
@@ -403,10 +408,11 @@ class MF:
 
     def upload(self, arrays):
         buf = np.zeros(self.nbytes // self.item, dtype=self.npdtype)
-        for a, off, shp in zip(arrays, self.offsets, self.shapes):
+        for a, off, shp, al, xo in zip(arrays, self.offsets, self.shapes, self.alloc, self.xoff):
             a = np.ascontiguousarray(a, dtype=self.npdtype)
             assert a.shape == shp, (a.shape, shp)
-            buf[off // self.item: off // self.item + a.size] = a.reshape(-1)
+            view = buf[off // self.item: off // self.item + int(np.prod(al))].reshape(al)
+            view[..., xo:xo + shp[3]] = a
         check(lib().lbx_mf_upload(self.h, buf.ctypes.data, self.nbytes))
         sync()
 
@@ -414,8 +420,8 @@ class MF:
         buf = np.empty(self.nbytes // self.item, dtype=self.npdtype)
         check(lib().lbx_mf_download(self.h, buf.ctypes.data, self.nbytes))
         sync()
-        return [buf[off // self.item: off // self.item + int(np.prod(shp))].reshape(shp).copy()
-                for off, shp in zip(self.offsets, self.shapes)]
+        return [buf[off // self.item: off // self.item + int(np.prod(al))].reshape(al)[..., xo:xo + shp[3]].copy()
+                for off, shp, al, xo in zip(self.offsets, self.shapes, self.alloc, self.xoff)]
 
     def setval(self, v):
         check(lib().lbx_mf_setval(self.h, float(v)))
@@ -456,6 +462,10 @@ def mf_collide_stream(src_valid, src_ghost, dst, omega_s, omega_b, mask=None, fi
 
 def mf_stream(src, dst):
     check(lib().lbx_mf_stream(src.h, dst.h))
+
+
+def mf_average_down(fine, crse, ratio=2):
+    check(lib().lbx_mf_average_down(fine.h, crse.h, int(ratio)))
 
 
 def mf_lincomb(dst, a, x, b, y):

@@ -500,3 +500,44 @@ def test_linear_moment_fields_through_amrsim(coracle):
         if lev == 1:
             assert np.all(vel[~own] == -3e8) and (~own).any()
     sim.close()
+
+
+@pytest.mark.parametrize("max_level", [0, 1, 2])
+def test_fused_level_step_equals_literal_pass_sequence(max_level):
+    """lbx_mf_collide_stream_level (CollideLevel + Stream of a level in one launch, time-interpolated
+    coarse ghost data) reproduces the literal FillPatch / Collide / FillBoundary / Stream sequence bit
+    for bit: every cell of NOW, ghost rings included, on every level, through a mid-run regrid."""
+    nx, ny, nz = 16, 12, 20
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    rho = rho * workloads.pulse_density(nx, ny, nz)
+    sims = []
+    for fused in (True, False):
+        sim = AmrSim(nx, ny, nz, max_level, PER, 0.5, 0.5)
+        sim.SetRohdeFusion(fused)
+        sim.SetUniformFastPath(False)
+        sim.SetCoupling(amrsim.SUBCYCLE)
+        sim.SetMaxGridSize(8)
+        sim.SetInitialDensity(rho)
+        sim.SetInitialVelocity(u)
+        sim.InitFromScratch(0.0)
+        if max_level >= 1:
+            sim.SetStaticRefinement(0, (3, 2, 4), (11, 9, 14))
+        if max_level == 2:
+            sim.SetStaticRefinement(1, (10, 8, 12), (19, 15, 25))
+        assert sim.finestLevel() == max_level
+        sims.append(sim)
+    for it in range(4):
+        if it == 2 and max_level >= 1:
+            for sim in sims:
+                sim.SetStaticRefinement(0, (4, 2, 5), (12, 9, 15))
+        for sim in sims:
+            sim.Iterate(1)
+        for lev in range(max_level + 1):
+            assert sims[0].FieldBoxes(lev, amrsim.DISTFN) == sims[1].FieldBoxes(lev, amrsim.DISTFN)
+            for b in range(len(sims[0].FieldBoxes(lev, amrsim.DISTFN))):
+                a = sims[0].FieldFab(lev, amrsim.DISTFN, b, 2, 15)
+                c = sims[1].FieldFab(lev, amrsim.DISTFN, b, 2, 15)
+                assert np.array_equal(a, c), (it, lev, b, float(np.max(np.abs(a - c))))
+            assert sims[0].GetTimeStep(lev) == sims[1].GetTimeStep(lev) == (it + 1) * 2 ** lev
+    for sim in sims:
+        sim.close()
