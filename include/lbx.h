@@ -62,6 +62,9 @@ enum {
                                   aligned valid rows (x extent padded, see lbx_mf_fab); 0 (default) = tight.
                                   Measured (profiles/r01_alignment.md): 1.5x on kernels that write valid
                                   cells only, 0.7x on the passes that also write ghost cells            */
+  LBX_OPT_XGHOST_IN_ROW = 6,   /* lbx_mf_collide_stream (ghosts from own cells): the warp of a valid row also pushes
+                                  the row's 4 x-ghost cells, completing the row's partial end sectors at once */
+  LBX_OPT_PLAIN_STORES = 7,    /* lbx_mf_collide_stream*: valid-cell pushes as write-back instead of streaming stores */
   LBX_OPT_DEBUG_SKIP = 4,      /* PROFILING ONLY (results are wrong): bit 0 skips the valid-cell work of
                                   lbx_mf_collide_stream*, bit 1 the ghost-cell work                  */
 };

@@ -517,6 +517,9 @@ struct CSPlan {                    // ghosts-only FillPatch plan of the level be
   double wa, wb;
 };
 constexpr int CSX = 32, CSY = 8;
+#ifndef LBX_MF_CS_MIN_CTAS
+#define LBX_MF_CS_MIN_CTAS 1     // 4 (64 registers, 32 warps/SM) measured 4 % SLOWER than the natural 3 CTAs/SM (profiles/r01_alignment.md)
+#endif
 static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
 
 // LINEAR (valid tiles): false = CSY rows of one z-plane per CTA, a warp per row (no per-thread
@@ -527,7 +530,7 @@ static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
 // LEVELSTEP: the conventional level step (CollideLevel + Stream, src/AmrSim.cpp:124-135, 109-122) instead
 // of the Rohde pair: needs a plan; see CSPlan and ghost_push_level.
 template <class C, bool LINEAR, bool LEVELSTEP = false>
-__global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
+__global__ void __launch_bounds__(MFT, LBX_MF_CS_MIN_CTAS) k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
                                                            const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
                                                            const DFabT* __restrict__ gt, CSPlan plan, int nfabs,
                                                            int ytiles, int valid_tiles, double omega_s, double omega_b,
@@ -585,8 +588,24 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
           if (!mf_in_valid(D, i + cx(p), j + cy(p), k + cz(p)) && !mf_in_valid(D, i - cx(p), j - cy(p), k - cz(p)))
             f[p] = 0.0;
       }
+      if (flags & 0x800) {           // plain write-back stores: partial end sectors stay in L2 until completed
 #pragma unroll
-      for (int p = 0; p < NV; ++p) __stcs(drow + p * sc + x + (cx(p) + cy(p) * dy + cz(p) * dz), f[p]);
+        for (int p = 0; p < NV; ++p) drow[p * sc + x + (cx(p) + cy(p) * dy + cz(p) * dz)] = f[p];
+      } else {
+#pragma unroll
+        for (int p = 0; p < NV; ++p) __stcs(drow + p * sc + x + (cx(p) + cy(p) * dy + cz(p) * dz), f[p]);
+      }
+    }
+    // x-ghost cells of this row pushed by the row's own warp (flags bit 10, own-ghost mode): the partial
+    // sectors its valid cells left at the two row ends are completed microseconds later by the same
+    // warp instead of by an x-slab ghost CTA much later in launch order (profiles/r01_alignment.md)
+    if (!LINEAR && !LEVELSTEP && (flags & 0x400) && !plan.dsts && gt) {
+      const int tx = tid % CSX;
+      if (tx < 2 * HALO) {
+        const int gi = tx < HALO ? D.vlo[0] - HALO + tx : D.vhi[0] + 1 + (tx - HALO);
+        const DFabT S = gt[b];
+        ghost_push(D, gi, j, k, static_cast<const double*>(S.p) + mf_off(S, gi, j, k), mf_stride(S), zero_invalid);
+      }
     }
     return;
   }
@@ -596,6 +615,7 @@ __global__ void __launch_bounds__(MFT) k_mf_collide_stream(const double* __restr
   if (!plan.dsts) {
     // ---- ghost source cells pushing their own values -------------------------------------------
     if (!gt || !mf_shell_cell(D, gtile * MFT + tid, i, j, k)) return;
+    if (!LINEAR && (flags & 0x400) && j >= D.vlo[1] && j <= D.vhi[1] && k >= D.vlo[2] && k <= D.vhi[2]) return;   // x slabs: done by the rows
     const DFabT S = gt[b];
     ghost_push(D, i, j, k, static_cast<const double*>(S.p) + mf_off(S, i, j, k), mf_stride(S), zero_invalid);
     return;

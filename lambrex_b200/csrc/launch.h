@@ -11,6 +11,10 @@ extern int g_smem_pad;
 extern int g_valid_linear;
 // 1: fabs with ghost cells are allocated with sector-aligned valid rows (LBX_OPT_ALIGN_ROWS); default 0
 extern int g_align_rows;
+// 1: the valid-row warps of k_mf_collide_stream also push their row's x-ghost cells (LBX_OPT_XGHOST_IN_ROW)
+extern int g_xghost_in_row;
+// 1: valid-cell pushes of k_mf_collide_stream use write-back instead of streaming stores (LBX_OPT_PLAIN_STORES)
+extern int g_plain_stores;
 // profiling only (LBX_OPT_DEBUG_SKIP): bit 0 skips the valid tiles' work, bit 1 the ghost tiles' (results are wrong)
 extern int g_debug_skip;
 struct Launchers {

@@ -19,6 +19,8 @@ namespace lbx {
 int g_smem_pad = 0;
 int g_valid_linear = 0;
 int g_align_rows = 0;
+int g_xghost_in_row = 0;
+int g_plain_stores = 0;
 int g_debug_skip = 0;
 Ctx g_ctx;
 thread_local std::string g_err;
@@ -371,7 +373,12 @@ int lbx_set_option(int key, int value) {
       if (value < 0 || value > 48 * 1024) return fail("lbx_set_option: LBX_OPT_SMEM_PAD must be 0..49152");
       lbx::g_smem_pad = value;
       return 0;
-    case LBX_OPT_ALIGN_ROWS: lbx::g_align_rows = (value != 0); return 0;
+    case LBX_OPT_XGHOST_IN_ROW: lbx::g_xghost_in_row = (value != 0); return 0;
+    case LBX_OPT_PLAIN_STORES: lbx::g_plain_stores = (value != 0); return 0;
+    case LBX_OPT_ALIGN_ROWS:
+      if (value != 0 && value != 1 && value != 4 && value != 8 && value != 16) return fail("lbx_set_option: LBX_OPT_ALIGN_ROWS takes 0, 4, 8 or 16 (doubles)");
+      lbx::g_align_rows = value == 1 ? 4 : value;
+      return 0;
     case LBX_OPT_VALID_TILING: lbx::g_valid_linear = (value != 0); return 0;
     case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 3; return 0;
     default: return fail("lbx_set_option: unknown key");

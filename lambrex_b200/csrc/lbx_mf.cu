@@ -119,7 +119,7 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
         // put the first valid cell of every row on a sector boundary and the row pitch is a whole
         // number of sectors, so out-of-place row stores are whole sectors instead of partial ones
         // that the L2 has to complete from DRAM (measured: 1.5x on the out-of-place collision).
-        const int A = 4, lead = (A - ngrow % A) % A;
+        const int A = lbx::g_align_rows, lead = (A - ngrow % A) % A;     // A doubles: 4 = a 32 B sector, 8 = a 64 B burst, 16 = a line
         f.lo[0] -= lead;
         f.n[0] = (f.n[0] + lead + A - 1) / A * A;
       }

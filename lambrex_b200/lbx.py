@@ -14,8 +14,9 @@ NV, ND, HALO = 15, 3, 2
 F64, I32 = 0, 1
 PUSH, PULL = 0, 1
 OPT_COLLIDE_LITERAL = 1
-OPT_VALID_TILING, OPT_DEBUG_SKIP, OPT_ALIGN_ROWS = 3, 4, 5
+OPT_VALID_TILING, OPT_DEBUG_SKIP, OPT_ALIGN_ROWS, OPT_XGHOST_IN_ROW, OPT_PLAIN_STORES = 3, 4, 5, 6, 7
 DEFAULT_VALID_TILING = 0      # lbx_abi.cu g_valid_linear
+DEFAULT_XGHOST_IN_ROW = 0     # lbx_abi.cu g_xghost_in_row
 OPT_SMEM_PAD = 2
 IPC_HANDLE_BYTES = 64
 FACE_XP, FACE_XM, FACE_YP, FACE_YM, FACE_ZP, FACE_ZM = range(6)

@@ -28,8 +28,17 @@ def main():
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--box", type=int, default=32)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--xghost-in-row", type=int, default=0)
+    ap.add_argument("--only", default="", help="substring filter on kernel names")
+    ap.add_argument("--plain-stores", type=int, default=0)
+    ap.add_argument("--align-rows", type=int, default=0)
+    ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 skip valid tiles, 2 skip ghost tiles")
     args = ap.parse_args()
     lbx.init()
+    lbx.set_option(lbx.OPT_XGHOST_IN_ROW, args.xghost_in_row)
+    lbx.set_option(lbx.OPT_DEBUG_SKIP, args.debug_skip)
+    lbx.set_option(lbx.OPT_PLAIN_STORES, args.plain_stores)
+    lbx.set_option(lbx.OPT_ALIGN_ROWS, args.align_rows)
     n, b = args.grid, args.box
     boxes = [((i, j, k), (i + b - 1, j + b - 1, k + b - 1))
              for k in range(0, n, b) for j in range(0, n, b) for i in range(0, n, b)]
@@ -95,6 +104,8 @@ def main():
     ]
     pk = peak()
     for name, nbytes, fn in cases:
+        if args.only and args.only not in name:
+            continue
         for _ in range(3):
             fn()
         lbx.sync()
