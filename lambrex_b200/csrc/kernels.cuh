@@ -517,8 +517,13 @@ struct CSPlan {                    // ghosts-only FillPatch plan of the level be
   double wa, wb;
 };
 constexpr int CSX = 32, CSY = 8;
-#ifndef LBX_MF_CS_MIN_CTAS
-#define LBX_MF_CS_MIN_CTAS 1     // 4 (64 registers, 32 warps/SM) measured 4 % SLOWER than the natural 3 CTAs/SM (profiles/r01_alignment.md)
+// -DLBX_MF_CS_MIN_CTAS=4 (64 registers, 32 warps/SM) measured 4 % SLOWER than the natural 71-75 registers /
+// 3 CTAs per SM (profiles/r01_alignment.md); note that a second launch-bound argument of 1 makes ptxas
+// spend 96 registers (2 CTAs/SM)
+#ifdef LBX_MF_CS_MIN_CTAS
+#define LBX_MF_CS_BOUNDS __launch_bounds__(MFT, LBX_MF_CS_MIN_CTAS)
+#else
+#define LBX_MF_CS_BOUNDS __launch_bounds__(MFT)
 #endif
 static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
 
@@ -530,7 +535,7 @@ static_assert(CSX * CSY == MFT, "valid and ghost tiles share one CTA shape");
 // LEVELSTEP: the conventional level step (CollideLevel + Stream, src/AmrSim.cpp:124-135, 109-122) instead
 // of the Rohde pair: needs a plan; see CSPlan and ghost_push_level.
 template <class C, bool LINEAR, bool LEVELSTEP = false>
-__global__ void __launch_bounds__(MFT, LBX_MF_CS_MIN_CTAS) k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
+__global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ vbase, double* __restrict__ dbase,
                                                            const DFabT* __restrict__ dt, const DFabT* __restrict__ mt,
                                                            const DFabT* __restrict__ gt, CSPlan plan, int nfabs,
                                                            int ytiles, int valid_tiles, double omega_s, double omega_b,

@@ -40,3 +40,15 @@ def test_tables_query_needs_no_gpu():
     import numpy as np
     assert np.allclose(M @ Mi, np.eye(15), atol=1e-15)
     assert abs(w.sum() - 1.0) < 1e-15 and (c[0] == 0).all()
+
+
+def test_host_library_exports_every_symbol_of_lambrex_c_h():
+    """liblambrex.so (the C mirror of AmrSim, include/lambrex_c.h): every declared entry point is
+    exported and bound by lambrex_b200/amrsim.py."""
+    from lambrex_b200 import amrsim
+    L = amrsim.lib()
+    names = declared_symbols("lambrex_c.h")
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(L, n), "liblambrex.so does not export " + n
+    assert names == set(amrsim.SYMBOLS), names ^ set(amrsim.SYMBOLS)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--xghost-in-row", type=int, default=0)
     ap.add_argument("--only", default="", help="substring filter on kernel names")
     ap.add_argument("--plain-stores", type=int, default=0)
+    ap.add_argument("--valid-tiling", type=int, default=0)
     ap.add_argument("--align-rows", type=int, default=0)
     ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 skip valid tiles, 2 skip ghost tiles")
     args = ap.parse_args()
@@ -38,6 +39,7 @@ def main():
     lbx.set_option(lbx.OPT_XGHOST_IN_ROW, args.xghost_in_row)
     lbx.set_option(lbx.OPT_DEBUG_SKIP, args.debug_skip)
     lbx.set_option(lbx.OPT_PLAIN_STORES, args.plain_stores)
+    lbx.set_option(lbx.OPT_VALID_TILING, args.valid_tiling)
     lbx.set_option(lbx.OPT_ALIGN_ROWS, args.align_rows)
     n, b = args.grid, args.box
     boxes = [((i, j, k), (i + b - 1, j + b - 1, k + b - 1))
