@@ -82,6 +82,11 @@ int lbx_sim_get_velocity_field(const lbx_sim *sim, int level, double *out, size_
  * level does not hold = sentinel. */
 int lbx_sim_get_linear_moment_field(const lbx_sim *sim, int level, const double *weights, int ncomp,
                                     int per_unit_density, double sentinel, double *out, size_t n);
+/* addition (the reference has no I/O): checkpoint of clocks, tau ladder, refinement criteria,
+ * box lists and valid-cell populations; read into a sim created with the same extents and max level.  A
+ * restarted run continues bit for bit. */
+int lbx_sim_write_checkpoint(lbx_sim *sim, const char *path);
+int lbx_sim_read_checkpoint(lbx_sim *sim, const char *path);
 /* GetTime, GetTimeStep, GetDims, GetExtent (:130-139, 154) */
 int lbx_sim_get_time(const lbx_sim *sim, int level, double *out);
 int lbx_sim_get_time_step(const lbx_sim *sim, int level, int *out);

@@ -37,6 +37,7 @@ SYMBOLS = {
     "lbx_sim_destroy": (_i, [_vp]),
     "lbx_sim_set_max_grid_size": (_i, [_vp, _i]), "lbx_sim_set_uniform_fast_path": (_i, [_vp, _i]),
     "lbx_sim_set_rohde_fusion": (_i, [_vp, _i]), "lbx_sim_set_coupling": (_i, [_vp, _i]),
+    "lbx_sim_write_checkpoint": (_i, [_vp, ctypes.c_char_p]), "lbx_sim_read_checkpoint": (_i, [_vp, ctypes.c_char_p]),
     "lbx_sim_get_linear_moment_field": (_i, [_vp, _i, _dp, _i, _i, _d, _dp, _sz]),
     "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
     "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
@@ -273,6 +274,12 @@ class AmrSim:
         _check(lib().lbx_sim_get_linear_moment_field(self._h, level, w.ctypes.data_as(_dp), w.shape[0], int(per_unit_density),
                                                      float(sentinel), out.ctypes.data_as(_dp), out.size))
         return out
+
+    def WriteCheckpoint(self, path):
+        _check(lib().lbx_sim_write_checkpoint(self._h, os.fsencode(path)))
+
+    def ReadCheckpoint(self, path):
+        _check(lib().lbx_sim_read_checkpoint(self._h, os.fsencode(path)))
 
     def GetTime(self, level):
         v = _d()

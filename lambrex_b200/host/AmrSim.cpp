@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include "AmrSim.h"
 
+#include <cstdio>
+#include <cstring>
 #include <iostream>
 #include <stdexcept>
 
@@ -775,4 +777,112 @@ void AmrSim::UnsetGradientRefinement(int const level) {
   gradient_threshold.at(level) = 0.0;
   regrid(level, GetTime(level));
   MakeFineMask(level);
+}
+
+// ----------------------------------------------------------------------------- checkpoint / restart
+namespace {
+constexpr char CHK_MAGIC[8] = {'L', 'B', 'X', 'C', 'H', 'K', '1', 0};
+struct ChkFile {
+  std::FILE* f;
+  explicit ChkFile(const std::string& path, const char* mode) : f(std::fopen(path.c_str(), mode)) {
+    if (!f) amrex::Abort(("checkpoint: cannot open " + path).c_str());
+  }
+  ~ChkFile() { if (f) std::fclose(f); }
+  void put(const void* p, size_t n) { if (std::fwrite(p, 1, n, f) != n) amrex::Abort("checkpoint: short write"); }
+  void get(void* p, size_t n) { if (std::fread(p, 1, n, f) != n) amrex::Abort("checkpoint: short read / truncated file"); }
+  template <class T> void put(const T& v) { put(&v, sizeof(T)); }
+  template <class T> T get() { T v; get(&v, sizeof(T)); return v; }
+};
+}  // namespace
+
+void AmrSim::WriteCheckpoint(const std::string& path) {
+  if (DistributionMapping::NProcs() > 1) amrex::Abort("WriteCheckpoint: single-process runs only");
+  ChkFile c(path, "wb");
+  c.put(CHK_MAGIC, sizeof(CHK_MAGIC));
+  for (int v : {NX, NY, NZ, max_level, finest_level, (int)coupling, regrid_int, steps_since_regrid, num_regrids}) c.put<int32_t>(v);
+  for (int l = 0; l <= max_level; ++l) {
+    c.put<double>(tau_s[l]); c.put<double>(tau_b[l]); c.put<double>(mass[l]);
+    c.put<double>(levels[l].time.current); c.put<double>(levels[l].time.delta); c.put<int32_t>(levels[l].time.step);
+    c.put<double>(gradient_threshold[l]);
+    c.put<int32_t>((int)static_tags[l].size());
+    for (long q = 0; q < static_tags[l].size(); ++q)
+      for (int d = 0; d < 3; ++d) { c.put<int32_t>(static_tags[l][q].smallEnd(d)); c.put<int32_t>(static_tags[l][q].bigEnd(d)); }
+  }
+  for (int l = 0; l <= finest_level; ++l) {
+    const MultiFab& f = levels[l].now.get<DistFn>();
+    const BoxArray& ba = f.boxArray();
+    c.put<int32_t>((int)ba.size());
+    for (long q = 0; q < ba.size(); ++q)
+      for (int d = 0; d < 3; ++d) { c.put<int32_t>(ba[q].smallEnd(d)); c.put<int32_t>(ba[q].bigEnd(d)); }
+    // valid cells only, box after box, [comp][z][y][x]: a ghost-free copy on the device, one download
+    MultiFab tight(ba, f.DistributionMap(), NMODES, 0);
+    amrex::CopyValid(tight, f);
+    const std::vector<double>& h = tight.hostMirror();
+    c.put<uint64_t>((uint64_t)h.size());
+    c.put(h.data(), h.size() * sizeof(double));
+  }
+}
+
+void AmrSim::ReadCheckpoint(const std::string& path) {
+  if (DistributionMapping::NProcs() > 1) amrex::Abort("ReadCheckpoint: single-process runs only");
+  ChkFile c(path, "rb");
+  char magic[8];
+  c.get(magic, sizeof(magic));
+  if (std::memcmp(magic, CHK_MAGIC, sizeof(magic)) != 0) amrex::Abort("ReadCheckpoint: not a lambrex-b200 checkpoint");
+  const int nx = c.get<int32_t>(), ny = c.get<int32_t>(), nz = c.get<int32_t>(), ml = c.get<int32_t>();
+  if (nx != NX || ny != NY || nz != NZ || ml != max_level)
+    amrex::Abort("ReadCheckpoint: the checkpoint was written by a simulation with other extents or max level");
+  const int new_finest = c.get<int32_t>();
+  coupling = c.get<int32_t>() == (int)Coupling::SUBCYCLE ? Coupling::SUBCYCLE : Coupling::ROHDE;
+  regrid_int = c.get<int32_t>();
+  steps_since_regrid = c.get<int32_t>();
+  num_regrids = c.get<int32_t>();
+  for (int l = 0; l <= max_level; ++l) {
+    tau_s[l] = c.get<double>(); tau_b[l] = c.get<double>(); mass[l] = c.get<double>();
+    levels[l].time.current = c.get<double>(); levels[l].time.delta = c.get<double>(); levels[l].time.step = c.get<int32_t>();
+    gradient_threshold[l] = c.get<double>();
+    const int nst = c.get<int32_t>();
+    amrex::BoxList bl;
+    for (int q = 0; q < nst; ++q) {
+      IntVect lo, hi;
+      for (int d = 0; d < 3; ++d) { lo[d] = c.get<int32_t>(); hi[d] = c.get<int32_t>(); }
+      bl.push_back(Box(lo, hi));
+    }
+    if (nst) static_tags[l].define(bl); else static_tags[l].clear();
+  }
+  amrex::ClearPlanCache();
+  for (int l = 0; l <= max_level; ++l) {
+    const TimeData keep = levels[l].time;
+    if (l > new_finest) {
+      if (!levels[l].now.get<DistFn>().empty()) { ClearLevel(l); ClearBoxArray(l); ClearDistributionMap(l); }
+      levels[l].time = keep;
+      continue;
+    }
+    const int nb = c.get<int32_t>();
+    amrex::BoxList bl;
+    for (int q = 0; q < nb; ++q) {
+      IntVect lo, hi;
+      for (int d = 0; d < 3; ++d) { lo[d] = c.get<int32_t>(); hi[d] = c.get<int32_t>(); }
+      bl.push_back(Box(lo, hi));
+    }
+    const BoxArray ba(bl);
+    const DistributionMapping dm(ba);
+    velocity[l].define(ba, dm, NDIMS, 0);
+    levels[l].Define(ba, dm);                    // per-box storage; Iterate re-lays level 0 out when it is alone
+    levels[l].time = keep;
+    stream_scratch[l].clear();
+    valid_pending[l] = false;
+    SetBoxArray(l, ba);
+    SetDistributionMap(l, dm);
+    MultiFab tight(ba, dm, NMODES, 0);
+    const uint64_t n = c.get<uint64_t>();
+    std::vector<double> h((size_t)n);
+    c.get(h.data(), h.size() * sizeof(double));
+    tight.upload(h);
+    amrex::CopyValid(levels[l].now.get<DistFn>(), tight);
+    levels[l].now.get<DistFn>().touch();
+  }
+  finest_level = new_finest;
+  for (int l = 0; l <= finest_level; ++l) CalcHydroVars(l);
+  for (int l = 0; l < finest_level; ++l) MakeFineMask(l);
 }

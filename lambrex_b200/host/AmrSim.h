@@ -16,6 +16,7 @@
 #define LBX_AMRSIM_H
 
 #include <array>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -77,6 +78,12 @@ class AmrSim : public amrex::AmrCore {
   // the level's domain, C-ordered [i][j][k][c]; cells the level does not hold carry `sentinel`
   void GetLinearMomentField(int const level, const double* weights, int const ncomp, bool const per_unit_density,
                             double const sentinel, double* out, size_t n) const;
+  // checkpoint / restart (the reference has no I/O).  The file holds the clocks, the tau
+  // ladder, the refinement criteria, every level's box list and the VALID-cell populations of NOW;
+  // ghost cells, densities, velocities and masks are recomputed.  ReadCheckpoint needs a sim constructed
+  // with the same extents and max level (single process); a restarted run continues bit for bit.
+  void WriteCheckpoint(const std::string& path);
+  void ReadCheckpoint(const std::string& path);
   // zero-copy inputs: the arrays (same C ordering) are read at InitFromScratch directly from
   // caller memory -- pinned memory makes that one DMA -- and must stay valid until it returns.
   void SetInitialDensityView(const double* rho_init, size_t n) { density_view = rho_init; density_view_n = n; }

@@ -108,6 +108,9 @@ int lbx_sim_get_linear_moment_field(const lbx_sim* sim, int level, const double*
   return guarded([&] { sim->s.GetLinearMomentField(level, weights, ncomp, per_unit_density != 0, sentinel, out, n); });
 }
 
+int lbx_sim_write_checkpoint(lbx_sim* sim, const char* path) { return guarded([&] { sim->s.WriteCheckpoint(path); }); }
+int lbx_sim_read_checkpoint(lbx_sim* sim, const char* path) { return guarded([&] { sim->s.ReadCheckpoint(path); }); }
+
 int lbx_sim_set_coupling(lbx_sim* sim, int coupling) {
   return guarded([&] {
     if (coupling != LBX_COUPLING_ROHDE && coupling != LBX_COUPLING_SUBCYCLE) amrex::Abort("unknown coupling");
