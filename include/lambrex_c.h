@@ -132,6 +132,9 @@ int lbx_meta_max_size(const int *in_boxes, int n, int chunk, int *boxes, int cap
 int lbx_meta_simplify(const int *in_boxes, int n, int *boxes, int cap);
 int lbx_meta_complement(const int region[6], const int *in_boxes, int n, int *boxes, int cap);
 int lbx_meta_cluster(const int *points /* [3 * npoints] */, int npoints, double efficiency, int *boxes, int cap);
+/* box ownership of a distributed run (amrex::DistributionMapping(ba, nprocs)): owners[i] = rank of box i --
+ * contiguous chunks of the box list balanced by cell count; the same on every rank by construction */
+int lbx_meta_distribution(const int *in_boxes, int n, int nprocs, int *owners);
 /* A field-less AmrCore with the reference's static-box tagging (TagCell, src/AmrSim.cpp:413-417):
  * create, InitFromScratch, then set / unset static boxes (each triggers regrid(level)), query grids. */
 typedef struct lbx_meta_mesh lbx_meta_mesh;

@@ -69,7 +69,7 @@ SYMBOLS = {
     "lbx_sim_call_clear_level": (_i, [_vp, _i]),
     "lbx_meta_base_grids": (_i, [_ip, _i, _ip, _i]), "lbx_meta_max_size": (_i, [_ip, _i, _i, _ip, _i]),
     "lbx_meta_simplify": (_i, [_ip, _i, _ip, _i]), "lbx_meta_complement": (_i, [_ip, _ip, _i, _ip, _i]),
-    "lbx_meta_cluster": (_i, [_ip, _i, _d, _ip, _i]),
+    "lbx_meta_cluster": (_i, [_ip, _i, _d, _ip, _i]), "lbx_meta_distribution": (_i, [_ip, _i, _i, _ip]),
     "lbx_meta_mesh_create": (_i, [_ip, _i, _i, ctypes.POINTER(_vp)]), "lbx_meta_mesh_destroy": (_i, [_vp]),
     "lbx_meta_mesh_set_static": (_i, [_vp, _i, _ip, _ip]), "lbx_meta_mesh_unset_static": (_i, [_vp, _i]),
     "lbx_meta_mesh_finest_level": (_i, [_vp]), "lbx_meta_mesh_boxes": (_i, [_vp, _i, _ip, _i]),
@@ -110,9 +110,19 @@ def lambrexInitParallel(group=None):
     """One process per GPU (torchrun): boxes of every level are owned by ranks, neighbours' boxes
     are read over NVLink through CUDA-IPC.  torch.distributed (an initialised process group whose
     CPU backend is gloo) is the host plumbing: it only carries IPC handles.  Collective."""
-    import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cb = make_allgather_hook(group)
+    _check(lib().lbx_sim_global_init_parallel(rank, world, cb, None))
+
+
+def make_allgather_hook(group=None):
+    """The C callback lbx_sim_global_init_parallel takes -- allgather(send, nbytes, recv, user): `nbytes`
+    from every rank into `recv`, rank order -- over torch.distributed's CPU backend.  It carries CUDA-IPC
+    handles at allocation time and the tag runs of a regrid; no field data."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
 
     def allgather(send, nbytes, recv, _user):
         try:
@@ -127,7 +137,7 @@ def lambrexInitParallel(group=None):
 
     cb = _ALLGATHER_T(allgather)
     _par_keep.append(cb)
-    _check(lib().lbx_sim_global_init_parallel(rank, world, cb, None))
+    return cb
 
 
 def setParallelView(rank, nranks):
@@ -441,6 +451,13 @@ def meta_complement(region, boxes):
     arr, n = _boxes_in(boxes)
     reg = (ctypes.c_int * 6)(*region[0], *region[1])
     return _meta_call(lib().lbx_meta_complement, reg, arr, n)
+
+
+def meta_distribution(boxes, nprocs):
+    arr, n = _boxes_in(boxes)
+    out = (_i * max(n, 1))()
+    _check(lib().lbx_meta_distribution(arr, n, int(nprocs), out))
+    return [int(out[i]) for i in range(n)]
 
 
 def meta_cluster(points, efficiency=0.7):

@@ -352,6 +352,16 @@ int lbx_meta_cluster(const int* points, int npoints, double eff, int* boxes, int
       })) return -1;
   return r;
 }
+int lbx_meta_distribution(const int* in_boxes, int n, int nprocs, int* owners) {
+  return guarded([&] {
+    amrex::BoxList bl;
+    for (int i = 0; i < n; ++i)
+      bl.push_back(amrex::Box(amrex::IntVect(in_boxes[6 * i], in_boxes[6 * i + 1], in_boxes[6 * i + 2]),
+                              amrex::IntVect(in_boxes[6 * i + 3], in_boxes[6 * i + 4], in_boxes[6 * i + 5])));
+    const amrex::DistributionMapping dm(amrex::BoxArray(bl), nprocs);
+    for (int i = 0; i < n; ++i) owners[i] = dm[i];
+  });
+}
 int lbx_meta_mesh_create(const int dims[3], int max_level, int max_grid_size, lbx_meta_mesh** out) {
   return guarded([&] { *out = new lbx_meta_mesh(dims, max_level, max_grid_size); (*out)->m.InitFromScratch(0.0); });
 }

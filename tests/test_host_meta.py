@@ -116,3 +116,23 @@ def test_regrid_sequences_match_oracle(dims, max_level, ops, coracle):
             cells = ao.complement_in(c, sim.grids[lev - 1])
             for r in cells:      # anything uncovered must be outside the domain (periodic wrap)
                 assert ao.isect(r, dom) is None or lev - 1 == 0
+
+
+def test_box_ownership_of_a_distributed_level():
+    """amrex::DistributionMapping(ba, nprocs) as the distributed AMR path uses it (SURVEY 8e): contiguous
+    chunks of the box list, every rank non-empty and within one box of the mean cell count; identical
+    on every rank by construction (no communication)."""
+    ba = amrsim.meta_base_grids((256, 256, 256))
+    assert len(ba) == 512
+    for nprocs in (1, 2, 4, 8):
+        own = amrsim.meta_distribution(ba, nprocs)
+        assert own == sorted(own) and set(own) == set(range(nprocs))          # contiguous chunks, nobody idle
+        counts = [own.count(r) for r in range(nprocs)]
+        assert max(counts) - min(counts) <= 1
+    # ragged boxes: balance by CELLS, not by box count
+    ragged = [((0, 0, 0), (63, 63, 63))] + [((64 + 8 * i, 0, 0), (71 + 8 * i, 7, 7)) for i in range(64)]
+    own = amrsim.meta_distribution(ragged, 2)
+    cells = [0, 0]
+    for (lo, hi), r in zip(ragged, own):
+        cells[r] += int(np.prod([h - l + 1 for l, h in zip(lo, hi)]))
+    assert own[0] == 0 and own[-1] == 1 and cells[0] >= 64 ** 3

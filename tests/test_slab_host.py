@@ -92,3 +92,48 @@ def test_halo_message_pairing_over_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def _allgather_worker(rank, world, port, q):
+    import ctypes
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lambrex_b200 import amrsim
+        hook = amrsim.make_allgather_hook()
+        # the two message kinds of the distributed AMR path: a 64-byte CUDA-IPC handle per allocation and a
+        # padded list of 16-byte tag runs per regrid (TagBoxArray::collate)
+        for nbytes in (64, 16 * 37):
+            send = (ctypes.c_ubyte * nbytes)(*[(7 * rank + i) % 251 for i in range(nbytes)])
+            recv = (ctypes.c_ubyte * (nbytes * world))()
+            assert hook(ctypes.cast(send, ctypes.c_void_p), nbytes, ctypes.cast(recv, ctypes.c_void_p), None) == 0
+            for r in range(world):
+                assert list(recv[r * nbytes:(r + 1) * nbytes]) == [(7 * r + i) % 251 for i in range(nbytes)]
+        # ownership is computed, not communicated: every rank derives the same map
+        ba = amrsim.meta_base_grids((64, 64, 128))
+        own = amrsim.meta_distribution(ba, world)
+        got = allgather_objects(own)
+        assert all(g == own for g in got)
+        q.put((rank, "ok"))
+    except Exception as e:       # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_amr_allgather_hook_and_ownership_over_gloo():
+    """Host plumbing of the distributed AMR path (lambrexInitParallel) on CPU, world_size 2."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_allgather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
