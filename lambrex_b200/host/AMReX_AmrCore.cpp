@@ -180,15 +180,26 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
   if ((int)new_grids.size() < max_crse + 2) new_grids.resize(max_crse + 2);
   // proper-nesting domains (blocking factor 1 on this path: no tag coarsening)
   Vector<BoxList> p_n(max_level), p_n_comp(max_level);
+  auto TP = std::chrono::steady_clock::now();
+  auto plap = [&](const char* what) {
+    if (!getenv("LBX_HOST_TIMING")) return;
+    auto T1 = std::chrono::steady_clock::now();
+    std::cerr << "  [regrid lbase " << lbase << "] proper nesting: " << what << " " << std::chrono::duration<double>(T1 - TP).count() << " s\n";
+    TP = T1;
+  };
   {
     BoxList bl = grids[lbase].boxList();
     simplify(bl);
+    plap("simplify(level grids)");
     p_n_comp[lbase] = complementIn(geom[lbase].Domain(), bl);
+    plap("complementIn");
     simplify(p_n_comp[lbase]);
+    plap("simplify(complement)");
     for (Box& b : p_n_comp[lbase]) b.grow(n_proper);
     if (geom[lbase].isAnyPeriodic()) proj_periodic(p_n_comp[lbase], geom[lbase].Domain(), geom[lbase]);
     p_n[lbase] = complementIn(geom[lbase].Domain(), p_n_comp[lbase]);
     simplify(p_n[lbase]);
+    plap("grow/periodic/complement/simplify");
   }
   for (int i = lbase + 1; i <= max_crse; ++i) {
     p_n_comp[i] = p_n_comp[i - 1];
@@ -197,6 +208,7 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
     if (geom[i].isAnyPeriodic()) proj_periodic(p_n_comp[i], geom[i].Domain(), geom[i]);
     p_n[i] = complementIn(geom[i].Domain(), p_n_comp[i]);
     simplify(p_n[i]);
+    plap("finer level");
   }
   new_finest = lbase;
   for (int levc = max_crse; levc >= lbase; --levc) {

@@ -56,32 +56,56 @@ BoxList complementIn(const Box& region, const BoxList& bl) {
   return cur;
 }
 
-void simplify(BoxList& bl) {
-  // repeatedly coalesce pairs that abut along exactly one direction with equal extents in
-  // the others; a joined box replaces the LATER of the two (list order otherwise kept)
-  bool changed = true;
-  while (changed) {
-    changed = false;
-    for (size_t a = 0; a < bl.size() && !changed; ++a) {
-      for (size_t b = a + 1; b < bl.size(); ++b) {
-        int lo[3], hi[3], joincnt = 0;
-        bool canjoin = true;
-        for (int d = 0; d < 3 && canjoin; ++d) {
-          const int alo = bl[a].smallEnd(d), ahi = bl[a].bigEnd(d), blo = bl[b].smallEnd(d), bhi = bl[b].bigEnd(d);
-          if (alo == blo && ahi == bhi) { lo[d] = alo; hi[d] = ahi; }
-          else if (alo <= blo && blo <= ahi + 1) { lo[d] = alo; hi[d] = std::max(ahi, bhi); ++joincnt; }
-          else if (blo <= alo && alo <= bhi + 1) { lo[d] = blo; hi[d] = std::max(ahi, bhi); ++joincnt; }
-          else canjoin = false;
-        }
-        if (canjoin && joincnt <= 1) {
-          bl[b] = Box(IntVect(lo), IntVect(hi));
-          bl.erase(bl.begin() + a);
-          changed = true;
-          break;
-        }
-      }
-    }
+namespace {
+// a and b abut along exactly one direction (or overlap there) with equal extents in the others
+inline bool joinable(const Box& A, const Box& B, Box& joined) {
+  int lo[3], hi[3], joincnt = 0;
+  for (int d = 0; d < 3; ++d) {
+    const int alo = A.smallEnd(d), ahi = A.bigEnd(d), blo = B.smallEnd(d), bhi = B.bigEnd(d);
+    if (alo == blo && ahi == bhi) { lo[d] = alo; hi[d] = ahi; }
+    else if (alo <= blo && blo <= ahi + 1) { lo[d] = alo; hi[d] = std::max(ahi, bhi); ++joincnt; }
+    else if (blo <= alo && alo <= bhi + 1) { lo[d] = blo; hi[d] = std::max(ahi, bhi); ++joincnt; }
+    else return false;
   }
+  if (joincnt > 1) return false;
+  joined = Box(IntVect(lo), IntVect(hi));
+  return true;
+}
+}  // namespace
+
+void simplify(BoxList& bl) {
+  // Semantics: repeatedly take the FIRST pair (a < b, lexicographic) that can be coalesced; the joined
+  // box replaces the later of the two, the earlier one is removed, list order otherwise kept; restart.
+  // Restarting from scratch is O(n^3); the same sequence of merges is found incrementally: after
+  // merging (a, b) every pair (x, y) with x < a is unchanged and known not to join, except the
+  // pairs (x, new box) -- so only those are re-examined, and the scan otherwise resumes at a.
+  std::vector<Box> v(bl.begin(), bl.end());
+  std::vector<char> dead(v.size(), 0);          // removed boxes are skipped, compacted at the end
+  size_t a = 0;
+  const size_t n = v.size();
+  auto next_alive = [&](size_t q) { while (q < n && dead[q]) ++q; return q; };
+  a = next_alive(0);
+  while (a < n) {
+    bool merged = false;
+    Box j;
+    for (size_t b = next_alive(a + 1); b < n; b = next_alive(b + 1)) {
+      if (!joinable(v[a], v[b], j)) continue;
+      v[b] = j;
+      dead[a] = 1;
+      merged = true;
+      // earlier boxes against the new box: the first that joins becomes the next pair's first index
+      size_t x = next_alive(0);
+      Box jj;
+      for (; x < a; x = next_alive(x + 1))
+        if (joinable(v[x], v[b], jj)) break;
+      a = (x < a) ? x : next_alive(a + 1);
+      break;
+    }
+    if (!merged) a = next_alive(a + 1);
+  }
+  bl.clear();
+  for (size_t q = 0; q < n; ++q)
+    if (!dead[q]) bl.push_back(v[q]);
 }
 
 void maxSize(BoxList& bl, const IntVect& chunk) {
