@@ -543,9 +543,13 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   LBX_NEED_INIT();
   if (!p || !dst) return fail("lbx_plan_apply: null plan or destination");
   if (op != LBX_OP_COPY && op != LBX_OP_ADD) return fail("lbx_plan_apply: unknown op");
-  if (p->descs.empty()) return 0;
-  if (validate_plan(p, dst, src0, src1)) return 1;
   const bool remote = (src0 && src0->dist) || (src1 && src1->dist);   // sources may sit in peers' HBM
+  if (p->descs.empty()) {
+    // a rank that owns no box of the destination still takes part in the two all-rank barriers
+    if (remote && (lbx::par_barrier() || lbx::par_barrier())) return 1;
+    return 0;
+  }
+  if (validate_plan(p, dst, src0, src1)) return 1;
   if (remote && lbx::par_barrier()) return 1;
   const dim3 grid = lbx::mf_grid(p->max_cells, (int)p->dsts.size());
   const lbx::DFabT* t0 = src0 ? src0->table : nullptr;
@@ -608,7 +612,12 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   long long ghost_tiles = 0;
   if (plan) {
     if (plan->has_avg || plan->has_const) return fail("lbx_mf_collide_stream_fillpatch: only COPY / PC / NONE descriptors can be pushed");
-    if (plan->descs.empty()) return fail("lbx_mf_collide_stream_fillpatch: empty plan");
+    if (plan->descs.empty()) {      // this rank owns no box of the level: only the collective part remains
+      const bool rem = (src0 && src0->dist) || (src1 && src1->dist) || (src1b && src1b->dist);
+      if (!dst->dist) return fail("lbx_mf_collide_stream_fillpatch: empty plan");
+      if (rem && (lbx::par_barrier() || lbx::par_barrier())) return 1;
+      return 0;
+    }
     if (validate_plan(plan, dst, src0, src1)) return 1;
     if (plan->fab_first_n != dst->nfabs) {            // first group of every fab (groups are sorted by fab)
       std::vector<int> first((size_t)dst->nfabs + 1, 0);

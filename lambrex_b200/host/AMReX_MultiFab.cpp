@@ -425,7 +425,9 @@ BoxList tile_regions(const Box& want, const Box& valid, bool shell_only) {
   return r;
 }
 
-lbx_plan* cached(const std::string& key, const std::function<void(std::vector<lbx_gather>&)>& build) {
+lbx_plan* cached(const std::string& key0, const std::function<void(std::vector<lbx_gather>&)>& build) {
+  // plans describe this rank's own destination boxes only: the ownership view is part of the identity
+  const std::string key = key0 + "|" + std::to_string(DistributionMapping::NProcs()) + "." + std::to_string(DistributionMapping::MyProc());
   auto it = g_plans.find(key);
   if (it != g_plans.end()) return it->second.get();
   std::vector<lbx_gather> descs;
@@ -549,6 +551,7 @@ void ParallelCopy(MultiFab& dst, const MultiFab& src, int src_ng, int dst_ng, co
     const BoxHash sh(sv);
     const std::vector<IntVect> shifts = period.shiftIntVect();
     for (int k = 0; k < dst.numStorageFabs(); ++k) {
+      if (!dst.isLocal(k)) continue;            // another rank fills its own boxes
       g_group = 0;
       for (const Box& reg : tile_regions(amrex::grow(dst.storageValid(k), dst_ng), dst.storageValid(k), ghosts_only)) {
         if (ghosts_only) whole_region(d, k, reg);
@@ -571,6 +574,7 @@ void FillBoundary(MultiFab& mf, const Periodicity& period) {
     const BoxHash sh(sv);
     const std::vector<IntVect> shifts = period.shiftIntVect();
     for (int k = 0; k < mf.numStorageFabs(); ++k) {
+      if (!mf.isLocal(k)) continue;
       g_group = 0;
       for (const Box& reg : tile_regions(mf.storageBox(k), mf.storageValid(k), true)) {
         copy_descs(d, k, reg, sv, sh, 0, shifts, 0, true, k);
@@ -613,6 +617,7 @@ static void two_level_fill(MultiFab& dst, const MultiFab& crse, const MultiFab* 
     const BoxHash fh(fv);
     const std::vector<IntVect> fs = fgeom.periodicity().shiftIntVect();
     for (int k = 0; k < dst.numStorageFabs(); ++k) {
+      if (!dst.isLocal(k)) continue;
       g_group = 0;
       for (const Box& reg : tile_regions(dst.storageBox(k), dst.storageValid(k), ghosts_only)) {
         if (ghosts_only) whole_region(d, k, reg);
@@ -683,6 +688,7 @@ void average_down(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, co
     }
     const BoxHash fh(cf);
     for (int k = 0; k < (int)crse.size(); ++k) {
+      if (!crse.isLocal(k)) continue;
       const Box want = crse.box(k);
       const size_t from = d.size();
       for (int i : fh.query(want)) {
@@ -714,6 +720,7 @@ iMultiFab makeFineMask(const MultiFab& cmf, const BoxArray& fba, const IntVect& 
   const BoxHash fh(cf);
   std::vector<lbx_gather> d;
   for (int k = 0; k < (int)mask.size(); ++k) {
+    if (!mask.isLocal(k)) continue;
     const Box want = mask.fabbox(k);
     for (int i : fh.query(want)) d.push_back(make_desc(k, 0, 0, LBX_G_CONST, 1, IntVect(0), cf[i] & want, (double)fine_value));
   }
