@@ -132,6 +132,12 @@ int lbx_meta_max_size(const int *in_boxes, int n, int chunk, int *boxes, int cap
 int lbx_meta_simplify(const int *in_boxes, int n, int *boxes, int cap);
 int lbx_meta_complement(const int region[6], const int *in_boxes, int n, int *boxes, int cap);
 int lbx_meta_cluster(const int *points /* [3 * npoints] */, int npoints, double efficiency, int *boxes, int cap);
+/* distributed grid generation WITHOUT a GPU (tests of the host logic over gloo / MPI): after this, the
+ * lbx_meta_mesh of every rank tags only the boxes it owns and regrid merges the tag runs through
+ * `allgather` -- the same code path lbx_sim_global_init_parallel runs on the GPU box. */
+int lbx_meta_parallel_init(int rank, int nranks,
+                           int (*allgather)(const void *send, size_t bytes, void *recv, void *user), void *user);
+int lbx_meta_parallel_finalise(void);
 /* box ownership of a distributed run (amrex::DistributionMapping(ba, nprocs)): owners[i] = rank of box i --
  * contiguous chunks of the box list balanced by cell count; the same on every rank by construction */
 int lbx_meta_distribution(const int *in_boxes, int n, int nprocs, int *owners);

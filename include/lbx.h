@@ -94,6 +94,11 @@ int lbx_set_stream(void *cuda_stream);   /* NULL: back to the library's own stre
  * it only carries IPC handles when fields are created.  lbx_par_init is collective. */
 int lbx_par_init(int rank, int world, int (*allgather)(const void *send, size_t bytes, void *recv, void *user),
                  void *user);
+/* host-only variant (no CUDA device): rank / world / allgather for the grid-generation metadata of a
+ * distributed regrid; device collectives stay unavailable.  Not combinable with lbx_init. */
+int lbx_par_init_host(int rank, int world, int (*allgather)(const void *send, size_t bytes, void *recv, void *user),
+                      void *user);
+int lbx_par_finalize_host(void);
 int lbx_par_info(int *rank, int *world, uint64_t *barriers);
 int lbx_par_barrier(void);
 /* the registered allgather, for host metadata the ranks must agree on (regrid tag lists):

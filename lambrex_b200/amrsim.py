@@ -70,6 +70,7 @@ SYMBOLS = {
     "lbx_meta_base_grids": (_i, [_ip, _i, _ip, _i]), "lbx_meta_max_size": (_i, [_ip, _i, _i, _ip, _i]),
     "lbx_meta_simplify": (_i, [_ip, _i, _ip, _i]), "lbx_meta_complement": (_i, [_ip, _ip, _i, _ip, _i]),
     "lbx_meta_cluster": (_i, [_ip, _i, _d, _ip, _i]), "lbx_meta_distribution": (_i, [_ip, _i, _i, _ip]),
+    "lbx_meta_parallel_init": (_i, [_i, _i, _vp, _vp]), "lbx_meta_parallel_finalise": (_i, []),
     "lbx_meta_mesh_create": (_i, [_ip, _i, _i, ctypes.POINTER(_vp)]), "lbx_meta_mesh_destroy": (_i, [_vp]),
     "lbx_meta_mesh_set_static": (_i, [_vp, _i, _ip, _ip]), "lbx_meta_mesh_unset_static": (_i, [_vp, _i]),
     "lbx_meta_mesh_finest_level": (_i, [_vp]), "lbx_meta_mesh_boxes": (_i, [_vp, _i, _ip, _i]),
@@ -451,6 +452,17 @@ def meta_complement(region, boxes):
     arr, n = _boxes_in(boxes)
     reg = (ctypes.c_int * 6)(*region[0], *region[1])
     return _meta_call(lib().lbx_meta_complement, reg, arr, n)
+
+
+def metaParallelInit(group=None):
+    """Distributed grid generation on the CPU (no GPU): MetaMesh objects tag the boxes this rank owns and
+    merge the tag runs through torch.distributed -- the regrid path of lambrexInitParallel."""
+    import torch.distributed as dist
+    _check(lib().lbx_meta_parallel_init(dist.get_rank(group), dist.get_world_size(group), make_allgather_hook(group), None))
+
+
+def metaParallelFinalise():
+    _check(lib().lbx_meta_parallel_finalise())
 
 
 def meta_distribution(boxes, nprocs):

@@ -338,6 +338,21 @@ int lbx_par_init(int rank, int world, int (*allgather)(const void*, size_t, void
   std::vector<unsigned char> toks(world);
   return lbx::par_allgather(&tok, 1, toks.data());
 }
+/* Host-only variant for the grid-generation metadata (no CUDA device needed): registers rank, world and the
+ * allgather callback so that lbx_par_allgather works -- what the distributed regrid (tag runs merged across
+ * ranks) needs.  No device barrier flags are set up: device collectives stay unavailable. */
+int lbx_par_init_host(int rank, int world, int (*allgather)(const void*, size_t, void*, void*), void* user) {
+  if (g.ready) return fail("lbx_par_init_host: a device context exists; use lbx_par_init");
+  if (world < 1 || rank < 0 || rank >= world || world > 32) return fail("lbx_par_init_host: bad rank/world (1..32 ranks)");
+  if (world > 1 && !allgather) return fail("lbx_par_init_host: null allgather callback");
+  g.rank = rank; g.world = world; g.allgather = world > 1 ? allgather : nullptr; g.allgather_user = user;
+  return 0;
+}
+int lbx_par_finalize_host(void) {
+  if (g.ready) return fail("lbx_par_finalize_host: a device context exists; use lbx_finalize");
+  g.rank = 0; g.world = 1; g.allgather = nullptr; g.allgather_user = nullptr;
+  return 0;
+}
 int lbx_par_info(int* rank, int* world, uint64_t* barriers) {
   if (rank) *rank = g.rank;
   if (world) *world = g.world;
@@ -345,7 +360,7 @@ int lbx_par_info(int* rank, int* world, uint64_t* barriers) {
   return 0;
 }
 int lbx_par_allgather(const void* send, size_t bytes, void* recv) {
-  LBX_NEED_INIT();
+  if (!g.ready && !g.allgather && g.world > 1) return fail("lbx_par_allgather: not initialised");
   return lbx::par_allgather(send, bytes, recv);
 }
 int lbx_par_barrier(void) {

@@ -352,6 +352,18 @@ int lbx_meta_cluster(const int* points, int npoints, double eff, int* boxes, int
       })) return -1;
   return r;
 }
+int lbx_meta_parallel_init(int rank, int nranks, int (*allgather)(const void*, size_t, void*, void*), void* user) {
+  return guarded([&] {
+    amrex::lbx_check(lbx_par_init_host(rank, nranks, allgather, user), "lbx_meta_parallel_init");
+    amrex::DistributionMapping::SetParallel(rank, nranks);
+  });
+}
+int lbx_meta_parallel_finalise(void) {
+  return guarded([&] {
+    amrex::lbx_check(lbx_par_finalize_host(), "lbx_meta_parallel_finalise");
+    amrex::DistributionMapping::SetParallel(0, 1);
+  });
+}
 int lbx_meta_distribution(const int* in_boxes, int n, int nprocs, int* owners) {
   return guarded([&] {
     amrex::BoxList bl;

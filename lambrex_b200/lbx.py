@@ -70,6 +70,7 @@ SYMBOLS = {
     "lbx_arena_release": (_i, []),
     "lbx_par_init": (_i, [_i, _i, _vp, _vp]),
     "lbx_par_info": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_uint64)]),
+    "lbx_par_init_host": (_i, [_i, _i, _vp, _vp]), "lbx_par_finalize_host": (_i, []),
     "lbx_par_barrier": (_i, []),
     "lbx_par_allgather": (_i, [_vp, _sz, _vp]),
     "lbx_mf_create_dist": (_i, [_vp, _i, _i, _i, _i, _vp, ctypes.POINTER(_vp)]),

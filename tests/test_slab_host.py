@@ -137,3 +137,62 @@ def test_amr_allgather_hook_and_ownership_over_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def _regrid_worker(rank, world, port, q, want):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lambrex_b200 import amrsim
+        amrsim.metaParallelInit()
+        m = amrsim.MetaMesh((64, 48, 32), 2, 16)
+        got = []
+        m.set_static(0, (10, 8, 6), (41, 30, 21))
+        got.append([m.boxes(l) for l in range(3)])
+        m.set_static(1, (40, 30, 20), (75, 55, 37))
+        got.append([m.boxes(l) for l in range(3)])
+        m.set_static(0, (12, 8, 6), (43, 30, 21))            # moves level 1 (and what nests in it)
+        got.append([m.boxes(l) for l in range(3)])
+        m.unset_static(1)
+        got.append([m.boxes(l) for l in range(3)])
+        fin = m.finest_level()
+        del m
+        amrsim.metaParallelFinalise()
+        q.put((rank, "ok" if (got == want["grids"] and fin == want["finest"]) else "grids differ from the single-process run"))
+    except Exception as e:       # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_regrid_gives_the_single_process_grids_over_gloo(world):
+    """The distributed regrid of the AMR path on CPU: every rank tags only the boxes it owns
+    (TagBoxArray without storage for the others), TagBoxArray::collate merges the tag runs through the
+    allgather hook, and every rank must arrive at exactly the box lists of a single-process run."""
+    import torch.multiprocessing as mp
+    from lambrex_b200 import amrsim
+    m = amrsim.MetaMesh((64, 48, 32), 2, 16)
+    grids = []
+    m.set_static(0, (10, 8, 6), (41, 30, 21))
+    grids.append([m.boxes(l) for l in range(3)])
+    m.set_static(1, (40, 30, 20), (75, 55, 37))
+    grids.append([m.boxes(l) for l in range(3)])
+    m.set_static(0, (12, 8, 6), (43, 30, 21))
+    grids.append([m.boxes(l) for l in range(3)])
+    m.unset_static(1)
+    grids.append([m.boxes(l) for l in range(3)])
+    want = {"grids": grids, "finest": m.finest_level()}
+    assert len(grids[1][2]) > 0 and grids[1] != grids[2] and len(grids[3][2]) == 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_regrid_worker, args=(r, world, port, q, want)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
