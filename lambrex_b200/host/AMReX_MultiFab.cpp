@@ -145,6 +145,8 @@ template class DeviceFabArray<int, LBX_I32>;
 void TagBox::setVal(char v, const Box& region) {
   const Box r = region & box_;
   if (!r.ok() || !allocated()) return;
+  if (v == CLEAR && d_.empty()) return;          // nothing tagged yet: already clear
+  materialise();
   for (int k = r.smallEnd(2); k <= r.bigEnd(2); ++k)
     for (int j = r.smallEnd(1); j <= r.bigEnd(1); ++j) {
       char* row = &d_[index(IntVect(r.smallEnd(0), j, k))];
@@ -164,7 +166,7 @@ static inline int next_nonclear(const char* row, int x, int n) {
 }
 
 void TagBox::buffer(int nbuf, const Box& interior) {
-  if (nbuf <= 0 || !allocated()) return;
+  if (nbuf <= 0 || !allocated() || d_.empty()) return;
   const Box in = interior & box_;
   if (!in.ok()) return;
   struct Run { int i0, i1, j, k; };
@@ -231,7 +233,7 @@ void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std
     return lo + (((v - lo) % len) + len) % len;
   };
   for (const TagBox& t : fabs_) {
-    if (!t.allocated()) continue;
+    if (!t.allocated() || !t.hasStorage()) continue;
     const Box& b = t.box();
     const int n = b.length(0);
     for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
@@ -239,7 +241,7 @@ void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std
         bool ok = true;
         const int jj = wrap1(j, 1, ok), kk = wrap1(k, 2, ok);
         if (!ok) continue;
-        const char* row = &t(IntVect(b.smallEnd(0), j, k));
+        const char* row = t.row(IntVect(b.smallEnd(0), j, k));
         for (int x = next_nonclear(row, 0, n); x < n;) {
           int y = x;
           while (y + 1 < n && row[y + 1] != TagBox::CLEAR) ++y;

@@ -247,11 +247,12 @@ int lbx_sim_call_error_est(lbx_sim* sim, int level, const int* tag_boxes, int nt
     size_t q = 0;
     for (amrex::MFIter mfi(tba); mfi.isValid(); ++mfi) {
       const amrex::Box b = mfi.validbox();
+      const amrex::TagBox& t = static_cast<const amrex::TagBoxArray&>(tba)[mfi];      // const read: no storage is forced
       for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
         for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j)
           for (int i = b.smallEnd(0); i <= b.bigEnd(0); ++i) {
             if (q >= n) amrex::Abort("lbx_sim_call_error_est: buffer too small");
-            out[q++] = tba[mfi](amrex::IntVect(i, j, k));
+            out[q++] = t(amrex::IntVect(i, j, k));
           }
     }
   });
