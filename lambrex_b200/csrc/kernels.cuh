@@ -552,14 +552,24 @@ __global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ 
     // ---- valid source cells: collide, push ---------------------------------------------------
     int i0, j, k, istep;
     if (LINEAR) {
-      const unsigned nx = D.vhi[0] - D.vlo[0] + 1, ny = D.vhi[1] - D.vlo[1] + 1, nz = D.vhi[2] - D.vlo[2] + 1;
+      // own-ghost mode with flags bit 10: the rows are tiled INCLUDING their 2 + 2 x-ghost cells, so that
+      // consecutive threads cover consecutive memory across row ends and the x-ghost pushes / ring-2
+      // zeros that complete a row's end sectors come from the same or the neighbouring warp
+      const bool xrows = (flags & 0x400) && !plan.dsts && gt && !LEVELSTEP;
+      const unsigned gx = xrows ? HALO : 0;
+      const unsigned nx = D.vhi[0] - D.vlo[0] + 1 + 2 * gx, ny = D.vhi[1] - D.vlo[1] + 1, nz = D.vhi[2] - D.vlo[2] + 1;
       unsigned t = blockIdx.x * MFT + tid;
       if (t >= nx * ny * nz) return;
-      i0 = D.vlo[0] + (int)(t % nx);
+      i0 = D.vlo[0] - (int)gx + (int)(t % nx);
       t /= nx;
       j = D.vlo[1] + (int)(t % ny);
       k = D.vlo[2] + (int)(t / ny);
       istep = 1 << 30;                                    // one cell per thread
+      if (i0 < D.vlo[0] || i0 > D.vhi[0]) {               // an x-ghost cell of a valid row: push its own value
+        const DFabT S = gt[b];
+        ghost_push(D, i0, j, k, static_cast<const double*>(S.p) + mf_off(S, i0, j, k), mf_stride(S), zero_invalid);
+        return;
+      }
     } else {
       const int ty = tid / CSX, tx = tid % CSX;
       j = D.vlo[1] + ((int)blockIdx.x % ytiles) * CSY + ty;
@@ -620,7 +630,7 @@ __global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ 
   if (!plan.dsts) {
     // ---- ghost source cells pushing their own values -------------------------------------------
     if (!gt || !mf_shell_cell(D, gtile * MFT + tid, i, j, k)) return;
-    if (!LINEAR && (flags & 0x400) && j >= D.vlo[1] && j <= D.vhi[1] && k >= D.vlo[2] && k <= D.vhi[2]) return;   // x slabs: done by the rows
+    if ((flags & 0x400) && j >= D.vlo[1] && j <= D.vhi[1] && k >= D.vlo[2] && k <= D.vhi[2]) return;   // x slabs: done by the rows
     const DFabT S = gt[b];
     ghost_push(D, i, j, k, static_cast<const double*>(S.p) + mf_off(S, i, j, k), mf_stride(S), zero_invalid);
     return;

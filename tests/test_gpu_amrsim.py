@@ -321,15 +321,16 @@ def test_three_level_shear_matches_oracle(coracle):
     assert (sim.GetTime(2), sim.GetTimeStep(2)) == (o.levels[2].time, o.levels[2].step)
 
 
-@pytest.mark.parametrize("tiling", [0, 1, 2])
+@pytest.mark.parametrize("tiling", [0, 1, 2, 3])
 @pytest.mark.parametrize("max_level", [1, 2])
 def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level, tiling):
     """The fused collide+Stream(+ZeroInvalidComponents) passes reproduce the reference's literal
     sequence of passes bit for bit: every cell of NOW (ghost rings included) on every level."""
     from lambrex_b200 import lbx
     # valid tiles: 0 a warp per row / 1 256 consecutive cells / 2 a warp per row that also pushes the row's x-ghost cells
-    lbx.set_option(lbx.OPT_VALID_TILING, 1 if tiling == 1 else 0)
-    lbx.set_option(lbx.OPT_XGHOST_IN_ROW, 1 if tiling == 2 else 0)
+    # 3: 256 consecutive cells of the rows INCLUDING their x-ghost cells
+    lbx.set_option(lbx.OPT_VALID_TILING, 1 if tiling in (1, 3) else 0)
+    lbx.set_option(lbx.OPT_XGHOST_IN_ROW, 1 if tiling in (2, 3) else 0)
     nx, ny, nz = 16, 12, 20
     rho, u = workloads.shear_wave(nx, ny, nz)
     rho = rho * workloads.pulse_density(nx, ny, nz)

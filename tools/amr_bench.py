@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--regrid-every", type=int, default=0, help="coarse steps between regrids (0: never)")
     ap.add_argument("--no-fusion", action="store_true", help="Rohde cycle as the literal pass sequence")
     ap.add_argument("--valid-tiling", default=None, choices=["rows", "linear"], help="valid-cell tiles of the fused pass")
+    ap.add_argument("--xghost-in-row", type=int, default=0)
     ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 skip valid tiles, 2 skip ghost tiles")
     ap.add_argument("--coupling", default="rohde", choices=["rohde", "subcycle"],
                     help="rohde: the reference's live RohdeCycle; subcycle: conventional subcycling (FillPatch with "
@@ -57,6 +58,7 @@ def main():
         amrsim.lambrexInit()
     if args.valid_tiling:
         lbx.set_option(lbx.OPT_VALID_TILING, 1 if args.valid_tiling == "linear" else 0)
+    lbx.set_option(lbx.OPT_XGHOST_IN_ROW, args.xghost_in_row)
     n = args.grid
     sim = amrsim.AmrSim(n, n, n, args.levels - 1, (1, 1, 1), 0.5, 0.5)
     sim.SetMaxGridSize(args.max_grid)
