@@ -356,14 +356,18 @@ __global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ st
 // The ghost cells are pushed from their own values or, with DistFnFillPatch folded in, from
 // wherever FillPatch takes them (k_mf_collide_stream below), loading only the populations that
 // have a destination.
+// The shell INCLUDES the row-alignment cells of the allocated box in x (LBX_OPT_ALIGN_ROWS: lead-in / tail
+// cells beyond the 2 ghost cells): they behave like ghost rings >= 2 -- nothing is pushed from them and
+// they zero themselves -- so that a pass writes every sector of the destination completely.
 __device__ __forceinline__ bool mf_shell_cell(const DFabT& f, unsigned t, int& i, int& j, int& k) {
   constexpr unsigned h = HALO;
   const unsigned v0 = f.vhi[0] - f.vlo[0] + 1, v1 = f.vhi[1] - f.vlo[1] + 1, v2 = f.vhi[2] - f.vlo[2] + 1;
-  const unsigned n0 = v0 + 2 * h, n1 = v1 + 2 * h;
-  const unsigned A = n0 * n1 * h, B = n0 * h * v2, Cc = h * v1 * v2;     // a fab holds < 2^31 cells
+  const unsigned n0 = f.n[0], n1 = v1 + 2 * h;                           // x: the whole allocated row
+  const unsigned hl = f.vlo[0] - f.lo[0], hr = n0 - v0 - hl;             // cells left / right of the valid row
+  const unsigned A = n0 * n1 * h, B = n0 * h * v2, Cl = hl * v1 * v2, Cr = hr * v1 * v2;   // a fab holds < 2^31 cells
   if (t < 2 * A) {                      // z-low / z-high slabs: full x-y planes
     const unsigned s = t >= A, r = t - s * A;
-    i = f.vlo[0] - (int)h + (int)(r % n0);
+    i = f.lo[0] + (int)(r % n0);
     j = f.vlo[1] - (int)h + (int)((r / n0) % n1);
     k = (s ? f.vhi[2] + 1 : f.vlo[2] - (int)h) + (int)(r / (n0 * n1));
     return true;
@@ -371,17 +375,23 @@ __device__ __forceinline__ bool mf_shell_cell(const DFabT& f, unsigned t, int& i
   t -= 2 * A;
   if (t < 2 * B) {                      // y-low / y-high slabs over the valid z range
     const unsigned s = t >= B, r = t - s * B;
-    i = f.vlo[0] - (int)h + (int)(r % n0);
+    i = f.lo[0] + (int)(r % n0);
     j = (s ? f.vhi[1] + 1 : f.vlo[1] - (int)h) + (int)((r / n0) % h);
     k = f.vlo[2] + (int)(r / (n0 * h));
     return true;
   }
   t -= 2 * B;
-  if (t < 2 * Cc) {                     // x-low / x-high slabs over the valid y-z range
-    const unsigned s = t >= Cc, r = t - s * Cc;
-    i = (s ? f.vhi[0] + 1 : f.vlo[0] - (int)h) + (int)(r % h);
-    j = f.vlo[1] + (int)((r / h) % v1);
-    k = f.vlo[2] + (int)(r / (h * v1));
+  if (t < Cl) {                         // x-low slab over the valid y-z range
+    i = f.lo[0] + (int)(t % hl);
+    j = f.vlo[1] + (int)((t / hl) % v1);
+    k = f.vlo[2] + (int)(t / (hl * v1));
+    return true;
+  }
+  t -= Cl;
+  if (t < Cr) {                         // x-high slab
+    i = f.vhi[0] + 1 + (int)(t % hr);
+    j = f.vlo[1] + (int)((t / hr) % v1);
+    k = f.vlo[2] + (int)(t / (hr * v1));
     return true;
   }
   return false;

@@ -30,11 +30,14 @@ struct lbx_mf {
     for (const auto& f : host) m = std::max(m, f.vhi[dir] - f.vlo[dir] + 1);
     return m;
   }
-  long long max_shell(int grow) const {     // most ghost-shell cells (grown minus valid) of any fab
+  long long max_shell(int grow) const {     // most ghost-shell cells (grown minus valid) of any fab, incl. x alignment cells
     long long m = 0;
     for (const auto& f : host) {
       long long v = 1, c = 1;
-      for (int d = 0; d < 3; ++d) { v *= (f.vhi[d] - f.vlo[d] + 1); c *= (f.vhi[d] - f.vlo[d] + 1 + 2 * grow); }
+      for (int d = 0; d < 3; ++d) {
+        v *= (f.vhi[d] - f.vlo[d] + 1);
+        c *= d == 0 ? (long long)f.n[0] : (f.vhi[d] - f.vlo[d] + 1 + 2 * grow);
+      }
       m = std::max(m, c - v);
     }
     return m;
@@ -114,7 +117,7 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
       if (valid[i].hi[d] < valid[i].lo[d]) { delete m; return fail("lbx_mf_create: empty box"); }
       f.vlo[d] = valid[i].lo[d]; f.vhi[d] = valid[i].hi[d];
       f.lo[d] = f.vlo[d] - ngrow; f.n[d] = f.vhi[d] - f.vlo[d] + 1 + 2 * ngrow;
-      if (d == 0 && dtype == LBX_F64 && ngrow > 0 && lbx::g_align_rows) {
+      if (d == 0 && ngrow > 0 && lbx::g_align_rows) {      // int masks too: the fused pass indexes them with the populations' row offsets
         // 32-byte sector alignment of the VALID rows (profiles/r01_alignment.md): unused lead-in cells
         // put the first valid cell of every row on a sector boundary and the row pitch is a whole
         // number of sectors, so out-of-place row stores are whole sectors instead of partial ones

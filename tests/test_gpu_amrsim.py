@@ -593,3 +593,34 @@ def test_restart_from_checkpoint_continues_bit_for_bit(tmp_path, case):
         AmrSim(nx, ny, nz + 1, max_level, PER, 0.5, 0.5).ReadCheckpoint(path)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("align", [4, 16])
+def test_sector_aligned_fab_layout_is_bit_identical(align):
+    """LBX_OPT_ALIGN_ROWS pads the x extent of ghosted fabs so that valid rows start on a sector / line
+    boundary; it must not change a single value (fabs are read back in their logical shape)."""
+    from lambrex_b200 import lbx
+    nx, ny, nz = 16, 12, 20
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    rho = rho * workloads.pulse_density(nx, ny, nz)
+    sims = []
+    try:
+        for a in (0, align):
+            lbx.set_option(lbx.OPT_ALIGN_ROWS, a)
+            sim = AmrSim(nx, ny, nz, 1, PER, 0.3, 0.4)
+            sim.SetMaxGridSize(8)
+            sim.SetInitialDensity(rho)
+            sim.SetInitialVelocity(u)
+            sim.InitFromScratch(0.0)
+            sim.SetStaticRefinement(0, (3, 2, 4), (11, 9, 14))
+            sim.Iterate(3)
+            sims.append(sim)
+        for lev in (0, 1):
+            for b in range(len(sims[0].FieldBoxes(lev, amrsim.DISTFN))):
+                x = sims[0].FieldFab(lev, amrsim.DISTFN, b, 2, 15)
+                y = sims[1].FieldFab(lev, amrsim.DISTFN, b, 2, 15)
+                assert x.shape == y.shape and np.array_equal(x, y), (lev, b)
+    finally:
+        lbx.set_option(lbx.OPT_ALIGN_ROWS, 0)
+        for sim in sims:
+            sim.close()
