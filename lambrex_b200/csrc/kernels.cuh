@@ -566,11 +566,12 @@ __global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ 
       // consecutive threads cover consecutive memory across row ends and the x-ghost pushes / ring-2
       // zeros that complete a row's end sectors come from the same or the neighbouring warp
       const bool xrows = (flags & 0x400) && !plan.dsts && gt && !LEVELSTEP;
-      const unsigned gx = xrows ? HALO : 0;
-      const unsigned nx = D.vhi[0] - D.vlo[0] + 1 + 2 * gx, ny = D.vhi[1] - D.vlo[1] + 1, nz = D.vhi[2] - D.vlo[2] + 1;
+      // with x rows: the whole ALLOCATED row (ghost cells and alignment cells included)
+      const unsigned nx = xrows ? (unsigned)D.n[0] : (unsigned)(D.vhi[0] - D.vlo[0] + 1);
+      const unsigned ny = D.vhi[1] - D.vlo[1] + 1, nz = D.vhi[2] - D.vlo[2] + 1;
       unsigned t = blockIdx.x * MFT + tid;
       if (t >= nx * ny * nz) return;
-      i0 = D.vlo[0] - (int)gx + (int)(t % nx);
+      i0 = (xrows ? D.lo[0] : D.vlo[0]) + (int)(t % nx);
       t /= nx;
       j = D.vlo[1] + (int)(t % ny);
       k = D.vlo[2] + (int)(t / ny);
@@ -626,8 +627,9 @@ __global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ 
     // warp instead of by an x-slab ghost CTA much later in launch order (profiles/r01_alignment.md)
     if (!LINEAR && !LEVELSTEP && (flags & 0x400) && !plan.dsts && gt) {
       const int tx = tid % CSX;
-      if (tx < 2 * HALO) {
-        const int gi = tx < HALO ? D.vlo[0] - HALO + tx : D.vhi[0] + 1 + (tx - HALO);
+      const int hl = D.vlo[0] - D.lo[0], hr = D.n[0] - (D.vhi[0] - D.vlo[0] + 1) - hl;   // ghost + alignment cells left / right
+      if (tx < hl + hr) {
+        const int gi = tx < hl ? D.lo[0] + tx : D.vhi[0] + 1 + (tx - hl);
         const DFabT S = gt[b];
         ghost_push(D, gi, j, k, static_cast<const double*>(S.p) + mf_off(S, gi, j, k), mf_stride(S), zero_invalid);
       }
