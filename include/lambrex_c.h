@@ -55,6 +55,9 @@ int lbx_sim_set_gradient_refinement(lbx_sim *sim, int level, double threshold);
 int lbx_sim_unset_gradient_refinement(lbx_sim *sim, int level);
 int lbx_sim_set_regrid_interval(lbx_sim *sim, int n);
 int lbx_sim_num_regrids(const lbx_sim *sim);
+/* gather plans currently cached (process-wide): bounded over any number of regrids (generation sweep in
+ * AmrCore::regrid + LRU cap); a diagnostic for long dynamic-AMR runs */
+int lbx_sim_plan_cache_size(void);
 
 /* SetInitialDensity / SetInitialVelocity (:141-144); n == 1 selects the scalar overloads */
 int lbx_sim_set_initial_density(lbx_sim *sim, const double *rho, size_t n);

@@ -41,6 +41,7 @@ SYMBOLS = {
     "lbx_sim_get_linear_moment_field": (_i, [_vp, _i, _dp, _i, _i, _d, _dp, _sz]),
     "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
     "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
+    "lbx_sim_plan_cache_size": (_i, []),
     "lbx_sim_global_init_parallel": (_i, [_i, _i, _vp, _vp]), "lbx_sim_set_parallel_view": (_i, [_i, _i]),
     "lbx_sim_owner": (_i, [_vp, _i, _i, ctypes.POINTER(_i)]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
@@ -212,6 +213,10 @@ class AmrSim:
 
     def NumRegrids(self):
         return int(lib().lbx_sim_num_regrids(self._h))
+
+    @staticmethod
+    def PlanCacheSize():
+        return int(lib().lbx_sim_plan_cache_size())
 
     def _set(self, fn, v):
         a = np.ascontiguousarray(np.atleast_1d(np.asarray(v, dtype=np.float64)).reshape(-1))

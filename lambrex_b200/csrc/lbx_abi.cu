@@ -126,6 +126,7 @@ int par_allgather(const void* send, size_t bytes, void* recv) {
 int par_barrier() {
   Ctx& g = g_ctx;
   if (g.world == 1) return 0;
+  if (*g.peer_err) return fail("par_barrier: an earlier peer wait or barrier timed out; the run is no longer synchronised");
   int* derr = nullptr;
   cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&derr), g.peer_err, 0);
   if (e != cudaSuccess) return fail("par_barrier: cudaHostGetDevicePointer");
@@ -141,6 +142,11 @@ int after_launch(const char* what) {
   ++g_ctx.launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
+  // STICKY peer error: once a peer wait / all-rank barrier has timed out, the work queued behind it ran on
+  // unsynchronised peer data; every later call fails (host-mapped flag, no synchronisation needed) until
+  // lbx_peer_error() acknowledges it, so a caller's step loop cannot run on silently
+  if (g_ctx.peer_err && *g_ctx.peer_err)
+    return fail(std::string(what) + ": a peer wait or all-rank barrier timed out earlier (a neighbour GPU did not signal); results since then are invalid");
   if (g_ctx.conc_next >= 0) {      // concurrent section: the next launch gets the next auxiliary stream
     Ctx& g = g_ctx;
     g.conc_next = (g.conc_next + 1) % Ctx::NAUX;

@@ -167,13 +167,21 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
   }
   for (int i = 0; i < nfabs; ++i) m->host[i].p = bases[m->owner[i]] + m->own_off[i];
   e = lbx::arena_alloc(reinterpret_cast<void**>(&m->table), sizeof(lbx::DFabT) * nfabs);
-  if (e != cudaSuccess) { lbx::arena_free(m->base); delete m; return fail("lbx_mf_create: cudaMalloc(table)"); }
   // pageable-host async copy: the driver stages it before returning, so `host` may change later
-  LBX_CUDA(cudaMemcpyAsync(m->table, m->host.data(), sizeof(lbx::DFabT) * nfabs, cudaMemcpyHostToDevice, g.cur));
-  if (mine) LBX_CUDA(cudaMemsetAsync(m->base, 0, mine, g.cur));     // NEW_FAB_FILL = 0
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->table, m->host.data(), sizeof(lbx::DFabT) * nfabs, cudaMemcpyHostToDevice, g.cur);
+  if (e == cudaSuccess && mine) e = cudaMemsetAsync(m->base, 0, mine, g.cur);     // NEW_FAB_FILL = 0
   // a recycled arena block may still be read by a slow peer under its previous identity: nobody
-  // proceeds until every rank has got here (and has therefore finished what it queued before)
-  if (m->dist && lbx::par_barrier()) return 1;
+  // proceeds until every rank has got here (and has therefore finished what it queued before).  A rank
+  // whose own set-up failed still takes part in the collective, so the peers are not left spinning.
+  const int brc = m->dist ? lbx::par_barrier() : 0;
+  if (e != cudaSuccess || brc) {
+    if (e != cudaSuccess) fail(std::string("lbx_mf_create: ") + cudaGetErrorString(e));
+    cudaStreamSynchronize(g.cur);
+    lbx::arena_free(m->base);
+    if (m->table) lbx::arena_free(m->table);
+    delete m;
+    return 1;
+  }
   *out = m;
   return 0;
 }

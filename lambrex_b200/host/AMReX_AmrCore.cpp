@@ -221,23 +221,35 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
       std::cerr << "  [regrid levc " << levc << "] " << what << " " << std::chrono::duration<double>(T1 - T0).count() << " s\n";
       T0 = T1;
     };
-    TagBoxArray tags(grids[levc], dmap[levc], nbuf);
-    lap("alloc tags");
-    ErrorEst(levc, tags, time, 0);
-    lap("ErrorEst");
-    tags.buffer(nbuf);
-    lap("buffer");
+    // AMReX's order [AMReX, unverified; ADVICE r01]: the new grids two levels up are projected down to levc
+    // FIRST, the tag boxes are allocated wide enough to hold that projection (ngrow = how far grids[levc]
+    // must grow to contain it; 0 under proper nesting), the projection is SET before buffering -- so it is
+    // buffered like the user's tags -- and the buffer width is n_error_buf + ngrow.
+    BoxList proj;
+    int ngrow = 0;
     if (levf < new_finest) {
-      // project the new grids two levels up down to levc so that the new levf contains them
-      BoxList proj;
       for (const Box& b : new_grids[levf + 1].boxList()) {
         Box c = amrex::coarsen(b, ref_ratio[levf]);
         c.grow(n_proper);
         c.coarsen(ref_ratio[levc]);
         proj.push_back(c);
       }
-      tags.setVal(proj, TagBox::SET);
+      auto covered = [&](int g) {
+        BoxList grown = grids[levc].boxList();
+        for (Box& b : grown) b.grow(g);
+        for (const Box& c : proj)
+          if (!complementIn(c, grown).empty()) return false;
+        return true;
+      };
+      while (ngrow < 64 && !covered(ngrow)) ++ngrow;
     }
+    TagBoxArray tags(grids[levc], dmap[levc], nbuf + ngrow);
+    lap("alloc tags");
+    ErrorEst(levc, tags, time, 0);
+    lap("ErrorEst");
+    if (!proj.empty()) tags.setVal(proj, TagBox::SET);
+    tags.buffer(nbuf + ngrow);
+    lap("buffer");
     std::vector<TagRun> tagvec;
     // cells outside the proper nesting domain are dropped while collating
     tags.collate(tagvec, geom[levc].Domain(), geom[levc].isPeriodicArray(), p_n_comp[levc].empty() ? nullptr : &p_n_comp[levc]);
@@ -315,10 +327,11 @@ void AmrCore::regrid(int lbase, Real time, bool) {
   };
   MakeNewGrids(lbase, time, new_finest, new_grids);
   lap("MakeNewGrids", lbase);
-  bool coarse_ba_changed = false;
+  bool coarse_ba_changed = false, grids_changed = new_finest != finest_level;
   for (int lev = lbase + 1; lev <= new_finest; ++lev) {
     if (lev <= finest_level) {                 // an existing level
       const bool ba_changed = (new_grids[lev] != grids[lev]);
+      grids_changed = grids_changed || ba_changed;
       if (ba_changed || coarse_ba_changed) {
         BoxArray level_grids = grids[lev];
         DistributionMapping level_dmap = dmap[lev];
@@ -346,6 +359,7 @@ void AmrCore::regrid(int lbase, Real time, bool) {
     ClearDistributionMap(lev);
   }
   finest_level = new_finest;
+  if (grids_changed) PlanCacheNewGeneration();     // gather plans of grids that no longer exist are dropped
   if (verbose > 0)
     std::cout << "REGRID: finest level " << finest_level << std::endl;
 }

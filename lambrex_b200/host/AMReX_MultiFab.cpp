@@ -333,7 +333,19 @@ void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std
 namespace {
 
 struct PlanDeleter { void operator()(lbx_plan* p) const { lbx_plan_destroy(p); } };
-std::map<std::string, std::unique_ptr<lbx_plan, PlanDeleter>> g_plans;
+// Plan cache.  A plan is identified by the geometry of the MultiFabs it moves data between, so every regrid
+// that changes a BoxArray creates new keys and strands the old ones (64 B per descriptor on the device:
+// tens of MB per plan at 10^4 boxes).  Two bounds keep a long dynamic-AMR run from growing: (1) a
+// generation sweep -- AmrCore::regrid calls PlanCacheNewGeneration() when the grids changed, and plans that
+// were not used since the regrid before that are destroyed; (2) an LRU cap on the number of plans.
+struct CachedPlan {
+  std::unique_ptr<lbx_plan, PlanDeleter> plan;
+  uint64_t stamp = 0;        // last use (monotonic counter)
+  uint64_t generation = 0;   // regrid generation of the last use
+};
+std::map<std::string, CachedPlan> g_plans;
+uint64_t g_plan_clock = 0, g_plan_generation = 0;
+constexpr size_t PLAN_CACHE_CAP = 64;
 std::map<std::string, MultiFab> g_coarsened;     // sum_fine_to_coarse temporaries, one per fine BoxArray
 
 uint64_t fnv(uint64_t h, int64_t v) {
@@ -431,7 +443,11 @@ lbx_plan* cached(const std::string& key0, const std::function<void(std::vector<l
   // plans describe this rank's own destination boxes only: the ownership view is part of the identity
   const std::string key = key0 + "|" + std::to_string(DistributionMapping::NProcs()) + "." + std::to_string(DistributionMapping::MyProc());
   auto it = g_plans.find(key);
-  if (it != g_plans.end()) return it->second.get();
+  if (it != g_plans.end()) {
+    it->second.stamp = ++g_plan_clock;
+    it->second.generation = g_plan_generation;
+    return it->second.plan.get();
+  }
   std::vector<lbx_gather> descs;
   const auto T0 = std::chrono::steady_clock::now();
   build(descs);
@@ -442,7 +458,17 @@ lbx_plan* cached(const std::string& key0, const std::function<void(std::vector<l
     std::cerr << "  [plan " << key.substr(0, 3) << "] " << descs.size() << " descriptors: intersections "
               << std::chrono::duration<double>(T1 - T0).count() << " s, upload "
               << std::chrono::duration<double>(std::chrono::steady_clock::now() - T1).count() << " s\n";
-  g_plans[key].reset(p);
+  CachedPlan& slot = g_plans[key];
+  slot.plan.reset(p);
+  slot.stamp = ++g_plan_clock;
+  slot.generation = g_plan_generation;
+  while (g_plans.size() > PLAN_CACHE_CAP) {       // least recently used first; never the one just built
+    auto victim = g_plans.end();
+    for (auto q = g_plans.begin(); q != g_plans.end(); ++q)
+      if (q->second.plan.get() != p && (victim == g_plans.end() || q->second.stamp < victim->second.stamp)) victim = q;
+    if (victim == g_plans.end()) break;
+    g_plans.erase(victim);
+  }
   return p;
 }
 
@@ -510,6 +536,15 @@ void pc_descs(std::vector<lbx_gather>& out, int k, const Box& want, const std::v
 
 void ClearPlanCache() { g_plans.clear(); g_coarsened.clear(); }
 size_t PlanCacheSize() { return g_plans.size(); }
+void PlanCacheNewGeneration() {
+  // plans last used before the PREVIOUS regrid belong to grids that no longer exist (a plan of a level
+  // the regrid left alone was used in between and survives)
+  for (auto q = g_plans.begin(); q != g_plans.end();) {
+    if (q->second.generation + 1 < g_plan_generation + 1 && q->second.generation < g_plan_generation) q = g_plans.erase(q);
+    else ++q;
+  }
+  ++g_plan_generation;
+}
 
 namespace {
 // ghosts-only plans open every ghost slab with a source-less descriptor spanning the slab, so

@@ -33,7 +33,29 @@ lbx_box to_lbx(const Box& b) {
   for (int d = 0; d < 3; ++d) { r.lo[d] = b.smallEnd(d); r.hi[d] = b.bigEnd(d); }
   return r;
 }
+// entry (m, p) of the moment basis / its inverse as the device library defines them
+double table_entry(bool inverse, int r, int c) {
+  struct Tables {
+    double M[NMODES * NMODES], Mi[NMODES * NMODES], w[NMODES];
+    int32_t c[NMODES * NDIMS];
+    Tables() { lbx_d3q15_tables(M, Mi, c, w); }
+  };
+  static const Tables t;
+  return (inverse ? t.Mi : t.M)[r * NMODES + c];
+}
 }  // namespace
+
+// src/AmrSim.cpp:1033-1073 (static member definitions)
+const double AmrSim::DELTA[NDIMS][NDIMS] = {{1.0 / NMODES, 0.0, 0.0}, {0.0, 1.0 / NMODES, 0.0}, {0.0, 0.0, 1.0 / NMODES}};
+#define LBX_ROW(I, r) {table_entry(I, r, 0), table_entry(I, r, 1), table_entry(I, r, 2), table_entry(I, r, 3), table_entry(I, r, 4), \
+                       table_entry(I, r, 5), table_entry(I, r, 6), table_entry(I, r, 7), table_entry(I, r, 8), table_entry(I, r, 9), \
+                       table_entry(I, r, 10), table_entry(I, r, 11), table_entry(I, r, 12), table_entry(I, r, 13), table_entry(I, r, 14)}
+#define LBX_ROWS(I) {LBX_ROW(I, 0), LBX_ROW(I, 1), LBX_ROW(I, 2), LBX_ROW(I, 3), LBX_ROW(I, 4), LBX_ROW(I, 5), LBX_ROW(I, 6), LBX_ROW(I, 7), \
+                     LBX_ROW(I, 8), LBX_ROW(I, 9), LBX_ROW(I, 10), LBX_ROW(I, 11), LBX_ROW(I, 12), LBX_ROW(I, 13), LBX_ROW(I, 14)}
+const double AmrSim::MODE_MATRIX[NMODES][NMODES] = LBX_ROWS(false);
+const double AmrSim::MODE_MATRIX_INVERSE[NMODES][NMODES] = LBX_ROWS(true);
+#undef LBX_ROWS
+#undef LBX_ROW
 
 // src/AmrSim.cpp:753-802
 AmrSim::AmrSim(int const nx, int const ny, int const nz, int const max_ref_level,
@@ -60,6 +82,13 @@ AmrSim::AmrSim(int const nx, int const ny, int const nz, int const max_ref_level
   tau_s.at(0) = tau_s_0;
   tau_b.at(0) = tau_b_0;
   if (!lbx_initialized()) amrex::Abort("AmrSim: call lambrexInit() first (no CUDA context; there is no CPU path)");
+  // default coupling of refined hierarchies for callers that cannot call SetCoupling -- the reference's own,
+  // unmodified test and example sources (oracle/Makefile ref_tests): LBX_COUPLING=subcycle|rohde
+  if (const char* c = std::getenv("LBX_COUPLING")) {
+    if (!std::strcmp(c, "subcycle")) coupling = Coupling::SUBCYCLE;
+    else if (!std::strcmp(c, "rohde")) coupling = Coupling::ROHDE;
+    else amrex::Abort("LBX_COUPLING must be 'rohde' or 'subcycle'");
+  }
 }
 
 AmrSim::~AmrSim() {
@@ -781,7 +810,8 @@ void AmrSim::UnsetGradientRefinement(int const level) {
 
 // ----------------------------------------------------------------------------- checkpoint / restart
 namespace {
-constexpr char CHK_MAGIC[8] = {'L', 'B', 'X', 'C', 'H', 'K', '1', 0};
+constexpr char CHK_MAGIC[8] = {'L', 'B', 'X', 'C', 'H', 'K', '2', 0};
+constexpr uint32_t CHK_ENDIAN = 0x01020304u;     // written natively after the magic: a byte-swapped reader sees 0x04030201
 struct ChkFile {
   std::FILE* f;
   explicit ChkFile(const std::string& path, const char* mode) : f(std::fopen(path.c_str(), mode)) {
@@ -799,6 +829,7 @@ void AmrSim::WriteCheckpoint(const std::string& path) {
   if (DistributionMapping::NProcs() > 1) amrex::Abort("WriteCheckpoint: single-process runs only");
   ChkFile c(path, "wb");
   c.put(CHK_MAGIC, sizeof(CHK_MAGIC));
+  c.put<uint32_t>(CHK_ENDIAN);
   for (int v : {NX, NY, NZ, max_level, finest_level, (int)coupling, regrid_int, steps_since_regrid, num_regrids}) c.put<int32_t>(v);
   for (int l = 0; l <= max_level; ++l) {
     c.put<double>(tau_s[l]); c.put<double>(tau_b[l]); c.put<double>(mass[l]);
@@ -828,11 +859,13 @@ void AmrSim::ReadCheckpoint(const std::string& path) {
   ChkFile c(path, "rb");
   char magic[8];
   c.get(magic, sizeof(magic));
-  if (std::memcmp(magic, CHK_MAGIC, sizeof(magic)) != 0) amrex::Abort("ReadCheckpoint: not a lambrex-b200 checkpoint");
+  if (std::memcmp(magic, CHK_MAGIC, sizeof(magic)) != 0) amrex::Abort("ReadCheckpoint: not a lambrex-b200 checkpoint (format 2)");
+  if (c.get<uint32_t>() != CHK_ENDIAN) amrex::Abort("ReadCheckpoint: the checkpoint was written with another byte order");
   const int nx = c.get<int32_t>(), ny = c.get<int32_t>(), nz = c.get<int32_t>(), ml = c.get<int32_t>();
   if (nx != NX || ny != NY || nz != NZ || ml != max_level)
     amrex::Abort("ReadCheckpoint: the checkpoint was written by a simulation with other extents or max level");
   const int new_finest = c.get<int32_t>();
+  if (new_finest < 0 || new_finest > max_level) amrex::Abort("ReadCheckpoint: corrupt file (finest level outside 0..max_level)");
   coupling = c.get<int32_t>() == (int)Coupling::SUBCYCLE ? Coupling::SUBCYCLE : Coupling::ROHDE;
   regrid_int = c.get<int32_t>();
   steps_since_regrid = c.get<int32_t>();
@@ -842,10 +875,12 @@ void AmrSim::ReadCheckpoint(const std::string& path) {
     levels[l].time.current = c.get<double>(); levels[l].time.delta = c.get<double>(); levels[l].time.step = c.get<int32_t>();
     gradient_threshold[l] = c.get<double>();
     const int nst = c.get<int32_t>();
+    if (nst < 0 || nst > (1 << 20)) amrex::Abort("ReadCheckpoint: corrupt file (static-tag box count)");
     amrex::BoxList bl;
     for (int q = 0; q < nst; ++q) {
       IntVect lo, hi;
       for (int d = 0; d < 3; ++d) { lo[d] = c.get<int32_t>(); hi[d] = c.get<int32_t>(); }
+      if (!Box(lo, hi).ok()) amrex::Abort("ReadCheckpoint: corrupt file (empty static-tag box)");
       bl.push_back(Box(lo, hi));
     }
     if (nst) static_tags[l].define(bl); else static_tags[l].clear();
@@ -859,10 +894,13 @@ void AmrSim::ReadCheckpoint(const std::string& path) {
       continue;
     }
     const int nb = c.get<int32_t>();
+    if (nb < 1 || nb > (1 << 24)) amrex::Abort("ReadCheckpoint: corrupt file (box count of a level)");
     amrex::BoxList bl;
     for (int q = 0; q < nb; ++q) {
       IntVect lo, hi;
       for (int d = 0; d < 3; ++d) { lo[d] = c.get<int32_t>(); hi[d] = c.get<int32_t>(); }
+      if (!Box(lo, hi).ok() || !geom[l].Domain().contains(Box(lo, hi)))
+        amrex::Abort("ReadCheckpoint: corrupt file (a box is empty or outside its level's domain)");
       bl.push_back(Box(lo, hi));
     }
     const BoxArray ba(bl);
@@ -876,6 +914,7 @@ void AmrSim::ReadCheckpoint(const std::string& path) {
     SetDistributionMap(l, dm);
     MultiFab tight(ba, dm, NMODES, 0);
     const uint64_t n = c.get<uint64_t>();
+    if (n != (uint64_t)ba.numPts() * NMODES) amrex::Abort("ReadCheckpoint: corrupt file (payload size does not match the box list)");
     std::vector<double> h((size_t)n);
     c.get(h.data(), h.size() * sizeof(double));
     tight.upload(h);

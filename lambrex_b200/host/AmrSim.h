@@ -120,6 +120,12 @@ class AmrSim : public amrex::AmrCore {
   constexpr static double CS2 = 1.0 / 3.0;
   constexpr static double NL_DENSITY = -1.0;
   constexpr static double NL_VELOCITY = -3E8;
+  // include/AmrSim.h:37-39.  The kernels carry their own constexpr copy (csrc/d3q15.cuh, generated
+  // from exact rationals); these host-side members hold the same values (lbx_d3q15_tables) for
+  // subclasses that read them.  DELTA is diag(1 / NMODES), sic (src/AmrSim.cpp:1033-1035).
+  static const double DELTA[NDIMS][NDIMS];
+  static const double MODE_MATRIX[NMODES][NMODES];
+  static const double MODE_MATRIX_INVERSE[NMODES][NMODES];
   std::vector<double> initial_density;
   std::vector<double> initial_velocity;
   std::vector<amrex::BoxArray> static_tags;

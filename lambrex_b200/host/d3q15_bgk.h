@@ -22,7 +22,7 @@ struct D3Q15 : VelocitySet<D3Q15, 3, 15, 2> {
 struct DistFn : Component<D3Q15> {};
 
 // rho = sum_i f_i, as a device reduction over the 15 planes (k_mf_moments also yields u)
-struct Density : DerivedVar<Density, 1, DistFn> {
+struct Density : DerivedVar<Density, ScalarTag, DistFn> {
   static void fill(amrex::MultiFab& rho, amrex::MultiFab& u_scratch, const amrex::MultiFab& f) {
     amrex::lbx_check(lbx_mf_moments(f.mf(), rho.mf(), u_scratch.mf()), "Density::fill");
     rho.touch();

@@ -10,13 +10,29 @@
 
 #include "AMReX_MultiFab.H"
 
-struct ScalarTag {};
+// dimensionality tags of a derived variable (derived_var.h:12-15; the reference sketches ElementTag /
+// VectorTag in comments :17-31 -- ElementTag<N> is the N-component form used by LinearMoment below)
+struct ScalarTag {
+  static constexpr std::size_t RANK = 0;
+  static constexpr std::size_t SIZE = 1;
+};
+template <std::size_t N>
+struct ElementTag {
+  static_assert(N > 0, "Invalid dimension of zero");
+  static constexpr std::size_t RANK = 1;
+  static constexpr std::size_t SIZE = N;
+};
+template <std::size_t N>
+using VectorTag = ElementTag<N>;
 
-template <typename Impl, std::size_t DIM, typename... Deps>
+// CRTP base (derived_var.h:55-91): Impl, a dimensionality tag, the fields it is computed from
+template <typename Impl, typename DIM, typename... Deps>
 struct DerivedVar {
-  static constexpr std::size_t NELEM = DIM;
+  using dim_type = DIM;
+  using base_type = DerivedVar<Impl, DIM, Deps...>;
   using dependencies = std::tuple<Deps...>;
-  static constexpr bool is_derived_var = true;
+  static constexpr std::size_t NELEM = DIM::SIZE;
+  static constexpr std::size_t HALO = 0;
 };
 
 // Generic device path for derived variables that are linear moments of a distribution function
@@ -28,7 +44,7 @@ struct DerivedVar {
 // every valid cell of the level in one launch (lbx_mf_linear_moments) -- a new moment needs no
 // new kernel.  Density, MomentumDensity, Velocity and Stress in d3q15_bgk.h are such moments.
 template <typename Impl, std::size_t DIM, typename DistT>
-struct LinearMoment : DerivedVar<Impl, DIM, DistT> {
+struct LinearMoment : DerivedVar<Impl, ElementTag<DIM>, DistT> {
   static void fill(amrex::MultiFab& out, const amrex::MultiFab& f) {
     static_assert(DIM >= 1 && DIM <= 10, "lbx_mf_linear_moments takes 1..10 weight rows");
     if (out.boxArray() != f.boxArray() || out.layout() != f.layout() || out.nComp() < (int)DIM)

@@ -9,23 +9,36 @@
 #include "component.h"
 #include "derived_var.h"
 
-namespace lbx_detail {
-template <typename T, typename = void>
-struct has_velocity_set : std::false_type {};
+// category detection, same names as the reference's namespace detail (field.h:49-84; pinned by the
+// reference's compile-time test tests/meta_basic.cpp:25-31)
+namespace detail {
+struct component_tag {};
+struct derived_var_tag {};
+
+// T is a Component: it derives from Component<T::VelocitySet>
+template <typename T, typename Enable = void>
+struct is_component : std::false_type {};
 template <typename T>
-struct has_velocity_set<T, std::void_t<typename T::VelocitySet>> : std::true_type {};
-template <typename T, typename = void>
-struct has_dv_marker : std::false_type {};
+struct is_component<T, std::enable_if_t<std::is_base_of_v<Component<typename T::VelocitySet>, T>>> : std::true_type {};
 template <typename T>
-struct has_dv_marker<T, std::void_t<decltype(T::is_derived_var)>> : std::true_type {};
-}  // namespace lbx_detail
+inline constexpr bool is_component_v = is_component<T>::value;
+
+// T is a DerivedVar: a T* converts to a pointer to some DerivedVar<Impl, DIM, deps...> base
+template <typename Impl, typename DIM, typename... dependencies>
+constexpr bool blah(const DerivedVar<Impl, DIM, dependencies...>*) { return true; }
+constexpr bool foo(...) { return false; }
+template <typename T>
+constexpr auto foo(const T* t = nullptr) -> decltype(blah(t)) { return true; }
+template <typename T>
+inline constexpr bool is_derived_var_v = foo(static_cast<const T*>(nullptr));
+}  // namespace detail
 
 template <typename F>
-struct is_component : lbx_detail::has_velocity_set<F> {};
+using is_component = detail::is_component<F>;
 template <typename F>
-inline constexpr bool is_component_v = is_component<F>::value;
+inline constexpr bool is_component_v = detail::is_component_v<F>;
 template <typename F>
-inline constexpr bool is_derived_var_v = lbx_detail::has_dv_marker<F>::value;
+inline constexpr bool is_derived_var_v = detail::is_derived_var_v<F>;
 
 template <typename F, typename = void>
 struct field_traits;

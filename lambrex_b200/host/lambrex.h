@@ -5,6 +5,8 @@
 #ifndef LBX_LAMBREX_H
 #define LBX_LAMBREX_H
 #include <cstddef>
+
+#include "AmrSim.h"   // as /root/reference/include/lambrex.h:4: one include gives callers the whole API
 void lambrexInit();
 void lambrexFinalise();
 // Addition: distributed start-up, one process per GPU of one NVSwitch box (the role MPI_Init plays

@@ -102,6 +102,7 @@ int lbx_sim_set_gradient_refinement(lbx_sim* sim, int level, double threshold) {
 int lbx_sim_unset_gradient_refinement(lbx_sim* sim, int level) { return guarded([&] { sim->s.UnsetGradientRefinement(level); }); }
 int lbx_sim_set_regrid_interval(lbx_sim* sim, int n) { return guarded([&] { sim->s.SetRegridInterval(n); }); }
 int lbx_sim_num_regrids(const lbx_sim* sim) { return sim->s.NumRegrids(); }
+int lbx_sim_plan_cache_size(void) { return (int)amrex::PlanCacheSize(); }
 
 int lbx_sim_get_linear_moment_field(const lbx_sim* sim, int level, const double* weights, int ncomp, int per_unit_density,
                                     double sentinel, double* out, size_t n) {

@@ -737,34 +737,46 @@ class AmrSimOracle:
             core[g2 > thr2] = TAG_SET
 
     def _tag_points(self, levc, extra_boxes):
-        """Tagged cells of level levc after ErrorEst, buffering, projection of finer grids and
-        periodic mapping: sorted unique points inside the level's domain."""
-        nb = self.n_error_buf
+        """Tagged cells of level levc after ErrorEst, projection of finer new grids, buffering and periodic
+        mapping: sorted unique points inside the level's domain.  Order as in AmrMesh::MakeNewGrids [AMReX,
+        unverified]: the tag boxes are allocated with n_error_buf + ngrow ghost cells (ngrow = how far the
+        level's grids must grow to contain the projection), the projection is SET BEFORE buffering, and the
+        buffer width is n_error_buf + ngrow; TagBox::buffer spreads only SET cells of the VALID region."""
         boxes = self.grids[levc]
+        ngrow = 0
+        if extra_boxes:
+            def covered(g):
+                grown = [grow(b, g) for b in boxes]
+                return all(not complement_in(e, grown) for e in extra_boxes)
+            while ngrow < 64 and not covered(ngrow):
+                ngrow += 1
+        nb = self.n_error_buf + ngrow
         tags = {"ng": nb, "fabs": [np.zeros(tuple(h - l + 1 + 2 * nb for l, h in zip(*b))[::-1], dtype=np.uint8)
                                    for b in boxes]}
         self.error_est(levc, tags)
         pts = []
         per = self.period(levc)
         for b, t in zip(boxes, tags["fabs"]):
+            for e in extra_boxes:                  # proper-nesting projection of finer new grids: SET
+                r = isect(e, grow(b, nb))
+                if r is not None:
+                    o = tuple(b[0][d] - nb for d in range(3))
+                    t[r[0][2] - o[2]:r[1][2] - o[2] + 1, r[0][1] - o[1]:r[1][1] - o[1] + 1,
+                      r[0][0] - o[0]:r[1][0] - o[0] + 1] = TAG_SET
             # TagBox::buffer: SET cells of the valid region spread BUF over +-nb
-            setm = (t == TAG_SET)
+            setm = np.zeros(t.shape, dtype=bool)
+            if nb:
+                setm[nb:-nb, nb:-nb, nb:-nb] = (t[nb:-nb, nb:-nb, nb:-nb] == TAG_SET)
             if nb and setm.any():
                 grown = setm.copy()
                 for dz in range(-nb, nb + 1):
                     for dy in range(-nb, nb + 1):
                         for dx in range(-nb, nb + 1):
-                            grown |= np.roll(setm, (dz, dy, dx), axis=(0, 1, 2))   # SET never touches the rim
+                            grown |= np.roll(setm, (dz, dy, dx), axis=(0, 1, 2))   # valid cells are >= nb from the rim
                 t[grown & (t == TAG_CLEAR)] = TAG_BUF
             z, y, x = np.nonzero(t)
             if len(x):
                 pts.append(np.stack([x + b[0][0] - nb, y + b[0][1] - nb, z + b[0][2] - nb], axis=1))
-        for e in extra_boxes:                      # proper-nesting projection of finer new grids
-            for b in boxes:
-                r = isect(e, grow(b, nb))
-                if r is not None:
-                    g = np.mgrid[r[0][0]:r[1][0] + 1, r[0][1]:r[1][1] + 1, r[0][2]:r[1][2] + 1].reshape(3, -1).T
-                    pts.append(g)
         if not pts:
             return np.zeros((0, 3), dtype=np.int64)
         p = np.concatenate(pts).astype(np.int64)

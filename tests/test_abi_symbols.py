@@ -52,3 +52,15 @@ def test_host_library_exports_every_symbol_of_lambrex_c_h():
     for n in names:
         assert hasattr(L, n), "liblambrex.so does not export " + n
     assert names == set(amrsim.SYMBOLS), names ^ set(amrsim.SYMBOLS)
+
+
+def test_product_tables_equal_the_reference_matrices_bit_for_bit():
+    """The kernels' moment basis (csrc/d3q15.cuh generators, queried through lbx_d3q15_tables) against the
+    matrices parsed from /root/reference/src/AmrSim.cpp:1037-1073 and include/d3q15_bgk.h:14-28
+    (tests/golden/mode_matrices.npz): identical doubles, not just close."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mode_matrices.npz"))
+    M, Mi, c, w = lbx.tables()
+    assert np.array_equal(M, g["MODE_MATRIX"]) and np.array_equal(Mi, g["MODE_MATRIX_INVERSE"])
+    assert np.array_equal(c[:, 0], g["CX"]) and np.array_equal(c[:, 1], g["CY"]) and np.array_equal(c[:, 2], g["CZ"])
+    assert np.array_equal(w, g["W"])

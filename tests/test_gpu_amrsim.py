@@ -624,3 +624,26 @@ def test_sector_aligned_fab_layout_is_bit_identical(align):
         lbx.set_option(lbx.OPT_ALIGN_ROWS, 0)
         for sim in sims:
             sim.close()
+
+
+# ------------------------------------------------------------------ plan cache stays bounded
+def test_plan_cache_is_bounded_over_repeated_regrids():
+    """Every regrid that changes a BoxArray creates new gather-plan keys; the plans of grids that no longer
+    exist must be evicted (generation sweep in AmrCore::regrid + LRU cap), or a long dynamic-AMR run grows
+    device memory without bound."""
+    n = 32
+    sim = AmrSim(n, n, n, 1, PER, 0.5, 0.5)
+    sim.SetMaxGridSize(16)
+    sim.SetInitialDensity(workloads.pulse_density(n, n, n))
+    sim.SetInitialVelocity(0.0)
+    sim.InitFromScratch(0.0)
+    sizes = []
+    for shift in range(12):                      # a static box translated cell by cell: new fine grids every time
+        lo = (4 + shift, 6, 8)
+        sim.SetStaticRefinement(0, lo, tuple(v + 9 for v in lo))
+        sim.Iterate(2)
+        sizes.append(AmrSim.PlanCacheSize())
+    assert len(set(tuple(b) for b in sim.boxArray(1))) > 0
+    assert max(sizes[4:]) <= max(sizes[:4]) + 2, sizes      # steady state: no growth with the number of regrids
+    assert max(sizes) <= 64, sizes
+    sim.close()
