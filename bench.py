@@ -110,40 +110,94 @@ def base_grid_edges(n, max_grid=32):
     return chop_1d(n, max_grid)
 
 
-def cpu_reference(sample_n, steps, warmup, tau=0.5):
-    """Time the oracle's restatement of the reference's pass structure (CPU)."""
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference(sample_n, steps, warmup, tau=0.5, threads=None, loop_order=0, shear=False):
+    """Time the oracle's restatement of the reference's pass structure (CPU).  threads=1 with loop_order=1
+    (k innermost, /root/reference/include/amr_help.h:87-92) is the FAITHFUL figure: the reference has no OpenMP
+    and its AMReX recipe disables it (amrex_cmake.sh:9-10); all cores with x innermost is the generous one."""
     from lambrex_b200 import workloads
     from oracle import lbm_oracle as orc
     co = orc.COracle()
+    all_threads = co.max_threads()
+    co.set_threads(threads or all_threads)
     n = sample_n
     w = workloads.omega(tau)
-    rho = orc.user_to_fab(workloads.pulse_density(n, n, n), n, n, n)
-    f = co.equilibrium(rho, np.zeros((3, n, n, n)))
+    if shear:
+        rho = np.ones((n, n, n))
+        u = np.zeros((3, n, n, n))
+        u[0] = (0.01 * np.sin(2.0 * np.pi * np.arange(n) / n))[None, :, None]
+    else:
+        rho = orc.user_to_fab(workloads.pulse_density(n, n, n), n, n, n)
+        u = np.zeros((3, n, n, n))
+    f = co.equilibrium(rho, u)
     edges = [base_grid_edges(n)] * 3
     if warmup:
-        f, _ = co.ref_passes(f, w, w, warmup, edges)
-    f, secs = co.ref_passes(f, w, w, steps, edges)
+        f, _ = co.ref_passes(f, w, w, warmup, edges, loop_order)
+    f, secs = co.ref_passes(f, w, w, steps, edges, loop_order)
+    co.set_threads(all_threads)
     cells = float(n) ** 3
-    return {"mlups": cells * steps / secs / 1e6, "secs": secs, "cores": co.max_threads(),
-            "sample": "%d^3 periodic pulse, %d steps after %d warm-up, 32^3 ghosted boxes, "
-                      "reference pass structure, gcc -O3 -fopenmp" % (n, steps, warmup)}
+    return {"mlups": cells * steps / secs / 1e6, "secs": secs, "cores": threads or all_threads,
+            "sample": "%d^3 periodic %s, %d steps after %d warm-up, 32^3 ghosted boxes, reference pass structure "
+                      "(FillPatch copy, in-place collide, FillBoundary, stream into a fresh fab, swap), %s loop order, "
+                      "gcc -O3 -fopenmp, %d thread%s" % (n, "shear wave" if shear else "pulse", steps, warmup,
+                                                        "k-innermost (the reference's)" if loop_order else "x-innermost",
+                                                        threads or all_threads, "" if (threads or all_threads) == 1 else "s")}
+
+
+def cpu_baseline_block(sample_n):
+    """cpu_baseline of the GPU arm's line: the all-core figure (value) and the faithful 1-thread figure."""
+    r = cpu_reference(sample_n, 4, 1)
+    one = cpu_reference(min(sample_n, 64), 2, 1, threads=1, loop_order=1)
+    return {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+            "cpu_model": cpu_model(),
+            "faithful_1thread": {"value": one["mlups"], "unit": "MLUPS", "cores": 1, "sample": one["sample"],
+                                 "why": "the reference contains no OpenMP and its AMReX recipe sets ENABLE_OMP=OFF "
+                                        "(amrex_cmake.sh:9-10); loop order of include/amr_help.h:87-92"}}
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (kind "port": the oracle's C
+    restatement of its pass structure; the real reference needs AMReX + gfortran and cannot be built here) on all
+    host cores.  N = 1: the labelled configuration itself (256^3 pulse), a few steps.  N > 1: 1024^3 does not fit a
+    host, so each step is a bounded 256^3 sample of the shear-wave workload -- the label says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                      # under torchrun only rank 0 measures the CPU arm
-    steps = max(1, min(args.steps, 8))
+    steps = max(1, min(args.steps, 4))
     warm = max(0, min(args.warmup, 1))
-    r = cpu_reference(args.cpu_sample, steps, warm)
+    n = args.cpu_ref_grid
+    shear = args.gpus > 1
+    try:
+        r = cpu_reference(n, steps, warm, tau=0.1 if shear else 0.5, shear=shear)
+    except MemoryError:
+        n = 128
+        r = cpu_reference(n, steps, warm, tau=0.1 if shear else 0.5, shear=shear)
+    cfg = workload_config(args.gpus)
+    if shear:
+        cfg["workload"] += " -- CPU arm: bounded %d^3 sample of it per step (1024^3 does not fit a host)" % n
+    elif n != 256:
+        cfg["workload"] += " -- CPU arm: bounded %d^3 sample of it" % n
+    cfg["grid"] = [n, n, n]
+    one = cpu_reference(64, 2, 1, threads=1, loop_order=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["mlups"], "unit": "MLUPS",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": r["secs"] / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port",
-                         "sample": r["sample"]},
+                         "sample": r["sample"], "cpu_model": cpu_model(),
+                         "faithful_1thread": {"value": one["mlups"], "unit": "MLUPS", "cores": 1, "sample": one["sample"]}},
         "e2e": {"value": r["mlups"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -247,10 +301,7 @@ def run_single(args):
     roofline = {"bound": "hbm", "kernel": "k_collide_stream<push>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source")}
-    cpu = None
-    if not args.no_cpu:
-        r = cpu_reference(args.cpu_sample, 4, 1)
-        cpu = {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    cpu = None if args.no_cpu else cpu_baseline_block(args.cpu_sample)
     line = {"metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
@@ -345,10 +396,7 @@ def run_single_raw(args):
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source")}
 
-    cpu = None
-    if not args.no_cpu:
-        r = cpu_reference(args.cpu_sample, 4, 1)
-        cpu = {"value": r["mlups"], "unit": "MLUPS", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    cpu = None if args.no_cpu else cpu_baseline_block(args.cpu_sample)
 
     line = {"metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -385,7 +433,8 @@ def main():
     ap.add_argument("--no-split", action="store_true",
                     help="N>1, p2p: one slab-kernel launch per step instead of boundary planes + interior")
     ap.add_argument("--grid-multi", type=int, default=1024, help="N>1 cubic grid edge (default 1024 = configs[2])")
-    ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU-baseline sample grid")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU-baseline sample grid (cpu_baseline of the GPU arm)")
+    ap.add_argument("--cpu-ref-grid", type=int, default=256, help="--impl reference: cubic grid edge (256 = the N=1 configuration itself)")
     ap.add_argument("--e2e-repeat", type=int, default=3, help="N=1: end-to-end jobs run (median reported)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -252,6 +252,14 @@ int lbx_init(int device) {
   g.cur = g.own;
   g.device = device;
   g.ready = true;
+  // LBX_COLLIDE=literal: start in the reference's operation order without FMA contraction (LBX_OPT_COLLIDE_LITERAL)
+  // -- for callers that cannot call lbx_set_option, e.g. the reference's own unmodified test binaries, whose
+  // golden velocities carry 1e-18 round-off noise that only bit-compatible arithmetic reproduces
+  if (const char* c = getenv("LBX_COLLIDE")) {
+    if (!strcmp(c, "literal")) g.literal = true;
+    else if (!strcmp(c, "fast")) g.literal = false;
+    else return fail("lbx_init: LBX_COLLIDE must be 'literal' or 'fast'");
+  }
   return 0;
 }
 

@@ -67,6 +67,15 @@ int orc_max_threads(void) {
 #endif
 }
 
+/* threads used by the OpenMP loops from now on (bench.py: 1 = the faithful figure, the reference has no OpenMP) */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ---- per-cell kernels --------------------------------------------------- */
 
 /* Second-order equilibrium, expanded form.  src/AmrSim.cpp:879-927. */

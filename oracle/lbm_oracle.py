@@ -209,6 +209,9 @@ class COracle:
     def max_threads(self):
         return int(self.L.orc_max_threads())
 
+    def set_threads(self, n):
+        self.L.orc_set_threads(int(n))
+
     def tables(self):
         Mm = np.empty((NV, NV))
         Mi = np.empty((NV, NV))

@@ -11,7 +11,8 @@
 //
 // Command line of a test binary:  [name-substring] [--list-tests]
 // Environment: CATCH_SHIM_CONTINUE=1 turns REQUIRE into CHECK (count every failing assertion instead of aborting
-// the test case at the first one) -- used to count how many points of `ml_pulse Regression` agree.
+// the test case at the first one) -- used to count how many points of `ml_pulse Regression` agree;
+// CATCH_SHIM_MAX_PRINT=n reports the first n failing assertions in full (default 20).
 // Last line of output:  "catch-shim: test cases: N | passed P | failed F | assertions: A | failed assertions: X".
 #ifndef LBX_CATCH_SHIM_HPP
 #define LBX_CATCH_SHIM_HPP
@@ -101,6 +102,7 @@ struct Registry {
   Totals totals;
   bool soft_require = false;
   bool case_failed = false;
+  long max_print = 20;                     // failing assertions reported in full (CATCH_SHIM_MAX_PRINT)
   static Registry& get() { static Registry r; return r; }
 };
 
@@ -148,7 +150,7 @@ inline void assertion(bool ok, bool fatal, const char* macro, const char* expr, 
   if (ok) return;
   ++r.totals.failedAssertions;
   r.case_failed = true;
-  if (r.totals.failedAssertions <= 20) {
+  if (r.totals.failedAssertions <= r.max_print) {
     std::cout << file << ":" << line << ": FAILED: " << macro << "( " << expr << " )\n";
     for (const auto& s : r.infos) std::cout << "  with message: " << s << "\n";
   }
@@ -165,6 +167,7 @@ inline int run(int argc, char** argv) {
   }
   const char* soft = std::getenv("CATCH_SHIM_CONTINUE");
   r.soft_require = soft && soft[0] && soft[0] != '0';
+  if (const char* mp = std::getenv("CATCH_SHIM_MAX_PRINT")) r.max_print = std::atol(mp);
   if (list) {
     for (const auto& c : r.cases) std::cout << c.name << "  " << c.tags << "\n";
     return 0;

@@ -41,10 +41,29 @@ def test_reference_c2InitTests_pass_unchanged():
 
 
 def test_reference_pulse_regression_passes_unchanged():
-    """tests/catch2RegressionTests.cpp:6-93 -- all 3 x (5000 + 15000) golden values through AmrSim on the GPU."""
-    p, s = run_binary("c2RegressionTests", "pulse Regression")
+    """tests/catch2RegressionTests.cpp:6-93 -- all 3 x (5000 + 15000) golden values through AmrSim on the GPU.
+    The golden velocities hold 1e-18 round-off noise (u_x, u_y of a z-pulse) compared RELATIVELY by Catch2's
+    Approx, so only arithmetic bit-compatible with the build that wrote them can pass: the literal collision
+    mode (reference operation order, no FMA contraction; LBX_COLLIDE=literal) does, unchanged."""
+    p, s = run_binary("c2RegressionTests", "pulse Regression", env={"LBX_COLLIDE": "literal"})
     # the name filter is a substring match: "ml_pulse Regression" runs too; judge the single-level case alone
     assert "[  OK  ] pulse Regression" in p.stdout, p.stdout[-3000:]
+
+
+def test_reference_pulse_regression_fast_arithmetic_differs_only_in_roundoff_noise():
+    """The product's fast collision (FMA, restructured moments): every density assertion passes, and the only
+    failing velocity assertions are those whose GOLDEN value is round-off noise (|golden| < 1e-12 in lattice
+    units, where Approx demands 1.2e-5 RELATIVE agreement with noise, or exact equality with 0)."""
+    import numpy as np
+    p, s = run_binary("c2RegressionTests", "pulse Regression", env={"CATCH_SHIM_CONTINUE": "1", "CATCH_SHIM_MAX_PRINT": "1000000"})
+    out = p.stdout[:p.stdout.index("pulse Regression  (")]
+    assert "GetDensity" not in out, out[:3000]                 # no density assertion fails
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pulse_regression.npz"))
+    fails = re.findall(r"with message: t=(\d+) [^\n]*\n\s+with message: veldex=(\d+) n=(\d)", out)
+    assert len(fails) == out.count("FAILED:"), (len(fails), out.count("FAILED:"))
+    worst = max((abs(float(g["VEL_t%s" % t][int(v)])) for t, v, _ in fails), default=0.0)
+    print("fast arithmetic: %d of 60000 assertions differ, largest |golden| among them %.3e" % (len(fails), worst))
+    assert worst < 1e-12, worst
 
 
 def test_reference_c2AMRTests_pass_unchanged():
