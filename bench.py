@@ -5,8 +5,8 @@
 
 One "step" = one lattice time step (collide + stream) of the whole grid.
   N = 1 : BASELINE.json configs[1] -- uniform single-level periodic pulse, 256^3, fp64.
-  N > 1 : configs[2] -- uniform 1024^3 periodic shear wave, z-slabs over N GPUs
-          (launched under torchrun, one rank per GPU).
+  N > 1 : configs[2] -- uniform 1024^3 periodic shear wave through AmrSim on every rank (one z-slab of
+          level-0 boxes per GPU, face exchange fused into the step kernel; launched under torchrun).
 value   = MLUPS with the populations resident in HBM (device-timed, CUDA events).
 e2e     = MLUPS through the host-buffer API: pinned-host rho,u -> H2D -> equilibrium
           -> K steps -> moments -> D2H of rho,u, all inside the timed region.
@@ -307,9 +307,23 @@ def run_single(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "check": {"total_mass_over_cells": mass / cells}}
+    if not args.no_amr:
+        line["extra"] = {"amr": amr_leg_single(args, peak)}
     print(json.dumps(line), flush=True)
     del rho, vel, rho0, u0, rho_out, u_out, host
     lbx.check(L.lbx_host_free(hp))
+
+
+def amr_leg_single(args, peak):
+    """N = 1: BASELINE configs[3] (C4) -- 2-level AMR pulse, ratio 2, 256^3 base, static central-half box, both
+    couplings: the reference's live Rohde cycle (bug-compatible, diverges physically: see check) and conventional
+    subcycling (FillPatch with time interpolation + average_down)."""
+    from lambrex_b200.amr_workload import run_amr_case
+    out = {"config": "C4: 2-level AMR pulse (ref ratio 2), %d^3 base, static box = central half, 32^3 boxes, 1 B200 "
+                     "(BASELINE configs[3])" % args.amr_grid}
+    for coupling in ("rohde", "subcycle"):
+        out["C4_" + coupling] = run_amr_case(args.amr_grid, 2, args.amr_steps, 3, coupling, 0, 32, True, 0.0, None, peak)
+    return out
 
 
 def run_single_raw(args):
@@ -428,17 +442,24 @@ def main():
     ap.add_argument("--api", default="amrsim", choices=["amrsim", "raw"],
                     help="N=1: time AmrSim::Iterate (default) or the bare C-ABI kernels")
     ap.add_argument("--scheme", default="push", choices=["push", "pull", "slab"], help="kernel for --api raw")
-    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl", "slabsim-p2p"],
                     help="N>1 face exchange: peer stores fused into the step kernel, or packed NCCL send/recv")
-    ap.add_argument("--no-split", action="store_true",
-                    help="N>1, p2p: one slab-kernel launch per step instead of boundary planes + interior")
+    ap.add_argument("--max-grid-multi", type=int, default=32,
+                    help="N>1: max_grid_size of level 0 (AMReX default 32; ownership is by whole x-y layers of these boxes)")
     ap.add_argument("--grid-multi", type=int, default=1024, help="N>1 cubic grid edge (default 1024 = configs[2])")
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU-baseline sample grid (cpu_baseline of the GPU arm)")
     ap.add_argument("--cpu-ref-grid", type=int, default=256, help="--impl reference: cubic grid edge (256 = the N=1 configuration itself)")
     ap.add_argument("--e2e-repeat", type=int, default=3, help="N=1: end-to-end jobs run (median reported)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-amr", action="store_true", help="skip the AMR leg (extra.amr: C4 at N=1, C5 at N>1)")
+    ap.add_argument("--amr-grid", type=int, default=0, help="base grid edge of the AMR leg (default: 256 at N=1; 512 at N>=4, 256 at N=2)")
+    ap.add_argument("--amr-steps", type=int, default=0, help="coarse steps of the AMR leg (default: 12 at N=1, 32 at N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if not args.amr_grid:
+        args.amr_grid = 256 if args.gpus < 4 else 512
+    if not args.amr_steps:
+        args.amr_steps = 12 if args.gpus == 1 else 32
     if args.impl == "reference" or args.gpus == 1:
         # the CPU arm uses every host core it can: torchrun exports OMP_NUM_THREADS=1 to its workers,
         # which would time the OpenMP oracle on one thread (set before libgomp is loaded)

@@ -66,6 +66,20 @@ int lbx_sim_set_initial_velocity(lbx_sim *sim, const double *u, size_t n);
  * caller memory (one DMA when it is pinned, see lbx_host_alloc) and must stay valid until then */
 int lbx_sim_set_initial_density_view(lbx_sim *sim, const double *rho, size_t n);
 int lbx_sim_set_initial_velocity_view(lbx_sim *sim, const double *u, size_t n);
+/* ---- additions for distributed runs (one process per GPU): each rank states and reads ITS part ----
+ * separable initial conditions -- the field varies along one axis (0 x, 1 y, 2 z): n = extent(axis) values for
+ * the density, 3 * extent(axis) (component fastest) for the velocity; replace set_initial_density / velocity */
+int lbx_sim_set_initial_density_profile(lbx_sim *sim, int axis, const double *rho_of_axis, size_t n);
+int lbx_sim_set_initial_velocity_profile(lbx_sim *sim, int axis, const double *u_of_axis, size_t n);
+/* the box of level 0 this rank owns while the level is stored as one slab per rank (whole domain on one rank);
+ * available right after lbx_sim_create */
+int lbx_sim_local_box(lbx_sim *sim, int lo[3], int hi[3]);
+/* zero-copy initial arrays over that box, C-ordered [i][j][k]([n]); read by lbx_sim_init_from_scratch */
+int lbx_sim_set_initial_density_local_view(lbx_sim *sim, const double *rho, size_t n);
+int lbx_sim_set_initial_velocity_local_view(lbx_sim *sim, const double *u, size_t n);
+/* bulk output over that box (this rank's cells, no communication), C-ordered [i][j][k]([n]) */
+int lbx_sim_get_local_density_field(const lbx_sim *sim, int level, double *out, size_t n);
+int lbx_sim_get_local_velocity_field(const lbx_sim *sim, int level, double *out, size_t n);
 /* AmrCore::InitFromScratch, regrid */
 int lbx_sim_init_from_scratch(lbx_sim *sim, double time);
 int lbx_sim_regrid(lbx_sim *sim, int lbase, double time);

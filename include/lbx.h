@@ -135,6 +135,14 @@ int lbx_d2d(void *dev_dst, const void *dev_src, size_t bytes);
 int lbx_timer_start(void);
 int lbx_timer_stop(float *milliseconds);   /* synchronises on the stop event */
 
+/* live timing of the AMR path's dominant kernel: between begin and end every lbx_mf_collide_stream* launch
+ * (the fused collide + Stream of one level) is bracketed by CUDA events on the stream it is queued on.
+ * end synchronises and returns the summed kernel time, the number of launches, the VALID cells of this
+ * rank's boxes those launches updated (x 240 B = algorithmic bytes) and the launches not bracketed (event pool
+ * exhausted / inside a concurrent section).  For bench.py's roofline of the AMR leg. */
+int lbx_prof_begin(void);
+int lbx_prof_end(double *ms_total, uint64_t *launches, double *valid_cells, uint64_t *dropped);
+
 /* ---- kernels ---- */
 /* CalcEquilibriumDist, src/AmrSim.cpp:845-931: f <- f_eq(rho, u) on box. */
 int lbx_equilibrium(const lbx_fab *f, const lbx_fab *rho, const lbx_fab *u, const lbx_box *box);
@@ -178,6 +186,18 @@ int lbx_collide_stream_slab(const lbx_fab *src, const lbx_fab *dst, const lbx_fa
                             const lbx_fab *dst_up, const lbx_box *box, const lbx_domain *dom,
                             double omega_s, double omega_b);
 /* face: 0 +x, 1 -x, 2 +y, 3 -y, 4 +z, 5 -z; buf holds [5][cells of region] doubles. */
+/* The same step for a level stored as ONE ghost-free slab per rank (fab sets created with lbx_mf_create_dist:
+ * nfabs == world, owner[r] == r, ngrow 0; slab r spans the periodic domain in x and y), with the neighbour
+ * ordering folded into the kernel: ONE launch per time step and rank.  Boundary-plane CTAs wait for the
+ * neighbours' previous step, store the 5 face-crossing populations into the neighbours' `next` over NVLink and
+ * the last of them publishes this step; interior CTAs never synchronise.  Every rank calls it once per step
+ * (same sequence on every rank).  Replaces CollideLevel + FillBoundary + Stream + UpdateNow
+ * (src/AmrSim.cpp:124-135, 109-122; include/AmrSim.h:89-94) across GPUs.  With one rank: the plain fused step. */
+typedef struct lbx_mf lbx_mf;
+int lbx_mf_collide_stream_slab(const lbx_mf *now, lbx_mf *next, const lbx_domain *dom, double omega_s, double omega_b);
+/* queue a wait (stream, not host) until both neighbours have published the last step queued with
+ * lbx_mf_collide_stream_slab: their face stores into this rank's slab are then complete and visible */
+int lbx_par_step_finish(void);
 int lbx_halo_pack(const lbx_fab *f, const lbx_box *region, int face, double *buf);
 int lbx_halo_unpack(const lbx_fab *f, const lbx_box *region, int face, const double *buf);
 
@@ -186,7 +206,6 @@ int lbx_halo_unpack(const lbx_fab *f, const lbx_box *region, int face, const dou
  * grown by `ngrow` ghosts, `ncomp` SoA planes, zero-filled at creation -- the device side of
  * an amrex::MultiFab / iMultiFab (include/field.h:124-129, src/AmrSim.cpp:668).  Every call
  * below is ONE kernel launch over all boxes of the set. */
-typedef struct lbx_mf lbx_mf;
 int lbx_mf_create(const lbx_box *valid, int nfabs, int ncomp, int ngrow, int dtype, lbx_mf **out);
 /* distributed (after lbx_par_init, COLLECTIVE, same arguments on every rank): owner[i] = rank that
  * holds box i (amrex::DistributionMapping).  This rank allocates its own boxes only; the others are
@@ -254,10 +273,27 @@ int lbx_mf_zero_ring(lbx_mf *f, int depth, int comp);
  * user[(((i-lo0)*NY + (j-lo1))*NZ + (k-lo2))*ncomp + n] over `domain`.  `user_dev` is DEVICE memory.
  * from_user: valid cells of every box <- user (InitDensity / InitVelocity, src/AmrSim.cpp:138-295);
  * to_user  : user <- valid cells; cells no box holds keep their content (GetDensity / GetVelocity
- *            :824-843 in bulk; pre-fill the sentinel with lbx_fill_f64). */
+ *            :824-843 in bulk; pre-fill the sentinel with lbx_fill_f64).
+ * `domain` may cover only an x-range (the slowest user index) of the boxes: cells outside it are skipped, so a
+ * large array can be staged through a small device buffer chunk by chunk; y and z must cover the boxes. */
 int lbx_mf_from_user(lbx_mf *mf, const double *user_dev, const lbx_box *domain, int ncomp);
 int lbx_mf_to_user(const lbx_mf *mf, double *user_dev, const lbx_box *domain, int ncomp);
+/* distributed runs: only THIS rank's boxes (which must lie inside `domain`, e.g. the rank's slab); not collective */
+int lbx_mf_to_user_local(const lbx_mf *mf, double *user_dev, const lbx_box *domain, int ncomp);
+/* The same two moves with the user array in HOST memory (pinned memory gives full PCIe speed): staged through
+ * two device buffers of the library chunk by chunk along x, on two streams, so that the copy of one chunk
+ * overlaps the transposing kernel of the other -- no whole-array device copy is ever allocated.
+ * from_user_host is asynchronous like every other call (user_host must stay valid until lbx_sync);
+ * to_user_host returns when user_host is complete.  local_only: this rank's boxes only (no communication);
+ * fill != 0: cells no box holds receive fill_value (the off-level sentinels of GetDensity / GetVelocity). */
+int lbx_mf_from_user_host(lbx_mf *mf, const double *user_host, const lbx_box *domain, int ncomp);
+int lbx_mf_to_user_host(const lbx_mf *mf, double *user_host, const lbx_box *domain, int ncomp, int local_only, int fill,
+                        double fill_value);
 int lbx_fill_f64(double *dev, size_t n, double value);
+/* separable initial condition (addition; a 1024^3 domain cannot be initialised from whole-domain host arrays):
+ * valid cells of every local box <- profile_dev[(x_axis - axis_lo) * ncomp + n], a DEVICE array of
+ * axis_len * ncomp doubles -- fields that vary along one axis (planar pulse along z, shear wave u_x(y)) */
+int lbx_mf_fill_profile(lbx_mf *mf, const double *profile_dev, int axis, int axis_lo, int axis_len, int ncomp);
 
 /* Gather plans: the box-intersection metadata of AMReX's ParallelCopy-type calls, computed
  * once on the host, executed as one launch (one thread per destination cell).

@@ -42,6 +42,13 @@ SYMBOLS = {
     "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
     "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
     "lbx_sim_plan_cache_size": (_i, []),
+    "lbx_sim_set_initial_density_profile": (_i, [_vp, _i, _dp, _sz]),
+    "lbx_sim_set_initial_velocity_profile": (_i, [_vp, _i, _dp, _sz]),
+    "lbx_sim_local_box": (_i, [_vp, _ip, _ip]),
+    "lbx_sim_set_initial_density_local_view": (_i, [_vp, _dp, _sz]),
+    "lbx_sim_set_initial_velocity_local_view": (_i, [_vp, _dp, _sz]),
+    "lbx_sim_get_local_density_field": (_i, [_vp, _i, _dp, _sz]),
+    "lbx_sim_get_local_velocity_field": (_i, [_vp, _i, _dp, _sz]),
     "lbx_sim_global_init_parallel": (_i, [_i, _i, _vp, _vp]), "lbx_sim_set_parallel_view": (_i, [_i, _i]),
     "lbx_sim_owner": (_i, [_vp, _i, _i, ctypes.POINTER(_i)]),
     "lbx_sim_set_initial_density": (_i, [_vp, _dp, _sz]), "lbx_sim_set_initial_velocity": (_i, [_vp, _dp, _sz]),
@@ -238,6 +245,47 @@ class AmrSim:
         assert u.dtype == np.float64 and u.flags["C_CONTIGUOUS"]
         self._keep = (self._keep or []) + [u]
         _check(lib().lbx_sim_set_initial_velocity_view(self._h, u.ctypes.data_as(_dp), u.size))
+
+    # ---- distributed runs: each rank states and reads its own part (include/lambrex_c.h)
+    def SetInitialDensityProfile(self, axis, rho_of_axis):
+        a = np.ascontiguousarray(rho_of_axis, dtype=np.float64).reshape(-1)
+        _check(lib().lbx_sim_set_initial_density_profile(self._h, int(axis), a.ctypes.data_as(_dp), a.size))
+
+    def SetInitialVelocityProfile(self, axis, u_of_axis):
+        a = np.ascontiguousarray(u_of_axis, dtype=np.float64).reshape(-1)
+        _check(lib().lbx_sim_set_initial_velocity_profile(self._h, int(axis), a.ctypes.data_as(_dp), a.size))
+
+    def LocalBox(self):
+        lo, hi = _i3(0, 0, 0), _i3(0, 0, 0)
+        _check(lib().lbx_sim_local_box(self._h, lo, hi))
+        return tuple(lo), tuple(hi)
+
+    def SetInitialDensityLocalView(self, rho):
+        assert rho.dtype == np.float64 and rho.flags["C_CONTIGUOUS"]
+        self._keep = (self._keep or []) + [rho]
+        _check(lib().lbx_sim_set_initial_density_local_view(self._h, rho.ctypes.data_as(_dp), rho.size))
+
+    def SetInitialVelocityLocalView(self, u):
+        assert u.dtype == np.float64 and u.flags["C_CONTIGUOUS"]
+        self._keep = (self._keep or []) + [u]
+        _check(lib().lbx_sim_set_initial_velocity_local_view(self._h, u.ctypes.data_as(_dp), u.size))
+
+    def GetLocalDensityField(self, level, out=None):
+        """this rank's cells of the level, [nx, ny, nz_local] (C order); no communication"""
+        lo, hi = self.LocalBox()
+        dims = tuple(h - l + 1 for l, h in zip(lo, hi))
+        if out is None:
+            out = np.empty(dims)
+        _check(lib().lbx_sim_get_local_density_field(self._h, level, out.ctypes.data_as(_dp), out.size))
+        return out.reshape(dims)
+
+    def GetLocalVelocityField(self, level, out=None):
+        lo, hi = self.LocalBox()
+        dims = tuple(h - l + 1 for l, h in zip(lo, hi)) + (3,)
+        if out is None:
+            out = np.empty(dims)
+        _check(lib().lbx_sim_get_local_velocity_field(self._h, level, out.ctypes.data_as(_dp), out.size))
+        return out.reshape(dims)
 
     def InitFromScratch(self, time=0.0):
         _check(lib().lbx_sim_init_from_scratch(self._h, time))

@@ -27,6 +27,29 @@ struct Ctx {
   unsigned long long** d_bar_peers = nullptr;        // device array [world]: every rank's flag array
   unsigned long long bar_epoch = 0;
   uint64_t barriers = 0;
+  // neighbour ordering of the distributed uniform path (lbx_mf_collide_stream_slab): four 8-byte words per rank
+  // behind the barrier slots of bar_flags -- [0] written by the rank that owns the planes below this rank's
+  // slab, [1] by the rank above, [2] the boundary-CTA counter of the step kernel, [3] spare
+  static constexpr int STEP_WORDS = 4;
+  unsigned long long* step_flags = nullptr;          // = bar_flags + step_off
+  unsigned long long* peer_flag_base[32] = {};       // every rank's bar_flags (own pointer for this rank)
+  int step_off = 0;
+  unsigned long long step_epoch = 0;                 // steps queued so far (the same on every rank)
+  // staged host <-> fab-set transfers (lbx_mf_from_user_host / lbx_mf_to_user_host): two device staging
+  // buffers on two streams, so that the PCIe copy of one chunk overlaps the transposing kernel of the other
+  static constexpr size_t STAGE_BYTES = size_t(64) << 20;
+  cudaStream_t xfer[2] = {nullptr, nullptr};
+  cudaEvent_t xfer_done[2] = {nullptr, nullptr}, xfer_fork = nullptr;
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;          // current size of each staging buffer (>= STAGE_BYTES, grown to one x-plane if larger)
+  // live profiling of the AMR path's dominant kernel (lbx_prof_begin / lbx_prof_end): every
+  // lbx_mf_collide_stream* launch is bracketed by CUDA events on the stream it is queued on
+  bool prof = false;
+  static constexpr int PROF_MAX = 8192;
+  cudaEvent_t* prof_ev = nullptr;       // [2 * PROF_MAX], created on first use
+  int prof_n = 0;
+  double prof_cells = 0.0;              // valid cells of this rank's boxes over the bracketed launches
+  uint64_t prof_dropped = 0;
   int conc_next = -1;              // >= 0: inside a concurrent section; index of the stream in use
   int conc_used = 0;
 };

@@ -169,6 +169,113 @@ __global__ void __launch_bounds__(BX) k_collide_stream_slab(DFab src, DFab dst, 
 }
 
 // ---------------------------------------------------------------------------
+// The same step with the cross-GPU ORDERING folded in: ONE launch per time step per rank, no separate
+// wait / signal kernels (lbx_mf_collide_stream_slab).  The two boundary planes of the slab are mapped to
+// blockIdx.z = 0, 1 so that their CTAs are dispatched first:
+//   * a boundary CTA first waits (thread 0 spins with acquire loads at system scope, wall-clock timeout)
+//     until both neighbours have published `wait_value` -- their boundary planes of the previous step,
+//     which stored 5 populations per face cell into THIS rank's source fab, are complete (RAW), and they
+//     no longer read the planes of their fab that this step overwrites (WAR of the ping-pong);
+//   * after its stores (5 populations per face cell go straight into the neighbour's fab over NVLink) every
+//     thread fences at system scope; the last boundary CTA to finish publishes `sig_value` into the
+//     neighbours' flags with a release store.  Interior CTAs never touch a flag: they keep HBM busy while
+//     the boundary CTAs wait, store remotely and signal.
+// The neighbours' progress never depends on this launch (they wait for the PREVIOUS signal), so spinning
+// boundary CTAs cannot deadlock the grid.
+// ---------------------------------------------------------------------------
+struct SlabSync {
+  const unsigned long long* wait_a;   // this rank's flags: written by the rank below / above (null: no wait)
+  const unsigned long long* wait_b;
+  unsigned long long wait_value;
+  unsigned long long* sig_a;          // the rank below's "above" flag, the rank above's "below" flag (peer memory)
+  unsigned long long* sig_b;
+  unsigned long long sig_value;
+  unsigned long long* counter;        // boundary CTAs that have finished (local; reset by the last one)
+  unsigned long long nboundary;       // CTAs of the boundary planes
+  unsigned long long timeout_ns;
+  int* err;                           // host-mapped: set on timeout (sticky)
+};
+
+template <class C>
+__global__ void __launch_bounds__(BX) k_collide_stream_slab_sync(DFab src, DFab dst, DFab dn, DFab up, DBox box,
+                                                                 DDom dom, double omega_s, double omega_b, SlabSync sy) {
+  const int z = blockIdx.z;
+  const int k = z == 0 ? box.lo[2] : z == 1 ? box.hi[2] : box.lo[2] + (z - 1);
+  const bool boundary = z < 2;
+  if (boundary && sy.wait_a) {
+    if (threadIdx.x == 0 && !*reinterpret_cast<volatile int*>(sy.err)) {
+      unsigned long long t0, t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+      for (int which = 0; which < 2; ++which) {
+        const unsigned long long* fl = which ? sy.wait_b : sy.wait_a;
+        for (;;) {
+          unsigned long long v;
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(fl) : "memory");
+          if (v >= sy.wait_value) break;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+          if (t - t0 > sy.timeout_ns) { *sy.err = 1; __threadfence_system(); which = 2; break; }
+          __nanosleep(100);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int i = box.lo[0] + blockIdx.x * BX + threadIdx.x;
+  const int j = box.lo[1] + blockIdx.y;
+  if (i <= box.hi[0]) {
+    int ip = i + 1, im = i - 1, jp = j + 1, jm = j - 1, kp = k + 1, km = k - 1;
+    if (dom.periodic[0]) { if (ip > dom.hi[0]) ip = dom.lo[0]; if (im < dom.lo[0]) im = dom.hi[0]; }
+    if (dom.periodic[1]) { if (jp > dom.hi[1]) jp = dom.lo[1]; if (jm < dom.lo[1]) jm = dom.hi[1]; }
+    if (dom.periodic[2]) { if (kp > dom.hi[2]) kp = dom.lo[2]; if (km < dom.lo[2]) km = dom.hi[2]; }
+    const DFab& fp = has_plane(dst, kp) ? dst : up;
+    const DFab& fm = has_plane(dst, km) ? dst : dn;
+    const long long sc0 = plane_stride(dst), scp = plane_stride(fp), scm = plane_stride(fm);
+    double* d[NV];
+    {
+      const long long r00 = row_off(dst, j, k), rp0 = row_off(dst, jp, k), rm0 = row_off(dst, jm, k);
+      d[0] = dst.p + r00 + i;
+      d[1] = dst.p + 1 * sc0 + r00 + ip;
+      d[2] = dst.p + 2 * sc0 + r00 + im;
+      d[3] = dst.p + 3 * sc0 + rp0 + i;
+      d[4] = dst.p + 4 * sc0 + rm0 + i;
+      const long long r0p = row_off(fp, j, kp), rpp = row_off(fp, jp, kp), rmp = row_off(fp, jm, kp);
+      d[5] = fp.p + 5 * scp + r0p + i;
+      d[7] = fp.p + 7 * scp + rpp + ip;
+      d[9] = fp.p + 9 * scp + rmp + ip;
+      d[11] = fp.p + 11 * scp + rpp + im;
+      d[13] = fp.p + 13 * scp + rmp + im;
+      const long long r0m = row_off(fm, j, km), rpm = row_off(fm, jp, km), rmm = row_off(fm, jm, km);
+      d[6] = fm.p + 6 * scm + r0m + i;
+      d[8] = fm.p + 8 * scm + rpm + ip;
+      d[10] = fm.p + 10 * scm + rmm + ip;
+      d[12] = fm.p + 12 * scm + rpm + im;
+      d[14] = fm.p + 14 * scm + rmm + im;
+    }
+    const long long ssc = plane_stride(src), o = row_off(src, j, k) + i;
+    double f[NV];
+#pragma unroll
+    for (int p = 0; p < NV; ++p) f[p] = __ldcs(src.p + p * ssc + o);
+    C::collide(f, omega_s, omega_b);
+#pragma unroll
+    for (int p = 0; p < NV; ++p) __stcs(d[p], f[p]);
+  }
+  if (boundary && sy.sig_a) {
+    __threadfence_system();            // this thread's stores (local and remote) before the CTA's arrival below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();          // cumulative over the CTA's stores observed through the barrier
+      const unsigned long long done = atomicAdd(sy.counter, 1ull) + 1ull;
+      if (done == sy.nboundary) {      // the last boundary CTA of this launch: every face store has been fenced
+        *sy.counter = 0ull;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sy.sig_a), "l"(sy.sig_value) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sy.sig_b), "l"(sy.sig_value) : "memory");
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Collide valid cells (src -> dst, may alias).  Optional int mask (1 comp, any
 // ghost width): cells with mask == fine_val get all 15 populations zeroed
 // (CoarseCollide, src/AmrSim.cpp:499-500).

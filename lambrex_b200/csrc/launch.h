@@ -25,6 +25,8 @@ struct Launchers {
   void (*collide_stream)(cudaStream_t, DFab src, DFab dst, DBox box, DDom dom, double ws, double wb, int scheme);
   void (*collide_stream_slab)(cudaStream_t, DFab src, DFab dst, DFab dn, DFab up, DBox box, DDom dom, double ws,
                               double wb);
+  void (*collide_stream_slab_sync)(cudaStream_t, DFab src, DFab dst, DFab dn, DFab up, DBox box, DDom dom, double ws,
+                                   double wb, SlabSync sy);
   void (*mf_collide)(cudaStream_t, const DFabT* src, const DFabT* f, const DFabT* mask, int nfabs, long long max_cells, double ws,
                      double wb, int fine_val);
   void (*mf_collide_stream)(cudaStream_t, const double* vbase, double* dbase, const DFabT* dst, const DFabT* mask,

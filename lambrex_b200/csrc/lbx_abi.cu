@@ -306,12 +306,22 @@ int lbx_finalize(void) {
     std::vector<unsigned char> toks(g.world);
     lbx::par_allgather(&tok, 1, toks.data());
   }
+  for (int a = 0; a < 2; ++a) {
+    if (g.xfer[a]) { cudaStreamSynchronize(g.xfer[a]); cudaStreamDestroy(g.xfer[a]); }
+    if (g.xfer_done[a]) cudaEventDestroy(g.xfer_done[a]);
+    if (g.stage[a]) cudaFree(g.stage[a]);
+  }
+  if (g.xfer_fork) cudaEventDestroy(g.xfer_fork);
   for (int a = 0; a < lbx::Ctx::NAUX; ++a) {
     if (g.aux[a]) { cudaStreamSynchronize(g.aux[a]); cudaStreamDestroy(g.aux[a]); }
     if (g.join_ev[a]) cudaEventDestroy(g.join_ev[a]);
   }
   if (g.fork_ev) cudaEventDestroy(g.fork_ev);
   lbx::arena_release();
+  if (g.prof_ev) {
+    for (int i = 0; i < 2 * lbx::Ctx::PROF_MAX; ++i) cudaEventDestroy(g.prof_ev[i]);
+    delete[] g.prof_ev;
+  }
   cudaEventDestroy(g.t0);
   cudaEventDestroy(g.t1);
   cudaStreamDestroy(g.own);
@@ -332,8 +342,12 @@ int lbx_par_init(int rank, int world, int (*allgather)(const void*, size_t, void
   if (world == 1) return 0;
   if (!allgather) return fail("lbx_par_init: null allgather callback");
   g.rank = rank; g.world = world; g.allgather = allgather; g.allgather_user = user;
-  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&g.bar_flags), sizeof(unsigned long long) * world));
-  LBX_CUDA(cudaMemset(g.bar_flags, 0, sizeof(unsigned long long) * world));
+  g.step_off = (world + 3) / 4 * 4;                  // step-ordering words behind the barrier slots, 32 B aligned
+  const size_t flag_words = (size_t)g.step_off + lbx::Ctx::STEP_WORDS;
+  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&g.bar_flags), sizeof(unsigned long long) * flag_words));
+  LBX_CUDA(cudaMemset(g.bar_flags, 0, sizeof(unsigned long long) * flag_words));
+  g.step_flags = g.bar_flags + g.step_off;
+  g.step_epoch = 0;
   cudaIpcMemHandle_t mine;
   LBX_CUDA(cudaIpcGetMemHandle(&mine, g.bar_flags));
   std::vector<unsigned char> all((size_t)world * LBX_IPC_HANDLE_BYTES);
@@ -345,6 +359,7 @@ int lbx_par_init(int rank, int world, int (*allgather)(const void*, size_t, void
     if (lbx::ipc_open_cached(all.data() + (size_t)r * LBX_IPC_HANDLE_BYTES, &base)) return 1;
     peers[r] = static_cast<unsigned long long*>(base);
   }
+  for (int r = 0; r < world; ++r) g.peer_flag_base[r] = peers[r];
   LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&g.d_bar_peers), sizeof(void*) * world));
   LBX_CUDA(cudaMemcpy(g.d_bar_peers, peers.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
   // nobody may signal before every rank has zeroed and published its flags
@@ -599,6 +614,14 @@ int lbx_peer_wait(const uint64_t* a, const uint64_t* b, uint64_t value, uint64_t
   lbx::k_peer_wait<<<1, 1, 0, g.cur>>>(reinterpret_cast<const unsigned long long*>(a),
                                        reinterpret_cast<const unsigned long long*>(b), value, timeout_ns, derr);
   return after_launch("lbx_peer_wait");
+}
+int lbx_par_step_finish(void) {
+  LBX_NEED_INIT();
+  if (g.world == 1) return 0;
+  int* derr = nullptr;
+  LBX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&derr), g.peer_err, 0));
+  lbx::k_peer_wait<<<1, 1, 0, g.cur>>>(g.step_flags, g.step_flags + 1, g.step_epoch, 30000000000ull, derr);
+  return after_launch("lbx_par_step_finish");
 }
 int lbx_peer_error(void) {   // returns the flag and clears it
   if (!g.ready || !g.peer_err) return 0;

@@ -397,18 +397,21 @@ int lbx_mf_zero_ring(lbx_mf* f, int depth, int comp) {
   return lbx::after_launch("lbx_mf_zero_ring");
 }
 
-static int user_common(const lbx_mf* m, const void* user, const lbx_box* dom, int ncomp, const char* what) {
+static int user_common(const lbx_mf* m, const void* user, const lbx_box* dom, int ncomp, const char* what, bool local_only) {
   if (need(m, ncomp, LBX_F64, 0, what)) return 1;
   if (!user || !dom) return fail(std::string(what) + ": null argument");
-  for (const auto& f : m->host)
-    for (int d = 0; d < 3; ++d)
+  for (const auto& f : m->host) {
+    if (local_only && !f.local) continue;
+    // x (the slowest user index) may be covered partially: cells outside [lo0, hi0] are skipped (chunked staging)
+    for (int d = 1; d < 3; ++d)
       if (f.vlo[d] < dom->lo[d] || f.vhi[d] > dom->hi[d]) return fail(std::string(what) + ": a box lies outside the user array's domain");
+  }
   return 0;
 }
 }  // extern "C"
 // tiled launch when the shape allows it (1 or 3 components, grid limits), else the plain kernel
 template <bool TO_FAB>
-static bool user_tiled(const lbx_mf* m, double* user, const lbx_box* dom, int ncomp) {
+static bool user_tiled(const lbx_mf* m, double* user, const lbx_box* dom, int ncomp, int local_only = 0) {
   int mx = 0, my = 0, mz = 0;
   for (const auto& f : m->host) {
     mx = std::max(mx, f.vhi[0] - f.vlo[0] + 1);
@@ -418,34 +421,248 @@ static bool user_tiled(const lbx_mf* m, double* user, const lbx_box* dom, int nc
   if ((ncomp != 1 && ncomp != 3) || m->nfabs > 65535 || my > 65535) return false;
   const int tx = (mx + lbx::UT - 1) / lbx::UT, tz = (mz + lbx::UT - 1) / lbx::UT;
   const dim3 grid((unsigned)(tx * tz), (unsigned)my, (unsigned)m->nfabs), block(lbx::UT, 8);
-  const int ny = dom->hi[1] - dom->lo[1] + 1, nz = dom->hi[2] - dom->lo[2] + 1;
+  const int nx = dom->hi[0] - dom->lo[0] + 1, ny = dom->hi[1] - dom->lo[1] + 1, nz = dom->hi[2] - dom->lo[2] + 1;
   if (ncomp == 1)
-    lbx::k_mf_user_tiled<TO_FAB, 1><<<grid, block, 0, g.cur>>>(m->table, user, tx, dom->lo[0], dom->lo[1], dom->lo[2], ny, nz);
+    lbx::k_mf_user_tiled<TO_FAB, 1><<<grid, block, 0, g.cur>>>(m->table, user, tx, dom->lo[0], dom->lo[1], dom->lo[2], nx, ny, nz, local_only);
   else
-    lbx::k_mf_user_tiled<TO_FAB, 3><<<grid, block, 0, g.cur>>>(m->table, user, tx, dom->lo[0], dom->lo[1], dom->lo[2], ny, nz);
+    lbx::k_mf_user_tiled<TO_FAB, 3><<<grid, block, 0, g.cur>>>(m->table, user, tx, dom->lo[0], dom->lo[1], dom->lo[2], nx, ny, nz, local_only);
   return true;
 }
 extern "C" {
 int lbx_mf_from_user(lbx_mf* m, const double* user_dev, const lbx_box* dom, int ncomp) {
   LBX_NEED_INIT();
-  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_from_user")) return 1;
+  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_from_user", true)) return 1;      // writes this rank's boxes only
   if (!user_tiled<true>(m, const_cast<double*>(user_dev), dom, ncomp))
     lbx::k_mf_user<true><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
-        m->table, m->nfabs, const_cast<double*>(user_dev), dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
-        dom->hi[2] - dom->lo[2] + 1, ncomp);
+        m->table, m->nfabs, const_cast<double*>(user_dev), dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[0] - dom->lo[0] + 1,
+        dom->hi[1] - dom->lo[1] + 1, dom->hi[2] - dom->lo[2] + 1, ncomp, 0);
   return lbx::after_launch("lbx_mf_from_user");
+}
+int lbx_mf_to_user_local(const lbx_mf* m, double* user_dev, const lbx_box* dom, int ncomp) {
+  LBX_NEED_INIT();
+  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_to_user_local", true)) return 1;
+  if (!user_tiled<false>(m, user_dev, dom, ncomp, 1))
+    lbx::k_mf_user<false><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
+        m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[0] - dom->lo[0] + 1,
+        dom->hi[1] - dom->lo[1] + 1, dom->hi[2] - dom->lo[2] + 1, ncomp, 1);
+  return lbx::after_launch("lbx_mf_to_user_local");
 }
 int lbx_mf_to_user(const lbx_mf* m, double* user_dev, const lbx_box* dom, int ncomp) {
   LBX_NEED_INIT();
-  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_to_user")) return 1;
+  if (user_common(m, user_dev, dom, ncomp, "lbx_mf_to_user", false)) return 1;
   if (m->dist && lbx::par_barrier()) return 1;          // reads every rank's boxes
   if (!user_tiled<false>(m, user_dev, dom, ncomp))
     lbx::k_mf_user<false><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(
-        m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[1] - dom->lo[1] + 1,
-        dom->hi[2] - dom->lo[2] + 1, ncomp);
+        m->table, m->nfabs, user_dev, dom->lo[0], dom->lo[1], dom->lo[2], dom->hi[0] - dom->lo[0] + 1,
+        dom->hi[1] - dom->lo[1] + 1, dom->hi[2] - dom->lo[2] + 1, ncomp, 0);
   if (lbx::after_launch("lbx_mf_to_user")) return 1;
   return m->dist ? lbx::par_barrier() : 0;
 }
+int lbx_mf_fill_profile(lbx_mf* m, const double* profile_dev, int axis, int axis_lo, int axis_len, int ncomp) {
+  LBX_NEED_INIT();
+  if (need(m, ncomp, LBX_F64, 0, "lbx_mf_fill_profile")) return 1;
+  if (!profile_dev || axis < 0 || axis > 2 || axis_len < 1 || ncomp < 1) return fail("lbx_mf_fill_profile: bad arguments");
+  for (const auto& f : m->host)
+    if (f.local && (f.vlo[axis] < axis_lo || f.vhi[axis] >= axis_lo + axis_len))
+      return fail("lbx_mf_fill_profile: a box reaches outside the profile");
+  lbx::k_mf_fill_profile<<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(m->table, m->nfabs, ncomp, profile_dev, axis,
+                                                                                      axis_lo);
+  return lbx::after_launch("lbx_mf_fill_profile");
+}
+
+// ----------------------------------------------------------------------------- distributed uniform path
+namespace {
+lbx::DFab dfab_of(const lbx::DFabT& t) {
+  lbx::DFab d;
+  d.p = static_cast<double*>(t.p);
+  for (int a = 0; a < 3; ++a) { d.lo[a] = t.lo[a]; d.n[a] = t.n[a]; }
+  return d;
+}
+// rank whose slab holds plane k (same x-y extent as `mine`), or -1
+int slab_owner(const lbx_mf* m, const lbx::DFabT& mine, int k) {
+  for (int r = 0; r < m->nfabs; ++r) {
+    const lbx::DFabT& f = m->host[r];
+    if (k >= f.vlo[2] && k <= f.vhi[2] && f.vlo[0] == mine.vlo[0] && f.vhi[0] == mine.vhi[0] && f.vlo[1] == mine.vlo[1] &&
+        f.vhi[1] == mine.vhi[1])
+      return r;
+  }
+  return -1;
+}
+}  // namespace
+
+int lbx_mf_collide_stream_slab(const lbx_mf* now, lbx_mf* next, const lbx_domain* dom, double omega_s, double omega_b) {
+  LBX_NEED_INIT();
+  const char* what = "lbx_mf_collide_stream_slab";
+  if (!dom) return fail(std::string(what) + ": null domain");
+  if (need(now, LBX_NV, LBX_F64, 0, what) || need(next, LBX_NV, LBX_F64, 0, what)) return 1;
+  if (now->geom != next->geom || now->ngrow != 0 || now->ncomp != LBX_NV) return fail(std::string(what) + ": now and next must be ghost-free 15-component sets over the same slabs");
+  if (now->base == next->base) return fail(std::string(what) + ": next aliases now");
+  if (now->nfabs != g.world) return fail(std::string(what) + ": one slab per rank expected");
+  for (int r = 0; r < now->nfabs; ++r)
+    if (now->owner[r] != (now->dist ? r : 0)) return fail(std::string(what) + ": slab r must belong to rank r");
+  const lbx::DFabT& S = now->host[g.rank];
+  const lbx::DFabT& D = next->host[g.rank];
+  lbx::DBox box;
+  lbx::DDom dd;
+  for (int a = 0; a < 3; ++a) {
+    box.lo[a] = S.vlo[a]; box.hi[a] = S.vhi[a];
+    dd.lo[a] = dom->lo[a]; dd.hi[a] = dom->hi[a]; dd.periodic[a] = dom->periodic[a];
+  }
+  for (int a = 0; a < 2; ++a)
+    if (box.lo[a] != dd.lo[a] || box.hi[a] != dd.hi[a] || !dd.periodic[a])
+      return fail(std::string(what) + ": a slab spans the periodic domain in x and y");
+  if (box.hi[1] - box.lo[1] >= 65535 || box.hi[2] - box.lo[2] >= 65535) return fail(std::string(what) + ": slab exceeds 65535 rows/planes per launch");
+  int kp = box.hi[2] + 1, km = box.lo[2] - 1;
+  if (dd.periodic[2]) { if (kp > dd.hi[2]) kp = dd.lo[2]; if (km < dd.lo[2]) km = dd.hi[2]; }
+  else return fail(std::string(what) + ": the domain must be periodic in z");
+  const int up = slab_owner(next, D, kp), dn = slab_owner(next, D, km);
+  if (up < 0 || dn < 0) return fail(std::string(what) + ": no slab holds the plane above / below this rank's slab");
+  lbx::SlabSync sy;
+  memset(&sy, 0, sizeof(sy));
+  if (g.world > 1) {
+    // flags: [0] is written by the rank below, [1] by the rank above (ctx.h); this rank is "above" its lower
+    // neighbour and "below" its upper neighbour
+    sy.wait_a = g.step_flags;
+    sy.wait_b = g.step_flags + 1;
+    sy.wait_value = g.step_epoch;
+    sy.sig_a = g.peer_flag_base[dn] + g.step_off + 1;
+    sy.sig_b = g.peer_flag_base[up] + g.step_off + 0;
+    sy.sig_value = ++g.step_epoch;
+    sy.counter = g.step_flags + 2;
+    sy.timeout_ns = 30000000000ull;
+    LBX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&sy.err), g.peer_err, 0));
+  }
+  L().collide_stream_slab_sync(g.cur, dfab_of(S), dfab_of(D), dfab_of(next->host[dn]), dfab_of(next->host[up]), box, dd, omega_s,
+                               omega_b, sy);
+  return lbx::after_launch(what);
+}
+
+// ----------------------------------------------------------------------------- staged host transfers
+}  // extern "C"
+namespace {
+int stage_setup(size_t plane_bytes) {
+  const size_t want = std::max(lbx::Ctx::STAGE_BYTES, plane_bytes);
+  for (int a = 0; a < 2; ++a) {
+    if (!g.xfer[a]) LBX_CUDA(cudaStreamCreateWithFlags(&g.xfer[a], cudaStreamNonBlocking));
+    if (!g.xfer_done[a]) LBX_CUDA(cudaEventCreateWithFlags(&g.xfer_done[a], cudaEventDisableTiming));
+    if (g.stage[a] && g.stage_bytes < want) {
+      LBX_CUDA(cudaStreamSynchronize(g.xfer[a]));
+      LBX_CUDA(cudaFree(g.stage[a]));
+      g.stage[a] = nullptr;
+    }
+    if (!g.stage[a]) LBX_CUDA(cudaMalloc(&g.stage[a], want));
+  }
+  g.stage_bytes = want;
+  if (!g.xfer_fork) LBX_CUDA(cudaEventCreateWithFlags(&g.xfer_fork, cudaEventDisableTiming));
+  return 0;
+}
+// kernels of one chunk on stream `st`: user_dev covers the x-range [c0, c1] of dom
+template <bool TO_FAB>
+int stage_kernel(const lbx_mf* m, double* user_dev, const lbx_box* dom, int c0, int c1, int ncomp, int local_only, cudaStream_t st) {
+  lbx_box cb = *dom;
+  cb.lo[0] = c0;
+  cb.hi[0] = c1;
+  cudaStream_t keep = g.cur;
+  g.cur = st;
+  if (!user_tiled<TO_FAB>(m, user_dev, &cb, ncomp, local_only))
+    lbx::k_mf_user<TO_FAB><<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, st>>>(
+        m->table, m->nfabs, user_dev, cb.lo[0], cb.lo[1], cb.lo[2], cb.hi[0] - cb.lo[0] + 1, cb.hi[1] - cb.lo[1] + 1,
+        cb.hi[2] - cb.lo[2] + 1, ncomp, local_only);
+  g.cur = keep;
+  return lbx::after_launch("staged user transfer");
+}
+}  // namespace
+extern "C" {
+
+int lbx_mf_from_user_host(lbx_mf* m, const double* user_host, const lbx_box* dom, int ncomp) {
+  LBX_NEED_INIT();
+  if (user_common(m, user_host, dom, ncomp, "lbx_mf_from_user_host", true)) return 1;
+  if (g.conc_next >= 0) return fail("lbx_mf_from_user_host: must not be called inside a concurrent section");
+  const size_t plane = (size_t)(dom->hi[1] - dom->lo[1] + 1) * (dom->hi[2] - dom->lo[2] + 1) * ncomp * sizeof(double);
+  if (stage_setup(plane)) return 1;
+  const int per = (int)std::max<size_t>(1, g.stage_bytes / plane);
+  LBX_CUDA(cudaEventRecord(g.xfer_fork, g.cur));
+  for (int a = 0; a < 2; ++a) LBX_CUDA(cudaStreamWaitEvent(g.xfer[a], g.xfer_fork, 0));
+  int c = 0;
+  for (int x0 = dom->lo[0]; x0 <= dom->hi[0]; x0 += per, ++c) {
+    const int x1 = std::min(dom->hi[0], x0 + per - 1), s = c & 1;
+    const char* src = reinterpret_cast<const char*>(user_host) + (size_t)(x0 - dom->lo[0]) * plane;
+    LBX_CUDA(cudaMemcpyAsync(g.stage[s], src, (size_t)(x1 - x0 + 1) * plane, cudaMemcpyHostToDevice, g.xfer[s]));
+    if (stage_kernel<true>(m, static_cast<double*>(g.stage[s]), dom, x0, x1, ncomp, 0, g.xfer[s])) return 1;
+  }
+  for (int a = 0; a < 2; ++a) {
+    LBX_CUDA(cudaEventRecord(g.xfer_done[a], g.xfer[a]));
+    LBX_CUDA(cudaStreamWaitEvent(g.cur, g.xfer_done[a], 0));
+  }
+  return 0;
+}
+
+int lbx_mf_to_user_host(const lbx_mf* m, double* user_host, const lbx_box* dom, int ncomp, int local_only, int fill,
+                        double fill_value) {
+  LBX_NEED_INIT();
+  if (user_common(m, user_host, dom, ncomp, "lbx_mf_to_user_host", local_only != 0)) return 1;
+  if (g.conc_next >= 0) return fail("lbx_mf_to_user_host: must not be called inside a concurrent section");
+  const size_t plane = (size_t)(dom->hi[1] - dom->lo[1] + 1) * (dom->hi[2] - dom->lo[2] + 1) * ncomp * sizeof(double);
+  if (stage_setup(plane)) return 1;
+  const int per = (int)std::max<size_t>(1, g.stage_bytes / plane);
+  const bool remote = m->dist && !local_only;            // reads every rank's boxes
+  if (remote && lbx::par_barrier()) return 1;
+  LBX_CUDA(cudaEventRecord(g.xfer_fork, g.cur));
+  for (int a = 0; a < 2; ++a) LBX_CUDA(cudaStreamWaitEvent(g.xfer[a], g.xfer_fork, 0));
+  int c = 0;
+  for (int x0 = dom->lo[0]; x0 <= dom->hi[0]; x0 += per, ++c) {
+    const int x1 = std::min(dom->hi[0], x0 + per - 1), s = c & 1;
+    const size_t bytes = (size_t)(x1 - x0 + 1) * plane;
+    if (fill) {
+      const size_t n = bytes / sizeof(double);
+      lbx::k_fill_f64<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, g.xfer[s]>>>(static_cast<double*>(g.stage[s]),
+                                                                                               (long long)n, fill_value);
+      if (lbx::after_launch("lbx_mf_to_user_host")) return 1;
+    }
+    if (stage_kernel<false>(m, static_cast<double*>(g.stage[s]), dom, x0, x1, ncomp, local_only ? 1 : 0, g.xfer[s])) return 1;
+    char* dst = reinterpret_cast<char*>(user_host) + (size_t)(x0 - dom->lo[0]) * plane;
+    LBX_CUDA(cudaMemcpyAsync(dst, g.stage[s], bytes, cudaMemcpyDeviceToHost, g.xfer[s]));
+  }
+  for (int a = 0; a < 2; ++a) {
+    LBX_CUDA(cudaEventRecord(g.xfer_done[a], g.xfer[a]));
+    LBX_CUDA(cudaStreamWaitEvent(g.cur, g.xfer_done[a], 0));
+  }
+  if (remote && lbx::par_barrier()) return 1;
+  LBX_CUDA(cudaStreamSynchronize(g.cur));               // the caller reads user_host next
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- live kernel timing
+int lbx_prof_begin(void) {
+  LBX_NEED_INIT();
+  if (!g.prof_ev) {
+    g.prof_ev = new cudaEvent_t[2 * lbx::Ctx::PROF_MAX];
+    for (int i = 0; i < 2 * lbx::Ctx::PROF_MAX; ++i) LBX_CUDA(cudaEventCreate(&g.prof_ev[i]));
+  }
+  g.prof = true;
+  g.prof_n = 0;
+  g.prof_cells = 0.0;
+  g.prof_dropped = 0;
+  return 0;
+}
+int lbx_prof_end(double* ms_total, uint64_t* launches, double* valid_cells, uint64_t* dropped) {
+  LBX_NEED_INIT();
+  if (!g.prof) return fail("lbx_prof_end: lbx_prof_begin was not called");
+  g.prof = false;
+  LBX_CUDA(cudaStreamSynchronize(g.cur));
+  double ms = 0.0;
+  for (int i = 0; i < g.prof_n; ++i) {
+    float t = 0.f;
+    LBX_CUDA(cudaEventElapsedTime(&t, g.prof_ev[2 * i], g.prof_ev[2 * i + 1]));
+    ms += t;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = (uint64_t)g.prof_n;
+  if (valid_cells) *valid_cells = g.prof_cells;
+  if (dropped) *dropped = g.prof_dropped;
+  return 0;
+}
+
 int lbx_fill_f64(double* dev, size_t n, double value) {
   LBX_NEED_INIT();
   if (!dev) return fail("lbx_fill_f64: null pointer");
@@ -658,10 +875,19 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   }
   const bool remote = plan && ((src0 && src0->dist) || (src1 && src1->dist) || (src1b && src1b->dist));
   if (remote && lbx::par_barrier()) return 1;
+  const bool timed = g.prof && g.prof_n < lbx::Ctx::PROF_MAX && g.conc_next < 0;
+  if (g.prof && !timed) ++g.prof_dropped;
+  if (timed) LBX_CUDA(cudaEventRecord(g.prof_ev[2 * g.prof_n], g.cur));
   L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
                         mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
                         dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val,
                         (zero_invalid ? 1 : 0) | (level_step ? 2 : 0));
+  if (timed) {
+    LBX_CUDA(cudaEventRecord(g.prof_ev[2 * g.prof_n + 1], g.cur));
+    ++g.prof_n;
+    for (const auto& f : dst->host)
+      if (f.local) g.prof_cells += (double)(f.vhi[0] - f.vlo[0] + 1) * (f.vhi[1] - f.vlo[1] + 1) * (f.vhi[2] - f.vlo[2] + 1);
+  }
   if (lbx::after_launch(what)) return 1;
   return remote ? lbx::par_barrier() : 0;
 }

@@ -219,13 +219,14 @@ __global__ void __launch_bounds__(MFT) k_mf_linear_moments(const DFabT* __restri
 // else  : user <- valid cells (bulk form of GetDensity / GetVelocity, :824-843).
 template <bool TO_FAB>
 __global__ void __launch_bounds__(MFT) k_mf_user(const DFabT* __restrict__ ft, int nfabs, double* __restrict__ user,
-                                                 int d0, int d1, int d2, int ny, int nz, int ncomp) {
+                                                 int d0, int d1, int d2, int nx, int ny, int nz, int ncomp, int local_only) {
   const int b = mf_fab_index();
   if (b >= nfabs) return;
   const DFabT F = ft[b];
-  if (TO_FAB && !F.local) return;              // reading (to user) also takes peers' boxes, over NVLink
+  if ((TO_FAB || local_only) && !F.local) return;   // reading (to user) also takes peers' boxes over NVLink, unless local_only
   int i, j, k;
   if (!mf_cell(F, 0, i, j, k)) return;
+  if (i < d0 || i >= d0 + nx) return;               // the user array may cover an x-range of the boxes only (chunked staging)
   double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
   const long long sc = mf_stride(F);
   double* up = user + ((((long long)(i - d0) * ny + (j - d1)) * nz + (k - d2)) * ncomp);
@@ -241,13 +242,14 @@ __global__ void __launch_bounds__(MFT) k_mf_user(const DFabT* __restrict__ ft, i
 constexpr int UT = 32;
 template <bool TO_FAB, int NC>
 __global__ void __launch_bounds__(UT * 8) k_mf_user_tiled(const DFabT* __restrict__ ft, double* __restrict__ user,
-                                                          int tiles_x, int d0, int d1, int d2, int ny, int nz) {
+                                                          int tiles_x, int d0, int d1, int d2, int nx, int ny, int nz, int local_only) {
   __shared__ double tile[NC][UT][UT + 1];     // [n][z][x]
   const DFabT F = ft[blockIdx.z];
-  if (TO_FAB && !F.local) return;
+  if ((TO_FAB || local_only) && !F.local) return;
   const int j = F.vlo[1] + blockIdx.y;
   const int i0 = F.vlo[0] + (blockIdx.x % tiles_x) * UT, k0 = F.vlo[2] + (blockIdx.x / tiles_x) * UT;
   if (j > F.vhi[1] || i0 > F.vhi[0] || k0 > F.vhi[2]) return;           // block-uniform
+  if (i0 + UT <= d0 || i0 >= d0 + nx) return;                             // block-uniform: tile outside the user array's x-range
   const int ni = min(UT, F.vhi[0] - i0 + 1), nk = min(UT, F.vhi[2] - k0 + 1);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long long sc = mf_stride(F);
@@ -261,16 +263,18 @@ __global__ void __launch_bounds__(UT * 8) k_mf_user_tiled(const DFabT* __restric
       }
     __syncthreads();
     for (int ii = ty; ii < ni; ii += 8) {
+      if (i0 + ii < d0 || i0 + ii >= d0 + nx) continue;       // outside the x-range the user array covers
       double* up = user + (((long long)(i0 + ii - d0) * ny + (j - d1)) * nz + (k0 - d2)) * NC;
       for (int e = tx; e < nk * NC; e += UT) up[e] = tile[e % NC][e / NC][ii];
     }
   } else {
     for (int ii = ty; ii < ni; ii += 8) {
+      if (i0 + ii < d0 || i0 + ii >= d0 + nx) continue;
       const double* up = user + (((long long)(i0 + ii - d0) * ny + (j - d1)) * nz + (k0 - d2)) * NC;
       for (int e = tx; e < nk * NC; e += UT) tile[e % NC][e / NC][ii] = up[e];
     }
     __syncthreads();
-    if (tx < ni)
+    if (tx < ni && i0 + tx >= d0 && i0 + tx < d0 + nx)
       for (int kk = ty; kk < nk; kk += 8) {
         const long long o = mf_off(F, i0 + tx, j, k0 + kk);
 #pragma unroll
@@ -282,6 +286,23 @@ __global__ void __launch_bounds__(UT * 8) k_mf_user_tiled(const DFabT* __restric
 __global__ void k_fill_f64(double* __restrict__ p, long long n, double v) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
     p[t] = v;
+}
+
+// Separable initial condition: f(i,j,k,n) = profile[(x_axis - axis_lo) * ncomp + n] on the valid cells of every
+// local box -- a field that varies along ONE axis (the planar pulse varies along z, the shear wave u_x along y),
+// stated by a profile of axis-length entries instead of a whole-domain host array (1024^3: 34 GB per rank).
+__global__ void __launch_bounds__(MFT) k_mf_fill_profile(const DFabT* __restrict__ ft, int nfabs, int ncomp,
+                                                         const double* __restrict__ profile, int axis, int axis_lo) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT F = ft[b];
+  if (!F.local) return;
+  int i, j, k;
+  if (!mf_cell(F, 0, i, j, k)) return;
+  const int a = (axis == 0 ? i : axis == 1 ? j : k) - axis_lo;
+  double* fp = static_cast<double*>(F.p) + mf_off(F, i, j, k);
+  const long long sc = mf_stride(F);
+  for (int n = 0; n < ncomp; ++n) fp[n * sc] = profile[(long long)a * ncomp + n];
 }
 
 template <class T>

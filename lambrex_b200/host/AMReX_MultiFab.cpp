@@ -35,12 +35,22 @@ void DeviceFabArray<T, DTYPE>::define(const BoxArray& ba, const DistributionMapp
   lay_ = lay;
   if (ba.empty()) return;
   std::vector<lbx_box> vb;
+  std::vector<int> slab_owner;
   int sg = ngrow;
+  slabs_.clear();
   if (lay == Layout::FLAT) {
     const Box mb = ba.minimalBox();
     if (mb.numPts() != ba.numPts()) Abort("FLAT layout needs a BoxArray that tiles its minimal box");
-    vb.resize(1);
-    for (int d = 0; d < 3; ++d) { vb[0].lo[d] = mb.smallEnd(d); vb[0].hi[d] = mb.bigEnd(d); }
+    const int np = DistributionMapping::NProcs();
+    if (np > 1) {
+      if (!SlabOwnership(ba, dm, np, &slabs_)) Abort("FLAT storage in a distributed run needs one z-slab per rank (SlabOwnership)");
+      for (int r = 0; r < np; ++r) slab_owner.push_back(r);
+    } else {
+      slabs_.assign(1, mb);
+    }
+    vb.resize(slabs_.size());
+    for (size_t s = 0; s < slabs_.size(); ++s)
+      for (int d = 0; d < 3; ++d) { vb[s].lo[d] = slabs_[s].smallEnd(d); vb[s].hi[d] = slabs_[s].bigEnd(d); }
     sg = 0;
   } else {
     vb.resize(ba.size());
@@ -50,10 +60,8 @@ void DeviceFabArray<T, DTYPE>::define(const BoxArray& ba, const DistributionMapp
   st_ = std::make_shared<Storage>();
   // distributed run: box i lives on rank dm[i] (BOXES storage; FLAT is single-rank only)
   const bool dist = DistributionMapping::NProcs() > 1 && lay == Layout::BOXES && dm.size() == ba.size();
-  if (DistributionMapping::NProcs() > 1 && lay == Layout::FLAT) Abort("FLAT storage is not available in a distributed run");
-  lbx_check(lbx_mf_create_dist(vb.data(), (int)vb.size(), ncomp, sg, DTYPE, dist ? dm.ProcessorMap().data() : nullptr,
-                               &st_->mf),
-            "MultiFab::define");
+  const int* owners = !slab_owner.empty() ? slab_owner.data() : dist ? dm.ProcessorMap().data() : nullptr;
+  lbx_check(lbx_mf_create_dist(vb.data(), (int)vb.size(), ncomp, sg, DTYPE, owners, &st_->mf), "MultiFab::define");
   size_t bytes = 0;
   lbx_check(lbx_mf_info(st_->mf, nullptr, nullptr, nullptr, nullptr, &bytes), "MultiFab::define");
   st_->elems = bytes / sizeof(T);
@@ -72,6 +80,7 @@ void DeviceFabArray<T, DTYPE>::clear() {
   ba_.clear();
   dm_ = DistributionMapping();
   ncomp_ = ngrow_ = 0;
+  slabs_.clear();
   mirror_.clear();
   mirror_ok_ = false;
 }
@@ -114,7 +123,11 @@ void DeviceFabArray<T, DTYPE>::upload(const std::vector<T>& host) {
 template <class T, int DTYPE>
 T DeviceFabArray<T, DTYPE>::hostValue(int bi, const IntVect& p, int comp) const {
   const std::vector<T>& m = hostMirror();
-  const int s = isFlat() ? 0 : bi;
+  int s = bi;
+  if (isFlat()) {                  // the slab that holds p
+    s = 0;
+    while (s + 1 < (int)slabs_.size() && !slabs_[s].contains(p)) ++s;
+  }
   if (!storageBox(s).contains(p)) Abort("MultiFab::hostValue: cell outside the fab");
   // the ALLOCATED fab may be wider in x than valid + ghosts (sector alignment, lbx_mf_fab)
   lbx_fab fd;
@@ -130,6 +143,7 @@ void DeviceFabArray<double, LBX_F64>::relayout(Layout lay) {
   MultiFab fresh(ba_, dm_, ncomp_, ngrow_, lay);
   CopyValid(fresh, *this);
   st_ = fresh.st_;
+  slabs_ = fresh.slabs_;
   lay_ = lay;
   touch();
 }

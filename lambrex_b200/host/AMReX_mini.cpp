@@ -1,6 +1,7 @@
 // amrex-mini: box calculus (see AMReX_mini.H).  Restated from AMReX semantics
 //  [AMReX, unverified]; nothing here is copied from AMReX or the reference.
 #include "AMReX_mini.H"
+#include <map>
 
 #include <cstring>
 #include <iostream>
@@ -228,12 +229,58 @@ void DistributionMapping::SetParallel(int myproc, int nprocs) {
   g_nprocs = nprocs;
 }
 
+namespace {
+// The boxes as whole x-y LAYERS stacked along z: every box's z-range is one of a set of disjoint ranges that
+// together cover the minimal box, and the boxes of one range tile its whole x-y extent (true for every level-0
+// BoxArray: MakeBaseGrids chops the domain as a tensor product).  layers: (zlo, zhi) ascending.
+bool z_layers(const BoxArray& ba, std::vector<std::pair<int, int>>& layers) {
+  layers.clear();
+  if (ba.empty()) return false;
+  const Box mb = ba.minimalBox();
+  std::map<std::pair<int, int>, long> area;      // (zlo, zhi) -> cells of the layer's boxes
+  for (long i = 0; i < ba.size(); ++i) area[{ba[i].smallEnd(2), ba[i].bigEnd(2)}] += ba[i].numPts();
+  int next = mb.smallEnd(2);
+  for (const auto& kv : area) {                  // sorted by zlo: must be contiguous and disjoint
+    if (kv.first.first != next) return false;
+    const long want = (long)mb.length(0) * mb.length(1) * (kv.first.second - kv.first.first + 1);
+    if (kv.second != want) return false;
+    next = kv.first.second + 1;
+    layers.push_back(kv.first);
+  }
+  return next == mb.bigEnd(2) + 1;
+}
+}  // namespace
+
 DistributionMapping::DistributionMapping(const BoxArray& ba, int nprocs) {
-  // contiguous chunks of the box list balanced by cell count (boxes of one level are listed in
-  // a spatially coherent order by the grid generator); a single rank owns everything.
   const long n = ba.size();
   p_.assign(n, 0);
   if (nprocs <= 1 || n == 0) return;
+  // (1) a BoxArray made of whole x-y layers (every level 0): contiguous runs of layers per rank, balanced by
+  // plane count -- each rank owns ONE z-slab, which is what the distributed uniform path stores as a single
+  // ghost-free fab per GPU (SlabOwnership below) and a spatially compact share for the AMR path
+  std::vector<std::pair<int, int>> layers;
+  if (z_layers(ba, layers) && (int)layers.size() >= nprocs) {
+    const Box mb = ba.minimalBox();
+    const double total = (double)mb.length(2);
+    std::map<int, int> owner_of_zlo;
+    double acc = 0.0;
+    for (const auto& l : layers) {
+      const double planes = l.second - l.first + 1, mid = acc + 0.5 * planes;
+      owner_of_zlo[l.first] = std::min(nprocs - 1, (int)(mid / total * nprocs));
+      acc += planes;
+    }
+    // every rank must end up with at least one layer (it does unless the layers are very uneven)
+    std::vector<int> count(nprocs, 0);
+    for (const auto& kv : owner_of_zlo) ++count[kv.second];
+    bool all = true;
+    for (int c : count) all = all && c > 0;
+    if (all) {
+      for (long i = 0; i < n; ++i) p_[i] = owner_of_zlo[ba[i].smallEnd(2)];
+      return;
+    }
+  }
+  // (2) any other BoxArray (refined levels): contiguous chunks of the box list balanced by cell count (boxes of
+  // one level are listed in a spatially coherent order by the grid generator)
   const double total = (double)ba.numPts();
   double acc = 0.0;
   for (long i = 0; i < n; ++i) {
@@ -241,6 +288,30 @@ DistributionMapping::DistributionMapping(const BoxArray& ba, int nprocs) {
     p_[i] = std::min(nprocs - 1, (int)(mid / total * nprocs));
     acc += (double)ba[i].numPts();
   }
+}
+
+// Does every rank own exactly one full x-y slab of the BoxArray's minimal box?  slabs[r] = rank r's slab.
+bool SlabOwnership(const BoxArray& ba, const DistributionMapping& dm, int nprocs, std::vector<Box>* slabs) {
+  if (ba.empty() || dm.size() != ba.size() || nprocs < 1) return false;
+  const Box mb = ba.minimalBox();
+  if (mb.numPts() != ba.numPts()) return false;
+  std::vector<Box> mine((size_t)nprocs);
+  std::vector<long> cells((size_t)nprocs, 0);
+  std::vector<char> seen((size_t)nprocs, 0);
+  for (long i = 0; i < ba.size(); ++i) {
+    const int r = dm[i];
+    if (r < 0 || r >= nprocs) return false;
+    mine[r] = seen[r] ? mine[r].minBox(ba[i]) : ba[i];
+    seen[r] = 1;
+    cells[r] += ba[i].numPts();
+  }
+  for (int r = 0; r < nprocs; ++r) {
+    if (!seen[r] || mine[r].numPts() != cells[r]) return false;
+    for (int d = 0; d < 2; ++d)
+      if (mine[r].smallEnd(d) != mb.smallEnd(d) || mine[r].bigEnd(d) != mb.bigEnd(d)) return false;
+  }
+  if (slabs) *slabs = mine;
+  return true;
 }
 
 }  // namespace amrex

@@ -96,38 +96,79 @@ AmrSim::~AmrSim() {
 }
 
 // ----------------------------------------------------------------------------- input / output
-void AmrSim::SetInitialDensity(double const rho_init) { density_view = nullptr; initial_density.assign(NUMEL, rho_init); }
-void AmrSim::SetInitialDensity(std::vector<double> rho_init) { density_view = nullptr; initial_density = std::move(rho_init); }
-void AmrSim::SetInitialVelocity(double const u_init) { velocity_view = nullptr; initial_velocity.assign(3 * (size_t)NUMEL, u_init); }
-void AmrSim::SetInitialVelocity(std::vector<double> u_init) { velocity_view = nullptr; initial_velocity = std::move(u_init); }
+void AmrSim::SetInitialDensity(double const rho_init) { density_view = nullptr; density_profile_axis = -1; initial_density.assign(NUMEL, rho_init); }
+void AmrSim::SetInitialDensity(std::vector<double> rho_init) { density_view = nullptr; density_profile_axis = -1; initial_density = std::move(rho_init); }
+void AmrSim::SetInitialVelocity(double const u_init) { velocity_view = nullptr; velocity_profile_axis = -1; initial_velocity.assign(3 * (size_t)NUMEL, u_init); }
+void AmrSim::SetInitialVelocity(std::vector<double> u_init) { velocity_view = nullptr; velocity_profile_axis = -1; initial_velocity = std::move(u_init); }
+void AmrSim::SetInitialDensityProfile(int const axis, std::vector<double> rho_of_axis) {
+  if (axis < 0 || axis >= NDIMS || (int)rho_of_axis.size() != geom[0].Domain().length(axis))
+    amrex::Abort("SetInitialDensityProfile: one value per cell along the axis");
+  density_view = nullptr;
+  density_profile_axis = axis;
+  density_profile = std::move(rho_of_axis);
+}
+void AmrSim::SetInitialVelocityProfile(int const axis, std::vector<double> u_of_axis) {
+  if (axis < 0 || axis >= NDIMS || (int)u_of_axis.size() != NDIMS * geom[0].Domain().length(axis))
+    amrex::Abort("SetInitialVelocityProfile: three values per cell along the axis");
+  velocity_view = nullptr;
+  velocity_profile_axis = axis;
+  velocity_profile = std::move(u_of_axis);
+}
+
+// the box this rank owns of level 0 in a distributed uniform run (its z-slab); the whole domain on one rank
+Box AmrSim::LocalBox() {
+  const int np = DistributionMapping::NProcs();
+  if (np <= 1) return geom[0].Domain();
+  const BoxArray ba = grids[0].empty() ? MakeBaseGrids() : grids[0];
+  const DistributionMapping dm = (dmap[0].size() == ba.size()) ? dmap[0] : DistributionMapping(ba);
+  std::vector<Box> slabs;
+  if (!amrex::SlabOwnership(ba, dm, np, &slabs)) amrex::Abort("LocalBox: level 0 is not owned as one slab per rank");
+  return slabs[DistributionMapping::MyProc()];
+}
+
+void AmrSim::upload_profile(MultiFab& mf, const std::vector<double>& profile, int axis, int ncomp) {
+  void* dev = nullptr;
+  lbx_check(lbx_malloc(&dev, profile.size() * sizeof(double)), "upload_profile");
+  int rc = lbx_h2d(dev, profile.data(), profile.size() * sizeof(double));
+  if (!rc) rc = lbx_mf_fill_profile(mf.mf(), static_cast<const double*>(dev), axis, geom[0].Domain().smallEnd(axis),
+                                    geom[0].Domain().length(axis), ncomp);
+  const int rc2 = lbx_free(dev);          // synchronises the stream first
+  lbx_check(rc, "upload_profile");
+  lbx_check(rc2, "upload_profile");
+  mf.touch();
+}
 
 // user array (C-ordered, i slowest, component fastest) -> device field in fab order: one
-// host->device copy of the raw array, then a transposing kernel
-void AmrSim::upload_user_field(MultiFab& mf, const double* user, size_t n, int ncomp) {
-  const size_t need = (size_t)NUMEL * ncomp;
+// host->device copy of the raw array, then a transposing kernel.  local: the array covers this rank's
+// slab only (SetInitial*LocalView).
+void AmrSim::upload_user_field(MultiFab& mf, const double* user, size_t n, int ncomp, bool local) {
+  if (local && !mf.isFlat()) amrex::Abort("local initial arrays need level 0 stored as one slab per rank");
+  const Box ub = local ? mf.storageValid(mf.localSlab()) : geom[0].Domain();
+  const size_t need = (size_t)ub.numPts() * ncomp;
   if (n < need) throw std::out_of_range("AmrSim: initial field has fewer than NX*NY*NZ*ncomp entries");
-  void* dev = nullptr;
-  lbx_check(lbx_malloc(&dev, need * sizeof(double)), "upload_user_field");
-  const lbx_box dom = to_lbx(geom[0].Domain());
-  int rc = lbx_h2d(dev, user, need * sizeof(double));
-  if (!rc) rc = lbx_mf_from_user(mf.mf(), static_cast<const double*>(dev), &dom, ncomp);
-  const int rc2 = lbx_free(dev);          // synchronises the stream first
-  lbx_check(rc, "upload_user_field");
-  lbx_check(rc2, "upload_user_field");
+  // staged through the library's device buffers chunk by chunk (copies overlap the transposing kernels);
+  // `user` must stay valid until the stream is drained: vectors owned by this object do, views are the
+  // caller's promise (until InitFromScratch returns) -- so drain here
+  const lbx_box dom = to_lbx(ub);
+  lbx_check(lbx_mf_from_user_host(mf.mf(), user, &dom, ncomp), "upload_user_field");
+  lbx_check(lbx_sync(), "upload_user_field");
   mf.touch();
 }
 
 // src/AmrSim.cpp:138-214
 void AmrSim::InitDensity(int const level) {
   if (level) amrex::Abort("Only level 0 should be initialised from scratch currently.");
-  if (density_view) upload_user_field(levels.at(level).now.get<Density>(), density_view, density_view_n, 1);
-  else upload_user_field(levels.at(level).now.get<Density>(), initial_density.data(), initial_density.size(), 1);
+  MultiFab& rho = levels.at(level).now.get<Density>();
+  if (density_view) upload_user_field(rho, density_view, density_view_n, 1, views_local);
+  else if (density_profile_axis >= 0) upload_profile(rho, density_profile, density_profile_axis, 1);
+  else upload_user_field(rho, initial_density.data(), initial_density.size(), 1, false);
 }
 // src/AmrSim.cpp:217-295
 void AmrSim::InitVelocity(int const level) {
   if (level) amrex::Abort("Only LEVEL 0 should be initialised from scratch currently.");
-  if (velocity_view) upload_user_field(velocity.at(level), velocity_view, velocity_view_n, NDIMS);
-  else upload_user_field(velocity.at(level), initial_velocity.data(), initial_velocity.size(), NDIMS);
+  if (velocity_view) upload_user_field(velocity.at(level), velocity_view, velocity_view_n, NDIMS, views_local);
+  else if (velocity_profile_axis >= 0) upload_profile(velocity.at(level), velocity_profile, velocity_profile_axis, NDIMS);
+  else upload_user_field(velocity.at(level), initial_velocity.data(), initial_velocity.size(), NDIMS, false);
 }
 
 // src/AmrSim.cpp:824-843
@@ -147,27 +188,27 @@ double AmrSim::GetVelocity(int const i, int const j, int const k, int const n, i
 }
 
 // dense C-ordered copy of a field into caller memory (device-side transpose, one D2H copy)
-void AmrSim::dense_field_into(const MultiFab& mf, int level, double sentinel, double* out, size_t n) const {
-  const Box domb = geom.at(level).Domain();
-  const int nc = mf.nComp() > 0 ? mf.nComp() : 1;
+void AmrSim::dense_field_into(const MultiFab& mf, int level, double sentinel, double* out, size_t n, bool local) const {
   if (mf.empty()) amrex::Abort("dense field requested on an empty level");
+  if (local && !mf.isFlat()) amrex::Abort("local fields need the level stored as one slab per rank");
+  const Box domb = local ? mf.storageValid(mf.localSlab()) : geom.at(level).Domain();
+  const int nc = mf.nComp() > 0 ? mf.nComp() : 1;
   if (n != (size_t)domb.numPts() * nc) amrex::Abort("dense field: buffer size mismatch");
-  void* dev = nullptr;
-  lbx_check(lbx_malloc(&dev, n * sizeof(double)), "dense_field");
   const lbx_box dom = to_lbx(domb);
-  int rc = 0;
-  if (mf.boxArray().numPts() != domb.numPts()) rc = lbx_fill_f64(static_cast<double*>(dev), n, sentinel);
-  if (!rc) rc = lbx_mf_to_user(mf.mf(), static_cast<double*>(dev), &dom, nc);
-  if (!rc) rc = lbx_d2h(out, dev, n * sizeof(double));
-  const int rc2 = lbx_free(dev);          // synchronises the stream first
-  lbx_check(rc, "dense_field");
-  lbx_check(rc2, "dense_field");
+  const bool holes = !local && mf.boxArray().numPts() != domb.numPts();      // cells the level does not hold: sentinel
+  lbx_check(lbx_mf_to_user_host(mf.mf(), out, &dom, nc, local ? 1 : 0, holes ? 1 : 0, sentinel), "dense_field");
 }
 void AmrSim::GetDensityField(int const level, double* out, size_t n) const {
   dense_field_into(levels.at(level).now.get<Density>(), level, NL_DENSITY, out, n);
 }
 void AmrSim::GetVelocityField(int const level, double* out, size_t n) const {
   dense_field_into(velocity.at(level), level, NL_VELOCITY, out, n);
+}
+void AmrSim::GetLocalDensityField(int const level, double* out, size_t n) const {
+  dense_field_into(levels.at(level).now.get<Density>(), level, NL_DENSITY, out, n, true);
+}
+void AmrSim::GetLocalVelocityField(int const level, double* out, size_t n) const {
+  dense_field_into(velocity.at(level), level, NL_VELOCITY, out, n, true);
 }
 void AmrSim::GetLinearMomentField(int const level, const double* weights, int const ncomp, bool const per_unit_density,
                                   double const sentinel, double* out, size_t n) const {
@@ -196,9 +237,21 @@ std::pair<std::array<int, NDIMS>, std::array<int, NDIMS>> AmrSim::GetExtent(int 
 }
 
 // ----------------------------------------------------------------------------- layouts
-Layout AmrSim::PreferredLayout(int const level) const {
-  const bool alone = (level == 0 && finest_level == 0 && uniform_fast_path && DistributionMapping::NProcs() == 1);
-  return alone ? Layout::FLAT : Layout::BOXES;
+// Level 0 while it is the only level: ONE ghost-free fab per rank (FLAT) -- the whole periodic domain on a
+// single GPU, the rank's z-slab in a distributed run (box ownership by whole x-y layers, SlabOwnership) --
+// so that a time step is one fused launch per GPU.  Anything else: per-box storage with ghost cells.
+Layout AmrSim::PreferredLayout(int const level) const { return PreferredLayout(level, grids[level], dmap[level]); }
+Layout AmrSim::PreferredLayout(int const level, const BoxArray& ba, const DistributionMapping& dm) const {
+  if (!(level == 0 && finest_level == 0 && uniform_fast_path)) return Layout::BOXES;
+  const int np = DistributionMapping::NProcs();
+  if (np == 1) return Layout::FLAT;
+  return amrex::SlabOwnership(ba, dm, np) ? Layout::FLAT : Layout::BOXES;
+}
+
+void AmrSim::FinishPeerStores() {
+  if (!peer_stores_pending) return;
+  lbx_check(lbx_par_step_finish(), "FinishPeerStores");
+  peer_stores_pending = false;
 }
 
 void AmrSim::SetLevelLayout(int const level, Layout lay) {
@@ -225,6 +278,7 @@ void AmrSim::CalcEquilibriumDist(int const level) {
 
 // src/AmrSim.cpp:938-979
 void AmrSim::CalcHydroVars(int const level) {
+  FinishPeerStores();
   auto& state = levels.at(level).now;
   Density::fill(state.get<Density>(), velocity.at(level), state.get<DistFn>());
 }
@@ -287,7 +341,6 @@ void AmrSim::CollideAndStream(int const level) {
   MultiFab& now_f = lvl.now.get<DistFn>();
   if (now_f.isFlat()) {
     MultiFab& next_f = lvl.next.get<DistFn>();
-    const lbx_fab src = now_f.fabDesc(0), dst = next_f.fabDesc(0);
     const lbx_box box = to_lbx(geom[level].Domain());
     lbx_domain dom;
     for (int d = 0; d < 3; ++d) {
@@ -295,9 +348,17 @@ void AmrSim::CollideAndStream(int const level) {
       dom.hi[d] = box.hi[d];
       dom.periodic[d] = geom[level].isPeriodic(d) ? 1 : 0;
     }
-    lbx_check(lbx_collide_stream(&src, &dst, &box, &dom, 1.0 / (tau_s.at(level) + 0.5), 1.0 / (tau_b.at(level) + 0.5),
-                                 LBX_PUSH),
-              "CollideAndStream");
+    const double omega_s = 1.0 / (tau_s.at(level) + 0.5), omega_b = 1.0 / (tau_b.at(level) + 0.5);
+    if (now_f.numStorageFabs() > 1) {
+      // one slab per rank: the FillBoundary between boxes of different GPUs (src/AmrSim.cpp:132) is fused into
+      // the step -- boundary-plane CTAs store the face-crossing populations into the neighbours' NEXT over
+      // NVLink and order themselves against the neighbours' steps; one launch per step and rank
+      lbx_check(lbx_mf_collide_stream_slab(now_f.mf(), next_f.mf(), &dom, omega_s, omega_b), "CollideAndStream");
+      peer_stores_pending = true;
+    } else {
+      const lbx_fab src = now_f.fabDesc(0), dst = next_f.fabDesc(0);
+      lbx_check(lbx_collide_stream(&src, &dst, &box, &dom, omega_s, omega_b, LBX_PUSH), "CollideAndStream");
+    }
     next_f.touch();
   } else if (rohde_fused && CanFuseLevelStep(level)) {
     LevelStepFused(level);
@@ -658,6 +719,7 @@ void AmrSim::Iterate(int const nsteps) {
     }
     RegridIfDue();
   }
+  FinishPeerStores();
 }
 
 // AMReX's regrid_int: after every regrid_int-th coarse step, regrid from level 0 up (tags from
@@ -718,7 +780,7 @@ void AmrSim::GradientTags(int const level, amrex::TagBoxArray& tba) {
 // src/AmrSim.cpp:665-687
 void AmrSim::MakeNewLevelFromScratch(int level, double time, const BoxArray& ba, const DistributionMapping& dm) {
   auto& lvl = levels[level];
-  const Layout lay = (level == 0) ? PreferredLayout(0) : Layout::BOXES;
+  const Layout lay = (level == 0) ? PreferredLayout(0, ba, dm) : Layout::BOXES;
   velocity[level].define(ba, dm, NDIMS, 0, lay);
   lvl.Define(ba, dm, lay);
   stream_scratch[level].clear();

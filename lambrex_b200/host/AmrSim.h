@@ -88,6 +88,22 @@ class AmrSim : public amrex::AmrCore {
   // caller memory -- pinned memory makes that one DMA -- and must stay valid until it returns.
   void SetInitialDensityView(const double* rho_init, size_t n) { density_view = rho_init; density_view_n = n; }
   void SetInitialVelocityView(const double* u_init, size_t n) { velocity_view = u_init; velocity_view_n = n; }
+  // ---- distributed runs (lambrexInitParallel): large domains cannot be initialised from, or returned as,
+  // whole-domain host arrays (1024^3: 8.6 + 25.8 GB per rank), so each rank states and reads ITS part.
+  // Separable initial conditions: the field varies along one axis only (planar pulse: rho(z); shear wave:
+  // u(y)); profile[a] resp. profile[a * 3 + n] for a = 0 .. extent(axis) - 1.  Replace SetInitial{Density,Velocity}.
+  void SetInitialDensityProfile(int const axis, std::vector<double> rho_of_axis);
+  void SetInitialVelocityProfile(int const axis, std::vector<double> u_of_axis);
+  // This rank's part of level 0 while it is stored as one slab per rank (uniform path): the box a rank
+  // will own, available right after construction (grid generation is deterministic) ...
+  amrex::Box LocalBox();
+  // ... initial arrays over that box, C-ordered [i][j][k]([n]) like the whole-domain ones (read at
+  // InitFromScratch; must stay valid until it returns; pinned memory makes it one DMA) ...
+  void SetInitialDensityLocalView(const double* rho_init, size_t n) { density_view = rho_init; density_view_n = n; views_local = true; }
+  void SetInitialVelocityLocalView(const double* u_init, size_t n) { velocity_view = u_init; velocity_view_n = n; views_local = true; }
+  // ... and the matching bulk getters (this rank's cells only; no communication)
+  void GetLocalDensityField(int const level, double* out, size_t n) const;
+  void GetLocalVelocityField(int const level, double* out, size_t n) const;
   // false: run level 0 through the reference's literal pass structure on per-box storage even
   // when it is the only level (FillPatch, collide, FillBoundary, stream, swap).  Default true.
   void SetUniformFastPath(bool on) { uniform_fast_path = on; }
@@ -188,6 +204,7 @@ class AmrSim : public amrex::AmrCore {
   // storage layout of a level (see AMReX_MultiFab.H)
   void SetLevelLayout(int const level, amrex::Layout lay);
   amrex::Layout PreferredLayout(int const level) const;
+  amrex::Layout PreferredLayout(int const level, const amrex::BoxArray& ba, const amrex::DistributionMapping& dm) const;
 
  private:
   std::vector<amrex::MultiFab> stream_scratch;   // third population buffer per level
@@ -216,11 +233,19 @@ class AmrSim : public amrex::AmrCore {
   void CoarseStatesAt(int const coarse_level, double const t, const amrex::MultiFab*& a, double& wa,
                       const amrex::MultiFab*& b, double& wb);
   std::vector<amrex::MultiFab> coarse_interp;    // LinComb scratch per coarse level (SUBCYCLE)
-  void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp);
+  void upload_user_field(amrex::MultiFab& mf, const double* user, size_t n, int ncomp, bool local);
+  void upload_profile(amrex::MultiFab& mf, const std::vector<double>& profile, int axis, int ncomp);
+  std::vector<double> density_profile, velocity_profile;
+  int density_profile_axis = -1, velocity_profile_axis = -1;
+  bool views_local = false;
+  // distributed uniform path: the neighbours' face stores of the last queued step are not yet known to be
+  // complete; FinishPeerStores queues the wait (lbx_par_step_finish) before anything else reads the populations
+  bool peer_stores_pending = false;
+  void FinishPeerStores();
   const double* density_view = nullptr;
   const double* velocity_view = nullptr;
   size_t density_view_n = 0, velocity_view_n = 0;
-  void dense_field_into(const amrex::MultiFab& mf, int level, double sentinel, double* out, size_t n) const;
+  void dense_field_into(const amrex::MultiFab& mf, int level, double sentinel, double* out, size_t n, bool local = false) const;
 };
 
 #endif

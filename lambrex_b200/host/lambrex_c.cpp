@@ -137,6 +137,30 @@ int lbx_sim_set_initial_density_view(lbx_sim* sim, const double* rho, size_t n) 
 int lbx_sim_set_initial_velocity_view(lbx_sim* sim, const double* u, size_t n) {
   return guarded([&] { sim->s.SetInitialVelocityView(u, n); });
 }
+int lbx_sim_set_initial_density_profile(lbx_sim* sim, int axis, const double* v, size_t n) {
+  return guarded([&] { sim->s.SetInitialDensityProfile(axis, std::vector<double>(v, v + n)); });
+}
+int lbx_sim_set_initial_velocity_profile(lbx_sim* sim, int axis, const double* v, size_t n) {
+  return guarded([&] { sim->s.SetInitialVelocityProfile(axis, std::vector<double>(v, v + n)); });
+}
+int lbx_sim_local_box(lbx_sim* sim, int lo[3], int hi[3]) {
+  return guarded([&] {
+    const amrex::Box b = sim->s.LocalBox();
+    for (int d = 0; d < 3; ++d) { lo[d] = b.smallEnd(d); hi[d] = b.bigEnd(d); }
+  });
+}
+int lbx_sim_set_initial_density_local_view(lbx_sim* sim, const double* rho, size_t n) {
+  return guarded([&] { sim->s.SetInitialDensityLocalView(rho, n); });
+}
+int lbx_sim_set_initial_velocity_local_view(lbx_sim* sim, const double* u, size_t n) {
+  return guarded([&] { sim->s.SetInitialVelocityLocalView(u, n); });
+}
+int lbx_sim_get_local_density_field(const lbx_sim* sim, int level, double* out, size_t n) {
+  return guarded([&] { sim->s.GetLocalDensityField(level, out, n); });
+}
+int lbx_sim_get_local_velocity_field(const lbx_sim* sim, int level, double* out, size_t n) {
+  return guarded([&] { sim->s.GetLocalVelocityField(level, out, n); });
+}
 int lbx_sim_init_from_scratch(lbx_sim* sim, double time) { return guarded([&] { sim->s.InitFromScratch(time); }); }
 int lbx_sim_regrid(lbx_sim* sim, int lbase, double time) { return guarded([&] { sim->s.regrid(lbase, time); }); }
 int lbx_sim_iterate(lbx_sim* sim, int nsteps) { return guarded([&] { sim->s.Iterate(nsteps); }); }

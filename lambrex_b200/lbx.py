@@ -123,7 +123,15 @@ SYMBOLS = {
     "lbx_mf_tag_gradient": (_i, [_vp, _d, _vp, _i]),
     "lbx_mf_from_user": (_i, [_vp, _vp, _bp, _i]),
     "lbx_mf_to_user": (_i, [_vp, _vp, _bp, _i]),
+    "lbx_mf_to_user_local": (_i, [_vp, _vp, _bp, _i]),
+    "lbx_mf_from_user_host": (_i, [_vp, _vp, _bp, _i]),
+    "lbx_mf_to_user_host": (_i, [_vp, _vp, _bp, _i, _i, _i, _d]),
     "lbx_fill_f64": (_i, [_vp, _sz, _d]),
+    "lbx_mf_fill_profile": (_i, [_vp, _vp, _i, _i, _i, _i]),
+    "lbx_mf_collide_stream_slab": (_i, [_vp, _vp, _dp, _d, _d]),
+    "lbx_par_step_finish": (_i, []),
+    "lbx_prof_begin": (_i, []),
+    "lbx_prof_end": (_i, [ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64)]),
     "lbx_plan_create": (_i, [ctypes.POINTER(lbx_gather), _i, ctypes.POINTER(_vp)]),
     "lbx_plan_apply": (_i, [_vp, _vp, _vp, _vp, _i]),
     "lbx_plan_destroy": (_i, [_vp]),
@@ -213,6 +221,17 @@ def domain(lo, hi, periodic=(1, 1, 1)):
     d.hi[:] = [int(x) for x in hi]
     d.periodic[:] = [int(x) for x in periodic]
     return d
+
+
+def prof_begin():
+    check(lib().lbx_prof_begin())
+
+
+def prof_end():
+    """{ms, launches, valid_cells, dropped} of the lbx_mf_collide_stream* launches since prof_begin()."""
+    ms, n, cells, dr = _d(0), ctypes.c_uint64(0), _d(0), ctypes.c_uint64(0)
+    check(lib().lbx_prof_end(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(cells), ctypes.byref(dr)))
+    return {"ms": ms.value, "launches": int(n.value), "valid_cells": cells.value, "dropped": int(dr.value)}
 
 
 class Timer:

@@ -119,16 +119,24 @@ def test_regrid_sequences_match_oracle(dims, max_level, ops, coracle):
 
 
 def test_box_ownership_of_a_distributed_level():
-    """amrex::DistributionMapping(ba, nprocs) as the distributed AMR path uses it (SURVEY 8e): contiguous
-    chunks of the box list, every rank non-empty and within one box of the mean cell count; identical
-    on every rank by construction (no communication)."""
+    """amrex::DistributionMapping(ba, nprocs) as the distributed paths use it (SURVEY 8e), identical on every
+    rank by construction (no communication).  A BoxArray made of whole x-y layers (every level 0): each rank
+    owns ONE z-slab -- consecutive layers, plane counts within one layer of the mean -- which the uniform
+    path stores as a single fab per GPU.  Any other BoxArray: contiguous chunks of the list by cell count."""
     ba = amrsim.meta_base_grids((256, 256, 256))
     assert len(ba) == 512
-    for nprocs in (1, 2, 4, 8):
+    for nprocs in (1, 2, 3, 4, 8):
         own = amrsim.meta_distribution(ba, nprocs)
-        assert own == sorted(own) and set(own) == set(range(nprocs))          # contiguous chunks, nobody idle
-        counts = [own.count(r) for r in range(nprocs)]
-        assert max(counts) - min(counts) <= 1
+        assert set(own) == set(range(nprocs))                                 # nobody idle
+        planes = []
+        for r in range(nprocs):
+            mine = [b for b, o in zip(ba, own) if o == r]
+            zlo, zhi = min(b[0][2] for b in mine), max(b[1][2] for b in mine)
+            assert sum(int(np.prod([h - l + 1 for l, h in zip(*b)])) for b in mine) == 256 * 256 * (zhi - zlo + 1)   # one full slab
+            planes.append((zlo, zhi))
+        assert sorted(planes) == planes and all(a[1] + 1 == b[0] for a, b in zip(planes, planes[1:]))   # rank order = z order
+        sizes = [hi - lo + 1 for lo, hi in planes]
+        assert max(sizes) - min(sizes) <= 32
     # ragged boxes: balance by CELLS, not by box count
     ragged = [((0, 0, 0), (63, 63, 63))] + [((64 + 8 * i, 0, 0), (71 + 8 * i, 7, 7)) for i in range(64)]
     own = amrsim.meta_distribution(ragged, 2)

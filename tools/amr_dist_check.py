@@ -17,11 +17,13 @@ from lambrex_b200 import amrsim, lbx, workloads   # noqa: E402
 PER = (1, 1, 1)
 
 
-def build(nx, ny, nz, max_level, boxes, max_grid):
+def build(nx, ny, nz, max_level, boxes, max_grid, fast=False):
     rho, u = workloads.shear_wave(nx, ny, nz)
     rho = rho * workloads.pulse_density(nx, ny, nz)
     sim = amrsim.AmrSim(nx, ny, nz, max_level, PER, 0.3, 0.4)
-    sim.SetUniformFastPath(False)        # per-box storage with ghost cells on every path
+    # fast: level 0 alone is stored as ONE ghost-free slab per rank and stepped by the fused kernel with peer
+    # stores (the uniform multi-GPU path inside AmrSim); else per-box storage with ghost cells on every path
+    sim.SetUniformFastPath(fast)
     if "--subcycle" in sys.argv:         # conventional subcycling + gradient tagging + regrid_int
         sim.SetCoupling(amrsim.SUBCYCLE)
     sim.SetMaxGridSize(max_grid)
@@ -46,6 +48,55 @@ def snapshot(sim, max_level):
     return out, rho
 
 
+def local_io_check(rank, world):
+    """Distributed uniform run stated per rank: profile initial conditions and local (slab) arrays in, local
+    fields out -- against the whole-domain API on a single GPU, bit for bit."""
+    nx, ny, nz, steps = 24, 20, 8 * max(world, 2), 9
+    rho3, u3 = workloads.shear_wave(nx, ny, nz)             # rho = 1, u_x(j)
+    rho3 = (rho3 * workloads.pulse_density(nx, ny, nz)).reshape(nx, ny, nz)       # rho(k)
+    u3 = u3.reshape(nx, ny, nz, 3)
+    good = True
+    for mode in ("profile", "local arrays"):
+        sim = amrsim.AmrSim(nx, ny, nz, 0, PER, 0.3, 0.4)
+        sim.SetMaxGridSize(8)
+        lo, hi = sim.LocalBox()
+        if mode == "profile":
+            sim.SetInitialDensityProfile(2, rho3[0, 0, :])
+            # a profile states ONE axis: u(y) of the shear wave; the density then carries no y dependence
+            sim.SetInitialVelocityProfile(1, u3[0, :, 0, :])
+        else:
+            sl = (slice(lo[0], hi[0] + 1), slice(lo[1], hi[1] + 1), slice(lo[2], hi[2] + 1))
+            rl, ul = np.ascontiguousarray(rho3[sl]), np.ascontiguousarray(u3[sl])
+            sim.SetInitialDensityLocalView(rl)
+            sim.SetInitialVelocityLocalView(ul)
+        sim.InitFromScratch(0.0)
+        sim.Iterate(steps)
+        sim.CalcHydroVars(0)
+        r_loc, u_loc = sim.GetLocalDensityField(0), sim.GetLocalVelocityField(0)
+        sim.close()
+        dist.barrier()
+        amrsim.setParallelView(0, 1)
+        ref = amrsim.AmrSim(nx, ny, nz, 0, PER, 0.3, 0.4)
+        ref.SetMaxGridSize(8)
+        ref.SetInitialDensity(rho3.reshape(-1))
+        ref.SetInitialVelocity(u3.reshape(-1))
+        ref.InitFromScratch(0.0)
+        ref.Iterate(steps)
+        ref.CalcHydroVars(0)
+        r_ref, u_ref = ref.GetDensityField(0), ref.GetVelocityField(0)
+        ref.close()
+        amrsim.setParallelView(rank, world)
+        sl = (slice(lo[0], hi[0] + 1), slice(lo[1], hi[1] + 1), slice(lo[2], hi[2] + 1))
+        same = np.array_equal(r_loc, r_ref[sl]) and np.array_equal(u_loc, u_ref[sl])
+        flag = torch.tensor([1 if same else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("amr_dist_check local i/o (%s) world=%d slab of rank 0 %s..%s bit-equal=%s" % (mode, world, lo, hi, bool(flag.item())),
+                  flush=True)
+        good = good and bool(flag.item())
+    return good
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -62,8 +113,9 @@ def main():
         cases = [("64^3 L2", (64, 64, 64), 1, [((16, 16, 16), (47, 47, 47))], 16, 3),
                  ("128^3 L2", (128, 128, 128), 1, [((32, 32, 32), (95, 95, 95))], 32, 3),
                  ("128^3 L3", (128, 128, 128), 2, [((32, 32, 32), (95, 95, 95)), ((96, 96, 96), (159, 159, 159))], 32, 2)]
-    for name, (nx, ny, nz), max_level, boxes, max_grid, steps in cases:
-        sim = build(nx, ny, nz, max_level, boxes, max_grid)
+    cases = [c + (False,) for c in cases] + [(c[0] + " (slab level 0)",) + c[1:] + (True,) for c in cases]
+    for name, (nx, ny, nz), max_level, boxes, max_grid, steps, fast in cases:
+        sim = build(nx, ny, nz, max_level, boxes, max_grid, fast)
         owners = [sorted({sim.Owner(lev, b) for b in range(len(sim.boxArray(lev)))}) for lev in range(max_level + 1)]
         sim.Iterate(steps)
         for lev in range(max_level + 1):
@@ -80,7 +132,7 @@ def main():
         dist.barrier()
 
         amrsim.setParallelView(0, 1)            # the same problem, alone on this GPU
-        ref = build(nx, ny, nz, max_level, boxes, max_grid)
+        ref = build(nx, ny, nz, max_level, boxes, max_grid, fast)
         ref.Iterate(steps)
         for lev in range(max_level + 1):
             ref.CalcHydroVars(lev)
@@ -121,6 +173,7 @@ def main():
             print("amr_dist_check %-8s world=%d owners per level=%s bit-equal=%s" % (name, world, owners, bool(flag.item())),
                   flush=True)
         ok = ok and bool(flag.item())
+    ok = local_io_check(rank, world) and ok
     info = lbx.par_info()
     if rank == 0:
         print("device barriers executed: %d" % info["barriers"], flush=True)

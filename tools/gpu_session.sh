@@ -24,6 +24,11 @@ for stage in "$@"; do
              timeout 300 python tools/amr_bench.py --grid 256 --levels 3 --steps 12 --regrid-every 4 2>/dev/null | grep '^{' >> $O/${T}_amr.jsonl ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
                --log-file $O/${T}_launches_bench.csv python bench.py --steps 10 --warmup 3 --no-cpu > $O/${T}_launches_bench.out 2>&1 ;;
+    dist)    NG=${NGPUS:-2}
+             ( time timeout 1200 python -m pytest tests/test_gpu_dist.py tests/test_gpu_slab.py -x -q -m gpu ) > $O/${T}_pytest_dist.log 2>&1 ;;
+    benchN)  NG=${NGPUS:-2}
+             timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29611 \
+               bench.py --gpus $NG --steps ${STEPS:-20} --warmup 3 > $O/${T}_bench_n$NG.json 2> $O/${T}_bench_n$NG.err ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

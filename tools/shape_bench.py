@@ -2,6 +2,7 @@
 from the multi-GPU exchange (a 1024 x 1024 x 128 slab on world = 1).  One JSON line per shape.
     python tools/shape_bench.py --dims 1024 1024 128 --dims 256 256 256 [--scheme push|slab] [--steps 20]"""
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -22,7 +23,7 @@ def peak():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dims", type=int, nargs=3, action="append", required=True)
-    ap.add_argument("--scheme", default="push", choices=["push", "pull", "slab"])
+    ap.add_argument("--scheme", default="push", choices=["push", "pull", "slab", "slabsync"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
@@ -34,12 +35,20 @@ def main():
         A, B = lbx.Fab(lo, hi, 15, zero=False), lbx.Fab(lo, hi, 15, zero=False)
         R, U = lbx.Fab(lo, hi, 1), lbx.Fab(lo, hi, 3)
         lbx.check(lbx.lib().lbx_memset(R.ptr, 0, R.nbytes))
-        lbx.equilibrium(A, R, U, bx)      # rho = 0 field: timing only
+        if args.scheme != "slabsync":
+            lbx.equilibrium(A, R, U, bx)      # rho = 0 field: timing only
+
+        if args.scheme == "slabsync":      # the distributed step kernel on one GPU (no flags): lbx_mf_collide_stream_slab
+            for f in (A, B):
+                f.free()
+            A, B = lbx.MF([(lo, hi)], 15, 0), lbx.MF([(lo, hi)], 15, 0)
 
         def steps(k):
             nonlocal A, B
             for _ in range(k):
-                if args.scheme == "slab":
+                if args.scheme == "slabsync":
+                    lbx.check(lbx.lib().lbx_mf_collide_stream_slab(A.h, B.h, ctypes.byref(dom), 1.0, 1.0))
+                elif args.scheme == "slab":
                     lbx.collide_stream_slab(A, B, B, B, bx, dom, 1.0, 1.0)
                 else:
                     lbx.collide_stream(A, B, bx, dom, 1.0, 1.0, lbx.PUSH if args.scheme == "push" else lbx.PULL)
@@ -56,6 +65,7 @@ def main():
               flush=True)
         for f in (A, B, R, U):
             f.free()
+
 
 
 if __name__ == "__main__":
