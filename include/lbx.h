@@ -65,6 +65,9 @@ enum {
   LBX_OPT_XGHOST_IN_ROW = 6,   /* lbx_mf_collide_stream (ghosts from own cells): the warp of a valid row also pushes
                                   the row's 4 x-ghost cells, completing the row's partial end sectors at once */
   LBX_OPT_PLAIN_STORES = 7,    /* lbx_mf_collide_stream*: valid-cell pushes as write-back instead of streaming stores */
+  LBX_OPT_ROW_KERNEL = 8,      /* lbx_mf_collide_stream*: 1 (default) = the row-owner kernel (a warp per source row of the grown
+                                  box writes whole destination rows: every sector completed by the warp that opens it);
+                                  0 = the round-1 tile kernel.  Results are bit-identical.                          */
   LBX_OPT_DEBUG_SKIP = 4,      /* PROFILING ONLY (results are wrong): bit 0 skips the valid-cell work of
                                   lbx_mf_collide_stream*, bit 1 the ghost-cell work                  */
 };

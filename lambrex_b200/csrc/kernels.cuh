@@ -196,14 +196,63 @@ struct SlabSync {
   int* err;                           // host-mapped: set on timeout (sticky)
 };
 
+// one cell of the slab step (the body of k_collide_stream_slab), shared by the two code paths below
+template <class C>
+__device__ __forceinline__ void slab_cell(const DFab& src, const DFab& dst, const DFab& dn, const DFab& up, const DBox& box,
+                                          const DDom& dom, double omega_s, double omega_b, int i, int j, int k) {
+  int ip = i + 1, im = i - 1, jp = j + 1, jm = j - 1, kp = k + 1, km = k - 1;
+  if (dom.periodic[0]) { if (ip > dom.hi[0]) ip = dom.lo[0]; if (im < dom.lo[0]) im = dom.hi[0]; }
+  if (dom.periodic[1]) { if (jp > dom.hi[1]) jp = dom.lo[1]; if (jm < dom.lo[1]) jm = dom.hi[1]; }
+  if (dom.periodic[2]) { if (kp > dom.hi[2]) kp = dom.lo[2]; if (km < dom.lo[2]) km = dom.hi[2]; }
+  const DFab& fp = has_plane(dst, kp) ? dst : up;
+  const DFab& fm = has_plane(dst, km) ? dst : dn;
+  const long long sc0 = plane_stride(dst), scp = plane_stride(fp), scm = plane_stride(fm);
+  double* d[NV];
+  {
+    const long long r00 = row_off(dst, j, k), rp0 = row_off(dst, jp, k), rm0 = row_off(dst, jm, k);
+    d[0] = dst.p + r00 + i;
+    d[1] = dst.p + 1 * sc0 + r00 + ip;
+    d[2] = dst.p + 2 * sc0 + r00 + im;
+    d[3] = dst.p + 3 * sc0 + rp0 + i;
+    d[4] = dst.p + 4 * sc0 + rm0 + i;
+    const long long r0p = row_off(fp, j, kp), rpp = row_off(fp, jp, kp), rmp = row_off(fp, jm, kp);
+    d[5] = fp.p + 5 * scp + r0p + i;
+    d[7] = fp.p + 7 * scp + rpp + ip;
+    d[9] = fp.p + 9 * scp + rmp + ip;
+    d[11] = fp.p + 11 * scp + rpp + im;
+    d[13] = fp.p + 13 * scp + rmp + im;
+    const long long r0m = row_off(fm, j, km), rpm = row_off(fm, jp, km), rmm = row_off(fm, jm, km);
+    d[6] = fm.p + 6 * scm + r0m + i;
+    d[8] = fm.p + 8 * scm + rpm + ip;
+    d[10] = fm.p + 10 * scm + rmm + ip;
+    d[12] = fm.p + 12 * scm + rpm + im;
+    d[14] = fm.p + 14 * scm + rmm + im;
+  }
+  const long long ssc = plane_stride(src), o = row_off(src, j, k) + i;
+  double f[NV];
+#pragma unroll
+  for (int p = 0; p < NV; ++p) f[p] = __ldcs(src.p + p * ssc + o);
+  C::collide(f, omega_s, omega_b);
+#pragma unroll
+  for (int p = 0; p < NV; ++p) __stcs(d[p], f[p]);
+}
+
 template <class C>
 __global__ void __launch_bounds__(BX) k_collide_stream_slab_sync(DFab src, DFab dst, DFab dn, DFab up, DBox box,
                                                                  DDom dom, double omega_s, double omega_b, SlabSync sy) {
   const int z = blockIdx.z;
-  const int k = z == 0 ? box.lo[2] : z == 1 ? box.hi[2] : box.lo[2] + (z - 1);
-  const bool boundary = z < 2;
-  if (boundary && sy.wait_a) {
-    if (threadIdx.x == 0 && !*reinterpret_cast<volatile int*>(sy.err)) {
+  const int i = box.lo[0] + blockIdx.x * BX + threadIdx.x;
+  const int j = box.lo[1] + blockIdx.y;
+  if (z >= 2) {
+    // interior planes: exactly the plain slab step (own copy of the code, so that the synchronisation below does not
+    // cost the bandwidth-bound path its uniform-datapath address arithmetic -- measured 6 % otherwise)
+    if (i > box.hi[0]) return;
+    slab_cell<C>(src, dst, dn, up, box, dom, omega_s, omega_b, i, j, box.lo[2] + (z - 1));
+    return;
+  }
+  const int k = z == 0 ? box.lo[2] : box.hi[2];
+  if (sy.wait_a) {
+    if (threadIdx.x == 0) {     // (never READ the host-mapped error word here: a zero-copy read costs a PCIe round trip per CTA)
       unsigned long long t0, t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
       for (int which = 0; which < 2; ++which) {
@@ -220,46 +269,8 @@ __global__ void __launch_bounds__(BX) k_collide_stream_slab_sync(DFab src, DFab 
     }
     __syncthreads();
   }
-  const int i = box.lo[0] + blockIdx.x * BX + threadIdx.x;
-  const int j = box.lo[1] + blockIdx.y;
-  if (i <= box.hi[0]) {
-    int ip = i + 1, im = i - 1, jp = j + 1, jm = j - 1, kp = k + 1, km = k - 1;
-    if (dom.periodic[0]) { if (ip > dom.hi[0]) ip = dom.lo[0]; if (im < dom.lo[0]) im = dom.hi[0]; }
-    if (dom.periodic[1]) { if (jp > dom.hi[1]) jp = dom.lo[1]; if (jm < dom.lo[1]) jm = dom.hi[1]; }
-    if (dom.periodic[2]) { if (kp > dom.hi[2]) kp = dom.lo[2]; if (km < dom.lo[2]) km = dom.hi[2]; }
-    const DFab& fp = has_plane(dst, kp) ? dst : up;
-    const DFab& fm = has_plane(dst, km) ? dst : dn;
-    const long long sc0 = plane_stride(dst), scp = plane_stride(fp), scm = plane_stride(fm);
-    double* d[NV];
-    {
-      const long long r00 = row_off(dst, j, k), rp0 = row_off(dst, jp, k), rm0 = row_off(dst, jm, k);
-      d[0] = dst.p + r00 + i;
-      d[1] = dst.p + 1 * sc0 + r00 + ip;
-      d[2] = dst.p + 2 * sc0 + r00 + im;
-      d[3] = dst.p + 3 * sc0 + rp0 + i;
-      d[4] = dst.p + 4 * sc0 + rm0 + i;
-      const long long r0p = row_off(fp, j, kp), rpp = row_off(fp, jp, kp), rmp = row_off(fp, jm, kp);
-      d[5] = fp.p + 5 * scp + r0p + i;
-      d[7] = fp.p + 7 * scp + rpp + ip;
-      d[9] = fp.p + 9 * scp + rmp + ip;
-      d[11] = fp.p + 11 * scp + rpp + im;
-      d[13] = fp.p + 13 * scp + rmp + im;
-      const long long r0m = row_off(fm, j, km), rpm = row_off(fm, jp, km), rmm = row_off(fm, jm, km);
-      d[6] = fm.p + 6 * scm + r0m + i;
-      d[8] = fm.p + 8 * scm + rpm + ip;
-      d[10] = fm.p + 10 * scm + rmm + ip;
-      d[12] = fm.p + 12 * scm + rpm + im;
-      d[14] = fm.p + 14 * scm + rmm + im;
-    }
-    const long long ssc = plane_stride(src), o = row_off(src, j, k) + i;
-    double f[NV];
-#pragma unroll
-    for (int p = 0; p < NV; ++p) f[p] = __ldcs(src.p + p * ssc + o);
-    C::collide(f, omega_s, omega_b);
-#pragma unroll
-    for (int p = 0; p < NV; ++p) __stcs(d[p], f[p]);
-  }
-  if (boundary && sy.sig_a) {
+  if (i <= box.hi[0]) slab_cell<C>(src, dst, dn, up, box, dom, omega_s, omega_b, i, j, k);
+  if (sy.sig_a) {
     __threadfence_system();            // this thread's stores (local and remote) before the CTA's arrival below
     __syncthreads();
     if (threadIdx.x == 0) {

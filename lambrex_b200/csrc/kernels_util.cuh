@@ -69,7 +69,6 @@ __global__ void k_peer_signal(unsigned long long* flag_a, unsigned long long* fl
 __global__ void k_peer_wait(const unsigned long long* flag_a, const unsigned long long* flag_b,
                             unsigned long long value, unsigned long long timeout_ns, int* err) {
   unsigned long long t0, t;
-  if (*reinterpret_cast<volatile int*>(err)) return;      // an earlier wait timed out: do not wait again (sticky error)
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   for (int which = 0; which < 2; ++which) {
     const unsigned long long* fl = which ? flag_b : flag_a;
@@ -97,11 +96,9 @@ __global__ void k_par_barrier(unsigned long long* const* __restrict__ peer_flags
                               int my_rank, int world, unsigned long long epoch, unsigned long long timeout_ns, int* err) {
   const int r = threadIdx.x;
   if (r >= world) return;
-  const bool broken = *reinterpret_cast<volatile int*>(err) != 0;    // sticky: still publish, but never wait again
   __threadfence_system();
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + my_rank), "l"(epoch) : "memory");
   unsigned long long t0, t;
-  if (broken) return;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   for (;;) {
     unsigned long long v;

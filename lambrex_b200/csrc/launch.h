@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels.cuh"
+#include "rows_kernel.cuh"
 
 namespace lbx {
 // dynamic shared memory added to the fused kernels' launches purely to cap resident CTAs/SM
@@ -17,6 +18,9 @@ extern int g_xghost_in_row;
 extern int g_plain_stores;
 // profiling only (LBX_OPT_DEBUG_SKIP): bit 0 skips the valid tiles' work, bit 1 the ghost tiles' (results are wrong)
 extern int g_debug_skip;
+// 1 (default): the row-owner kernel k_mf_cs_rows runs every fused collide + Stream that has a ghost source;
+// 0: the round-1 tile kernel k_mf_collide_stream (LBX_OPT_ROW_KERNEL)
+extern int g_row_kernel;
 struct Launchers {
   void (*equilibrium)(cudaStream_t, DFab f, DFab rho, DFab u, DBox box);
   void (*moments)(cudaStream_t, DFab f, DFab rho, DFab u, DBox box);
@@ -32,6 +36,8 @@ struct Launchers {
   void (*mf_collide_stream)(cudaStream_t, const double* vbase, double* dbase, const DFabT* dst, const DFabT* mask,
                             const DFabT* gsrc, CSPlan plan, int nfabs, int max_ny, int max_nz, long long max_valid,
                             long long ghost_tiles, double ws, double wb, int fine_val, int zero_invalid);
+  // mode 1 own ghost cells, 2 FillPatch plan, 3 conventional level step; max_rows = most grown rows of any fab
+  int (*mf_cs_rows)(cudaStream_t, ROArgs a, int mode, long long max_rows);
   void (*mf_moments)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs, long long max_cells);
   void (*mf_equilibrium)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs,
                          long long max_cells);

@@ -22,6 +22,7 @@ int g_align_rows = 0;
 int g_xghost_in_row = 0;
 int g_plain_stores = 0;
 int g_debug_skip = 0;
+int g_row_kernel = 1;
 Ctx g_ctx;
 thread_local std::string g_err;
 int fail(const std::string& msg) {
@@ -425,6 +426,7 @@ int lbx_set_option(int key, int value) {
       return 0;
     case LBX_OPT_VALID_TILING: lbx::g_valid_linear = (value != 0); return 0;
     case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 3; return 0;
+    case LBX_OPT_ROW_KERNEL: lbx::g_row_kernel = (value != 0); return 0;
     default: return fail("lbx_set_option: unknown key");
   }
 }

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <set>
 #include <string>
 #include <tuple>
@@ -25,6 +26,10 @@ struct lbx_mf {
   bool dist = false;                    // some fabs live in peers' HBM
   long long max_valid = 0;              // largest valid-box cell count
   uint64_t geom = 0;                    // signature of (boxes, ngrow, ncomp, dtype)
+  // row-owner kernel (rows_kernel.cuh): every fab is tight (valid + 2 ghost cells per side) with an even row length
+  bool rows_ok = false;
+  int max_n0 = 0;                       // longest allocated row
+  long long max_rows = 0;               // most grown rows (n1 * n2) of any fab
   int max_extent(int dir) const {           // largest valid-box extent along dir
     int m = 0;
     for (const auto& f : host) m = std::max(m, f.vhi[dir] - f.vlo[dir] + 1);
@@ -53,7 +58,12 @@ struct lbx_mf {
   }
 };
 
+struct lbx_resolved {                   // FillPatch sources per ghost cell of one destination geometry (k_plan_resolve)
+  int2* tab = nullptr;
+  long long* first = nullptr;
+};
 struct lbx_plan {
+  std::map<std::tuple<uint64_t, uint64_t, uint64_t>, lbx_resolved> resolved;
   std::vector<lbx::GDesc> descs;
   std::vector<lbx::GDst> dsts;
   lbx::GDesc* d_descs = nullptr;
@@ -145,6 +155,12 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
   m->bytes = off;
   m->geom = h;
   m->max_valid = m->max_cells(0);
+  m->rows_ok = (ngrow == 2);
+  for (const auto& f : m->host) {
+    if (f.n[0] != f.vhi[0] - f.vlo[0] + 5 || (f.n[0] & 1)) m->rows_ok = false;
+    m->max_n0 = std::max(m->max_n0, f.n[0]);
+    m->max_rows = std::max(m->max_rows, (long long)f.n[1] * f.n[2]);
+  }
   const size_t mine = m->dist ? per_rank[rank] : off;
   m->local_bytes = mine;
   cudaError_t e = lbx::arena_alloc(reinterpret_cast<void**>(&m->base), mine ? mine : 256);
@@ -729,6 +745,10 @@ int lbx_plan_destroy(lbx_plan* p) {
     lbx::arena_free(p->d_descs);
     lbx::arena_free(p->d_dsts);
     lbx::arena_free(p->d_fab_first);
+    for (auto& kv : p->resolved) {
+      lbx::arena_free(kv.second.tab);
+      lbx::arena_free(kv.second.first);
+    }
   }
   delete p;
   return 0;
@@ -820,6 +840,37 @@ int lbx_mf_collide_stream_level(const lbx_mf* now, lbx_mf* dst, double omega_s, 
                                wa, wb);
 }
 
+// the plan's FillPatch sources resolved per ghost cell of dst's boxes: built once per (plan, geometries)
+static int plan_resolved(lbx_plan* plan, const lbx_mf* dst, const lbx_mf* s0, const lbx_mf* s1, lbx_resolved* out) {
+  const auto key = std::make_tuple(dst->geom, s0 ? s0->geom : 0, s1 ? s1->geom : 0);
+  auto it = plan->resolved.find(key);
+  if (it != plan->resolved.end()) { *out = it->second; return 0; }
+  std::vector<long long> first((size_t)dst->nfabs, 0);
+  long long total = 0, most = 0;
+  for (int b = 0; b < dst->nfabs; ++b) {
+    const lbx::DFabT& f = dst->host[b];
+    if (!f.local) continue;
+    first[b] = total;
+    const long long n = lbx::ro_shell_size(f.n[0], f.n[1], f.n[2]);
+    total += n;
+    most = std::max(most, n);
+  }
+  lbx_resolved r;
+  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&r.tab), sizeof(int2) * (size_t)std::max<long long>(total, 1)));
+  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&r.first), sizeof(long long) * first.size()));
+  LBX_CUDA(cudaMemcpyAsync(r.first, first.data(), sizeof(long long) * first.size(), cudaMemcpyHostToDevice, g.cur));
+  LBX_CUDA(cudaStreamSynchronize(g.cur));          // `first` is a local
+  if (total > 0) {
+    lbx::k_plan_resolve<<<lbx::mf_grid(most, dst->nfabs), lbx::MFT, 0, g.cur>>>(dst->table, dst->nfabs, plan->d_dsts, plan->d_fab_first,
+                                                                              plan->d_descs, s0 ? s0->table : nullptr,
+                                                                              s1 ? s1->table : nullptr, r.tab, r.first);
+    if (lbx::after_launch("k_plan_resolve")) return 1;
+  }
+  plan->resolved[key] = r;
+  *out = r;
+  return 0;
+}
+
 static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghost, lbx_mf* dst, double omega_s, double omega_b,
                                  const lbx_mf* mask, int fine_val, int zero_invalid, lbx_plan* plan, const lbx_mf* src0,
                                  const lbx_mf* src1, const lbx_mf* fallback, bool level_step, const lbx_mf* src1b, double wa,
@@ -875,13 +926,40 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   }
   const bool remote = plan && ((src0 && src0->dist) || (src1 && src1->dist) || (src1b && src1b->dist));
   if (remote && lbx::par_barrier()) return 1;
+  // the row-owner kernel needs a ghost source, tight fabs with even rows, and a row buffer that fits shared memory
+  int ro_warps = 8;
+  const int ro_pitch = dst->max_n0 + 2;
+  while (ro_warps > 1 && (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) > 200 * 1024) ro_warps >>= 1;
+  const bool use_rows = lbx::g_row_kernel && (plan || src_ghost) && dst->rows_ok && !lbx::g_debug_skip &&
+                        (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) <= 200 * 1024;
+  lbx_resolved res;
+  if (use_rows && plan && plan_resolved(plan, dst, src0, src1, &res)) return 1;
   const bool timed = g.prof && g.prof_n < lbx::Ctx::PROF_MAX && g.conc_next < 0;
   if (g.prof && !timed) ++g.prof_dropped;
   if (timed) LBX_CUDA(cudaEventRecord(g.prof_ev[2 * g.prof_n], g.cur));
-  L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
-                        mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
-                        dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val,
-                        (zero_invalid ? 1 : 0) | (level_step ? 2 : 0));
+  if (use_rows) {
+    lbx::ROArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vbase = reinterpret_cast<const double*>(src_valid->base);
+    a.dbase = reinterpret_cast<double*>(dst->base);
+    a.dt = dst->table;
+    a.mt = mask ? mask->table : nullptr;
+    a.gt = src_ghost ? src_ghost->table : nullptr;
+    if (plan) {
+      a.plan.tab = res.tab;
+      a.plan.tab_first = res.first;
+      a.plan.s0 = cp.s0; a.plan.s1 = cp.s1; a.plan.s1b = cp.s1b; a.plan.fb = cp.fb;
+      a.plan.wa = wa; a.plan.wb = wb;
+    }
+    a.nfabs = dst->nfabs; a.warps = ro_warps; a.pitch = ro_pitch;
+    a.omega_s = omega_s; a.omega_b = omega_b; a.fine_val = fine_val; a.zero_invalid = zero_invalid ? 1 : 0;
+    if (L().mf_cs_rows(g.cur, a, level_step ? 3 : plan ? 2 : 1, dst->max_rows)) return fail("k_mf_cs_rows: cannot raise the shared-memory limit");
+  } else {
+    L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
+                          mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
+                          dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val,
+                          (zero_invalid ? 1 : 0) | (level_step ? 2 : 0));
+  }
   if (timed) {
     LBX_CUDA(cudaEventRecord(g.prof_ev[2 * g.prof_n + 1], g.cur));
     ++g.prof_n;

@@ -696,6 +696,13 @@ void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& 
 // nGrow/ratio ghost cells (one search-free kernel), (2) ParallelCopy that temporary into the coarse
 // valid cells with ADD and periodic wrap (src_ng = its ghosts, dst_ng = 0): a coarse cell under
 // the ghost overlap of neighbouring fine boxes receives every contribution, in ParallelCopy order.
+// Default (fused): ONE gather -- the ParallelCopy's descriptors with kind AVG instead of COPY, applied with ADD
+// straight from the fine level: a coarse cell forms the mean of the 8 fine cells of each contribution in
+// registers (amrex_avgdown's summation order) and adds them in the same list order, so the result is
+// bit-identical to the two steps while the coarsened temporary is never written or read.
+namespace { bool g_sum_fused = true; }
+void SetSumFineToCoarseFused(bool on) { g_sum_fused = on; }
+
 void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, const IntVect& ratio,
                         const Geometry& cgeom, const Geometry& /*fgeom*/) {
   if (fine.empty() || crse.empty()) return;
@@ -704,6 +711,34 @@ void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int nco
   const int r = ratio[0];
   if (fine.nGrow() % r != 0) Abort("sum_fine_to_coarse: fine.nGrow() must be a multiple of the ratio");
   const int cng = fine.nGrow() / r;
+  if (g_sum_fused && !crse.isFlat()) {
+    const Periodicity period = cgeom.periodicity();
+    const std::string key = "SF|" + gkey(crse) + "|" + gkey(fine) + "|" + pkey(period) + "|" + std::to_string(r);
+    lbx_plan* p = cached(key, [&](std::vector<lbx_gather>& d) {
+      std::vector<Box> cf(fine.size());                   // the coarsened fine boxes (valid part)
+      for (long i = 0; i < fine.size(); ++i) {
+        cf[i] = amrex::coarsen(fine.box((int)i), r);
+        if (amrex::refine(amrex::grow(cf[i], cng), r) != fine.fabbox((int)i)) Abort("sum_fine_to_coarse: fine box not aligned to the coarse grid");
+      }
+      const BoxHash sh(cf);
+      const std::vector<IntVect> shifts = period.shiftIntVect();
+      for (int k = 0; k < crse.numStorageFabs(); ++k) {
+        if (!crse.isLocal(k)) continue;
+        g_group = 0;
+        const size_t from = d.size();
+        copy_descs(d, k, crse.storageValid(k), cf, sh, cng, shifts, 0, false, k, true);      // ParallelCopy order (ADD)
+        for (size_t q = from; q < d.size(); ++q) {        // COPY from the temporary -> AVG from the fine box itself
+          d[q].kind = LBX_G_AVG;
+          d[q].ratio = r;
+          for (int a = 0; a < 3; ++a) d[q].shift[a] *= r;
+        }
+      }
+      g_group = 0;
+    });
+    lbx_check(lbx_plan_apply(p, crse.mf(), fine.mf(), nullptr, LBX_OP_ADD), "sum_fine_to_coarse");
+    crse.touch();
+    return;
+  }
   const std::string key = gkey(fine) + "|" + std::to_string(r) + "|" + std::to_string(DistributionMapping::NProcs()) + "." +
                           std::to_string(DistributionMapping::MyProc());
   if (!g_coarsened.count(key) && g_coarsened.size() >= 4) g_coarsened.clear();   // grids change at regrid: keep a few

@@ -18,6 +18,7 @@ OPT_VALID_TILING, OPT_DEBUG_SKIP, OPT_ALIGN_ROWS, OPT_XGHOST_IN_ROW, OPT_PLAIN_S
 DEFAULT_VALID_TILING = 0      # lbx_abi.cu g_valid_linear
 DEFAULT_XGHOST_IN_ROW = 0     # lbx_abi.cu g_xghost_in_row
 OPT_SMEM_PAD = 2
+OPT_ROW_KERNEL = 8
 IPC_HANDLE_BYTES = 64
 FACE_XP, FACE_XM, FACE_YP, FACE_YM, FACE_ZP, FACE_ZM = range(6)
 

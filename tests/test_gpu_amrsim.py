@@ -321,14 +321,16 @@ def test_three_level_shear_matches_oracle(coracle):
     assert (sim.GetTime(2), sim.GetTimeStep(2)) == (o.levels[2].time, o.levels[2].step)
 
 
-@pytest.mark.parametrize("tiling", [0, 1, 2, 3])
+@pytest.mark.parametrize("tiling", [4, 0, 1, 2, 3])
 @pytest.mark.parametrize("max_level", [1, 2])
 def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level, tiling):
     """The fused collide+Stream(+ZeroInvalidComponents) passes reproduce the reference's literal
     sequence of passes bit for bit: every cell of NOW (ghost rings included) on every level."""
     from lambrex_b200 import lbx
     # valid tiles: 0 a warp per row / 1 256 consecutive cells / 2 a warp per row that also pushes the row's x-ghost cells
-    # 3: 256 consecutive cells of the rows INCLUDING their x-ghost cells
+    # 3: 256 consecutive cells of the rows INCLUDING their x-ghost cells (0-3: the round-1 tile kernel)
+    # 4: the row-owner kernel (default): a warp per source row of the grown box writes whole destination rows
+    lbx.set_option(lbx.OPT_ROW_KERNEL, 1 if tiling == 4 else 0)
     lbx.set_option(lbx.OPT_VALID_TILING, 1 if tiling in (1, 3) else 0)
     lbx.set_option(lbx.OPT_XGHOST_IN_ROW, 1 if tiling in (2, 3) else 0)
     nx, ny, nz = 16, 12, 20
@@ -361,6 +363,7 @@ def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level, tiling):
         sim.close()
     lbx.set_option(lbx.OPT_VALID_TILING, lbx.DEFAULT_VALID_TILING)
     lbx.set_option(lbx.OPT_XGHOST_IN_ROW, lbx.DEFAULT_XGHOST_IN_ROW)
+    lbx.set_option(lbx.OPT_ROW_KERNEL, 1)
 
 
 # ------------------------------------------------------------------ conventional subcycling
@@ -506,11 +509,15 @@ def test_linear_moment_fields_through_amrsim(coracle):
     sim.close()
 
 
+@pytest.mark.parametrize("row_kernel", [1, 0])
 @pytest.mark.parametrize("max_level", [0, 1, 2])
-def test_fused_level_step_equals_literal_pass_sequence(max_level):
+def test_fused_level_step_equals_literal_pass_sequence(max_level, row_kernel):
     """lbx_mf_collide_stream_level (CollideLevel + Stream of a level in one launch, time-interpolated
     coarse ghost data) reproduces the literal FillPatch / Collide / FillBoundary / Stream sequence bit
-    for bit: every cell of NOW, ghost rings included, on every level, through a mid-run regrid."""
+    for bit: every cell of NOW, ghost rings included, on every level, through a mid-run regrid.  row_kernel:
+    the row-owner kernel (default) or the round-1 tile kernel."""
+    from lambrex_b200 import lbx
+    lbx.set_option(lbx.OPT_ROW_KERNEL, row_kernel)
     nx, ny, nz = 16, 12, 20
     rho, u = workloads.shear_wave(nx, ny, nz)
     rho = rho * workloads.pulse_density(nx, ny, nz)
@@ -545,6 +552,7 @@ def test_fused_level_step_equals_literal_pass_sequence(max_level):
             assert sims[0].GetTimeStep(lev) == sims[1].GetTimeStep(lev) == (it + 1) * 2 ** lev
     for sim in sims:
         sim.close()
+    lbx.set_option(lbx.OPT_ROW_KERNEL, 1)
 
 
 # ------------------------------------------------------------------ checkpoint / restart

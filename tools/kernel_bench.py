@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--valid-tiling", type=int, default=0)
     ap.add_argument("--align-rows", type=int, default=0)
     ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 skip valid tiles, 2 skip ghost tiles")
+    ap.add_argument("--row-kernel", type=int, default=1, help="1: row-owner kernel (default); 0: round-1 tile kernel")
     args = ap.parse_args()
     lbx.init()
     lbx.set_option(lbx.OPT_XGHOST_IN_ROW, args.xghost_in_row)
@@ -41,6 +42,7 @@ def main():
     lbx.set_option(lbx.OPT_PLAIN_STORES, args.plain_stores)
     lbx.set_option(lbx.OPT_VALID_TILING, args.valid_tiling)
     lbx.set_option(lbx.OPT_ALIGN_ROWS, args.align_rows)
+    lbx.set_option(lbx.OPT_ROW_KERNEL, args.row_kernel)
     n, b = args.grid, args.box
     boxes = [((i, j, k), (i + b - 1, j + b - 1, k + b - 1))
              for k in range(0, n, b) for j in range(0, n, b) for i in range(0, n, b)]
