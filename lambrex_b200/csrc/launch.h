@@ -36,8 +36,8 @@ struct Launchers {
   void (*mf_collide_stream)(cudaStream_t, const double* vbase, double* dbase, const DFabT* dst, const DFabT* mask,
                             const DFabT* gsrc, CSPlan plan, int nfabs, int max_ny, int max_nz, long long max_valid,
                             long long ghost_tiles, double ws, double wb, int fine_val, int zero_invalid);
-  // mode 1 own ghost cells, 2 FillPatch plan, 3 conventional level step; max_rows = most grown rows of any fab
-  int (*mf_cs_rows)(cudaStream_t, ROArgs a, int mode, long long max_rows);
+  // mode 1 own ghost cells, 2 FillPatch plan, 3 conventional level step; max_n1 / max_n2 = largest grown y / z extent of any fab
+  int (*mf_cs_rows)(cudaStream_t, ROArgs a, int mode, int max_n1, int max_n2);
   void (*mf_moments)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs, long long max_cells);
   void (*mf_equilibrium)(cudaStream_t, const DFabT* f, const DFabT* rho, const DFabT* u, int nfabs,
                          long long max_cells);

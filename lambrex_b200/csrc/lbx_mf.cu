@@ -928,10 +928,13 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   if (remote && lbx::par_barrier()) return 1;
   // the row-owner kernel needs a ghost source, tight fabs with even rows, and a row buffer that fits shared memory
   int ro_warps = 8;
-  const int ro_pitch = dst->max_n0 + 2;
-  while (ro_warps > 1 && (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) > 200 * 1024) ro_warps >>= 1;
-  const bool use_rows = lbx::g_row_kernel && (plan || src_ghost) && dst->rows_ok && !lbx::g_debug_skip &&
-                        (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) <= 200 * 1024;
+  const int ro_pitch = dst->max_n0 + 4;          // even; the row buffer keeps a zero pad on either side of the row
+  while (ro_warps > 1 && (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) > 199 * 1024) ro_warps >>= 1;
+  bool small = true;                 // 32-bit element offsets inside every fab the kernel touches
+  for (const lbx_mf* s : {(const lbx_mf*)dst, src0, src1, src1b})
+    if (s && (double)s->max_cells(s->ngrow) * LBX_NV >= 2147483648.0) small = false;
+  const bool use_rows = lbx::g_row_kernel && (plan || src_ghost) && dst->rows_ok && small && !lbx::g_debug_skip &&
+                        (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) <= 199 * 1024;
   lbx_resolved res;
   if (use_rows && plan && plan_resolved(plan, dst, src0, src1, &res)) return 1;
   const bool timed = g.prof && g.prof_n < lbx::Ctx::PROF_MAX && g.conc_next < 0;
@@ -953,7 +956,7 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
     }
     a.nfabs = dst->nfabs; a.warps = ro_warps; a.pitch = ro_pitch;
     a.omega_s = omega_s; a.omega_b = omega_b; a.fine_val = fine_val; a.zero_invalid = zero_invalid ? 1 : 0;
-    if (L().mf_cs_rows(g.cur, a, level_step ? 3 : plan ? 2 : 1, dst->max_rows)) return fail("k_mf_cs_rows: cannot raise the shared-memory limit");
+    if (L().mf_cs_rows(g.cur, a, level_step ? 3 : plan ? 2 : 1, dst->max_extent(1) + 4, dst->max_extent(2) + 4)) return fail("k_mf_cs_rows: cannot raise the shared-memory limit");
   } else {
     L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
                           mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),

@@ -49,6 +49,7 @@ struct ROArgs {
   const DFabT* gt;             // MODE 1: the set whose own ghost cells are pushed
   ROPlan plan;                 // MODE 2, 3
   int nfabs, warps, pitch;     // warps per CTA, shared-memory row pitch in doubles
+  int fab0;                    // first fab of this launch (grid.z covers at most 65535 fabs)
   double omega_s, omega_b;
   int fine_val, zero_invalid;
 };
@@ -131,44 +132,60 @@ static __global__ void __launch_bounds__(MFT) k_plan_resolve(const DFabT* __rest
   tab[tab_first[b] + t] = e;
 }
 
-// populations a ghost source cell (x, jr, kr relative to the grown box) pushes: bit p set iff dst = x + c_p lies
-// inside valid grown by 1 and (under ZeroInvalidComponents) is a VALID cell -- a ghost source reaches a ghost
-// destination only with x - c_p outside the valid box, which the filter zeroes
-__device__ __forceinline__ unsigned ro_need_mask(int x, int jr, int kr, int n0, int n1, int n2, bool zi) {
+// ---- separable population masks: bit p of dir_mask(axis, c) is set iff component `axis` of c_p equals c ------------
+__host__ __device__ constexpr unsigned dir_mask(int axis, int c) {
   unsigned m = 0;
-  const int lo = zi ? 2 : 1;                      // destination range per direction: [lo, n - 1 - lo]
-#pragma unroll
-  for (int p = 0; p < NV; ++p) {
-    const int dx = x + cx(p), dy = jr + cy(p), dz = kr + cz(p);
-    if (dx >= lo && dx < n0 - lo && dy >= lo && dy < n1 - lo && dz >= lo && dz < n2 - lo) m |= 1u << p;
-  }
+  for (int p = 0; p < NV; ++p)
+    if (cc(axis, p) == c) m |= 1u << p;
+  return m;
+}
+// populations whose step along `axis` from coordinate v lands in [lo, n - lo): one mask from three range tests
+// (the 15 populations factorise by direction, so "destination inside a box" is an AND of three such masks)
+__device__ __forceinline__ unsigned axis_sel(int axis_is, int v, int n, int lo, bool backwards, int step = 1) {
+  const unsigned M = axis_is == 0 ? dir_mask(0, -1) : axis_is == 1 ? dir_mask(1, -1) : dir_mask(2, -1);
+  const unsigned Z = axis_is == 0 ? dir_mask(0, 0) : axis_is == 1 ? dir_mask(1, 0) : dir_mask(2, 0);
+  const unsigned P = axis_is == 0 ? dir_mask(0, 1) : axis_is == 1 ? dir_mask(1, 1) : dir_mask(2, 1);
+  const int vm = backwards ? v + step : v - step, vp = backwards ? v - step : v + step;   // where a c = -1 / +1 population lands
+  unsigned m = 0;
+  if (vm >= lo && vm < n - lo) m |= M;
+  if (v >= lo && v < n - lo) m |= Z;
+  if (vp >= lo && vp < n - lo) m |= P;
   return m;
 }
 
-template <class C, int MODE>   // MODE 1: own ghost cells; 2: FillPatch plan (Rohde pair); 3: conventional level step
-__global__ void __launch_bounds__(RO_THREADS) k_mf_cs_rows(ROArgs a) {
+// MODE 1: own ghost cells; 2: FillPatch plan (Rohde pair); 3: conventional level step.  ZI: ZeroInvalidComponents folded in.
+// Fabs hold fewer than 2^31 / 15 cells (checked on the host): element offsets inside a fab are 32-bit.
+// Shared-memory row buffer of a warp: cell x of population p at sm[p * pitch + x]; sm[p * pitch - 1] and
+// sm[p * pitch + n0] are zero pads, so that the ring-2 destination cells x = 0 and x = n0 - 1 come out as 0 without a
+// test: they read the pad, or a ghost value phase 1 has already zeroed because it has no destination.
+#ifndef LBX_RO_MIN_CTAS
+#define LBX_RO_MIN_CTAS 3
+#endif
+template <class C, int MODE, bool ZI>
+__global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROArgs a) {
   extern __shared__ double ro_smem[];
-  const int b = mf_fab_index();
-  if (b >= a.nfabs) return;
+  // grid = (row tiles of one z-plane, z-planes of the largest fab, fabs): no division anywhere
+  const int b = a.fab0 + (int)blockIdx.z;
   const DFabT D = a.dt[b];
   if (!D.local) return;                                   // a peer's box: its owner streams it
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n0 = D.n[0], n1 = D.n[1], n2 = D.n[2];
-  const int row = (int)blockIdx.x * a.warps + w;
-  if (w >= a.warps || row >= n1 * n2) return;             // warp-uniform
-  const int jr = row % n1, kr = row / n1;
-  const int j = D.lo[1] + jr, k = D.lo[2] + kr;
-  const int ey = jr < 2 ? jr - 2 : jr >= n1 - 2 ? jr - (n1 - 3) : 0;
-  const int ez = kr < 2 ? kr - 2 : kr >= n2 - 2 ? kr - (n2 - 3) : 0;
-  const bool valid_row = ey == 0 && ez == 0;
-  double* sm = ro_smem + (size_t)w * NV * a.pitch;
-  const long long sc = mf_stride(D);
-  const long long rowoff = (long long)n0 * (jr + (long long)n1 * kr);
-  const bool zi = a.zero_invalid != 0;
+  const int jr = (int)blockIdx.x * a.warps + w, kr = (int)blockIdx.y;
+  if (w >= a.warps || jr >= n1 || kr >= n2) return;       // warp-uniform
+  const bool valid_row = jr >= 2 && jr < n1 - 2 && kr >= 2 && kr < n2 - 2;
+  // rows whose 15 destination rows are all rows of valid grown by 1 and -- under ZI -- all valid rows: phase 2 needs no
+  // per-population test at all
+  const bool deep = ZI ? (jr >= 3 && jr < n1 - 3 && kr >= 3 && kr < n2 - 3) : valid_row;
+  const int pitch = a.pitch;
+  double* sm = ro_smem + 2 + w * (NV * pitch);
+  const unsigned sc = (unsigned)n0 * (unsigned)n1 * (unsigned)n2;       // plane stride (elements)
+  const unsigned rowoff = (unsigned)n0 * ((unsigned)jr + (unsigned)n1 * (unsigned)kr);
+  double* dfab = static_cast<double*>(D.p);
+  if (lane < NV) { sm[lane * pitch - 1] = 0.0; sm[lane * pitch + n0] = 0.0; }
 
   // ------------------------------------------------------------------ phase 1: the row's populations -> sm[p][x]
   if (valid_row) {
-    const double* srow = a.vbase + (static_cast<double*>(D.p) - a.dbase) + rowoff;
+    const double* vfab = a.vbase + (dfab - a.dbase);
     const int* mrow = a.mt ? static_cast<const int*>(a.mt[b].p) + rowoff : nullptr;
     for (int x = 2 + lane; x < n0 - 2; x += 32) {
       double f[NV];
@@ -176,99 +193,134 @@ __global__ void __launch_bounds__(RO_THREADS) k_mf_cs_rows(ROArgs a) {
 #pragma unroll
         for (int p = 0; p < NV; ++p) f[p] = 0.0;
       } else {
+        const double* sp = vfab + (rowoff + (unsigned)x);
 #pragma unroll
-        for (int p = 0; p < NV; ++p) f[p] = __ldcs(srow + p * sc + x);
+        for (int p = 0; p < NV; ++p) f[p] = __ldcs(sp + (unsigned)p * sc);
         C::collide(f, a.omega_s, a.omega_b);
       }
+      double* s = sm + x;
 #pragma unroll
-      for (int p = 0; p < NV; ++p) sm[p * a.pitch + x] = f[p];
+      for (int p = 0; p < NV; ++p) s[p * pitch] = f[p];
     }
   }
-  // ghost cells of the row: all of it, or the 2 + 2 cells at the ends of a valid row
-  for (int q = lane; q < (valid_row ? 4 : n0); q += 32) {
-    const int x = valid_row ? (q < 2 ? q : n0 - 4 + q) : q;
-    const unsigned need = ro_need_mask(x, jr, kr, n0, n1, n2, zi);
-    const double* sp = nullptr;
-    const double* spb = nullptr;
-    long long ssc = sc;
-    bool collide_src = false;
-    if (MODE == 1) {
-      sp = static_cast<const double*>(a.gt[b].p) + rowoff + x;
-    } else {
-      const int2 e = a.plan.tab[a.plan.tab_first[b] + ro_shell_index(n0, n1, n2, x, jr, kr)];
-      const int kind = e.x & 3, fab = e.x >> 2;
-      if (kind) {
-        const DFabT* S = (kind == 1 ? a.plan.s0 : a.plan.s1) + fab;
-        const int4 h0 = reinterpret_cast<const int4*>(S)[0], h1 = reinterpret_cast<const int4*>(S)[1];   // p, lo0, lo1 | lo2, n0, n1, n2
-        const double* base = reinterpret_cast<const double*>(((unsigned long long)(unsigned)h0.y << 32) | (unsigned)h0.x);
-        ssc = (long long)h1.y * h1.z * h1.w;
-        sp = base + e.y;
-        if (MODE == 3) {
-          collide_src = kind == 1;
-          if (kind == 2 && a.plan.s1b) spb = static_cast<const double*>(a.plan.s1b[fab].p) + e.y;
-        }
-      } else if (a.plan.fb) {
-        sp = static_cast<const double*>(a.plan.fb[b].p) + rowoff + x;
-      }
-    }
-    double f[NV];
-    if (MODE == 3 && collide_src) {
-#pragma unroll
-      for (int p = 0; p < NV; ++p) f[p] = __ldcs(sp + p * ssc);
-      C::collide(f, a.omega_s, a.omega_b);
-    } else if (MODE == 3 && spb) {
+  // ghost cells of the row: all of it, or the 2 + 2 cells at the ends of a valid row.  Warp-uniform population masks of
+  // this source row (the y, z parts of every per-cell decision): a ghost source pushes p only into valid grown by 1 --
+  // under ZI only into valid cells
+  const unsigned NEEDROW = axis_sel(1, jr, n1, ZI ? 2 : 1, false) & axis_sel(2, kr, n2, ZI ? 2 : 1, false);
+  if (MODE == 1 && !valid_row) {
+    // own ghost cells of a whole ghost row: a plain copy of the needed planes, 16 bytes per lane (cells of a needed
+    // plane that have no destination are copied too: phase 2's general path tests for them)
+    const double2* g2 = reinterpret_cast<const double2*>(static_cast<const double*>(a.gt[b].p) + rowoff);
+    const unsigned sc2 = sc >> 1;
+    for (int q = lane; q < (n0 >> 1); q += 32) {
+      double2* s2 = reinterpret_cast<double2*>(sm + 2 * q);
 #pragma unroll
       for (int p = 0; p < NV; ++p)
-        f[p] = (need >> p & 1u) ? __dadd_rn(__dmul_rn(a.plan.wa, __ldcs(sp + p * ssc)), __dmul_rn(a.plan.wb, __ldcs(spb + p * ssc))) : 0.0;
-    } else {
-#pragma unroll
-      for (int p = 0; p < NV; ++p) f[p] = ((need >> p & 1u) && sp) ? __ldcs(sp + p * ssc) : 0.0;
+        if (NEEDROW >> p & 1u) s2[p * (pitch >> 1)] = __ldcs(g2 + (q + (unsigned)p * sc2));
     }
+  } else {
+    for (int q = lane; q < (valid_row ? 4 : n0); q += 32) {
+      const int x = valid_row ? (q < 2 ? q : n0 - 4 + q) : q;
+      const unsigned need = NEEDROW & axis_sel(0, x, n0, ZI ? 2 : 1, false);
+      const double* sp = nullptr;
+      const double* spb = nullptr;
+      unsigned ssc = sc;
+      bool collide_src = false;
+      if (MODE == 1) {
+        sp = static_cast<const double*>(a.gt[b].p) + (rowoff + (unsigned)x);
+      } else {
+        const int2 e = a.plan.tab[a.plan.tab_first[b] + ro_shell_index(n0, n1, n2, x, jr, kr)];
+        const int kind = e.x & 3, fab = e.x >> 2;
+        if (kind) {
+          const DFabT* S = (kind == 1 ? a.plan.s0 : a.plan.s1) + fab;
+          const int4 h0 = reinterpret_cast<const int4*>(S)[0], h1 = reinterpret_cast<const int4*>(S)[1];   // p, lo0, lo1 | lo2, n0, n1, n2
+          const double* base = reinterpret_cast<const double*>(((unsigned long long)(unsigned)h0.y << 32) | (unsigned)h0.x);
+          ssc = (unsigned)h1.y * (unsigned)h1.z * (unsigned)h1.w;
+          sp = base + e.y;
+          if (MODE == 3) {
+            collide_src = kind == 1;
+            if (kind == 2 && a.plan.s1b) spb = static_cast<const double*>(a.plan.s1b[fab].p) + e.y;
+          }
+        } else if (a.plan.fb) {
+          sp = static_cast<const double*>(a.plan.fb[b].p) + (rowoff + (unsigned)x);
+        }
+      }
+      double f[NV];
+      if (MODE == 3 && collide_src) {
 #pragma unroll
-    for (int p = 0; p < NV; ++p) sm[p * a.pitch + x] = f[p];
+        for (int p = 0; p < NV; ++p) f[p] = __ldcs(sp + (unsigned)p * ssc);
+        C::collide(f, a.omega_s, a.omega_b);
+        // the populations without a destination must read as 0 in phase 2's test-free path
+#pragma unroll
+        for (int p = 0; p < NV; ++p)
+          if (!(need >> p & 1u)) f[p] = 0.0;
+      } else if (MODE == 3 && spb) {
+#pragma unroll
+        for (int p = 0; p < NV; ++p)
+          f[p] = (need >> p & 1u) ? __dadd_rn(__dmul_rn(a.plan.wa, __ldcs(sp + (unsigned)p * ssc)), __dmul_rn(a.plan.wb, __ldcs(spb + (unsigned)p * ssc))) : 0.0;
+      } else {
+#pragma unroll
+        for (int p = 0; p < NV; ++p) f[p] = ((need >> p & 1u) && sp) ? __ldcs(sp + (unsigned)p * ssc) : 0.0;
+      }
+      double* s = sm + x;
+#pragma unroll
+      for (int p = 0; p < NV; ++p) s[p * pitch] = f[p];
+    }
   }
   __syncwarp();
 
   // ------------------------------------------------------------------ phase 2: whole destination rows, one per population
-  double* dfab = static_cast<double*>(D.p);
   const int npair = n0 >> 1;
+  const int oY = n0 >> 1, oZ = (n0 >> 1) * n1;            // row / plane pitch of the destination in 16-byte pairs
+  const unsigned sc2 = sc >> 1;
+  if (deep) {
+    for (int q = lane; q < npair; q += 32) {
+      double2* pd = reinterpret_cast<double2*>(dfab + rowoff) + q;
+      const double* ss = sm + 2 * q;
 #pragma unroll
-  for (int p = 0; p < NV; ++p) {
-    const int tj = jr + cy(p), tk = kr + cz(p);
-    if (tj >= 0 && tj < n1 && tk >= 0 && tk < n2) {
-      const bool zero_row = tj == 0 || tj == n1 - 1 || tk == 0 || tk == n2 - 1;       // ring 2 of the fresh fab
-      double2* drow = reinterpret_cast<double2*>(dfab + p * sc + (long long)n0 * (tj + (long long)n1 * tk));
-      if (zero_row) {
-        for (int q = lane; q < npair; q += 32) __stcs(drow + q, make_double2(0.0, 0.0));
-      } else {
-        const double* srow = sm + p * a.pitch - cx(p);
-        const bool t_valid = tj >= 2 && tj < n1 - 2 && tk >= 2 && tk < n2 - 2;         // destination row inside the valid y-z range
-        const bool s_valid = jr - cy(p) >= 2 && jr - cy(p) < n1 - 2 && kr - cz(p) >= 2 && kr - cz(p) < n2 - 2;   // (dst - 2c) in y, z
-        for (int q = lane; q < npair; q += 32) {
-          double v[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int x = 2 * q + e;
-            if (x == 0 || x == n0 - 1) {
-              v[e] = 0.0;                                                              // ring 2 in x
-            } else {
-              v[e] = srow[x];
-              if (zi) {
-                const bool dst_valid = t_valid && x >= 2 && x < n0 - 2;
-                const int x2 = x - 2 * cx(p);
-                if (!dst_valid && !(s_valid && x2 >= 2 && x2 < n0 - 2)) v[e] = 0.0;    // ZeroInvalidComponents
-              }
-            }
-          }
-          __stcs(drow + q, make_double2(v[0], v[1]));
-        }
+      for (int p = 0; p < NV; ++p) {
+        __stcs(pd + (cy(p) * oY + cz(p) * oZ), make_double2(ss[-cx(p)], ss[1 - cx(p)]));
+        pd += sc2;
+        ss += pitch;
       }
     }
-    // ring-2 rows: planes whose natural writer (j - c_y, k - c_z) lies outside the grown box are zeroed by the row itself
-    const int sj = jr - cy(p), sk = kr - cz(p);
-    if ((cy(p) != 0 || cz(p) != 0) && (sj < 0 || sj >= n1 || sk < 0 || sk >= n2)) {
-      double2* orow = reinterpret_cast<double2*>(dfab + p * sc + rowoff);
-      for (int q = lane; q < npair; q += 32) __stcs(orow + q, make_double2(0.0, 0.0));
+    return;
+  }
+  // Rows on the rim of the valid y-z range and ghost rows.  A row writes only destination rows of valid grown by 1 (mask
+  // NZ); a ring-2 row zeroes its own 15 planes itself (whole rows, whole sectors: the reference's fresh fab).
+  const unsigned NZ = axis_sel(1, jr, n1, 1, false) & axis_sel(2, kr, n2, 1, false);
+  const bool ring2 = jr == 0 || jr == n1 - 1 || kr == 0 || kr == n2 - 1;
+  unsigned TV = 0, SV = 0;
+  if (ZI) {
+    TV = axis_sel(1, jr, n1, 2, false) & axis_sel(2, kr, n2, 2, false);      // destination row lies in the valid y-z range
+    SV = axis_sel(1, jr, n1, 2, true) & axis_sel(2, kr, n2, 2, true);        // (destination - 2 c) lies in the valid y-z range
+  }
+  for (int q = lane; q < npair; q += 32) {
+    const int x0 = 2 * q;
+    double2* pd = reinterpret_cast<double2*>(dfab + rowoff) + q;
+    const double* ss = sm + x0;
+    // populations whose value survives in cell x0 / x0 + 1 of the destination row: not a ring-2 cell in x, and under
+    // ZeroInvalidComponents (:604-617) a valid destination cell or one whose (destination - 2 c) is valid
+    unsigned K0 = q == 0 ? 0u : NZ, K1 = q == npair - 1 ? 0u : NZ;
+    if (ZI) {
+      const int x1 = x0 + 1;
+      const unsigned all = (1u << NV) - 1;
+      const unsigned D0 = (x0 >= 2 && x0 < n0 - 2) ? all : 0u, D1 = (x1 >= 2 && x1 < n0 - 2) ? all : 0u;
+      K0 &= (TV & D0) | (SV & axis_sel(0, x0, n0, 2, true, 2));      // (destination - 2 c) valid in x
+      K1 &= (TV & D1) | (SV & axis_sel(0, x1, n0, 2, true, 2));
+    }
+#pragma unroll
+    for (int p = 0; p < NV; ++p) {
+      const unsigned bit = 1u << p;
+      if (NZ & bit) {
+        double2 v;
+        v.x = (K0 & bit) ? ss[-cx(p)] : 0.0;
+        v.y = (K1 & bit) ? ss[1 - cx(p)] : 0.0;
+        __stcs(pd + (cy(p) * oY + cz(p) * oZ), v);
+      }
+      if (ring2) __stcs(pd, make_double2(0.0, 0.0));
+      pd += sc2;
+      ss += pitch;
     }
   }
 }

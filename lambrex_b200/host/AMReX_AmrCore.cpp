@@ -234,11 +234,19 @@ void AmrMesh::MakeNewGrids(int lbase, Real time, int& new_finest, Vector<BoxArra
         c.coarsen(ref_ratio[levc]);
         proj.push_back(c);
       }
+      simplify(proj);        // thousands of fine boxes project onto a handful: the tag boxes stay in box mode
+      // containment against the SIMPLIFIED level grids (a handful of boxes): grow(union, g) = union of grown boxes
+      BoxList simp = grids[levc].boxList();
+      simplify(simp);
       auto covered = [&](int g) {
-        BoxList grown = grids[levc].boxList();
+        BoxList grown = simp;
         for (Box& b : grown) b.grow(g);
-        for (const Box& c : proj)
-          if (!complementIn(c, grown).empty()) return false;
+        for (const Box& c : proj) {
+          bool inside = false;
+          for (const Box& q : grown)
+            if (q.contains(c)) { inside = true; break; }
+          if (!inside && !complementIn(c, grown).empty()) return false;
+        }
         return true;
       };
       while (ngrow < 64 && !covered(ngrow)) ++ngrow;

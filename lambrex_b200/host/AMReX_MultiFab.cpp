@@ -156,16 +156,45 @@ template class DeviceFabArray<double, LBX_F64>;
 template class DeviceFabArray<int, LBX_I32>;
 
 // ----------------------------------------------------------------------------- tags
-void TagBox::setVal(char v, const Box& region) {
-  const Box r = region & box_;
-  if (!r.ok() || !allocated()) return;
-  if (v == CLEAR && d_.empty()) return;          // nothing tagged yet: already clear
-  materialise();
+void TagBox::fill(char v, const Box& r, bool only_clear) {
   for (int k = r.smallEnd(2); k <= r.bigEnd(2); ++k)
     for (int j = r.smallEnd(1); j <= r.bigEnd(1); ++j) {
       char* row = &d_[index(IntVect(r.smallEnd(0), j, k))];
-      std::memset(row, v, (size_t)r.length(0));
+      const int len = r.length(0);
+      if (!only_clear) { std::memset(row, v, (size_t)len); continue; }
+      // inside a solid tagged region the rows hold no CLEAR cell at all: libc's vectorised scan finds that out an
+      // order of magnitude faster than the byte loop
+      char* z = static_cast<char*>(std::memchr(row, CLEAR, (size_t)len));
+      if (!z) continue;
+      for (int x = (int)(z - row); x < len; ++x) row[x] = row[x] == CLEAR ? v : row[x];
     }
+}
+
+void TagBox::materialise() {
+  if (!d_.empty()) return;
+  d_.assign((size_t)box_.numPts(), (char)CLEAR);
+  const std::vector<Op> ops = std::move(ops_);
+  ops_.clear();
+  for (const Op& o : ops) fill(o.value, o.region, o.only_clear);
+}
+
+char TagBox::operator()(const IntVect& p) const {
+  if (!d_.empty()) return d_[index(p)];
+  char v = CLEAR;                              // box mode: replay the operations on this one cell
+  for (const Op& o : ops_)
+    if (o.region.contains(p) && !(o.only_clear && v != CLEAR)) v = o.value;
+  return v;
+}
+
+void TagBox::setVal(char v, const Box& region) {
+  const Box r = region & box_;
+  if (!r.ok() || !allocated()) return;
+  if (d_.empty()) {
+    if (v == CLEAR && ops_.empty()) return;          // nothing tagged yet: already clear
+    if (v != CLEAR && ops_.size() < MAX_OPS) { ops_.push_back({r, v, false}); return; }     // stay in box mode
+    materialise();
+  }
+  fill(v, r, false);
 }
 
 // Dilation of the SET cells inside `interior` by +-nbuf in every direction (a cube, so it is done
@@ -180,9 +209,27 @@ static inline int next_nonclear(const char* row, int x, int n) {
 }
 
 void TagBox::buffer(int nbuf, const Box& interior) {
-  if (nbuf <= 0 || !allocated() || d_.empty()) return;
+  if (nbuf <= 0 || !allocated() || !hasStorage()) return;
   const Box in = interior & box_;
   if (!in.ok()) return;
+  if (boxMode()) {
+    // every operation so far wrote SET (or BUF) over a box: the dilation of a SET box's part inside `interior` is that
+    // part grown by nbuf, written into CLEAR cells only.  (BUF regions of an earlier buffer() do not spread.)
+    bool simple = true;
+    for (const Op& o : ops_) simple = simple && (o.value == SET || o.only_clear);
+    if (simple && ops_.size() * 2 <= MAX_OPS) {
+      const size_t n = ops_.size();
+      for (size_t q = 0; q < n; ++q) {
+        if (ops_[q].value != SET) continue;
+        const Box core = ops_[q].region & in;
+        if (!core.ok()) continue;
+        const Box grown = amrex::grow(core, nbuf) & box_;
+        if (grown != core) ops_.push_back({grown, (char)BUF, true});
+      }
+      return;
+    }
+    materialise();
+  }
   struct Run { int i0, i1, j, k; };
   std::vector<Run> runs;
   for (int k = in.smallEnd(2); k <= in.bigEnd(2); ++k)
@@ -203,8 +250,6 @@ void TagBox::buffer(int nbuf, const Box& interior) {
       for (int j = std::max(r.j - nbuf, box_.smallEnd(1)); j <= std::min(r.j + nbuf, box_.bigEnd(1)); ++j) {
         char* row = &d_[index(IntVect(i0, j, k))];
         const int len = i1 - i0 + 1;
-        // inside a solid tagged region the neighbouring rows hold no CLEAR cell at all: libc's
-        // vectorised scan finds that out an order of magnitude faster than the byte loop
         char* z = static_cast<char*>(std::memchr(row, CLEAR, (size_t)len));
         if (!z) continue;
         for (int x = (int)(z - row); x < len; ++x) row[x] = row[x] == CLEAR ? (char)BUF : row[x];
@@ -246,8 +291,54 @@ void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std
     if (!is_per[d]) { ok = false; return v; }
     return lo + (((v - lo) % len) + len) % len;
   };
+  // the run [i0, i1] of row (j, k) in index space, cut at the domain faces and wrapped piece by piece
+  auto emit = [&](int i0, int i1, int jj, int kk) {
+    int a = i0;
+    while (a <= i1) {
+      const int lo = domain.smallEnd(0), len = domain.length(0);
+      const int cell0 = lo + (((a - lo) % len) + len) % len;         // image of a
+      const int room = domain.bigEnd(0) - cell0;                     // cells up to the face
+      const int piece = std::min(i1 - a, room);
+      const bool inside = a >= lo && a <= domain.bigEnd(0);
+      if (inside || is_per[0]) runs.push_back({cell0, cell0 + piece, jj, kk});
+      a += piece + 1;
+    }
+  };
+  // tagged regions of box-mode TagBoxes travel as BOXES (24 bytes for a solid 32^3 patch instead of a thousand runs):
+  // cut at the domain faces and wrapped piece by piece in every periodic direction
+  std::vector<Box> boxes;
+  auto wrap_box = [&](const Box& r) {
+    std::vector<Box> cur(1, r), nxt;
+    for (int d = 0; d < 3; ++d) {
+      const int lo = domain.smallEnd(d), hi = domain.bigEnd(d), len = domain.length(d);
+      nxt.clear();
+      for (const Box& b : cur) {
+        int a = b.smallEnd(d);
+        while (a <= b.bigEnd(d)) {
+          const int cell0 = lo + (((a - lo) % len) + len) % len;
+          const int piece = std::min(b.bigEnd(d) - a, hi - cell0);
+          const bool inside = a >= lo && a <= hi;
+          if (inside || is_per[d]) {
+            Box c = b;
+            c.setSmall(d, cell0);
+            c.setBig(d, cell0 + piece);
+            nxt.push_back(c);
+          }
+          a += piece + 1;
+        }
+      }
+      cur.swap(nxt);
+    }
+    boxes.insert(boxes.end(), cur.begin(), cur.end());
+  };
   for (const TagBox& t : fabs_) {
     if (!t.allocated() || !t.hasStorage()) continue;
+    if (t.boxMode()) {
+      // every operation of a box-mode TagBox wrote a non-CLEAR value: its regions ARE the tagged cells (overlaps
+      // are merged by the bitmap below)
+      for (const TagBox::Op& o : t.ops()) wrap_box(o.region);
+      continue;
+    }
     const Box& b = t.box();
     const int n = b.length(0);
     for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
@@ -259,44 +350,50 @@ void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std
         for (int x = next_nonclear(row, 0, n); x < n;) {
           int y = x;
           while (y + 1 < n && row[y + 1] != TagBox::CLEAR) ++y;
-          // the run [x, y] in index space, cut at the domain faces and wrapped piece by piece
-          int a = b.smallEnd(0) + x;
-          const int e = b.smallEnd(0) + y;
-          while (a <= e) {
-            const int lo = domain.smallEnd(0), len = domain.length(0);
-            const int cell0 = lo + (((a - lo) % len) + len) % len;         // image of a
-            const int room = domain.bigEnd(0) - cell0;                     // cells up to the face
-            const int piece = std::min(e - a, room);
-            const bool inside = a >= lo && a <= domain.bigEnd(0);
-            if (inside || is_per[0]) runs.push_back({cell0, cell0 + piece, jj, kk});
-            a += piece + 1;
-          }
+          emit(b.smallEnd(0) + x, b.smallEnd(0) + y, jj, kk);
           x = next_nonclear(row, y + 1, n);
         }
       }
   }
   if (DistributionMapping::NProcs() > 1) {
-    // every rank contributes the runs of its own boxes: sizes first, then the padded lists
+    // every rank contributes the runs and boxes of its own TagBoxes: sizes first, then the padded lists
     const int np = DistributionMapping::NProcs();
-    long long mine = (long long)runs.size();
-    std::vector<long long> counts(np);
-    lbx_check(lbx_par_allgather(&mine, sizeof(mine), counts.data()), "TagBoxArray::collate");
-    long long most = 0;
-    for (long long c : counts) most = std::max(most, c);
-    if (most == 0) return;
-    std::vector<Run> send((size_t)most, Run{0, -1, 0, 0}), all((size_t)most * np);
-    std::copy(runs.begin(), runs.end(), send.begin());
-    lbx_check(lbx_par_allgather(send.data(), sizeof(Run) * (size_t)most, all.data()), "TagBoxArray::collate");
-    runs.clear();
-    for (int r = 0; r < np; ++r) runs.insert(runs.end(), all.begin() + (size_t)r * most, all.begin() + (size_t)r * most + counts[r]);
+    long long mine[2] = {(long long)runs.size(), (long long)boxes.size()};
+    std::vector<long long> counts(2 * (size_t)np);
+    lbx_check(lbx_par_allgather(mine, sizeof(mine), counts.data()), "TagBoxArray::collate");
+    long long most_r = 0, most_b = 0;
+    for (int r = 0; r < np; ++r) { most_r = std::max(most_r, counts[2 * r]); most_b = std::max(most_b, counts[2 * r + 1]); }
+    if (most_r == 0 && most_b == 0) return;
+    if (most_r > 0) {
+      std::vector<Run> send((size_t)most_r, Run{0, -1, 0, 0}), all((size_t)most_r * np);
+      std::copy(runs.begin(), runs.end(), send.begin());
+      lbx_check(lbx_par_allgather(send.data(), sizeof(Run) * (size_t)most_r, all.data()), "TagBoxArray::collate");
+      runs.clear();
+      for (int r = 0; r < np; ++r) runs.insert(runs.end(), all.begin() + (size_t)r * most_r, all.begin() + (size_t)r * most_r + counts[2 * r]);
+    }
+    if (most_b > 0) {
+      struct B6 { int v[6]; };
+      std::vector<B6> send((size_t)most_b, B6{{0, 0, 0, -1, -1, -1}}), all((size_t)most_b * np);
+      for (size_t q = 0; q < boxes.size(); ++q)
+        for (int d = 0; d < 3; ++d) { send[q].v[d] = boxes[q].smallEnd(d); send[q].v[3 + d] = boxes[q].bigEnd(d); }
+      lbx_check(lbx_par_allgather(send.data(), sizeof(B6) * (size_t)most_b, all.data()), "TagBoxArray::collate");
+      boxes.clear();
+      for (int r = 0; r < np; ++r)
+        for (long long q = 0; q < counts[2 * r + 1]; ++q) {
+          const B6& e = all[(size_t)r * most_b + q];
+          boxes.push_back(Box(IntVect(e.v[0], e.v[1], e.v[2]), IntVect(e.v[3], e.v[4], e.v[5])));
+        }
+    }
   }
-  if (runs.empty()) return;
-  IntVect blo(runs[0].i0, runs[0].j, runs[0].k), bhi(runs[0].i1, runs[0].j, runs[0].k);
-  for (const Run& r : runs) {
-    blo[0] = std::min(blo[0], r.i0); bhi[0] = std::max(bhi[0], r.i1);
-    blo[1] = std::min(blo[1], r.j);  bhi[1] = std::max(bhi[1], r.j);
-    blo[2] = std::min(blo[2], r.k);  bhi[2] = std::max(bhi[2], r.k);
-  }
+  if (runs.empty() && boxes.empty()) return;
+  IntVect blo, bhi;
+  bool have = false;
+  auto widen = [&](const IntVect& lo, const IntVect& hi) {
+    if (!have) { blo = lo; bhi = hi; have = true; return; }
+    for (int d = 0; d < 3; ++d) { blo[d] = std::min(blo[d], lo[d]); bhi[d] = std::max(bhi[d], hi[d]); }
+  };
+  for (const Run& r : runs) widen(IntVect(r.i0, r.j, r.k), IntVect(r.i1, r.j, r.k));
+  for (const Box& b : boxes) widen(b.smallEnd(), b.bigEnd());
   const Box bb(blo, bhi);
   const size_t wpr = ((size_t)bb.length(0) + 63) / 64, ny = (size_t)bb.length(1), nz = (size_t)bb.length(2);
   std::vector<uint64_t> bits(wpr * ny * nz, 0);
@@ -311,6 +408,9 @@ void TagBoxArray::collate(std::vector<TagRun>& out, const Box& domain, const std
     }
   };
   for (const Run& r : runs) range(r.i0 - blo[0], r.i1 - blo[0], r.j, r.k, true);
+  for (const Box& b : boxes)
+    for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
+      for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j) range(b.smallEnd(0) - blo[0], b.bigEnd(0) - blo[0], j, k, true);
   if (remove)
     for (const Box& q : *remove) {
       const Box r = q & bb;
