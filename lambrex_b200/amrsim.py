@@ -14,7 +14,8 @@ import numpy as np
 from . import lbx as _lbx
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblambrex.so")
+# LBX_LIB_DIR: a build variant of the native libraries next to _lib (tuning experiments: make OUT=../_lib_x RO=...)
+LIB_PATH = os.path.join(_HERE, os.environ.get("LBX_LIB_DIR", "_lib"), "liblambrex.so")
 NL_DENSITY, NL_VELOCITY = -1.0, -3e8
 DISTFN, DENSITY, VELOCITY, DISTFN_NEXT, FINE_MASK = range(5)
 TAG_CLEAR, TAG_BUF, TAG_SET = 0, 1, 2

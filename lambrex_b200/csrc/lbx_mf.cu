@@ -805,7 +805,15 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   const int nd = (int)p->dsts.size();
 #define LBX_PLAN_LAUNCH(T, ADD, NC) \
   lbx::k_plan_apply<T, ADD, NC, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp)
-  if (dst->dtype == LBX_F64) {
+  if (dst->dtype == LBX_F64 && p->has_avg) {
+    // averaging plans (sum_fine_to_coarse fused, average_down): 8 fine cells per coarse value -- component-parallel
+    // launch, one thread per (cell, component), or a 15-component thread sits on 60 dependent 16-byte loads
+    const dim3 gridc = lbx::mf_grid(p->max_cells, nd, 0, dst->ncomp);
+    if (op == LBX_OP_COPY)
+      lbx::k_plan_apply<double, false, 1, true><<<gridc, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+    else
+      lbx::k_plan_apply<double, true, 1, true><<<gridc, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp);
+  } else if (dst->dtype == LBX_F64) {
     if (dst->ncomp == LBX_NV) {          // the populations: compile-time component count
       if (op == LBX_OP_COPY) LBX_PLAN_LAUNCH(double, false, LBX_NV);
       else LBX_PLAN_LAUNCH(double, true, LBX_NV);
@@ -927,7 +935,7 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
   const bool remote = plan && ((src0 && src0->dist) || (src1 && src1->dist) || (src1b && src1b->dist));
   if (remote && lbx::par_barrier()) return 1;
   // the row-owner kernel needs a ghost source, tight fabs with even rows, and a row buffer that fits shared memory
-  int ro_warps = 8;
+  int ro_warps = lbx::RO_THREADS / 32;
   const int ro_pitch = dst->max_n0 + 4;          // even; the row buffer keeps a zero pad on either side of the row
   while (ro_warps > 1 && (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) > 199 * 1024) ro_warps >>= 1;
   bool small = true;                 // 32-bit element offsets inside every fab the kernel touches

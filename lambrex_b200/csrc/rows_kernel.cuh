@@ -29,7 +29,10 @@
 
 namespace lbx {
 
-constexpr int RO_THREADS = 256;
+#ifndef LBX_RO_THREADS
+#define LBX_RO_THREADS 128
+#endif
+constexpr int RO_THREADS = LBX_RO_THREADS;      // threads per CTA = 32 x source rows per CTA (128 x 6 CTAs/SM measured best: profiles/r02_row_kernel.md)
 
 struct ROPlan {                // FillPatch sources resolved per ghost cell
   const int2* tab;             // x = kind | src_fab << 2 (kind: 0 none, 1 same level COPY, 2 coarse PC), y = source cell offset
@@ -159,7 +162,7 @@ __device__ __forceinline__ unsigned axis_sel(int axis_is, int v, int n, int lo, 
 // sm[p * pitch + n0] are zero pads, so that the ring-2 destination cells x = 0 and x = n0 - 1 come out as 0 without a
 // test: they read the pad, or a ghost value phase 1 has already zeroed because it has no destination.
 #ifndef LBX_RO_MIN_CTAS
-#define LBX_RO_MIN_CTAS 3
+#define LBX_RO_MIN_CTAS 6
 #endif
 template <class C, int MODE, bool ZI>
 __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROArgs a) {

@@ -796,11 +796,14 @@ void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& 
 // nGrow/ratio ghost cells (one search-free kernel), (2) ParallelCopy that temporary into the coarse
 // valid cells with ADD and periodic wrap (src_ng = its ghosts, dst_ng = 0): a coarse cell under
 // the ghost overlap of neighbouring fine boxes receives every contribution, in ParallelCopy order.
-// Default (fused): ONE gather -- the ParallelCopy's descriptors with kind AVG instead of COPY, applied with ADD
-// straight from the fine level: a coarse cell forms the mean of the 8 fine cells of each contribution in
-// registers (amrex_avgdown's summation order) and adds them in the same list order, so the result is
-// bit-identical to the two steps while the coarsened temporary is never written or read.
-namespace { bool g_sum_fused = true; }
+// Optional (fused, SetSumFineToCoarseFused): ONE gather -- the ParallelCopy's descriptors with kind AVG instead of
+// COPY, applied with ADD straight from the fine level: a coarse cell forms the mean of the 8 fine cells of each
+// contribution in registers (amrex_avgdown's summation order) and adds them in the same list order, so the result
+// is bit-identical to the two steps while the coarsened temporary is never written or read.  MEASURED SLOWER
+// (profiles/r02_launches_amr_2level_128.md: 282 us against 73 + 101 us at 128^3): every thread walks the whole
+// descriptor list of its coarse box (ADD cannot stop at the first match) with eight times the loads behind each
+// match, so the default stays with the two search-light steps.
+namespace { bool g_sum_fused = false; }
 void SetSumFineToCoarseFused(bool on) { g_sum_fused = on; }
 
 void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, const IntVect& ratio,

@@ -677,7 +677,6 @@ void AmrSim::FineCollide(int const level) {
 
 // src/AmrSim.cpp:592-602
 void AmrSim::SumFromFine(int const coarse_level) {
-  amrex::SetSumFineToCoarseFused(rohde_fused);      // the literal pass sequence keeps AMReX's two steps
   amrex::sum_fine_to_coarse(levels[coarse_level + 1].now.get<DistFn>(), levels[coarse_level].next.get<DistFn>(), 0, NMODES,
                             refRatio(coarse_level), geom[coarse_level], geom[coarse_level + 1]);
 }

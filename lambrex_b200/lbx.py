@@ -23,7 +23,8 @@ IPC_HANDLE_BYTES = 64
 FACE_XP, FACE_XM, FACE_YP, FACE_YM, FACE_ZP, FACE_ZM = range(6)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblbx.so")
+# LBX_LIB_DIR: a build variant of the native libraries next to _lib (tuning experiments: make OUT=../_lib_x RO=...)
+LIB_PATH = os.path.join(_HERE, os.environ.get("LBX_LIB_DIR", "_lib"), "liblbx.so")
 
 
 class LbxError(RuntimeError):
