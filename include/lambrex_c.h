@@ -112,6 +112,10 @@ int lbx_sim_get_extent(const lbx_sim *sim, int level, int lo[3], int hi[3]);
 /* SetStaticRefinement / UnsetStaticRefinement (:150-152) */
 int lbx_sim_set_static_refinement(lbx_sim *sim, int level, const int lo[3], const int hi[3]);
 int lbx_sim_unset_static_refinement(lbx_sim *sim, int level);
+/* addition: record the static box of `level` without regridding, then regrid every level once from level 0
+ * (moving the boxes of an L-level hierarchy costs one regrid instead of L) */
+int lbx_sim_set_static_box(lbx_sim *sim, int level, const int lo[3], const int hi[3]);
+int lbx_sim_regrid_all(lbx_sim *sim);
 /* AmrCore: maxLevel, finestLevel, refRatio, boxArray(level) */
 int lbx_sim_max_level(const lbx_sim *sim);
 int lbx_sim_finest_level(const lbx_sim *sim);

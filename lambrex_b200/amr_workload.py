@@ -67,7 +67,8 @@ def run_amr_case(n, levels, steps, warmup=3, coupling="rohde", regrid_every=0, m
         # one untimed regrid: the steady state of a periodically regridding run reuses the device blocks (and,
         # distributed, the CUDA-IPC mappings) the previous regrid released
         for lev, (lo, hi) in enumerate(static_boxes(n, levels, shift=2)):
-            sim.SetStaticRefinement(lev, lo, hi)
+            sim.SetStaticBox(lev, lo, hi)
+        sim.Regrid()
         sim.Iterate(1)
         lbx.sync()
     if dist:
@@ -89,7 +90,8 @@ def run_amr_case(n, levels, steps, warmup=3, coupling="rohde", regrid_every=0, m
                     r0 = time.perf_counter()
                     regrids += 1
                     for lev, (lo, hi) in enumerate(static_boxes(n, levels, shift=regrids % 3)):
-                        sim.SetStaticRefinement(lev, lo, hi)
+                        sim.SetStaticBox(lev, lo, hi)       # every level's box moves, then ONE regrid from level 0
+                    sim.Regrid()
                     regrid_host_s += time.perf_counter() - r0
         else:
             sim.Iterate(steps)

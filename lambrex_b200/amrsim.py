@@ -43,6 +43,7 @@ SYMBOLS = {
     "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
     "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
     "lbx_sim_plan_cache_size": (_i, []),
+    "lbx_sim_set_static_box": (_i, [_vp, _i, _ip, _ip]), "lbx_sim_regrid_all": (_i, [_vp]),
     "lbx_sim_set_initial_density_profile": (_i, [_vp, _i, _dp, _sz]),
     "lbx_sim_set_initial_velocity_profile": (_i, [_vp, _i, _dp, _sz]),
     "lbx_sim_local_box": (_i, [_vp, _ip, _ip]),
@@ -209,6 +210,13 @@ class AmrSim:
         """ROHDE (default, the reference's live path) or SUBCYCLE (conventional subcycling with
         time-interpolated FillPatch and average_down)."""
         _check(lib().lbx_sim_set_coupling(self._h, int(coupling)))
+
+    def SetStaticBox(self, level, lo, hi):
+        """record the static box of `level` without regridding (Regrid() then regrids every level once)"""
+        _check(lib().lbx_sim_set_static_box(self._h, level, _i3(*lo), _i3(*hi)))
+
+    def Regrid(self):
+        _check(lib().lbx_sim_regrid_all(self._h))
 
     def SetGradientRefinement(self, level, threshold):
         _check(lib().lbx_sim_set_gradient_refinement(self._h, level, float(threshold)))

@@ -64,6 +64,7 @@ void arena_free(void* p);
 void arena_release();                                    // cudaFree every cached block
 void arena_stats(size_t* in_use, size_t* cached, uint64_t* hits, uint64_t* misses);
 // distributed helpers (lbx_abi.cu)
+int step_wait_launch(unsigned long long value);         // one-thread wait for both neighbours' step flags (lbx_abi.cu)
 int par_barrier();                                       // device-side all-rank barrier on the current stream
 int par_allgather(const void* send, size_t bytes, void* recv);   // host, through the registered callback
 int ipc_open_cached(const unsigned char* handle, void** base);   // cudaIpcOpenMemHandle, once per handle

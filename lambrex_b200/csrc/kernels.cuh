@@ -194,6 +194,7 @@ struct SlabSync {
   unsigned long long nboundary;       // CTAs of the boundary planes
   unsigned long long timeout_ns;
   int* err;                           // host-mapped: set on timeout (sticky)
+  int ilv_shift;                      // every 2^ilv_shift-th row at the start of the grid is a boundary row (0: all first)
 };
 
 // one cell of the slab step (the body of k_collide_stream_slab), shared by the two code paths below
@@ -240,17 +241,34 @@ __device__ __forceinline__ void slab_cell(const DFab& src, const DFab& dst, cons
 template <class C>
 __global__ void __launch_bounds__(BX) k_collide_stream_slab_sync(DFab src, DFab dst, DFab dn, DFab up, DBox box,
                                                                  DDom dom, double omega_s, double omega_b, SlabSync sy) {
-  const int z = blockIdx.z;
+  // Row order of the launch (rows = (j, k) pairs, dispatched in blockIdx.y + ny * blockIdx.z order): the rows of the two
+  // boundary planes are INTERLEAVED with interior rows, one in every 2^ilv_shift, over about the first half of the
+  // grid instead of all coming first.  Their CTAs store 5 populations per cell over NVLink, which moves those 84 MB
+  // (1024^2 planes) at ~300 GB/s: bunched together they hold every CTA slot of the GPU while the link drains and the
+  // local HBM idles (0.3 ms per step, profiles/r02_scale.md); spread thin, the link runs at a few per cent duty
+  // beside the bandwidth-bound interior rows.  The signal leaves at about half of the step.
+  const int ny = box.hi[1] - box.lo[1] + 1, nzl = box.hi[2] - box.lo[2] + 1;
+  const int nb = (nzl < 2 ? nzl : 2) * ny;                  // boundary rows
+  const int r = (int)blockIdx.y + ny * (int)blockIdx.z;     // position in dispatch order
   const int i = box.lo[0] + blockIdx.x * BX + threadIdx.x;
-  const int j = box.lo[1] + blockIdx.y;
-  if (z >= 2) {
+  int rb = -1, ri;
+  if (nzl <= 2) rb = r;                                     // nothing but boundary rows
+  else if (sy.ilv_shift == 0) { if (r < nb) rb = r; else ri = r - nb; }   // thin slab: too few interior rows to interleave
+  else if (r < (nb << sy.ilv_shift)) {
+    if ((r & ((1 << sy.ilv_shift) - 1)) == 0) rb = r >> sy.ilv_shift;
+    else ri = r - (r >> sy.ilv_shift) - 1;
+  } else ri = r - nb;
+  if (rb < 0) {
     // interior planes: exactly the plain slab step (own copy of the code, so that the synchronisation below does not
     // cost the bandwidth-bound path its uniform-datapath address arithmetic -- measured 6 % otherwise)
     if (i > box.hi[0]) return;
-    slab_cell<C>(src, dst, dn, up, box, dom, omega_s, omega_b, i, j, box.lo[2] + (z - 1));
+    const int kq = ri / ny;
+    slab_cell<C>(src, dst, dn, up, box, dom, omega_s, omega_b, i, box.lo[1] + (ri - kq * ny), box.lo[2] + 1 + kq);
     return;
   }
-  const int k = z == 0 ? box.lo[2] : box.hi[2];
+  const int kb = rb / ny;
+  const int j = box.lo[1] + (rb - kb * ny);
+  const int k = kb == 0 ? box.lo[2] : box.hi[2];
   if (sy.wait_a) {
     if (threadIdx.x == 0) {     // (never READ the host-mapped error word here: a zero-copy read costs a PCIe round trip per CTA)
       unsigned long long t0, t;
@@ -271,10 +289,12 @@ __global__ void __launch_bounds__(BX) k_collide_stream_slab_sync(DFab src, DFab 
   }
   if (i <= box.hi[0]) slab_cell<C>(src, dst, dn, up, box, dom, omega_s, omega_b, i, j, k);
   if (sy.sig_a) {
-    __threadfence_system();            // this thread's stores (local and remote) before the CTA's arrival below
+    // the CTA's stores (local and remote) are ordered before its arrival below: barrier, then ONE system-scope fence
+    // by the arriving thread, which is cumulative over the writes it observes through the barrier (the pattern of
+    // cooperative-groups grid synchronisation); a fence per thread made every boundary CTA wait out 128 of them
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence_system();          // cumulative over the CTA's stores observed through the barrier
+      __threadfence_system();
       const unsigned long long done = atomicAdd(sy.counter, 1ull) + 1ull;
       if (done == sy.nboundary) {      // the last boundary CTA of this launch: every face store has been fenced
         *sy.counter = 0ull;

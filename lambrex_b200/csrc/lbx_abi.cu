@@ -425,7 +425,7 @@ int lbx_set_option(int key, int value) {
       lbx::g_align_rows = value == 1 ? 4 : value;
       return 0;
     case LBX_OPT_VALID_TILING: lbx::g_valid_linear = (value != 0); return 0;
-    case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 3; return 0;
+    case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 7; return 0;
     case LBX_OPT_ROW_KERNEL: lbx::g_row_kernel = (value != 0); return 0;
     default: return fail("lbx_set_option: unknown key");
   }
@@ -617,6 +617,15 @@ int lbx_peer_wait(const uint64_t* a, const uint64_t* b, uint64_t value, uint64_t
                                        reinterpret_cast<const unsigned long long*>(b), value, timeout_ns, derr);
   return after_launch("lbx_peer_wait");
 }
+}  // extern "C"
+// queue a one-thread wait until both neighbours have published `value` (lbx_mf_collide_stream_slab, lbx_mf.cu)
+int lbx::step_wait_launch(unsigned long long value) {
+  int* derr = nullptr;
+  LBX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&derr), g.peer_err, 0));
+  lbx::k_peer_wait<<<1, 1, 0, g.cur>>>(g.step_flags, g.step_flags + 1, value, 30000000000ull, derr);
+  return after_launch("lbx_mf_collide_stream_slab (neighbour wait)");
+}
+extern "C" {
 int lbx_par_step_finish(void) {
   LBX_NEED_INIT();
   if (g.world == 1) return 0;

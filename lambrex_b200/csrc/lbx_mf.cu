@@ -538,8 +538,12 @@ int lbx_mf_collide_stream_slab(const lbx_mf* now, lbx_mf* next, const lbx_domain
   if (g.world > 1) {
     // flags: [0] is written by the rank below, [1] by the rank above (ctx.h); this rank is "above" its lower
     // neighbour and "below" its upper neighbour
-    sy.wait_a = g.step_flags;
-    sy.wait_b = g.step_flags + 1;
+    // the wait for the neighbours' previous step is a one-thread launch ahead of the step (they publish at the START of
+    // their step, so it returns at once); folded into the kernel it made each of the 2 x 8192 boundary CTAs at 1024^2
+    // poll system-scope flags and cost 0.4 ms per step (profiles/r02_scale_n8.md).  The SIGNAL stays in the kernel.
+    if (lbx::step_wait_launch(g.step_epoch)) return 1;
+    sy.wait_a = nullptr;
+    sy.wait_b = nullptr;
     sy.wait_value = g.step_epoch;
     sy.sig_a = g.peer_flag_base[dn] + g.step_off + 1;
     sy.sig_b = g.peer_flag_base[up] + g.step_off + 0;
@@ -548,8 +552,11 @@ int lbx_mf_collide_stream_slab(const lbx_mf* now, lbx_mf* next, const lbx_domain
     sy.timeout_ns = 30000000000ull;
     LBX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&sy.err), g.peer_err, 0));
   }
-  L().collide_stream_slab_sync(g.cur, dfab_of(S), dfab_of(D), dfab_of(next->host[dn]), dfab_of(next->host[up]), box, dd, omega_s,
-                               omega_b, sy);
+  // PROFILING ONLY (LBX_OPT_DEBUG_SKIP bit 2, results are wrong): the face-crossing populations stay in this rank's own
+  // fab instead of going to the neighbours over NVLink -- isolates the cost of the remote stores
+  const bool local_faces = (lbx::g_debug_skip & 4) != 0;
+  L().collide_stream_slab_sync(g.cur, dfab_of(S), dfab_of(D), dfab_of(local_faces ? D : next->host[dn]),
+                               dfab_of(local_faces ? D : next->host[up]), box, dd, omega_s, omega_b, sy);
   return lbx::after_launch(what);
 }
 

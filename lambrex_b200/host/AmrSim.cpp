@@ -850,6 +850,16 @@ void AmrSim::SetStaticRefinement(int const level, const std::array<int, NDIMS>& 
               << " s, MakeFineMask " << std::chrono::duration<double>(std::chrono::steady_clock::now() - T1).count() << " s\n";
 }
 
+void AmrSim::SetStaticBox(int const level, const std::array<int, NDIMS>& lo_corner, const std::array<int, NDIMS>& hi_corner) {
+  static_tags.at(level).define(Box(IntVect(lo_corner), IntVect(hi_corner)));
+}
+void AmrSim::Regrid() {
+  if (max_level == 0) return;
+  ++num_regrids;
+  regrid(0, GetTime(0));
+  for (int l = 0; l < finest_level; ++l) MakeFineMask(l);
+}
+
 // src/AmrSim.cpp:1011-1017
 void AmrSim::UnsetStaticRefinement(int const level) {
   static_tags.at(level).clear();

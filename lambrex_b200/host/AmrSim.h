@@ -124,6 +124,12 @@ class AmrSim : public amrex::AmrCore {
   void SetGradientRefinement(int const level, double const threshold);
   void UnsetGradientRefinement(int const level);
   void SetRegridInterval(int const n) { regrid_int = n; }
+  // Static boxes of several levels changed together: SetStaticRefinement regrids at once, level by level (the
+  // reference, src/AmrSim.cpp:995-1009), so moving the boxes of an L-level hierarchy costs L regrids.
+  // SetStaticBox records the box of `level` WITHOUT regridding; Regrid() then regrids every level from 0 once
+  // (AmrCore::regrid(0, t)) and rebuilds the fine masks.
+  void SetStaticBox(int const level, const std::array<int, NDIMS>& lo_corner, const std::array<int, NDIMS>& hi_corner);
+  void Regrid();
   int NumRegrids() const { return num_regrids; }
   enum class Coupling { ROHDE = 0, SUBCYCLE = 1 };
   void SetCoupling(Coupling c) { coupling = c; }

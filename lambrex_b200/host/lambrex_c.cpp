@@ -195,6 +195,10 @@ int lbx_sim_get_extent(const lbx_sim* sim, int level, int lo[3], int hi[3]) {
 int lbx_sim_set_static_refinement(lbx_sim* sim, int level, const int lo[3], const int hi[3]) {
   return guarded([&] { sim->s.SetStaticRefinement(level, {{lo[0], lo[1], lo[2]}}, {{hi[0], hi[1], hi[2]}}); });
 }
+int lbx_sim_set_static_box(lbx_sim* sim, int level, const int lo[3], const int hi[3]) {
+  return guarded([&] { sim->s.SetStaticBox(level, {{lo[0], lo[1], lo[2]}}, {{hi[0], hi[1], hi[2]}}); });
+}
+int lbx_sim_regrid_all(lbx_sim* sim) { return guarded([&] { sim->s.Regrid(); }); }
 int lbx_sim_unset_static_refinement(lbx_sim* sim, int level) {
   return guarded([&] { sim->s.UnsetStaticRefinement(level); });
 }

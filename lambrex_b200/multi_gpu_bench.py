@@ -45,6 +45,9 @@ def run_multi(args, helpers):
         fits = torch.tensor([1 if need(n) < info["free_bytes"] else 0])
         dist.all_reduce(fits, op=dist.ReduceOp.MIN)
     nx = ny = nz = n
+    if args.grid_multi_z:
+        nz = args.grid_multi_z
+    lbx.set_option(lbx.OPT_DEBUG_SKIP, args.debug_skip)
     cells_total = float(nx) * ny * nz
     prof = U * np.sin(2.0 * np.pi * np.arange(ny, dtype=np.float64) / ny)
     u_profile = np.zeros((ny, 3))

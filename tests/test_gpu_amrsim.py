@@ -321,6 +321,33 @@ def test_three_level_shear_matches_oracle(coracle):
     assert (sim.GetTime(2), sim.GetTimeStep(2)) == (o.levels[2].time, o.levels[2].step)
 
 
+def test_static_boxes_of_all_levels_moved_with_one_regrid(coracle):
+    """SetStaticBox (record only) on every level + ONE Regrid() from level 0: the same AmrCore::regrid(0, t) the
+    oracle runs with both boxes set -- box lists, populations and clocks agree, before and after moving the boxes."""
+    nx = ny = nz = 16
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    sim, o = make_pair(nx, ny, nz, 2, 0.5, coracle, rho=rho, u=u)
+    for s, setf in ((sim, sim.SetStaticRefinement), (o, o.set_static_refinement)):
+        setf(0, (3, 3, 3), (12, 12, 12))
+        setf(1, (10, 10, 10), (21, 21, 21))
+    sim.Iterate(1)
+    o.iterate(1)
+    sim.SetStaticBox(0, (4, 3, 4), (13, 12, 13))
+    sim.SetStaticBox(1, (12, 10, 12), (23, 21, 23))
+    sim.Regrid()
+    o.static_tags[0] = ao.bx((4, 3, 4), (13, 12, 13))
+    o.static_tags[1] = ao.bx((12, 10, 12), (23, 21, 23))
+    o.regrid(0, o.levels[0].time)
+    for lev in range(o.finest_level):
+        o.make_fine_mask(lev)
+    assert sim.finestLevel() == 2 == o.finest_level
+    for lev in (1, 2):
+        assert sim.boxArray(lev) == o.grids[lev]
+    sim.Iterate(2)
+    o.iterate(2)
+    compare_levels(sim, o, (0, 1, 2))
+
+
 @pytest.mark.parametrize("tiling", [4, 0, 1, 2, 3])
 @pytest.mark.parametrize("max_level", [1, 2])
 def test_fused_rohde_cycle_equals_literal_pass_sequence(max_level, tiling):
