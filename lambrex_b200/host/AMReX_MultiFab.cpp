@@ -488,6 +488,7 @@ class BoxHash {
  public:
   explicit BoxHash(const std::vector<Box>& boxes) : boxes_(boxes) {
     bin_ = IntVect(1);
+    for (size_t i = 0; i < boxes.size(); ++i) bound_ = i ? bound_.minBox(boxes[i]) : boxes[i];
     for (const Box& b : boxes)
       for (int d = 0; d < 3; ++d) bin_[d] = std::max(bin_[d], b.length(d));
     for (size_t i = 0; i < boxes.size(); ++i) {
@@ -495,10 +496,13 @@ class BoxHash {
       map_[key(c)].push_back((int)i);
     }
   }
+  // bounding box of all boxes: a query outside it is empty -- what lets the plan builders skip 26 of the 27
+  // periodic shifts for every region that is not near a domain face
+  bool mayIntersect(const Box& q) const { return !boxes_.empty() && q.ok() && bound_.intersects(q); }
   // indices (ascending) of boxes intersecting q
   std::vector<int> query(const Box& q) const {
     std::vector<int> r;
-    if (!q.ok()) return r;
+    if (!mayIntersect(q)) return r;
     IntVect lo = cell(q.smallEnd()), hi = cell(q.bigEnd());
     for (int d = 0; d < 3; ++d) lo[d] -= 1;      // a box registered by its low corner may start one bin earlier
     for (int k = lo[2]; k <= hi[2]; ++k)
@@ -522,6 +526,7 @@ class BoxHash {
            (uint64_t)(uint32_t)(c[2] + (1 << 20));
   }
   const std::vector<Box>& boxes_;
+  Box bound_;
   IntVect bin_;
   std::unordered_map<uint64_t, std::vector<int>> map_;
 };

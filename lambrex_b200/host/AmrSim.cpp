@@ -813,21 +813,36 @@ void AmrSim::MakeNewLevelFromCoarse(int level, double time, const BoxArray& ba, 
 // leaves NEXT on the old BoxArray, which breaks the following step whenever the grids really
 // changed; NEXT is redefined on the new BoxArray here.
 void AmrSim::RemakeLevel(int level, double time, const BoxArray& ba, const DistributionMapping& dm) {
+  auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!getenv("LBX_HOST_TIMING")) return;
+    const auto T1 = std::chrono::steady_clock::now();
+    std::cerr << "    [RemakeLevel " << level << "] " << what << " " << std::chrono::duration<double>(T1 - T0).count() << " s\n";
+    T0 = T1;
+  };
   auto& lvl = levels[level];
   const Layout lay = lvl.now.get<DistFn>().empty() ? Layout::BOXES : lvl.now.get<DistFn>().layout();
   MultiFab new_u(ba, dm, NDIMS, 0, lay);
   MultiFab new_f = field_traits<DistFn>::MakeLevelData(ba, dm, lay);
   MultiFab new_rho = field_traits<Density>::MakeLevelData(ba, dm, lay);
+  lap("allocate u, f, rho");
   DistFnFillPatch(level, new_f);
+  lap("FillPatch (plan + launch)");
   auto& state = lvl.now;
   std::swap(new_f, state.get<DistFn>());
   std::swap(new_rho, state.get<Density>());
   std::swap(new_u, velocity[level]);
   lvl.next.Define(ba, dm, lay);
   stream_scratch[level].clear();
+  lap("swap, redefine NEXT, clear scratch");
   lvl.time.current = time;
   CalcHydroVars(level);
   if (level < finest_level) MakeFineMask(level);
+  lap("moments, fine mask");
+  new_f.clear();
+  new_rho.clear();
+  new_u.clear();
+  lap("release the old level");
 }
 
 // src/AmrSim.cpp:746-751
