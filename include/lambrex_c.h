@@ -32,6 +32,10 @@ int lbx_sim_set_parallel_view(int rank, int nranks);   /* testing aid: ownership
 int lbx_sim_owner(const lbx_sim *sim, int level, int box, int *rank);   /* DistributionMap(level)[box] */
 const char *lbx_sim_last_error(void);
 
+/* addition: allow non-periodic directions = solid no-slip walls (half-way bounce-back) on the
+ * uniform single-GPU path; process-wide, call before lbx_sim_create.  Default 0: non-periodic input fails like the
+ * reference's constructor aborts (src/AmrSim.cpp:788-797). */
+int lbx_sim_allow_walls(int on);
 /* AmrSim::AmrSim (include/AmrSim.h:128-129) */
 int lbx_sim_create(int nx, int ny, int nz, int max_level, const int periodicity[3], double tau_s,
                    double tau_b, lbx_sim **out);
@@ -102,6 +106,8 @@ int lbx_sim_get_linear_moment_field(const lbx_sim *sim, int level, const double 
 /* addition (the reference has no I/O): checkpoint of clocks, tau ladder, refinement criteria,
  * box lists and valid-cell populations; read into a sim created with the same extents and max level.  A
  * restarted run continues bit for bit. */
+/* addition: AMReX-format plotfile directory (Header, Level_l/Cell_H, Cell_D_00000) with rho, ux, uy, uz of every level */
+int lbx_sim_write_plotfile(lbx_sim *sim, const char *dir);
 int lbx_sim_write_checkpoint(lbx_sim *sim, const char *path);
 int lbx_sim_read_checkpoint(lbx_sim *sim, const char *path);
 /* GetTime, GetTimeStep, GetDims, GetExtent (:130-139, 154) */

@@ -46,9 +46,13 @@ enum { LBX_F64 = 0, LBX_I32 = 1 };
 
 typedef struct lbx_box { int32_t lo[3], hi[3]; } lbx_box;   /* inclusive */
 
-typedef struct lbx_domain {   /* index domain of a level + periodicity flags */
-  int32_t lo[3], hi[3], periodic[3];
+typedef struct lbx_domain {   /* index domain of a level + per-direction boundary treatment */
+  int32_t lo[3], hi[3];
+  int32_t periodic[3];        /* 1: periodic wrap; 0: the fab carries ghost cells in that direction;
+                                 2 (lbx_collide_stream, push scheme only): solid no-slip walls at both domain faces,
+                                 half-way bounce-back -- an addition, the reference aborts on non-periodic directions */
 } lbx_domain;
+enum { LBX_BC_GHOSTS = 0, LBX_BC_PERIODIC = 1, LBX_BC_WALL = 2 };
 
 /* options for lbx_set_option */
 enum {

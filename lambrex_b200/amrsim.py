@@ -42,7 +42,8 @@ SYMBOLS = {
     "lbx_sim_get_linear_moment_field": (_i, [_vp, _i, _dp, _i, _i, _d, _dp, _sz]),
     "lbx_sim_set_gradient_refinement": (_i, [_vp, _i, _d]), "lbx_sim_unset_gradient_refinement": (_i, [_vp, _i]),
     "lbx_sim_set_regrid_interval": (_i, [_vp, _i]), "lbx_sim_num_regrids": (_i, [_vp]),
-    "lbx_sim_plan_cache_size": (_i, []),
+    "lbx_sim_plan_cache_size": (_i, []), "lbx_sim_allow_walls": (_i, [_i]),
+    "lbx_sim_write_plotfile": (_i, [_vp, ctypes.c_char_p]),
     "lbx_sim_set_static_box": (_i, [_vp, _i, _ip, _ip]), "lbx_sim_regrid_all": (_i, [_vp]),
     "lbx_sim_set_initial_density_profile": (_i, [_vp, _i, _dp, _sz]),
     "lbx_sim_set_initial_velocity_profile": (_i, [_vp, _i, _dp, _sz]),
@@ -151,6 +152,12 @@ def make_allgather_hook(group=None):
     return cb
 
 
+def allowWalls(on=True):
+    """Non-periodic directions become solid no-slip walls (half-way bounce-back) instead of aborting like the
+    reference; uniform single-GPU path only.  Process-wide; call before constructing AmrSim."""
+    _check(lib().lbx_sim_allow_walls(int(bool(on))))
+
+
 def setParallelView(rank, nranks):
     _check(lib().lbx_sim_set_parallel_view(rank, nranks))
 
@@ -210,6 +217,10 @@ class AmrSim:
         """ROHDE (default, the reference's live path) or SUBCYCLE (conventional subcycling with
         time-interpolated FillPatch and average_down)."""
         _check(lib().lbx_sim_set_coupling(self._h, int(coupling)))
+
+    def WritePlotFile(self, directory):
+        """AMReX-format plotfile (rho, ux, uy, uz of every level on its boxes)"""
+        _check(lib().lbx_sim_write_plotfile(self._h, str(directory).encode()))
 
     def SetStaticBox(self, level, lo, hi):
         """record the static box of `level` without regridding (Regrid() then regrids every level once)"""

@@ -48,7 +48,15 @@ constexpr int BX = 128;   // threads per CTA along x
 // Directions flagged periodic wrap inside the kernel (no ghost cells needed);
 // other directions index straight into ghost planes of the fab.
 // ---------------------------------------------------------------------------
-template <class C, bool PUSH>
+// opposite population: c_opp(p) = -c_p (1<->2, 3<->4, 5<->6, 7<->14, 8<->13, 9<->12, 10<->11)
+__host__ __device__ constexpr int opp(int p) { return p == 0 ? 0 : p < 7 ? (p & 1 ? p + 1 : p - 1) : 21 - p; }
+
+// dom.periodic[d]: 1 = periodic wrap, 0 = the fab carries ghost cells in that direction, 2 = solid no-slip WALLS at both
+// domain faces (half-way bounce-back; addition -- the reference's constructor aborts on non-periodic directions,
+// src/AmrSim.cpp:788-797, and leaves DistFnFillShim :346-357 as the hook): a population that would leave the domain
+// through a wall returns to its own cell with the opposite velocity, f'(x, opp(p)) = f*(x, p).  WALLS selects the code
+// path at compile time so that the periodic kernel is unchanged.
+template <class C, bool PUSH, bool WALLS = false>
 __global__ void __launch_bounds__(BX) k_collide_stream(DFab src, DFab dst, DBox box, DDom dom,
                                                        double omega_s, double omega_b) {
   const int i = box.lo[0] + blockIdx.x * BX + threadIdx.x;
@@ -57,9 +65,9 @@ __global__ void __launch_bounds__(BX) k_collide_stream(DFab src, DFab dst, DBox 
   if (i > box.hi[0]) return;
 
   int ip = i + 1, im = i - 1, jp = j + 1, jm = j - 1, kp = k + 1, km = k - 1;
-  if (dom.periodic[0]) { if (ip > dom.hi[0]) ip = dom.lo[0]; if (im < dom.lo[0]) im = dom.hi[0]; }
-  if (dom.periodic[1]) { if (jp > dom.hi[1]) jp = dom.lo[1]; if (jm < dom.lo[1]) jm = dom.hi[1]; }
-  if (dom.periodic[2]) { if (kp > dom.hi[2]) kp = dom.lo[2]; if (km < dom.lo[2]) km = dom.hi[2]; }
+  if (dom.periodic[0] == 1) { if (ip > dom.hi[0]) ip = dom.lo[0]; if (im < dom.lo[0]) im = dom.hi[0]; }
+  if (dom.periodic[1] == 1) { if (jp > dom.hi[1]) jp = dom.lo[1]; if (jm < dom.lo[1]) jm = dom.hi[1]; }
+  if (dom.periodic[2] == 1) { if (kp > dom.hi[2]) kp = dom.lo[2]; if (km < dom.lo[2]) km = dom.hi[2]; }
 
   const DFab& nb = PUSH ? dst : src;   // the fab accessed at neighbour cells
   const DFab& own = PUSH ? src : dst;  // the fab accessed at (i,j,k)
@@ -92,8 +100,22 @@ __global__ void __launch_bounds__(BX) k_collide_stream(DFab src, DFab dst, DBox 
   }
   C::collide(f, omega_s, omega_b);
   if (PUSH) {
+    if (WALLS) {
+      // which faces of this cell are walls
+      const bool xl = dom.periodic[0] == 2 && i == dom.lo[0], xh = dom.periodic[0] == 2 && i == dom.hi[0];
+      const bool yl = dom.periodic[1] == 2 && j == dom.lo[1], yh = dom.periodic[1] == 2 && j == dom.hi[1];
+      const bool zl = dom.periodic[2] == 2 && k == dom.lo[2], zh = dom.periodic[2] == 2 && k == dom.hi[2];
+      const long long oo = row_off(dst, j, k) + i;
 #pragma unroll
-    for (int p = 0; p < NV; ++p) __stcs(dst.p + p * nsc + off[p], f[p]);
+      for (int p = 0; p < NV; ++p) {
+        const bool out = (cx(p) > 0 && xh) || (cx(p) < 0 && xl) || (cy(p) > 0 && yh) || (cy(p) < 0 && yl) ||
+                         (cz(p) > 0 && zh) || (cz(p) < 0 && zl);
+        __stcs(dst.p + (out ? opp(p) * nsc + oo : p * nsc + off[p]), f[p]);
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < NV; ++p) __stcs(dst.p + p * nsc + off[p], f[p]);
+    }
   } else {
 #pragma unroll
     for (int p = 0; p < NV; ++p) __stcs(dst.p + p * osc + o, f[p]);

@@ -179,11 +179,11 @@ int check_cover(const lbx_fab* f, const lbx_box* b, int grow, const lbx_domain* 
   for (int d = 0; d < 3; ++d) {
     if (b->hi[d] < b->lo[d]) return fail(std::string(what) + ": empty box");
     int lo = b->lo[d] - grow, hi = b->hi[d] + grow;
-    if (dom && dom->periodic[d]) {
+    if (dom && dom->periodic[d]) {      // 1 periodic wrap, 2 walls: neighbours stay inside the domain either way
       // wrapped neighbours stay inside the domain
       if (lo < dom->lo[d]) lo = dom->lo[d];
       if (hi > dom->hi[d]) hi = dom->hi[d];
-      if (grow && (b->lo[d] == dom->lo[d] || b->hi[d] == dom->hi[d])) {
+      if (dom->periodic[d] == 1 && grow && (b->lo[d] == dom->lo[d] || b->hi[d] == dom->hi[d])) {
         // wrap reaches the opposite side of the domain: fab must span it
         if (f->lo[d] > dom->lo[d] || f->lo[d] + f->n[d] - 1 < dom->hi[d])
           return fail(std::string(what) + ": periodic wrap needs a fab spanning the domain");
@@ -568,6 +568,10 @@ int lbx_collide_stream(const lbx_fab* src, const lbx_fab* dst, const lbx_box* bo
   LBX_NEED_INIT();
   if (!dom) return fail("lbx_collide_stream: null domain");
   if (scheme != LBX_PUSH && scheme != LBX_PULL) return fail("lbx_collide_stream: unknown scheme");
+  for (int d = 0; d < 3; ++d) {
+    if (dom->periodic[d] < 0 || dom->periodic[d] > 2) return fail("lbx_collide_stream: periodic[] takes 0 (ghost cells), 1 (periodic) or 2 (walls)");
+    if (dom->periodic[d] == 2 && scheme != LBX_PUSH) return fail("lbx_collide_stream: walls need the push scheme");
+  }
   if (check_fab(src, LBX_NV, LBX_F64, "lbx_collide_stream src") ||
       check_fab(dst, LBX_NV, LBX_F64, "lbx_collide_stream dst"))
     return 1;

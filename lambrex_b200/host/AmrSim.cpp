@@ -1,7 +1,10 @@
 // AmrSim on the GPU: host control flow of the reference's time stepping
 // (/root/reference/src/AmrSim.cpp), every field operation a kernel launch through
 // include/lbx.h.  Reference lines are cited per member.
+#include <algorithm>
+#include <cerrno>
 #include <chrono>
+#include <sys/stat.h>
 #include <cmath>
 #include <cstdlib>
 #include "AmrSim.h"
@@ -45,6 +48,10 @@ double table_entry(bool inverse, int r, int c) {
 }
 }  // namespace
 
+namespace { bool g_allow_walls = false; }
+void AmrSim::AllowWalls(bool on) { g_allow_walls = on; }
+bool AmrSim::WallsAllowed() { return g_allow_walls; }
+
 // src/AmrSim.cpp:1033-1073 (static member definitions)
 const double AmrSim::DELTA[NDIMS][NDIMS] = {{1.0 / NMODES, 0.0, 0.0}, {0.0, 1.0 / NMODES, 0.0}, {0.0, 0.0, 1.0 / NMODES}};
 #define LBX_ROW(I, r) {table_entry(I, r, 0), table_entry(I, r, 1), table_entry(I, r, 2), table_entry(I, r, 3), table_entry(I, r, 4), \
@@ -78,7 +85,10 @@ AmrSim::AmrSim(int const nx, int const ny, int const nz, int const max_ref_level
   gradient_threshold.assign(num_levels, 0.0);
   fine_masks.resize(num_levels);
   for (int d = 0; d < NDIMS; ++d)
-    if (!PERIODICITY[d]) amrex::Abort("Currently only periodic boundary conditions allowed.");
+    if (!PERIODICITY[d]) {
+      if (!WallsAllowed()) amrex::Abort("Currently only periodic boundary conditions allowed.");
+      has_walls = true;            // AllowWalls: this direction is closed by bounce-back walls
+    }
   tau_s.at(0) = tau_s_0;
   tau_b.at(0) = tau_b_0;
   if (!lbx_initialized()) amrex::Abort("AmrSim: call lambrexInit() first (no CUDA context; there is no CPU path)");
@@ -349,6 +359,11 @@ void AmrSim::CollideAndStream(int const level) {
       dom.periodic[d] = geom[level].isPeriodic(d) ? 1 : 0;
     }
     const double omega_s = 1.0 / (tau_s.at(level) + 0.5), omega_b = 1.0 / (tau_b.at(level) + 0.5);
+    if (has_walls) {
+      if (now_f.numStorageFabs() > 1) amrex::Abort("walls are not available in a distributed run");
+      for (int d = 0; d < 3; ++d)
+        if (!geom[level].isPeriodic(d)) dom.periodic[d] = LBX_BC_WALL;
+    }
     if (now_f.numStorageFabs() > 1) {
       // one slab per rank: the FillBoundary between boxes of different GPUs (src/AmrSim.cpp:132) is fused into
       // the step -- boundary-plane CTAs store the face-crossing populations into the neighbours' NEXT over
@@ -360,6 +375,8 @@ void AmrSim::CollideAndStream(int const level) {
       lbx_check(lbx_collide_stream(&src, &dst, &box, &dom, omega_s, omega_b, LBX_PUSH), "CollideAndStream");
     }
     next_f.touch();
+  } else if (has_walls) {
+    amrex::Abort("walls run on the uniform single-GPU path only (level 0 alone, uniform fast path on)");
   } else if (rohde_fused && CanFuseLevelStep(level)) {
     LevelStepFused(level);
   } else {
@@ -708,6 +725,7 @@ void AmrSim::Iterate(int const nsteps) {
       SetLevelLayout(0, PreferredLayout(0));
       IterateLevel(0);
     } else {
+      if (has_walls) amrex::Abort("walls run on the uniform single-GPU path only: no refined levels");
       for (int l = 0; l <= finest_level; ++l) SetLevelLayout(l, Layout::BOXES);
       if (coupling == Coupling::SUBCYCLE) {
         SubCycleAdvance(0);
@@ -911,6 +929,104 @@ struct ChkFile {
   template <class T> T get() { T v; get(&v, sizeof(T)); return v; }
 };
 }  // namespace
+
+void AmrSim::WritePlotFile(const std::string& dir) {
+  if (DistributionMapping::NProcs() > 1) amrex::Abort("WritePlotFile: single-process runs only");
+  auto mkdir_p = [](const std::string& d) {
+    if (::mkdir(d.c_str(), 0755) != 0 && errno != EEXIST) amrex::Abort(("WritePlotFile: cannot create " + d).c_str());
+  };
+  auto boxstr = [](const Box& b) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "((%d,%d,%d) (%d,%d,%d) (0,0,0))", b.smallEnd(0), b.smallEnd(1), b.smallEnd(2), b.bigEnd(0),
+                  b.bigEnd(1), b.bigEnd(2));
+    return std::string(buf);
+  };
+  mkdir_p(dir);
+  const char* names[4] = {"rho", "ux", "uy", "uz"};
+  std::FILE* h = std::fopen((dir + "/Header").c_str(), "w");
+  if (!h) amrex::Abort(("WritePlotFile: cannot open " + dir + "/Header").c_str());
+  std::fprintf(h, "HyperCLaw-V1.1\n4\n");
+  for (const char* n : names) std::fprintf(h, "%s\n", n);
+  std::fprintf(h, "3\n%.17g\n%d\n0 0 0\n1 1 1\n", GetTime(0), finest_level);
+  for (int l = 0; l < finest_level; ++l) std::fprintf(h, "%d ", refRatio(l)[0]);
+  std::fprintf(h, "\n");
+  for (int l = 0; l <= finest_level; ++l) std::fprintf(h, "%s ", boxstr(geom[l].Domain()).c_str());
+  std::fprintf(h, "\n");
+  for (int l = 0; l <= finest_level; ++l) std::fprintf(h, "%d ", GetTimeStep(l));
+  std::fprintf(h, "\n");
+  for (int l = 0; l <= finest_level; ++l) {
+    const Box& d = geom[l].Domain();
+    std::fprintf(h, "%.17g %.17g %.17g\n", 1.0 / d.length(0), 1.0 / d.length(1), 1.0 / d.length(2));
+  }
+  std::fprintf(h, "0\n0\n");
+  for (int l = 0; l <= finest_level; ++l) {
+    CalcHydroVars(l);
+    const MultiFab& rho = levels[l].now.get<Density>();
+    const MultiFab& u = velocity[l];
+    const std::vector<double>& hr = rho.hostMirror();
+    const std::vector<double>& hu = u.hostMirror();
+    const int nb = rho.numStorageFabs();
+    const Box& d = geom[l].Domain();
+    std::fprintf(h, "%d %d %.17g\n%d\n", l, nb, GetTime(l), GetTimeStep(l));
+    for (int s = 0; s < nb; ++s) {
+      const Box b = rho.storageValid(s);
+      for (int a = 0; a < 3; ++a)
+        std::fprintf(h, "%.17g %.17g\n", (double)(b.smallEnd(a) - d.smallEnd(a)) / d.length(a),
+                     (double)(b.bigEnd(a) + 1 - d.smallEnd(a)) / d.length(a));
+    }
+    std::fprintf(h, "Level_%d/Cell\n", l);
+    const std::string ldir = dir + "/Level_" + std::to_string(l);
+    mkdir_p(ldir);
+    std::FILE* fd = std::fopen((ldir + "/Cell_D_00000").c_str(), "wb");
+    if (!fd) amrex::Abort("WritePlotFile: cannot open the FAB file");
+    std::vector<long> offsets(nb);
+    std::vector<double> mins((size_t)nb * 4), maxs((size_t)nb * 4);
+    for (int s = 0; s < nb; ++s) {
+      const Box b = rho.storageValid(s);
+      const size_t n = (size_t)b.numPts();
+      offsets[s] = std::ftell(fd);
+      std::fprintf(fd, "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))%s 4\n", boxstr(b).c_str());
+      // density and velocity have no ghost cells: storage fab s = [comp][z][y][x] over its valid box (x rows may be
+      // padded when row alignment is on: copy row by row)
+      const lbx_fab fr = rho.fabDesc(s), fu = u.fabDesc(s);
+      std::vector<double> comp(n);
+      for (int c = 0; c < 4; ++c) {
+        const std::vector<double>& src = c == 0 ? hr : hu;
+        const lbx_fab& f = c == 0 ? fr : fu;
+        const size_t base = (c == 0 ? rho.storageOffset(s) : u.storageOffset(s)) + (size_t)(c == 0 ? 0 : c - 1) * f.n[0] * f.n[1] * f.n[2];
+        size_t q = 0;
+        for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k)
+          for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j) {
+            const size_t row = base + (size_t)f.n[0] * ((size_t)(j - f.lo[1]) + (size_t)f.n[1] * (size_t)(k - f.lo[2])) + (size_t)(b.smallEnd(0) - f.lo[0]);
+            std::memcpy(&comp[q], &src[row], sizeof(double) * (size_t)b.length(0));
+            q += (size_t)b.length(0);
+          }
+        mins[(size_t)s * 4 + c] = *std::min_element(comp.begin(), comp.end());
+        maxs[(size_t)s * 4 + c] = *std::max_element(comp.begin(), comp.end());
+        if (std::fwrite(comp.data(), sizeof(double), n, fd) != n) amrex::Abort("WritePlotFile: short write");
+      }
+    }
+    std::fclose(fd);
+    std::FILE* ch = std::fopen((ldir + "/Cell_H").c_str(), "w");
+    if (!ch) amrex::Abort("WritePlotFile: cannot open Cell_H");
+    std::fprintf(ch, "1\n1\n4\n0\n(%d 0\n", nb);
+    for (int s = 0; s < nb; ++s) std::fprintf(ch, "%s\n", boxstr(rho.storageValid(s)).c_str());
+    std::fprintf(ch, ")\n%d\n", nb);
+    for (int s = 0; s < nb; ++s) std::fprintf(ch, "FabOnDisk: Cell_D_00000 %ld\n", offsets[s]);
+    std::fprintf(ch, "\n%d,4\n", nb);
+    for (int s = 0; s < nb; ++s) {
+      for (int c = 0; c < 4; ++c) std::fprintf(ch, "%.17g,", mins[(size_t)s * 4 + c]);
+      std::fprintf(ch, "\n");
+    }
+    std::fprintf(ch, "\n%d,4\n", nb);
+    for (int s = 0; s < nb; ++s) {
+      for (int c = 0; c < 4; ++c) std::fprintf(ch, "%.17g,", maxs[(size_t)s * 4 + c]);
+      std::fprintf(ch, "\n");
+    }
+    std::fclose(ch);
+  }
+  std::fclose(h);
+}
 
 void AmrSim::WriteCheckpoint(const std::string& path) {
   if (DistributionMapping::NProcs() > 1) amrex::Abort("WriteCheckpoint: single-process runs only");

@@ -82,6 +82,10 @@ class AmrSim : public amrex::AmrCore {
   // ladder, the refinement criteria, every level's box list and the VALID-cell populations of NOW;
   // ghost cells, densities, velocities and masks are recomputed.  ReadCheckpoint needs a sim constructed
   // with the same extents and max level (single process); a restarted run continues bit for bit.
+  // plotfile (the reference has no I/O): an AMReX-format plotfile directory (HyperCLaw-V1.1 Header,
+  // Level_l/Cell_H + Cell_D_00000 with native fp64 FABs) holding rho, ux, uy, uz of every level on its boxes -- what
+  // amrex::WriteMultiLevelPlotfile would write for these fields; readable by yt / VisIt / Amrvis.  Single process.
+  void WritePlotFile(const std::string& dir);
   void WriteCheckpoint(const std::string& path);
   void ReadCheckpoint(const std::string& path);
   // zero-copy inputs: the arrays (same C ordering) are read at InitFromScratch directly from
@@ -104,6 +108,14 @@ class AmrSim : public amrex::AmrCore {
   // ... and the matching bulk getters (this rank's cells only; no communication)
   void GetLocalDensityField(int const level, double* out, size_t n) const;
   void GetLocalVelocityField(int const level, double* out, size_t n) const;
+  // Addition: solid no-slip walls.  The reference's constructor aborts on a non-periodic direction
+  // (src/AmrSim.cpp:788-797; DistFnFillShim :346-357 is its intended hook).  After AllowWalls(true) -- process-wide,
+  // before construction -- a direction with periodicity 0 is closed by walls at both domain faces (half-way
+  // bounce-back inside the fused step kernel: a population that would leave through a wall returns to its cell
+  // reversed).  Walls run on the uniform single-GPU path only (level 0 alone, one fab); refinement or a distributed
+  // run with walls aborts.  Default off: non-periodic input aborts like the reference.
+  static void AllowWalls(bool on);
+  static bool WallsAllowed();
   // false: run level 0 through the reference's literal pass structure on per-box storage even
   // when it is the only level (FillPatch, collide, FillBoundary, stream, swap).  Default true.
   void SetUniformFastPath(bool on) { uniform_fast_path = on; }
@@ -218,6 +230,7 @@ class AmrSim : public amrex::AmrCore {
   // the next collision reads them from there (valid-cell copy fused into the collision)
   std::vector<char> valid_pending;
   void FillPatchImpl(int const level, amrex::MultiFab& dest, bool ghosts_only, const amrex::GhostPush* push = nullptr);
+  bool has_walls = false;
   bool uniform_fast_path = true;
   bool rohde_fused = true;
   bool CanFuseRohde(int const level) const;

@@ -109,6 +109,7 @@ int lbx_sim_get_linear_moment_field(const lbx_sim* sim, int level, const double*
   return guarded([&] { sim->s.GetLinearMomentField(level, weights, ncomp, per_unit_density != 0, sentinel, out, n); });
 }
 
+int lbx_sim_write_plotfile(lbx_sim* sim, const char* dir) { return guarded([&] { sim->s.WritePlotFile(dir); }); }
 int lbx_sim_write_checkpoint(lbx_sim* sim, const char* path) { return guarded([&] { sim->s.WriteCheckpoint(path); }); }
 int lbx_sim_read_checkpoint(lbx_sim* sim, const char* path) { return guarded([&] { sim->s.ReadCheckpoint(path); }); }
 
@@ -199,6 +200,7 @@ int lbx_sim_set_static_box(lbx_sim* sim, int level, const int lo[3], const int h
   return guarded([&] { sim->s.SetStaticBox(level, {{lo[0], lo[1], lo[2]}}, {{hi[0], hi[1], hi[2]}}); });
 }
 int lbx_sim_regrid_all(lbx_sim* sim) { return guarded([&] { sim->s.Regrid(); }); }
+int lbx_sim_allow_walls(int on) { AmrSim::AllowWalls(on != 0); return 0; }
 int lbx_sim_unset_static_refinement(lbx_sim* sim, int level) {
   return guarded([&] { sim->s.UnsetStaticRefinement(level); });
 }

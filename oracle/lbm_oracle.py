@@ -136,6 +136,36 @@ def np_stream(f):
     return out
 
 
+OPP = np.array([0, 2, 1, 4, 3, 6, 5, 14, 13, 12, 11, 10, 9, 8, 7])     # c_OPP[p] = -c_p
+
+
+def np_stream_walls(f, walls):
+    """Addition (the reference aborts on non-periodic directions, src/AmrSim.cpp:788-797): streaming with solid
+    no-slip walls at both faces of every direction d with walls[d] (x, y, z), half-way bounce-back --
+        f'(x, p) = f(x - c_p, p)      if x - c_p lies inside the domain in every walled direction
+                 = f(x, OPP[p])       otherwise (the population that left through the wall comes back reversed);
+    periodic wrap in the other directions.  f is the POST-collision field [15, nz, ny, nx]."""
+    out = np.empty_like(f)
+    nz, ny, nx = f.shape[1:]
+    kk, jj, ii = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    for p in range(NV):
+        c = (int(CX[p]), int(CY[p]), int(CZ[p]))
+        rolled = np.roll(f[p], shift=(c[2], c[1], c[0]), axis=(0, 1, 2))
+        outside = np.zeros(f.shape[1:], dtype=bool)
+        for d, (idx, n) in enumerate(((ii, nx), (jj, ny), (kk, nz))):
+            if walls[d] and c[d] != 0:
+                src = idx - c[d]
+                outside |= (src < 0) | (src >= n)
+        out[p] = np.where(outside, f[OPP[p]], rolled)
+    return out
+
+
+def np_step_walls(f, omega_s, omega_b, walls, nsteps=1):
+    for _ in range(nsteps):
+        f = np_stream_walls(np_collide(f, omega_s, omega_b), walls)
+    return f
+
+
 def np_moments(f):
     """src/AmrSim.cpp:957-971: rho = row0 . f ; u_a = (row_{a+1} . f) / rho."""
     mode = np_modes(f, 4)

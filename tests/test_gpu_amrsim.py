@@ -682,3 +682,86 @@ def test_plan_cache_is_bounded_over_repeated_regrids():
     assert max(sizes[4:]) <= max(sizes[:4]) + 2, sizes      # steady state: no growth with the number of regrids
     assert max(sizes) <= 64, sizes
     sim.close()
+
+
+# ------------------------------------------------------------------ walls (addition)
+def test_walls_through_amrsim_match_oracle_and_stay_off_by_default():
+    """A non-periodic direction aborts like the reference (src/AmrSim.cpp:788-797) unless AllowWalls was called; then it
+    is closed by bounce-back walls on the uniform path: AmrSim == numpy oracle <= 1e-12, mass conserved; refinement with
+    walls is refused."""
+    from oracle import lbm_oracle as orc
+    nx, ny, nz, tau, steps = 12, 10, 16, 0.1, 15
+    with pytest.raises(amrsim.LambrexError):
+        AmrSim(nx, ny, nz, 0, (1, 1, 0), tau, tau)
+    amrsim.allowWalls(True)
+    try:
+        rho, u = workloads.shear_wave(nx, ny, nz)
+        rho = rho * workloads.pulse_density(nx, ny, nz)
+        sim = AmrSim(nx, ny, nz, 0, (1, 1, 0), tau, tau)
+        sim.SetInitialDensity(rho)
+        sim.SetInitialVelocity(u)
+        sim.InitFromScratch(0.0)
+        sim.Iterate(steps)
+        sim.CalcHydroVars(0)
+        got_r, got_u = sim.GetDensityField(0), sim.GetVelocityField(0)
+        sim.close()
+        w = workloads.omega(tau)
+        f0 = orc.np_equilibrium(orc.user_to_fab(rho, nx, ny, nz), orc.user_to_fab(u, nx, ny, nz, 3))
+        ro, uo = orc.np_moments(orc.np_step_walls(f0, w, w, (0, 0, 1), steps))
+        assert np.max(np.abs(got_r.transpose(2, 1, 0) - ro) / ro) < 1e-12
+        assert np.max(np.abs(got_u.transpose(3, 2, 1, 0) - uo)) < 1e-12
+        assert abs(got_r.sum() - rho.sum()) < 1e-10 * rho.sum()
+        sim = AmrSim(nx, ny, nz, 1, (1, 1, 0), tau, tau)
+        sim.SetInitialDensity(rho)
+        sim.SetInitialVelocity(u)
+        sim.InitFromScratch(0.0)
+        sim.SetStaticRefinement(0, (3, 3, 3), (8, 6, 9))
+        with pytest.raises(amrsim.LambrexError):
+            sim.Iterate(1)
+        sim.close()
+    finally:
+        amrsim.allowWalls(False)
+
+
+# ------------------------------------------------------------------ plotfile (addition, SURVEY.md 8f-4)
+def test_plotfile_is_a_readable_amrex_plotfile(tmp_path):
+    """WritePlotFile: AMReX plotfile layout (HyperCLaw-V1.1 Header, Level_l/Cell_H with box list + FabOnDisk offsets,
+    Cell_D_00000 with native fp64 FABs) -- parsed back here and compared with the bulk getters, both levels."""
+    import re
+    nx, ny, nz = 16, 12, 20
+    rho, u = workloads.shear_wave(nx, ny, nz)
+    rho = rho * workloads.pulse_density(nx, ny, nz)
+    sim = AmrSim(nx, ny, nz, 1, PER, 0.5, 0.5)
+    sim.SetMaxGridSize(8)
+    sim.SetCoupling(amrsim.SUBCYCLE)
+    sim.SetInitialDensity(rho)
+    sim.SetInitialVelocity(u)
+    sim.InitFromScratch(0.0)
+    sim.SetStaticRefinement(0, (3, 2, 4), (11, 9, 14))
+    sim.Iterate(3)
+    d = tmp_path / "plt00003"
+    sim.WritePlotFile(d)
+    head = (d / "Header").read_text().split("\n")
+    assert head[0] == "HyperCLaw-V1.1" and head[1] == "4" and head[2:6] == ["rho", "ux", "uy", "uz"] and head[6] == "3"
+    assert float(head[7]) == sim.GetTime(0) and int(head[8]) == sim.finestLevel() == 1
+    for lev in (0, 1):
+        sim.CalcHydroVars(lev)
+        want_r, want_u = sim.GetDensityField(lev), sim.GetVelocityField(lev)
+        ch = (d / ("Level_%d" % lev) / "Cell_H").read_text()
+        boxes = re.findall(r"\(\((-?\d+),(-?\d+),(-?\d+)\) \((-?\d+),(-?\d+),(-?\d+)\) \(0,0,0\)\)", ch)
+        offs = [int(x) for x in re.findall(r"FabOnDisk: Cell_D_00000 (\d+)", ch)]
+        assert len(boxes) == len(offs) == len(sim.boxArray(lev)) or lev == 0
+        raw = (d / ("Level_%d" % lev) / "Cell_D_00000").read_bytes()
+        seen = 0
+        for b, off in zip(boxes, offs):
+            lo, hi = [int(v) for v in b[:3]], [int(v) for v in b[3:]]
+            n = [h - l + 1 for l, h in zip(lo, hi)]
+            end = raw.index(b"\n", off)
+            assert raw[off:off + 4] == b"FAB " and raw[off:end].endswith(b" 4")
+            a = np.frombuffer(raw, dtype="<f8", count=4 * n[0] * n[1] * n[2], offset=end + 1).reshape(4, n[2], n[1], n[0])
+            sl = (slice(lo[0], hi[0] + 1), slice(lo[1], hi[1] + 1), slice(lo[2], hi[2] + 1))
+            assert np.array_equal(a[0].transpose(2, 1, 0), want_r[sl])
+            assert np.array_equal(a[1:].transpose(3, 2, 1, 0), want_u[sl])
+            seen += n[0] * n[1] * n[2]
+        assert seen == sum(int(np.prod([h - l + 1 for l, h in zip(*bb)])) for bb in sim.boxArray(lev))
+    sim.close()

@@ -251,3 +251,31 @@ def test_errors_are_loud():
         lbx.stream(A, A, lbx.box((0, 0, 0), (3, 3, 3)), lbx.domain((0, 0, 0), (3, 3, 3)))
     with pytest.raises(lbx.LbxError):     # box outside fab
         lbx.collide(A, B, lbx.box((0, 0, 0), (4, 3, 3)), 1.0, 1.0)
+
+
+# ------------------------------------------------------------------ walls (addition)
+@pytest.mark.parametrize("walls", [(0, 0, 1), (1, 1, 1), (1, 0, 1)])
+def test_fused_step_with_bounce_back_walls_matches_oracle(walls):
+    """lbx_collide_stream with lbx_domain.periodic[d] = 2: half-way bounce-back walls at both faces of direction d --
+    against the numpy restatement (oracle np_step_walls), populations <= 1e-12 relative, mass conserved."""
+    from oracle import lbm_oracle as orc
+    rng = np.random.default_rng(11)
+    nx, ny, nz, steps = 20, 9, 7, 12
+    rho = 1.0 + 0.01 * rng.standard_normal((nz, ny, nx))
+    u = 0.02 * rng.standard_normal((3, nz, ny, nx))
+    f0 = orc.np_equilibrium(rho, u)
+    w = 1.0 / 0.6
+    lo, hi = (0, 0, 0), (nx - 1, ny - 1, nz - 1)
+    bx = lbx.box(lo, hi)
+    dom = lbx.domain(lo, hi, tuple(2 if wl else 1 for wl in walls))
+    A, B = lbx.Fab(lo, hi, 15), lbx.Fab(lo, hi, 15)
+    A.upload(f0)
+    for _ in range(steps):
+        lbx.collide_stream(A, B, bx, dom, w, w, lbx.PUSH)
+        A, B = B, A
+    got = A.download()
+    want = orc.np_step_walls(f0, w, w, walls, steps)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-12
+    assert abs(got.sum() - f0.sum()) < 1e-12 * f0.sum()
+    with pytest.raises(lbx.LbxError):
+        lbx.collide_stream(A, B, bx, dom, w, w, lbx.PULL)       # walls exist in the push scheme only

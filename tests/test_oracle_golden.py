@@ -138,3 +138,25 @@ def test_linear_moments_restate_the_mode_matrix_rows(coracle):
     assert np.max(np.abs(orc.linear_moments(f, M[:1])[0] - rho)) < 1e-14
     assert np.max(np.abs(orc.linear_moments(f, M[1:4], per_unit_density=True) - u)) < 1e-14
     assert np.array_equal(orc.linear_moments(f, np.asarray(c, dtype=np.float64).T), orc.linear_moments(f, M[1:4]))
+
+
+def test_wall_oracle_reduces_to_periodic_and_conserves_mass():
+    """np_stream_walls (addition: half-way bounce-back walls): without walls it IS the periodic stream; with walls the
+    total mass is conserved exactly per population pair and the momentum of a closed box decays."""
+    import numpy as np
+    from oracle import lbm_oracle as orc
+    rng = np.random.default_rng(5)
+    nz, ny, nx = 6, 5, 7
+    rho = 1.0 + 0.01 * rng.standard_normal((nz, ny, nx))
+    u = 0.02 * rng.standard_normal((3, nz, ny, nx))
+    f = orc.np_equilibrium(rho, u)
+    assert np.array_equal(orc.np_stream_walls(f, (0, 0, 0)), orc.np_stream(f))
+    for walls in ((0, 0, 1), (1, 1, 1), (1, 0, 0)):
+        g = orc.np_step_walls(f, 1.0 / 0.6, 1.0 / 0.6, walls, 40)
+        assert abs(g.sum() - f.sum()) < 1e-12 * f.sum()
+    p0 = np.abs(orc.np_moments(f)[1] * rho).sum()
+    g = orc.np_step_walls(f, 1.0 / 0.6, 1.0 / 0.6, (1, 1, 1), 200)
+    r1, u1 = orc.np_moments(g)
+    assert np.abs(u1 * r1).sum() < 0.5 * p0          # no-slip walls drain the momentum of a closed box
+    assert (orc.OPP[orc.OPP] == np.arange(15)).all()
+    assert (orc.CX[orc.OPP] == -orc.CX).all() and (orc.CY[orc.OPP] == -orc.CY).all() and (orc.CZ[orc.OPP] == -orc.CZ).all()

@@ -1,4 +1,4 @@
 set -u
 O=gpurun_out; mkdir -p $O
-LBX_HOST_TIMING=1 timeout 600 python tools/amr_bench.py --grid 256 --levels 3 --steps 32 --regrid-every 16 > $O/r02z_amr3.jsonl 2> $O/r02z_amr3.err
-timeout 600 python tools/amr_bench.py --grid 256 --levels 3 --steps 16 >> $O/r02z_amr3.jsonl 2>> $O/r02z_amr3_static.err
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $O/r03b_pytest_gpu.log 2>&1
+timeout 300 python tools/shape_bench.py --scheme push --dims 256 256 256 > $O/r03b_shape.jsonl 2>&1
