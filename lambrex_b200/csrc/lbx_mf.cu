@@ -73,6 +73,7 @@ struct lbx_plan {
   int* d_fab_first = nullptr;           // [nfabs + 1] first group of each destination fab (lbx_mf_collide_stream_fillpatch)
   int fab_first_n = -1, max_groups = 0;
   std::set<std::tuple<uint64_t, uint64_t, uint64_t>> validated;
+  std::map<uint64_t, bool> shell_only;          // per destination geometry: every region lies in the ghost shell
 };
 
 namespace {
@@ -139,6 +140,7 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
       cells *= (size_t)f.n[d];
       if (cells >= (size_t(1) << 31)) { delete m; return fail("lbx_mf_create: a fab exceeds 2^31 cells"); }
       h = mix(mix(h, (uint64_t)(uint32_t)f.vlo[d]), (uint64_t)(uint32_t)f.vhi[d]);
+      h = mix(mix(h, (uint64_t)(uint32_t)f.lo[d]), (uint64_t)(uint32_t)f.n[d]);      // the layout too (LBX_OPT_ALIGN_ROWS)
     }
     const size_t fab_bytes = (cells * ncomp * item + 255) / 256 * 256;
     m->offset[i] = off;
@@ -761,6 +763,22 @@ int lbx_plan_destroy(lbx_plan* p) {
   return 0;
 }
 
+// first group of every destination fab (groups are sorted by fab): device array [nfabs + 1]
+static int plan_fab_first(lbx_plan* plan, const lbx_mf* dst) {
+  if (plan->fab_first_n == dst->nfabs) return 0;
+  std::vector<int> first((size_t)dst->nfabs + 1, 0);
+  int maxg = 0;
+  for (const auto& t : plan->dsts) ++first[(size_t)t.fab + 1];
+  for (int f = 0; f < dst->nfabs; ++f) { maxg = std::max(maxg, first[f + 1]); first[f + 1] += first[f]; }
+  if (plan->d_fab_first) lbx::arena_free(plan->d_fab_first);
+  LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&plan->d_fab_first), sizeof(int) * first.size()));
+  LBX_CUDA(cudaMemcpyAsync(plan->d_fab_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice, g.cur));
+  LBX_CUDA(cudaStreamSynchronize(g.cur));
+  plan->fab_first_n = dst->nfabs;
+  plan->max_groups = maxg;
+  return 0;
+}
+
 static int validate_plan(lbx_plan* p, const lbx_mf* dst, const lbx_mf* s0, const lbx_mf* s1) {
   const auto key = std::make_tuple(dst->geom, s0 ? s0->geom : 0, s1 ? s1->geom : 0);
   if (p->validated.count(key)) return 0;
@@ -794,6 +812,34 @@ static int validate_plan(lbx_plan* p, const lbx_mf* dst, const lbx_mf* s0, const
   return 0;
 }
 
+static int plan_resolved(lbx_plan* plan, const lbx_mf* dst, const lbx_mf* s0, const lbx_mf* s1, lbx_resolved* out);
+
+// every descriptor a set-0 COPY (or NONE) into the 2-cell ghost shell of tight boxes: the plan can run from the
+// resolved per-ghost-cell table (k_shell_copy) instead of the descriptor search
+static bool plan_shell_only(lbx_plan* p, const lbx_mf* dst) {
+  auto it = p->shell_only.find(dst->geom);
+  if (it != p->shell_only.end()) return it->second;
+  bool ok = dst->rows_ok && !p->has_avg && !p->has_const;
+  for (const auto& f : dst->host)
+    if (f.local && (f.n[1] != f.vhi[1] - f.vlo[1] + 5 || f.n[2] != f.vhi[2] - f.vlo[2] + 5)) ok = false;
+  for (size_t q = 0; ok && q < p->dsts.size(); ++q) {
+    const lbx::GDst& t = p->dsts[q];
+    if (t.fab < 0 || t.fab >= dst->nfabs) { ok = false; break; }
+    const lbx::DFabT& f = dst->host[t.fab];
+    for (int d = t.first; d < t.first + t.count; ++d) {
+      const lbx::GDesc& r = p->descs[d];
+      if (r.kind == lbx::G_NONE) continue;
+      if (r.kind != lbx::G_COPY || r.src_set != 0) { ok = false; break; }
+      bool meets_valid = true;
+      for (int k = 0; k < 3; ++k)
+        if (r.hi[k] < f.vlo[k] || r.lo[k] > f.vhi[k]) meets_valid = false;
+      if (meets_valid) { ok = false; break; }
+    }
+  }
+  p->shell_only[dst->geom] = ok;
+  return ok;
+}
+
 int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* src1, int op) {
   LBX_NEED_INIT();
   if (!p || !dst) return fail("lbx_plan_apply: null plan or destination");
@@ -805,6 +851,19 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
     return 0;
   }
   if (validate_plan(p, dst, src0, src1)) return 1;
+  if (op == LBX_OP_COPY && dst->dtype == LBX_F64 && src0 && lbx::g_row_kernel && !lbx::g_debug_skip && dst->rows_ok &&
+      plan_shell_only(p, dst)) {
+    lbx_resolved res;
+    if (plan_fab_first(p, dst) || plan_resolved(p, dst, src0, nullptr, &res)) return 1;
+    if (remote && lbx::par_barrier()) return 1;
+    const dim3 gs = lbx::mf_grid(dst->max_shell(2), dst->nfabs);
+    if (dst->ncomp == LBX_NV)
+      lbx::k_shell_copy<LBX_NV><<<gs, lbx::MFT, 0, g.cur>>>(dst->table, dst->nfabs, src0->table, res.tab, res.first, dst->ncomp);
+    else
+      lbx::k_shell_copy<0><<<gs, lbx::MFT, 0, g.cur>>>(dst->table, dst->nfabs, src0->table, res.tab, res.first, dst->ncomp);
+    if (lbx::after_launch("lbx_plan_apply (shell)")) return 1;
+    return remote ? lbx::par_barrier() : 0;
+  }
   if (remote && lbx::par_barrier()) return 1;
   const dim3 grid = lbx::mf_grid(p->max_cells, (int)p->dsts.size());
   const lbx::DFabT* t0 = src0 ? src0->table : nullptr;
@@ -913,18 +972,7 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
       return 0;
     }
     if (validate_plan(plan, dst, src0, src1)) return 1;
-    if (plan->fab_first_n != dst->nfabs) {            // first group of every fab (groups are sorted by fab)
-      std::vector<int> first((size_t)dst->nfabs + 1, 0);
-      int maxg = 0;
-      for (const auto& t : plan->dsts) ++first[(size_t)t.fab + 1];
-      for (int f = 0; f < dst->nfabs; ++f) { maxg = std::max(maxg, first[f + 1]); first[f + 1] += first[f]; }
-      if (plan->d_fab_first) lbx::arena_free(plan->d_fab_first);
-      LBX_CUDA(lbx::arena_alloc(reinterpret_cast<void**>(&plan->d_fab_first), sizeof(int) * first.size()));
-      LBX_CUDA(cudaMemcpyAsync(plan->d_fab_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice, g.cur));
-      LBX_CUDA(cudaStreamSynchronize(g.cur));
-      plan->fab_first_n = dst->nfabs;
-      plan->max_groups = maxg;
-    }
+    if (plan_fab_first(plan, dst)) return 1;
     cp.dsts = plan->d_dsts;
     cp.fab_first = plan->d_fab_first;
     cp.descs = plan->d_descs;

@@ -70,31 +70,33 @@ __device__ __forceinline__ long long ro_shell_index(int n0, int n1, int n2, int 
   if (jr >= n1 - 2) return 2 * A + B + ((long long)(kr - 2) * 2 + (jr - (n1 - 2))) * n0 + x;
   return 2 * A + 2 * B + ((long long)(kr - 2) * (n1 - 4) + (jr - 2)) * 4 + (x < 2 ? x : x - (n0 - 4));
 }
-// inverse: entry t -> (x, jr, kr) relative to the grown box
-__device__ __forceinline__ void ro_shell_cell(int n0, int n1, int n2, long long t, int& x, int& jr, int& kr) {
-  const long long A = 2ll * n0 * n1, B = 2ll * n0 * (n2 - 4);
+// inverse: entry t -> (x, jr, kr) relative to the grown box (a fab holds < 2^31 cells: 32-bit divisions)
+__device__ __forceinline__ void ro_shell_cell(int n0, int n1, int n2, long long tt, int& x, int& jr, int& kr) {
+  const unsigned A = 2u * n0 * n1, B = 2u * n0 * (n2 - 4), un0 = n0, un1 = n1;
+  unsigned t = (unsigned)tt;
   if (t < 2 * A) {
-    const int s = t >= A;
-    const long long r = t - s * A;
-    x = (int)(r % n0);
-    jr = (int)((r / n0) % n1);
-    kr = (s ? n2 - 2 : 0) + (int)(r / ((long long)n0 * n1));
+    const unsigned s = t >= A;
+    const unsigned r = t - s * A, row = r / un0;
+    x = (int)(r - row * un0);
+    const unsigned pl = row / un1;
+    jr = (int)(row - pl * un1);
+    kr = (s ? n2 - 2 : 0) + (int)pl;
     return;
   }
   t -= 2 * A;
   if (t < 2 * B) {
-    const int s = t >= B;
-    const long long r = t - s * B;
-    x = (int)(r % n0);
-    jr = (s ? n1 - 2 : 0) + (int)((r / n0) % 2);
-    kr = 2 + (int)(r / (2ll * n0));
+    const unsigned s = t >= B;
+    const unsigned r = t - s * B, row = r / un0;
+    x = (int)(r - row * un0);
+    jr = (s ? n1 - 2 : 0) + (int)(row & 1u);
+    kr = 2 + (int)(row >> 1);
     return;
   }
   t -= 2 * B;
-  const int q = (int)(t % 4);
-  x = q < 2 ? q : n0 - 4 + q;
-  jr = 2 + (int)((t / 4) % (n1 - 4));
-  kr = 2 + (int)(t / (4ll * (n1 - 4)));
+  const unsigned q = t & 3u, row = t >> 2, pl = row / (un1 - 4);
+  x = q < 2 ? (int)q : n0 - 4 + (int)q;
+  jr = 2 + (int)(row - pl * (un1 - 4));
+  kr = 2 + (int)pl;
 }
 
 // One launch per plan and geometry: the backward descriptor search of the tile kernel, done ONCE per ghost cell
@@ -133,6 +135,86 @@ static __global__ void __launch_bounds__(MFT) k_plan_resolve(const DFabT* __rest
     }
   }
   tab[tab_first[b] + t] = e;
+}
+
+// FillBoundary through the resolved table: one thread per ghost cell of the shell, NC components each (0: run-time
+// count).  The table already says which fab and element the cell copies, so the step is 8 B of table + 2 x 8 B x
+// ncomp of data per ghost cell, and whole ghost rows are read and written as contiguous runs.  Plans whose every
+// descriptor is a same-set COPY into the ghost shell qualify (lbx_plan_apply checks); entries with no source keep
+// their value, as the descriptor kernel leaves cells no region covers.
+// The x-ghost cells of a valid row share a 32-byte sector with two valid cells (rows are even and start on a sector
+// boundary): one thread per such sector reads its four cells, replaces the ghost pair and stores the WHOLE sector,
+// so that L2 never holds a half-written sector it must complete from DRAM (profiles/r02_shell_copy.md).  The valid
+// pair is stored back unchanged: a peer that reads it meanwhile sees the same bits.
+template <int NC>
+__global__ void __launch_bounds__(MFT) k_shell_copy(const DFabT* __restrict__ dt, int nfabs, const DFabT* __restrict__ st,
+                                                    const int2* __restrict__ tab, const long long* __restrict__ tab_first,
+                                                    int ncomp) {
+  const int b = mf_fab_index();
+  if (b >= nfabs) return;
+  const DFabT D = dt[b];
+  if (!D.local) return;
+  const int n0 = D.n[0], n1 = D.n[1], n2 = D.n[2];
+  const unsigned t = blockIdx.x * MFT + threadIdx.x;
+  const unsigned base3 = 4u * n0 * n1 + 4u * n0 * (n2 - 4);     // first x-ghost entry
+  const long long dsc = mf_stride(D);
+  const int nc = NC > 0 ? NC : ncomp;
+  if (t >= base3) {
+    const unsigned u = t - base3, rows = (unsigned)(n1 - 4) * (n2 - 4);
+    if (u >= 2 * rows) return;
+    const unsigned row = u >> 1, side = u & 1u, pl = row / (unsigned)(n1 - 4);
+    const int jr = 2 + (int)(row - pl * (n1 - 4)), kr = 2 + (int)pl;
+    const int4 ee = __ldg(reinterpret_cast<const int4*>(tab + tab_first[b] + base3 + 4 * row + 2 * side));
+    double* dp = static_cast<double*>(D.p) + ((side ? n0 - 4 : 0) + (long long)n0 * (jr + (long long)n1 * kr));
+    const int go = side ? 2 : 0, vo = 2 - go;                   // ghost pair / valid pair inside the sector
+    const bool h0 = (ee.x & 3) != 0, h1 = (ee.z & 3) != 0;
+    if (!h0 && !h1) return;
+    const DFabT S0 = st[h0 ? ee.x >> 2 : ee.z >> 2], S1 = st[h1 ? ee.z >> 2 : ee.x >> 2];
+    const double* s0 = static_cast<const double*>(S0.p) + ee.y;
+    const double* s1 = static_cast<const double*>(S1.p) + ee.w;
+    const long long sc0 = mf_stride(S0), sc1 = mf_stride(S1);
+    const bool pair = h0 && h1 && ee.x == ee.z && ee.w == ee.y + 1 && !(ee.y & 1);
+    constexpr int CH = 5;                                       // loads of a chunk in flight together, then its stores
+    for (int c0 = 0; c0 < nc; c0 += CH) {
+      double2 gv[CH], vv[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int c = min(c0 + q, nc - 1);
+        vv[q] = *reinterpret_cast<const double2*>(dp + c * dsc + vo);
+        if (pair) gv[q] = *reinterpret_cast<const double2*>(s0 + c * sc0);
+        else {
+          gv[q] = *reinterpret_cast<const double2*>(dp + c * dsc + go);
+          if (h0) gv[q].x = s0[c * sc0];
+          if (h1) gv[q].y = s1[c * sc1];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        if (c0 + q >= nc) break;
+        const int c = c0 + q;
+        *reinterpret_cast<double2*>(dp + c * dsc + go) = gv[q];
+        *reinterpret_cast<double2*>(dp + c * dsc + vo) = vv[q];
+      }
+    }
+    return;
+  }
+  const int2 e = __ldg(tab + tab_first[b] + t);
+  if ((e.x & 3) == 0) return;
+  int x, jr, kr;
+  ro_shell_cell(n0, n1, n2, t, x, jr, kr);
+  const DFabT S = st[e.x >> 2];
+  const long long ssc = mf_stride(S);
+  const double* sp = static_cast<const double*>(S.p) + e.y;
+  double* dp = static_cast<double*>(D.p) + (x + (long long)n0 * (jr + (long long)n1 * kr));
+  if (NC > 0) {
+    double v[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = sp[c * ssc];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dp[c * dsc] = v[c];
+  } else {
+    for (int c = 0; c < ncomp; ++c) dp[c * dsc] = sp[c * ssc];
+  }
 }
 
 // ---- separable population masks: bit p of dir_mask(axis, c) is set iff component `axis` of c_p equals c ------------

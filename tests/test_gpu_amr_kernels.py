@@ -169,6 +169,47 @@ def test_plan_copy_pc_avg_const_and_ordering():
     assert np.array_equal(got[:, 0:2, 2:-2, 2:-2], crse.fabs[0][:, 8:10, 2:-2, 2:-2])
 
 
+def test_fill_boundary_resolved_table_equals_descriptor_search():
+    """FillBoundary plans (same-set COPY into the ghost shell) run from the resolved per-ghost-cell table
+    (k_shell_copy); the descriptor kernel (LBX_OPT_ROW_KERNEL = 0) is the same copy -> same bytes.  Partly periodic
+    domain: ghost cells no descriptor covers keep their values on both paths."""
+    n, b = 16, 8
+    boxes = [((i, j, k), (i + b - 1, j + b - 1, k + b - 1)) for k in range(0, n, b) for j in range(0, n, b) for i in range(0, n, b)]
+    index = {lo: q for q, (lo, _) in enumerate(boxes)}
+    descs = []
+    for k, (lo, hi) in enumerate(boxes):
+        g = ao.grow((lo, hi), 2)
+        for dz in (-b, 0, b):
+            for dy in (-b, 0, b):
+                for dx in (-b, 0, b):
+                    nlo = (lo[0] + dx, lo[1] + dy, lo[2] + dz)
+                    if (dx, dy, dz) == (0, 0, 0) or not 0 <= nlo[2] < n:      # z is not periodic
+                        continue
+                    wrapped = tuple(v % n for v in nlo)
+                    r = ao.isect(g, (nlo, tuple(v + b - 1 for v in nlo)))
+                    descs.append(dict(dst_fab=k, src_fab=index[wrapped], kind=lbx.G_COPY,
+                                      shift=tuple(w - v for w, v in zip(wrapped, nlo)), lo=r[0], hi=r[1]))
+    plan = lbx.Plan(descs)
+    for ncomp in (15, 3):
+        m = rand_mf(boxes, ncomp, 2, 40 + ncomp)
+        out = []
+        for rows in (1, 0):
+            lbx.set_option(lbx.OPT_ROW_KERNEL, rows)
+            D = to_dev(m)
+            plan.apply(D, D)
+            out.append(D.download())
+        lbx.set_option(lbx.OPT_ROW_KERNEL, 1)
+        for k, (a, w) in enumerate(zip(*out)):
+            assert np.array_equal(a, w)
+            assert np.array_equal(a[:, 2:-2, 2:-2, 2:-2], m.fabs[k][:, 2:-2, 2:-2, 2:-2])     # valid cells untouched
+        lo_z = [k for k, (lo, _) in enumerate(boxes) if lo[2] == 0]
+        for k in lo_z:                                   # below the non-periodic face: nobody's ghost cells
+            assert np.array_equal(out[0][k][:, :2], m.fabs[k][:, :2])
+        # a filled ghost cell: the +x neighbour's first valid column
+        k0, k1 = index[(0, 0, 0)], index[(8, 0, 0)]
+        assert np.array_equal(out[0][k0][:, 2:-2, 2:-2, -2:], m.fabs[k1][:, 2:-2, 2:-2, 2:4])
+
+
 def test_plan_validation_is_loud():
     cb = [((0, 0, 0), (7, 7, 7))]
     A, B = lbx.MF(cb, 1, 1), lbx.MF(cb, 1, 1)

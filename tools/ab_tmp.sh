@@ -1,4 +1,6 @@
-set -u
-O=gpurun_out; mkdir -p $O
-( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $O/r03b_pytest_gpu.log 2>&1
-timeout 300 python tools/shape_bench.py --scheme push --dims 256 256 256 > $O/r03b_shape.jsonl 2>&1
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+python -m pytest tests/test_gpu_amr_kernels.py -x -q 2>&1 | tail -3
+python tools/kernel_bench.py --only FillBoundary 2>&1 | tail -1
+python tools/kernel_bench.py --only FillBoundary --grid 512 --box 64 2>&1 | tail -1
+python -m pytest tests/test_gpu_amrsim.py -x -q 2>&1 | tail -3
