@@ -440,12 +440,18 @@ struct DFabT {
   int lo[3], n[3];   // allocated box: lower corner, extents
   int vlo[3], vhi[3];  // valid box (inclusive)
   int local;         // 1: this rank owns the box; 0: it lives in a peer's HBM (read-only here)
-  int pad;
+  int lid;           // entry q of a table names the q-th box THIS RANK owns (a property of the table, not of box q)
 };
 static_assert(sizeof(DFabT) == 64, "DFabT is read as four 16-byte words");
 constexpr int MFT = 256;
 
 __device__ __forceinline__ int mf_fab_index() { return blockIdx.y + gridDim.y * blockIdx.z; }
+// Launches over "the boxes of a fab set" cover the boxes this rank owns only (`nlocal` of them): on 8 ranks a launch
+// over all boxes would start seven CTAs that exit for every one that works.  -1: past the end of the launch.
+__device__ __forceinline__ int mf_local_fab(const DFabT* __restrict__ t, int nlocal) {
+  const int q = mf_fab_index();
+  return q < nlocal ? t[q].lid : -1;
+}
 
 __device__ __forceinline__ bool mf_cell(const DFabT& f, int grow, int& i, int& j, int& k) {
   const int nx = f.vhi[0] - f.vlo[0] + 1 + 2 * grow, ny = f.vhi[1] - f.vlo[1] + 1 + 2 * grow,
@@ -473,8 +479,8 @@ template <class C>
 __global__ void __launch_bounds__(MFT) k_mf_collide(const DFabT* __restrict__ st, const DFabT* __restrict__ ft,
                                                     const DFabT* __restrict__ mt, int nfabs, double omega_s,
                                                     double omega_b, int fine_val) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;
@@ -711,8 +717,8 @@ __global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ 
                                                            int ytiles, int valid_tiles, double omega_s, double omega_b,
                                                            int fine_val, int flags) {
   __shared__ GDesc sd[PLAN_CHUNK];
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(dt, nfabs);
+  if (b < 0) return;
   const DFabT D = dt[b];
   if (!D.local) return;                                   // a peer's box: its owner streams it
   const int tid = threadIdx.x;
@@ -874,8 +880,8 @@ __global__ void LBX_MF_CS_BOUNDS k_mf_collide_stream(const double* __restrict__ 
 template <class C>
 __global__ void __launch_bounds__(MFT) k_mf_moments(const DFabT* __restrict__ ft, const DFabT* __restrict__ rt,
                                                     const DFabT* __restrict__ ut, int nfabs) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;
@@ -900,8 +906,8 @@ __global__ void __launch_bounds__(MFT) k_mf_moments(const DFabT* __restrict__ ft
 template <class C>
 __global__ void __launch_bounds__(MFT) k_mf_equilibrium(const DFabT* __restrict__ ft, const DFabT* __restrict__ rt,
                                                         const DFabT* __restrict__ ut, int nfabs) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;
@@ -918,6 +924,7 @@ __global__ void __launch_bounds__(MFT) k_mf_equilibrium(const DFabT* __restrict_
 }
 
 inline dim3 mf_grid(long long max_cells, int nfabs, long long extra_tiles = 0, int tile_mult = 1) {
+  if (nfabs < 1) nfabs = 1;                // a rank that owns no box still launches (one row of CTAs that exit)
   const unsigned gy = (unsigned)(nfabs < 65535 ? nfabs : 65535);
   return dim3((unsigned)(((max_cells + MFT - 1) / MFT + extra_tiles) * tile_mult), gy, (unsigned)((nfabs + gy - 1) / gy));
 }

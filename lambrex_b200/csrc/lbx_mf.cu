@@ -15,6 +15,7 @@
 
 struct lbx_mf {
   int nfabs = 0, ncomp = 0, ngrow = 0, dtype = LBX_F64;
+  int nlocal = 0;                       // boxes this rank owns: launches cover these (table entry q names the q-th in `lid`)
   size_t bytes = 0;                     // all fabs (host-mirror layout)
   size_t local_bytes = 0;               // what this rank allocated
   char* base = nullptr;                 // one device allocation: this rank's fabs
@@ -151,9 +152,11 @@ int lbx_mf_create_dist(const lbx_box* valid, int nfabs, int ncomp, int ngrow, in
     m->own_off[i] = per_rank[o];
     per_rank[o] += fab_bytes;
     f.local = (!m->dist || o == rank) ? 1 : 0;
-    f.pad = 0;
+    f.lid = 0;
     if (m->dist) h = mix(h, (uint64_t)o);
   }
+  for (int i = 0; i < nfabs; ++i)
+    if (m->host[i].local) m->host[m->nlocal++].lid = i;
   m->bytes = off;
   m->geom = h;
   m->max_valid = m->max_cells(0);
@@ -279,11 +282,11 @@ int lbx_mf_download(const lbx_mf* m, void* host, size_t bytes) {
 int lbx_mf_setval(lbx_mf* m, double value) {
   LBX_NEED_INIT();
   if (!m) return fail("lbx_mf_setval: null fab set");
-  const dim3 grid = lbx::mf_grid(m->max_cells(m->ngrow), m->nfabs);
+  const dim3 grid = lbx::mf_grid(m->max_cells(m->ngrow), m->nlocal);
   if (m->dtype == LBX_F64)
-    lbx::k_mf_setval<double><<<grid, lbx::MFT, 0, g.cur>>>(m->table, m->nfabs, m->ngrow, m->ncomp, value);
+    lbx::k_mf_setval<double><<<grid, lbx::MFT, 0, g.cur>>>(m->table, m->nlocal, m->ngrow, m->ncomp, value);
   else
-    lbx::k_mf_setval<int><<<grid, lbx::MFT, 0, g.cur>>>(m->table, m->nfabs, m->ngrow, m->ncomp, (int)value);
+    lbx::k_mf_setval<int><<<grid, lbx::MFT, 0, g.cur>>>(m->table, m->nlocal, m->ngrow, m->ncomp, (int)value);
   return lbx::after_launch("lbx_mf_setval");
 }
 
@@ -293,7 +296,7 @@ int lbx_mf_equilibrium(lbx_mf* f, const lbx_mf* rho, const lbx_mf* u) {
       need(u, 3, LBX_F64, 0, "lbx_mf_equilibrium u") || same_boxes(f, rho, "lbx_mf_equilibrium") ||
       same_boxes(f, u, "lbx_mf_equilibrium"))
     return 1;
-  L().mf_equilibrium(g.cur, f->table, rho->table, u->table, f->nfabs, f->max_valid);
+  L().mf_equilibrium(g.cur, f->table, rho->table, u->table, f->nlocal, f->max_valid);
   return lbx::after_launch("lbx_mf_equilibrium");
 }
 
@@ -303,7 +306,7 @@ int lbx_mf_moments(const lbx_mf* f, lbx_mf* rho, lbx_mf* u) {
       need(u, 3, LBX_F64, 0, "lbx_mf_moments u") || same_boxes(f, rho, "lbx_mf_moments") ||
       same_boxes(f, u, "lbx_mf_moments"))
     return 1;
-  L().mf_moments(g.cur, f->table, rho->table, u->table, f->nfabs, f->max_valid);
+  L().mf_moments(g.cur, f->table, rho->table, u->table, f->nlocal, f->max_valid);
   return lbx::after_launch("lbx_mf_moments");
 }
 
@@ -313,7 +316,7 @@ int lbx_mf_collide2(const lbx_mf* src, lbx_mf* dst, double omega_s, double omega
       same_boxes(src, dst, "lbx_mf_collide"))
     return 1;
   if (mask && (need(mask, 1, LBX_I32, 0, "lbx_mf_collide mask") || same_boxes(dst, mask, "lbx_mf_collide"))) return 1;
-  L().mf_collide(g.cur, src->table, dst->table, mask ? mask->table : nullptr, dst->nfabs, dst->max_valid, omega_s, omega_b,
+  L().mf_collide(g.cur, src->table, dst->table, mask ? mask->table : nullptr, dst->nlocal, dst->max_valid, omega_s, omega_b,
                  fine_val);
   return lbx::after_launch("lbx_mf_collide");
 }
@@ -338,8 +341,8 @@ int lbx_mf_stream(const lbx_mf* src, lbx_mf* dst) {
       same_boxes(src, dst, "lbx_mf_stream"))
     return 1;
   if (src->base == dst->base) return fail("lbx_mf_stream: src and dst must not alias");
-  lbx::k_mf_stream<<<lbx::mf_grid(dst->max_cells(dst->ngrow), dst->nfabs), lbx::MFT, 0, g.cur>>>(
-      src->table, dst->table, dst->nfabs, dst->ngrow);
+  lbx::k_mf_stream<<<lbx::mf_grid(dst->max_cells(dst->ngrow), dst->nlocal), lbx::MFT, 0, g.cur>>>(
+      src->table, dst->table, dst->nlocal, dst->ngrow);
   return lbx::after_launch("lbx_mf_stream");
 }
 
@@ -356,8 +359,8 @@ int lbx_mf_average_down(const lbx_mf* fine, lbx_mf* crse, int ratio) {
           f.vhi[d] + fine->ngrow != (c.vhi[d] + crse->ngrow) * ratio + ratio - 1)
         return fail("lbx_mf_average_down: fine box (with ghosts) is not the refinement of the coarse box (with ghosts)");
     }
-  lbx::k_mf_average_down<<<lbx::mf_grid(crse->max_cells(crse->ngrow), crse->nfabs), lbx::MFT, 0, g.cur>>>(
-      fine->table, crse->table, crse->nfabs, crse->ngrow, ratio);
+  lbx::k_mf_average_down<<<lbx::mf_grid(crse->max_cells(crse->ngrow), crse->nlocal), lbx::MFT, 0, g.cur>>>(
+      fine->table, crse->table, crse->nlocal, crse->ngrow, ratio);
   return lbx::after_launch("lbx_mf_average_down");
 }
 
@@ -367,7 +370,7 @@ int lbx_mf_lincomb(lbx_mf* dst, double a, const lbx_mf* x, double b, const lbx_m
       need(y, 1, LBX_F64, 0, "lbx_mf_lincomb y") || same_boxes(dst, x, "lbx_mf_lincomb") || same_boxes(dst, y, "lbx_mf_lincomb"))
     return 1;
   if (x->ncomp != dst->ncomp || y->ncomp != dst->ncomp) return fail("lbx_mf_lincomb: component counts differ");
-  lbx::k_mf_lincomb<<<lbx::mf_grid(dst->max_valid, dst->nfabs), lbx::MFT, 0, g.cur>>>(dst->table, x->table, y->table, dst->nfabs,
+  lbx::k_mf_lincomb<<<lbx::mf_grid(dst->max_valid, dst->nlocal), lbx::MFT, 0, g.cur>>>(dst->table, x->table, y->table, dst->nlocal,
                                                                                      dst->ncomp, a, b);
   return lbx::after_launch("lbx_mf_lincomb");
 }
@@ -378,7 +381,7 @@ int lbx_mf_tag_gradient(const lbx_mf* rho, double threshold, lbx_mf* tags, int s
       same_boxes(rho, tags, "lbx_mf_tag_gradient"))
     return 1;
   if (!(threshold >= 0.0)) return fail("lbx_mf_tag_gradient: threshold must be >= 0");
-  lbx::k_mf_tag_gradient<<<lbx::mf_grid(tags->max_valid, tags->nfabs), lbx::MFT, 0, g.cur>>>(rho->table, tags->table, tags->nfabs,
+  lbx::k_mf_tag_gradient<<<lbx::mf_grid(tags->max_valid, tags->nlocal), lbx::MFT, 0, g.cur>>>(rho->table, tags->table, tags->nlocal,
                                                                                             threshold * threshold, set_val);
   return lbx::after_launch("lbx_mf_tag_gradient");
 }
@@ -393,7 +396,7 @@ int lbx_mf_linear_moments(const lbx_mf* f, lbx_mf* out, const double* weights, i
   lbx::LMWeights W;
   memset(&W, 0, sizeof(W));
   memcpy(W.w, weights, sizeof(double) * (size_t)ncomp * LBX_NV);
-  lbx::k_mf_linear_moments<<<lbx::mf_grid(out->max_valid, out->nfabs), lbx::MFT, 0, g.cur>>>(f->table, out->table, out->nfabs,
+  lbx::k_mf_linear_moments<<<lbx::mf_grid(out->max_valid, out->nlocal), lbx::MFT, 0, g.cur>>>(f->table, out->table, out->nlocal,
                                                                                             ncomp, normalise ? 1 : 0, W);
   return lbx::after_launch("lbx_mf_linear_moments");
 }
@@ -401,7 +404,7 @@ int lbx_mf_linear_moments(const lbx_mf* f, lbx_mf* out, const double* weights, i
 int lbx_mf_zero_invalid(lbx_mf* f) {
   LBX_NEED_INIT();
   if (need(f, LBX_NV, LBX_F64, 1, "lbx_mf_zero_invalid")) return 1;
-  lbx::k_mf_zero_invalid<<<lbx::mf_grid(f->max_cells(f->ngrow), f->nfabs), lbx::MFT, 0, g.cur>>>(f->table, f->nfabs,
+  lbx::k_mf_zero_invalid<<<lbx::mf_grid(f->max_cells(f->ngrow), f->nlocal), lbx::MFT, 0, g.cur>>>(f->table, f->nlocal,
                                                                                                f->ngrow);
   return lbx::after_launch("lbx_mf_zero_invalid");
 }
@@ -410,7 +413,7 @@ int lbx_mf_zero_ring(lbx_mf* f, int depth, int comp) {
   LBX_NEED_INIT();
   if (need(f, 1, LBX_F64, 1, "lbx_mf_zero_ring")) return 1;
   if (comp < 0 || comp >= f->ncomp || depth < 1 || depth > f->ngrow) return fail("lbx_mf_zero_ring: bad comp/depth");
-  lbx::k_mf_zero_ring<<<lbx::mf_grid(f->max_cells(f->ngrow), f->nfabs), lbx::MFT, 0, g.cur>>>(f->table, f->nfabs,
+  lbx::k_mf_zero_ring<<<lbx::mf_grid(f->max_cells(f->ngrow), f->nlocal), lbx::MFT, 0, g.cur>>>(f->table, f->nlocal,
                                                                                             f->ngrow, depth, comp);
   return lbx::after_launch("lbx_mf_zero_ring");
 }
@@ -483,7 +486,7 @@ int lbx_mf_fill_profile(lbx_mf* m, const double* profile_dev, int axis, int axis
   for (const auto& f : m->host)
     if (f.local && (f.vlo[axis] < axis_lo || f.vhi[axis] >= axis_lo + axis_len))
       return fail("lbx_mf_fill_profile: a box reaches outside the profile");
-  lbx::k_mf_fill_profile<<<lbx::mf_grid(m->max_valid, m->nfabs), lbx::MFT, 0, g.cur>>>(m->table, m->nfabs, ncomp, profile_dev, axis,
+  lbx::k_mf_fill_profile<<<lbx::mf_grid(m->max_valid, m->nlocal), lbx::MFT, 0, g.cur>>>(m->table, m->nlocal, ncomp, profile_dev, axis,
                                                                                       axis_lo);
   return lbx::after_launch("lbx_mf_fill_profile");
 }
@@ -856,11 +859,11 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
     lbx_resolved res;
     if (plan_fab_first(p, dst) || plan_resolved(p, dst, src0, nullptr, &res)) return 1;
     if (remote && lbx::par_barrier()) return 1;
-    const dim3 gs = lbx::mf_grid(dst->max_shell(2), dst->nfabs);
+    const dim3 gs = lbx::mf_grid(dst->max_shell(2), dst->nlocal);
     if (dst->ncomp == LBX_NV)
-      lbx::k_shell_copy<LBX_NV><<<gs, lbx::MFT, 0, g.cur>>>(dst->table, dst->nfabs, src0->table, res.tab, res.first, dst->ncomp);
+      lbx::k_shell_copy<LBX_NV><<<gs, lbx::MFT, 0, g.cur>>>(dst->table, dst->nlocal, src0->table, res.tab, res.first, dst->ncomp);
     else
-      lbx::k_shell_copy<0><<<gs, lbx::MFT, 0, g.cur>>>(dst->table, dst->nfabs, src0->table, res.tab, res.first, dst->ncomp);
+      lbx::k_shell_copy<0><<<gs, lbx::MFT, 0, g.cur>>>(dst->table, dst->nlocal, src0->table, res.tab, res.first, dst->ncomp);
     if (lbx::after_launch("lbx_plan_apply (shell)")) return 1;
     return remote ? lbx::par_barrier() : 0;
   }
@@ -935,7 +938,7 @@ static int plan_resolved(lbx_plan* plan, const lbx_mf* dst, const lbx_mf* s0, co
   LBX_CUDA(cudaMemcpyAsync(r.first, first.data(), sizeof(long long) * first.size(), cudaMemcpyHostToDevice, g.cur));
   LBX_CUDA(cudaStreamSynchronize(g.cur));          // `first` is a local
   if (total > 0) {
-    lbx::k_plan_resolve<<<lbx::mf_grid(most, dst->nfabs), lbx::MFT, 0, g.cur>>>(dst->table, dst->nfabs, plan->d_dsts, plan->d_fab_first,
+    lbx::k_plan_resolve<<<lbx::mf_grid(most, dst->nlocal), lbx::MFT, 0, g.cur>>>(dst->table, dst->nlocal, plan->d_dsts, plan->d_fab_first,
                                                                               plan->d_descs, s0 ? s0->table : nullptr,
                                                                               s1 ? s1->table : nullptr, r.tab, r.first);
     if (lbx::after_launch("k_plan_resolve")) return 1;
@@ -1017,12 +1020,12 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
       a.plan.s0 = cp.s0; a.plan.s1 = cp.s1; a.plan.s1b = cp.s1b; a.plan.fb = cp.fb;
       a.plan.wa = wa; a.plan.wb = wb;
     }
-    a.nfabs = dst->nfabs; a.warps = ro_warps; a.pitch = ro_pitch;
+    a.nfabs = dst->nlocal; a.warps = ro_warps; a.pitch = ro_pitch;
     a.omega_s = omega_s; a.omega_b = omega_b; a.fine_val = fine_val; a.zero_invalid = zero_invalid ? 1 : 0;
     if (L().mf_cs_rows(g.cur, a, level_step ? 3 : plan ? 2 : 1, dst->max_extent(1) + 4, dst->max_extent(2) + 4)) return fail("k_mf_cs_rows: cannot raise the shared-memory limit");
   } else {
     L().mf_collide_stream(g.cur, reinterpret_cast<const double*>(src_valid->base), reinterpret_cast<double*>(dst->base), dst->table,
-                          mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nfabs, dst->max_extent(1),
+                          mask ? mask->table : nullptr, src_ghost ? src_ghost->table : nullptr, cp, dst->nlocal, dst->max_extent(1),
                           dst->max_extent(2), dst->max_valid, ghost_tiles, omega_s, omega_b, fine_val,
                           (zero_invalid ? 1 : 0) | (level_step ? 2 : 0));
   }

@@ -19,8 +19,8 @@ namespace lbx {
 // writes (policy NEW_FAB_FILL = 0).
 __global__ void __launch_bounds__(MFT) k_mf_stream(const DFabT* __restrict__ st, const DFabT* __restrict__ dt,
                                                    int nfabs, int grow_all) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(dt, nfabs);
+  if (b < 0) return;
   const DFabT D = dt[b];
   if (!D.local) return;
   int i, j, k;
@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(MFT) k_mf_stream(const DFabT* __restrict__ st,
 // For every cell of the ghost shell (all `grow_all` rings): component m survives only if
 // pos - 2 c_m lies in the box's valid region.
 __global__ void __launch_bounds__(MFT) k_mf_zero_invalid(const DFabT* __restrict__ ft, int nfabs, int grow_all) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;
@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(MFT) k_mf_zero_invalid(const DFabT* __restrict
 // comp <- 0 on the outermost `depth` rings of every (grown) fab box.
 __global__ void __launch_bounds__(MFT) k_mf_zero_ring(const DFabT* __restrict__ ft, int nfabs, int grow_all, int depth,
                                                       int comp) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(MFT) k_mf_zero_ring(const DFabT* __restrict__ 
 // then a plain ParallelCopy plan over these patches).
 __global__ void __launch_bounds__(MFT) k_mf_average_down(const DFabT* __restrict__ ft, const DFabT* __restrict__ ct, int nfabs,
                                                          int cgrow, int r) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ct, nfabs);
+  if (b < 0) return;
   const DFabT Cf = ct[b];
   if (!Cf.local) return;
   int i, j, k;
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(MFT) k_mf_average_down(const DFabT* __restrict
 // and sum are rounded separately (no FMA contraction): bit-identical to the CPU statement.
 __global__ void __launch_bounds__(MFT) k_mf_lincomb(const DFabT* __restrict__ dt, const DFabT* __restrict__ xt,
                                                     const DFabT* __restrict__ yt, int nfabs, int ncomp, double a, double b) {
-  const int q = mf_fab_index();
-  if (q >= nfabs) return;
+  const int q = mf_local_fab(dt, nfabs);
+  if (q < 0) return;
   const DFabT D = dt[q];
   if (!D.local) return;
   int i, j, k;
@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(MFT) k_mf_lincomb(const DFabT* __restrict__ dt
 // operation is rounded separately, in a fixed order: the tag set is bit-reproducible on the CPU.
 __global__ void __launch_bounds__(MFT) k_mf_tag_gradient(const DFabT* __restrict__ rt, const DFabT* __restrict__ tt, int nfabs,
                                                          double thr2, int set_val) {
-  const int q = mf_fab_index();
-  if (q >= nfabs) return;
+  const int q = mf_local_fab(tt, nfabs);
+  if (q < 0) return;
   const DFabT T = tt[q];
   if (!T.local) return;
   int i, j, k;
@@ -185,8 +185,8 @@ constexpr int LM_MAX = 10;
 struct LMWeights { double w[LM_MAX][NV]; };
 __global__ void __launch_bounds__(MFT) k_mf_linear_moments(const DFabT* __restrict__ ft, const DFabT* __restrict__ ot, int nfabs,
                                                            int ncomp, int normalise, const __grid_constant__ LMWeights W) {
-  const int q = mf_fab_index();
-  if (q >= nfabs) return;
+  const int q = mf_local_fab(ot, nfabs);
+  if (q < 0) return;
   const DFabT O = ot[q];
   if (!O.local) return;
   int i, j, k;
@@ -293,8 +293,8 @@ __global__ void k_fill_f64(double* __restrict__ p, long long n, double v) {
 // stated by a profile of axis-length entries instead of a whole-domain host array (1024^3: 34 GB per rank).
 __global__ void __launch_bounds__(MFT) k_mf_fill_profile(const DFabT* __restrict__ ft, int nfabs, int ncomp,
                                                          const double* __restrict__ profile, int axis, int axis_lo) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(MFT) k_mf_fill_profile(const DFabT* __restrict
 template <class T>
 __global__ void __launch_bounds__(MFT) k_mf_setval(const DFabT* __restrict__ ft, int nfabs, int grow_all, int ncomp,
                                                    T value) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(ft, nfabs);
+  if (b < 0) return;
   const DFabT F = ft[b];
   if (!F.local) return;
   int i, j, k;

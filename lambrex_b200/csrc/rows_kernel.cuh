@@ -105,8 +105,8 @@ static __global__ void __launch_bounds__(MFT) k_plan_resolve(const DFabT* __rest
                                                       const int* __restrict__ fab_first, const GDesc* __restrict__ descs,
                                                       const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
                                                       int2* __restrict__ tab, const long long* __restrict__ tab_first) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(dt, nfabs);
+  if (b < 0) return;
   const DFabT D = dt[b];
   if (!D.local) return;
   const int n0 = D.n[0], n1 = D.n[1], n2 = D.n[2];
@@ -150,8 +150,8 @@ template <int NC>
 __global__ void __launch_bounds__(MFT) k_shell_copy(const DFabT* __restrict__ dt, int nfabs, const DFabT* __restrict__ st,
                                                     const int2* __restrict__ tab, const long long* __restrict__ tab_first,
                                                     int ncomp) {
-  const int b = mf_fab_index();
-  if (b >= nfabs) return;
+  const int b = mf_local_fab(dt, nfabs);
+  if (b < 0) return;
   const DFabT D = dt[b];
   if (!D.local) return;
   const int n0 = D.n[0], n1 = D.n[1], n2 = D.n[2];
@@ -250,7 +250,7 @@ template <class C, int MODE, bool ZI>
 __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROArgs a) {
   extern __shared__ double ro_smem[];
   // grid = (row tiles of one z-plane, z-planes of the largest fab, fabs): no division anywhere
-  const int b = a.fab0 + (int)blockIdx.z;
+  const int b = a.dt[a.fab0 + (int)blockIdx.z].lid;       // a.nfabs counts the boxes this rank owns
   const DFabT D = a.dt[b];
   if (!D.local) return;                                   // a peer's box: its owner streams it
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
