@@ -334,19 +334,17 @@ __global__ void __launch_bounds__(MFT) k_mf_setval(const DFabT* __restrict__ ft,
 //   G_NONE  --                                   no source: the cell keeps its value; only widens the
 //                                                tiled bounding box of its group to the whole region
 // ---------------------------------------------------------------------------
-// one matching descriptor applied to one destination cell, components [c0, c0 + n).  NC > 0: the
-// count n is known at compile time (15 populations, or 1 in the component-parallel launch): every
-// load of the cell is issued before the first store, which is what keeps these gather kernels
-// bandwidth- rather than latency-bound.  dp already points at component c0 of the destination.
-template <class T, bool ADD, int NC>
-__device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
-                                        int i, int j, int k, T* __restrict__ dp, long long dsc, int c0, int ncomp_rt) {
-  const int ncomp = NC > 0 ? NC : ncomp_rt;
-  if (g.kind == G_NONE) return;
+// The value one matching descriptor gives one destination cell, components [c0, c0 + NC), into v.  Every load of
+// the cell is issued before the first use, which is what keeps these gather kernels bandwidth- rather than
+// latency-bound.  false: the descriptor is G_NONE (the cell keeps its value).
+template <class T, int NC>
+__device__ __forceinline__ bool g_fetch(const GDesc& g, const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
+                                        int i, int j, int k, int c0, T (&v)[NC]) {
+  if (g.kind == G_NONE) return false;
   if (g.kind == G_CONST) {
 #pragma unroll
-    for (int c = 0; c < ncomp; ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + (T)g.value) : (T)g.value;
-    return;
+    for (int c = 0; c < NC; ++c) v[c] = (T)g.value;
+    return true;
   }
   const DFabT S = (g.src_set ? s1 : s0)[g.src_fab];
   const long long ssc = mf_stride(S);
@@ -355,62 +353,69 @@ __device__ __forceinline__ void g_apply(const GDesc& g, const DFabT* __restrict_
     const int i0 = i * r + g.shift[0];
     const T* sp = static_cast<const T*>(S.p) + c0 * ssc + mf_off(S, i0, j * r + g.shift[1], k * r + g.shift[2]);
     const long long sy = S.n[0], sz = (long long)S.n[0] * S.n[1];
-    if (sizeof(T) == 8 && r == 2 && NC > 0) {
-      // ratio 2: the 8 fine cells of every component, all loads issued before the first use,
-      // summed in amrex_avgdown order (iref fastest, then jref, then kref)
+    if (sizeof(T) == 8 && r == 2) {
+      // ratio 2: the 8 fine cells of every component summed in amrex_avgdown order (iref fastest, then jref, kref)
       const double* dpp = reinterpret_cast<const double*>(sp);
-      double v[NC > 0 ? NC : 1];
       if (((i0 - S.lo[0]) & 1) == 0 && (S.n[0] & 1) == 0) {        // 16-byte aligned pairs
 #pragma unroll
-        for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
+        for (int c = 0; c < NC; ++c) {
           const double2 a = *reinterpret_cast<const double2*>(dpp + c * ssc);
           const double2 b = *reinterpret_cast<const double2*>(dpp + c * ssc + sy);
           const double2 cc = *reinterpret_cast<const double2*>(dpp + c * ssc + sz);
           const double2 d = *reinterpret_cast<const double2*>(dpp + c * ssc + sz + sy);
-          v[c] = ((((((a.x + a.y) + b.x) + b.y) + cc.x) + cc.y) + d.x + d.y) * 0.125;
+          v[c] = (T)(((((((a.x + a.y) + b.x) + b.y) + cc.x) + cc.y) + d.x + d.y) * 0.125);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
+        for (int c = 0; c < NC; ++c) {
           const double* q = dpp + c * ssc;
           const double a0 = q[0], a1 = q[1], b0 = q[sy], b1 = q[sy + 1], c0_ = q[sz], c1 = q[sz + 1], d0 = q[sz + sy],
                        d1 = q[sz + sy + 1];
-          v[c] = ((((((a0 + a1) + b0) + b1) + c0_) + c1) + d0 + d1) * 0.125;
+          v[c] = (T)(((((((a0 + a1) + b0) + b1) + c0_) + c1) + d0 + d1) * 0.125);
         }
       }
-#pragma unroll
-      for (int c = 0; c < (NC > 0 ? NC : 1); ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + (T)v[c]) : (T)v[c];
-      return;
+      return true;
     }
     const double w = 1.0 / (double)(r * r * r);
-    for (int c = 0; c < ncomp; ++c) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
       T acc = 0;
       for (int kr = 0; kr < r; ++kr)          // amrex_avgdown order: iref fastest
         for (int jr = 0; jr < r; ++jr)
           for (int ir = 0; ir < r; ++ir) acc += sp[c * ssc + kr * sz + jr * sy + ir];
-      const T val = (T)(acc * w);
-      dp[c * dsc] = ADD ? (T)(dp[c * dsc] + val) : val;
+      v[c] = (T)(acc * w);
     }
-    return;
+    return true;
   }
   int si = i, sj = j, sk = k;
   if (g.kind == G_PC) { si = fdiv(i, g.ratio); sj = fdiv(j, g.ratio); sk = fdiv(k, g.ratio); }
   const T* sp = static_cast<const T*>(S.p) + c0 * ssc + mf_off(S, si + g.shift[0], sj + g.shift[1], sk + g.shift[2]);
-  if (NC > 0) {
-    T v[NC > 0 ? NC : 1];
 #pragma unroll
-    for (int c = 0; c < (NC > 0 ? NC : 1); ++c) v[c] = sp[c * ssc];
-#pragma unroll
-    for (int c = 0; c < (NC > 0 ? NC : 1); ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + v[c]) : v[c];
-  } else {
-    for (int c = 0; c < ncomp; ++c) dp[c * dsc] = ADD ? (T)(dp[c * dsc] + sp[c * ssc]) : sp[c * ssc];
+  for (int c = 0; c < NC; ++c) v[c] = sp[c * ssc];
+  return true;
+}
+
+// run-time component count: one component at a time through the same fetch
+template <class T, bool ADD>
+__device__ __forceinline__ void g_apply_rt(const GDesc& g, const DFabT* __restrict__ s0, const DFabT* __restrict__ s1,
+                                           int i, int j, int k, T* __restrict__ dp, long long dsc, int ncomp) {
+  for (int c = 0; c < ncomp; ++c) {
+    T v[1];
+    if (!g_fetch<T, 1>(g, s0, s1, i, j, k, c, v)) return;
+    dp[c * dsc] = ADD ? (T)(dp[c * dsc] + v[0]) : v[0];
   }
 }
 
-
-// CPAR: component-parallel launch -- gridDim.x = tiles * ncomp and a thread handles ONE component
-// of its cell (NC must be 1).  Used for the averaging plans (sum_fine_to_coarse), whose 60 loads
-// per cell otherwise leave a 15-component thread latency-bound at low occupancy.
+// One CTA = 256 consecutive cells of one destination group's bounding box.  The group's descriptors pass through
+// shared memory in chunks; each WARP first keeps the descriptors that meet the bounding box of its 32 cells (one
+// descriptor per lane, one ballot per 32 descriptors), then every lane tests only those against its own cell: a
+// coarse box under 27 fine boxes costs a lane 1-3 box tests instead of 27 or more.  COPY walks the list backwards (the
+// last match wins) and stops at the first hit; ADD walks it forwards and sums in list order IN REGISTERS -- the
+// destination is read once before the first contribution and written once at the end, so the result has the bits of
+// the sequential read-modify-write loop (amrex::ParallelAdd order) at one RMW per cell.
+// CPAR: component-parallel launch -- gridDim.x = tiles * ncomp and a thread handles ONE component of its cell (NC
+// must be 1).  Used for the averaging plans, whose 60 loads per cell otherwise leave a 15-component thread
+// latency-bound at low occupancy.
 template <class T, bool ADD, int NC, bool CPAR>
 __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dsts, int ndst,
                                                     const GDesc* __restrict__ descs, const DFabT* __restrict__ dt,
@@ -434,9 +439,17 @@ __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dst
   if (!F.local) return;                        // block-uniform: a peer's box is filled by its owner
   const long long dsc = mf_stride(F);
   T* dp = static_cast<T*>(F.p) + c0 * dsc + (active ? mf_off(F, i, j, k) : 0);
+  // bounding box of the warp's cells
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int BIG = 0x7fffffff;
+  const int lane = threadIdx.x & 31;
+  const int w0 = __reduce_min_sync(FULL, active ? i : BIG), w1 = __reduce_max_sync(FULL, active ? i : -BIG);
+  const int w2 = __reduce_min_sync(FULL, active ? j : BIG), w3 = __reduce_max_sync(FULL, active ? j : -BIG);
+  const int w4 = __reduce_min_sync(FULL, active ? k : BIG), w5 = __reduce_max_sync(FULL, active ? k : -BIG);
+  T acc[NC > 0 ? NC : 1];
+  bool touched = false;                        // ADD: acc holds the destination plus the contributions so far
   const int nchunks = (D.count + PLAN_CHUNK - 1) / PLAN_CHUNK;
   for (int ch = 0; ch < nchunks; ++ch) {
-    // COPY walks the list backwards (the last match wins), ADD forwards (list order)
     const int cb = ADD ? ch * PLAN_CHUNK : max(D.count - (ch + 1) * PLAN_CHUNK, 0);
     const int ce = ADD ? min(cb + PLAN_CHUNK, D.count) : D.count - ch * PLAN_CHUNK;
     const int n = ce - cb;
@@ -446,24 +459,53 @@ __global__ void __launch_bounds__(MFT) k_plan_apply(const GDst* __restrict__ dst
       for (int w = threadIdx.x; w < n * (int)(sizeof(GDesc) / 16); w += MFT) dst[w] = src[w];
     }
     __syncthreads();
-    if (active) {
-      if (!ADD) {
-        for (int d = n - 1; d >= 0; --d) {
-          const GDesc& g = sd[d];
-          if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
-          g_apply<T, false, NC>(g, s0, s1, i, j, k, dp, dsc, c0, ncomp);
-          active = false;
-          break;
-        }
-      } else {
-        for (int d = 0; d < n; ++d) {
-          const GDesc& g = sd[d];
-          if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
-          g_apply<T, true, NC>(g, s0, s1, i, j, k, dp, dsc, c0, ncomp);
+    for (int part = 0; part < PLAN_CHUNK / 32; ++part) {
+      const int base = ADD ? part * 32 : (PLAN_CHUNK / 32 - 1 - part) * 32;
+      if (base >= n) continue;                 // block-uniform
+      const int mine = base + lane;
+      bool meets = false;
+      if (mine < n) {
+        const GDesc& g = sd[mine];
+        meets = g.lo[0] <= w1 && g.hi[0] >= w0 && g.lo[1] <= w3 && g.hi[1] >= w2 && g.lo[2] <= w5 && g.hi[2] >= w4;
+      }
+      unsigned m = __ballot_sync(FULL, meets);
+      while (m) {                              // warp-uniform loop
+        const int bit = ADD ? __ffs(m) - 1 : 31 - __clz(m);
+        m &= ~(1u << bit);
+        if (!active) continue;
+        const GDesc& g = sd[base + bit];
+        if (i < g.lo[0] || i > g.hi[0] || j < g.lo[1] || j > g.hi[1] || k < g.lo[2] || k > g.hi[2]) continue;
+        if (NC > 0) {
+          T v[NC > 0 ? NC : 1];
+          const bool has = g_fetch<T, (NC > 0 ? NC : 1)>(g, s0, s1, i, j, k, c0, v);
+          if (ADD) {
+            if (has) {
+              if (!touched) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[c] = dp[c * dsc];
+                touched = true;
+              }
+#pragma unroll
+              for (int c = 0; c < NC; ++c) acc[c] = (T)(acc[c] + v[c]);
+            }
+          } else {
+            if (has) {
+#pragma unroll
+              for (int c = 0; c < NC; ++c) dp[c * dsc] = v[c];
+            }
+            active = false;                    // the last matching descriptor wins, a G_NONE hit included
+          }
+        } else {
+          g_apply_rt<T, ADD>(g, s0, s1, i, j, k, dp, dsc, ncomp);
+          if (!ADD) active = false;
         }
       }
     }
     __syncthreads();
+  }
+  if (ADD && NC > 0 && touched) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dp[c * dsc] = acc[c];
   }
 }
 
