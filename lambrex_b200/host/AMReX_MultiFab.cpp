@@ -808,7 +808,7 @@ void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& 
 // (profiles/r02_launches_amr_2level_128.md: 282 us against 73 + 101 us at 128^3): every thread walks the whole
 // descriptor list of its coarse box (ADD cannot stop at the first match) with eight times the loads behind each
 // match, so the default stays with the two search-light steps.
-namespace { bool g_sum_fused = false; }
+namespace { bool g_sum_fused = [] { const char* e = std::getenv("LBX_SUM_FUSED"); return e && e[0] == '1'; }(); }
 void SetSumFineToCoarseFused(bool on) { g_sum_fused = on; }
 
 void sum_fine_to_coarse(const MultiFab& fine, MultiFab& crse, int scomp, int ncomp, const IntVect& ratio,

@@ -144,3 +144,15 @@ def test_box_ownership_of_a_distributed_level():
     for (lo, hi), r in zip(ragged, own):
         cells[r] += int(np.prod([h - l + 1 for l, h in zip(lo, hi)]))
     assert own[0] == 0 and own[-1] == 1 and cells[0] >= 64 ** 3
+    # a refined level of 17 x 17 x 17 boxes (C5's levels 1 and 2: 516^3 cells chopped at 32) on 8 ranks: whole layers
+    # would be 3 + 7 x 2 (1.41 x the mean on one rank); the level is cut inside layers instead, in (z, y, x) order
+    edges = [0] + list(np.cumsum([30] * 3 + [31] * 2 + [30] * 12))            # 17 pieces
+    fine = [((edges[i], edges[j], edges[k]), (edges[i + 1] - 1, edges[j + 1] - 1, edges[k + 1] - 1))
+            for i in range(17) for j in range(17) for k in range(17)]           # deliberately NOT in z order
+    own = amrsim.meta_distribution(fine, 8)
+    cells = np.zeros(8)
+    for (lo, hi), r in zip(fine, own):
+        cells[r] += np.prod([h - l + 1 for l, h in zip(lo, hi)])
+    assert cells.max() <= 1.01 * cells.mean()
+    zmin = [min(b[0][2] for b, o in zip(fine, own) if o == r) for r in range(8)]
+    assert zmin == sorted(zmin)                                                   # ranks follow z
