@@ -154,6 +154,16 @@ def main():
                     good = False
                     continue
                 for bi, (x, y) in enumerate(zip(fa, fb)):
+                    if fast and lv == 0 and max_level == 0:
+                        # a ghost-free level has no ghost cells to compare: what FieldFab shows around the valid box
+                        # depends on the storage (one slab per rank when the layers divide over the ranks, boxes
+                        # otherwise -- 3 layers on 8 ranks), the valid cells do not
+                        x, y = x[:, 2:-2, 2:-2, 2:-2], y[:, 2:-2, 2:-2, 2:-2]
+                        if np.array_equal(x, y):
+                            continue
+                        print("[rank %d] %s level 0 box %d: valid cells differ" % (rank, name, bi), flush=True)
+                        good = False
+                        continue
                     if not np.array_equal(x, y):
                         d = np.abs(x - y)
                         dv = float(np.max(d[:, 2:-2, 2:-2, 2:-2]))
