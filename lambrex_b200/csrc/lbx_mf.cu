@@ -545,7 +545,7 @@ int lbx_mf_collide_stream_slab(const lbx_mf* now, lbx_mf* next, const lbx_domain
     // neighbour and "below" its upper neighbour
     // the wait for the neighbours' previous step is a one-thread launch ahead of the step (they publish at the START of
     // their step, so it returns at once); folded into the kernel it made each of the 2 x 8192 boundary CTAs at 1024^2
-    // poll system-scope flags and cost 0.4 ms per step (profiles/r02_scale_n8.md).  The SIGNAL stays in the kernel.
+    // poll system-scope flags and cost 0.4 ms per step (profiles/r02_scale.md).  The SIGNAL stays in the kernel.
     if (lbx::step_wait_launch(g.step_epoch)) return 1;
     sy.wait_a = nullptr;
     sy.wait_b = nullptr;

@@ -805,9 +805,10 @@ void InterpFromCoarseLevel(MultiFab& dst, const MultiFab& crse, const Geometry& 
 // COPY, applied with ADD straight from the fine level: a coarse cell forms the mean of the 8 fine cells of each
 // contribution in registers (amrex_avgdown's summation order) and adds them in the same list order, so the result
 // is bit-identical to the two steps while the coarsened temporary is never written or read.  MEASURED SLOWER
-// (profiles/r02_launches_amr_2level_128.md: 282 us against 73 + 101 us at 128^3): every thread walks the whole
-// descriptor list of its coarse box (ADD cannot stop at the first match) with eight times the loads behind each
-// match, so the default stays with the two search-light steps.
+// (profiles/r02_launches_amr_2level_128_fused_sum.csv: 282 us against 73 + 101 us at 128^3; again after the warp-level
+// descriptor filter of k_plan_apply: C4 at 256^3 runs 8.9-9.4 GLUPS fused against 11.0 in two steps): a coarse cell
+// under the ghost overlap of several fine boxes pays eight times the loads behind EACH contribution, so the default
+// stays with the two steps.  LBX_SUM_FUSED=1 selects the one-gather form for experiments.
 namespace { bool g_sum_fused = [] { const char* e = std::getenv("LBX_SUM_FUSED"); return e && e[0] == '1'; }(); }
 void SetSumFineToCoarseFused(bool on) { g_sum_fused = on; }
 
