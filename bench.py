@@ -448,7 +448,6 @@ def main():
                     help="N>1: max_grid_size of level 0 (AMReX default 32; ownership is by whole x-y layers of these boxes)")
     ap.add_argument("--grid-multi", type=int, default=1024, help="N>1 cubic grid edge (default 1024 = configs[2])")
     ap.add_argument("--grid-multi-z", type=int, default=0, help="N>1 experiments: z extent if not cubic")
-    ap.add_argument("--debug-skip", type=int, default=0, help="PROFILING ONLY: LBX_OPT_DEBUG_SKIP (4 = face stores stay local)")
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU-baseline sample grid (cpu_baseline of the GPU arm)")
     ap.add_argument("--cpu-ref-grid", type=int, default=256, help="--impl reference: cubic grid edge (256 = the N=1 configuration itself)")
     ap.add_argument("--e2e-repeat", type=int, default=3, help="N=1: end-to-end jobs run (median reported)")

@@ -425,7 +425,7 @@ int lbx_set_option(int key, int value) {
       lbx::g_align_rows = value == 1 ? 4 : value;
       return 0;
     case LBX_OPT_VALID_TILING: lbx::g_valid_linear = (value != 0); return 0;
-    case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 7; return 0;
+    case LBX_OPT_DEBUG_SKIP: lbx::g_debug_skip = value & 3; return 0;
     case LBX_OPT_ROW_KERNEL: lbx::g_row_kernel = (value != 0); return 0;
     default: return fail("lbx_set_option: unknown key");
   }

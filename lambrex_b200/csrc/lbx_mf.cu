@@ -557,11 +557,8 @@ int lbx_mf_collide_stream_slab(const lbx_mf* now, lbx_mf* next, const lbx_domain
     sy.timeout_ns = 30000000000ull;
     LBX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&sy.err), g.peer_err, 0));
   }
-  // PROFILING ONLY (LBX_OPT_DEBUG_SKIP bit 2, results are wrong): the face-crossing populations stay in this rank's own
-  // fab instead of going to the neighbours over NVLink -- isolates the cost of the remote stores
-  const bool local_faces = (lbx::g_debug_skip & 4) != 0;
-  L().collide_stream_slab_sync(g.cur, dfab_of(S), dfab_of(D), dfab_of(local_faces ? D : next->host[dn]),
-                               dfab_of(local_faces ? D : next->host[up]), box, dd, omega_s, omega_b, sy);
+  L().collide_stream_slab_sync(g.cur, dfab_of(S), dfab_of(D), dfab_of(next->host[dn]), dfab_of(next->host[up]), box, dd, omega_s,
+                               omega_b, sy);
   return lbx::after_launch(what);
 }
 

@@ -47,7 +47,6 @@ def run_multi(args, helpers):
     nx = ny = nz = n
     if args.grid_multi_z:
         nz = args.grid_multi_z
-    lbx.set_option(lbx.OPT_DEBUG_SKIP, args.debug_skip)
     cells_total = float(nx) * ny * nz
     prof = U * np.sin(2.0 * np.pi * np.arange(ny, dtype=np.float64) / ny)
     u_profile = np.zeros((ny, 3))
