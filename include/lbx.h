@@ -73,8 +73,7 @@ enum {
                                   box writes whole destination rows: every sector completed by the warp that opens it);
                                   0 = the round-1 tile kernel.  Results are bit-identical.                          */
   LBX_OPT_DEBUG_SKIP = 4,      /* PROFILING ONLY (results are wrong): bit 0 skips the valid-cell work of
-                                  lbx_mf_collide_stream*, bit 1 the ghost-cell work (tile kernel); bit 2 keeps the
-                                  face-crossing populations of lbx_mf_collide_stream_slab on this GPU           */
+                                  lbx_mf_collide_stream*, bit 1 the ghost-cell work (tile kernel)               */
 };
 /* fused step schemes for lbx_collide_stream */
 enum {
