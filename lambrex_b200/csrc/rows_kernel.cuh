@@ -240,9 +240,13 @@ __device__ __forceinline__ unsigned axis_sel(int axis_is, int v, int n, int lo, 
 
 // MODE 1: own ghost cells; 2: FillPatch plan (Rohde pair); 3: conventional level step.  ZI: ZeroInvalidComponents folded in.
 // Fabs hold fewer than 2^31 / 15 cells (checked on the host): element offsets inside a fab are 32-bit.
-// Shared-memory row buffer of a warp: cell x of population p at sm[p * pitch + x]; sm[p * pitch - 1] and
-// sm[p * pitch + n0] are zero pads, so that the ring-2 destination cells x = 0 and x = n0 - 1 come out as 0 without a
-// test: they read the pad, or a ghost value phase 1 has already zeroed because it has no destination.
+// Shared-memory row buffer of a warp, stored ALREADY SHIFTED along x: population p of source cell x sits at
+// sm[p * pitch + x + c_x(p)], i.e. at the x of the cell it streams to, so that phase 2 reads one aligned 16-byte pair
+// per population and lane (read unshifted, the two 8-byte loads of a lane hit every other bank pair and the
+// shared-memory queue became the limiter on long rows).  sm[p * pitch - 1] and sm[p * pitch + n0] take the values that
+// leave the row; the slot nobody writes (x = 0 for c_x = +1, x = n0 - 1 for c_x = -1) is zeroed, so that the ring-2
+// destination cells x = 0 and x = n0 - 1 come out as 0 without a test: they read that slot, or a ghost value phase 1 has
+// already zeroed because it has no destination.
 #ifndef LBX_RO_MIN_CTAS
 #define LBX_RO_MIN_CTAS 6
 #endif
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROAr
   const unsigned sc = (unsigned)n0 * (unsigned)n1 * (unsigned)n2;       // plane stride (elements)
   const unsigned rowoff = (unsigned)n0 * ((unsigned)jr + (unsigned)n1 * (unsigned)kr);
   double* dfab = static_cast<double*>(D.p);
-  if (lane < NV) { sm[lane * pitch - 1] = 0.0; sm[lane * pitch + n0] = 0.0; }
+  if (lane < NV && cx(lane) != 0) sm[lane * pitch + (cx(lane) > 0 ? 0 : n0 - 1)] = 0.0;
 
   // ------------------------------------------------------------------ phase 1: the row's populations -> sm[p][x]
   if (valid_row) {
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROAr
       }
       double* s = sm + x;
 #pragma unroll
-      for (int p = 0; p < NV; ++p) s[p * pitch] = f[p];
+      for (int p = 0; p < NV; ++p) s[p * pitch + cx(p)] = f[p];
     }
   }
   // ghost cells of the row: all of it, or the 2 + 2 cells at the ends of a valid row.  Warp-uniform population masks of
@@ -298,10 +302,14 @@ __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROAr
     const double2* g2 = reinterpret_cast<const double2*>(static_cast<const double*>(a.gt[b].p) + rowoff);
     const unsigned sc2 = sc >> 1;
     for (int q = lane; q < (n0 >> 1); q += 32) {
-      double2* s2 = reinterpret_cast<double2*>(sm + 2 * q);
+      double* s = sm + 2 * q;
 #pragma unroll
       for (int p = 0; p < NV; ++p)
-        if (NEEDROW >> p & 1u) s2[p * (pitch >> 1)] = __ldcs(g2 + (q + (unsigned)p * sc2));
+        if (NEEDROW >> p & 1u) {
+          const double2 v = __ldcs(g2 + (q + (unsigned)p * sc2));
+          if (cx(p) == 0) *reinterpret_cast<double2*>(s + p * pitch) = v;
+          else { s[p * pitch + cx(p)] = v.x; s[p * pitch + cx(p) + 1] = v.y; }
+        }
     }
   } else {
     for (int q = lane; q < (valid_row ? 4 : n0); q += 32) {
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROAr
       }
       double* s = sm + x;
 #pragma unroll
-      for (int p = 0; p < NV; ++p) s[p * pitch] = f[p];
+      for (int p = 0; p < NV; ++p) s[p * pitch + cx(p)] = f[p];
     }
   }
   __syncwarp();
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROAr
       const double* ss = sm + 2 * q;
 #pragma unroll
       for (int p = 0; p < NV; ++p) {
-        __stcs(pd + (cy(p) * oY + cz(p) * oZ), make_double2(ss[-cx(p)], ss[1 - cx(p)]));
+        __stcs(pd + (cy(p) * oY + cz(p) * oZ), *reinterpret_cast<const double2*>(ss));
         pd += sc2;
         ss += pitch;
       }
@@ -398,9 +406,9 @@ __global__ void __launch_bounds__(RO_THREADS, LBX_RO_MIN_CTAS) k_mf_cs_rows(ROAr
     for (int p = 0; p < NV; ++p) {
       const unsigned bit = 1u << p;
       if (NZ & bit) {
-        double2 v;
-        v.x = (K0 & bit) ? ss[-cx(p)] : 0.0;
-        v.y = (K1 & bit) ? ss[1 - cx(p)] : 0.0;
+        double2 v = *reinterpret_cast<const double2*>(ss);
+        if (!(K0 & bit)) v.x = 0.0;
+        if (!(K1 & bit)) v.y = 0.0;
         __stcs(pd + (cy(p) * oY + cz(p) * oZ), v);
       }
       if (ring2) __stcs(pd, make_double2(0.0, 0.0));
