@@ -323,6 +323,9 @@ def amr_leg_single(args, peak):
                      "(BASELINE configs[3])" % args.amr_grid}
     for coupling in ("rohde", "subcycle"):
         out["C4_" + coupling] = run_amr_case(args.amr_grid, 2, args.amr_steps, 3, coupling, 0, 32, True, 0.0, None, peak)
+    # not a headline: the same case with AMReX's max_grid_size raised to 64 (what its GPU guidance suggests) -- less ghost
+    # shell per valid cell in every pass
+    out["C4_rohde_boxes64"] = run_amr_case(args.amr_grid, 2, args.amr_steps, 3, "rohde", 0, 64, True, 0.0, None, peak)
     return out
 
 

@@ -99,11 +99,17 @@ def run_amr_case(n, levels, steps, warmup=3, coupling="rohde", regrid_every=0, m
     launches = lbx.launch_count() - l0
     ms = t.ms
     kern_ms, kern_cells = prof["ms"], prof["valid_cells"]
+    per_rank_kernel_ms = [round(kern_ms, 3)]
     if dist:
         import torch
         tt = torch.tensor([ms, regrid_host_s], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, regrid_host_s = float(tt[0]), float(tt[1])
+        # the fused passes' summed time on every rank: tells load imbalance (spread) from exchange cost (all alike)
+        kk = torch.zeros(world, dtype=torch.float64)
+        kk[rank] = kern_ms
+        dist.all_reduce(kk, op=dist.ReduceOp.SUM)
+        per_rank_kernel_ms = [round(float(v), 3) for v in kk]
     work = sum(c * s for c, s in zip(cells, substeps))      # cells of the initial grids; regrids change them little
     cells_end = [_cells(sim, l) for l in range(sim.finestLevel() + 1)]
     # a cheap physics check without a whole-domain array: mean density of level 0 from one x-row per (y, z)?  The
@@ -124,7 +130,7 @@ def run_amr_case(n, levels, steps, warmup=3, coupling="rohde", regrid_every=0, m
            "gradient_threshold": gradient, "check": check,
            "roofline": {"bound": "hbm", "kernel": "k_mf_collide_stream (rank 0's boxes)", "achieved": achieved, "peak": peak_gbs,
                         "unit": "GB/s", "frac": achieved / peak_gbs if peak_gbs else None,
-                        "launches": prof["launches"], "kernel_ms_total": kern_ms, "share_of_timed_region": kern_ms / t.ms if t.ms else None,
+                        "launches": prof["launches"], "kernel_ms_total": kern_ms, "kernel_ms_total_per_rank": per_rank_kernel_ms, "share_of_timed_region": kern_ms / t.ms if t.ms else None,
                         "algorithmic_bytes": 240.0 * kern_cells, "not_bracketed": prof["dropped"],
                         "how": "240 B x valid cells of every launch / summed launch time, CUDA events around each launch on its stream"}}
     sim.close()

@@ -151,6 +151,8 @@ def run_multi(args, helpers):
         amr["C5_regrid16"] = run_amr_case(args.amr_grid, 3, args.amr_steps, 3, "rohde", 16, 32, True, 0.0, dist, pk)
         amr["C5_static"] = run_amr_case(args.amr_grid, 3, max(8, args.amr_steps // 2), 3, "rohde", 0, 32, True, 0.0, dist, pk)
         amr["C5_subcycle_regrid16"] = run_amr_case(args.amr_grid, 3, args.amr_steps, 3, "subcycle", 16, 32, True, 0.0, dist, pk)
+        # not a headline: max_grid_size 64 instead of AMReX's default 32
+        amr["C5_static_boxes64"] = run_amr_case(args.amr_grid, 3, max(8, args.amr_steps // 2), 3, "rohde", 0, 64, True, 0.0, dist, pk)
 
     if rank == 0:
         peak, peak_src = helpers["measured_peak"]()
