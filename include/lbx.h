@@ -149,6 +149,10 @@ int lbx_timer_stop(float *milliseconds);   /* synchronises on the stop event */
  * exhausted / inside a concurrent section).  For bench.py's roofline of the AMR leg. */
 int lbx_prof_begin(void);
 int lbx_prof_end(double *ms_total, uint64_t *launches, double *valid_cells, uint64_t *dropped);
+/* the same brackets by kind, as of the last lbx_prof_end: [0] fused level passes (what lbx_prof_end returns),
+ * [1] gather plans (lbx_plan_apply: FillBoundary, ParallelCopy, the ADD of sum_fine_to_coarse; their device barriers
+ * included), [2] lbx_mf_average_down, [3] unused.  ms4 and n4 hold 4 entries each. */
+int lbx_prof_breakdown(double *ms4, uint64_t *n4);
 
 /* ---- kernels ---- */
 /* CalcEquilibriumDist, src/AmrSim.cpp:845-931: f <- f_eq(rho, u) on box. */

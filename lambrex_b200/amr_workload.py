@@ -132,6 +132,7 @@ def run_amr_case(n, levels, steps, warmup=3, coupling="rohde", regrid_every=0, m
                         "unit": "GB/s", "frac": achieved / peak_gbs if peak_gbs else None,
                         "launches": prof["launches"], "kernel_ms_total": kern_ms, "kernel_ms_total_per_rank": per_rank_kernel_ms, "share_of_timed_region": kern_ms / t.ms if t.ms else None,
                         "algorithmic_bytes": 240.0 * kern_cells, "not_bracketed": prof["dropped"],
+                        "rank0_ms_by_kind": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in prof["by_kind"].items()},
                         "how": "240 B x valid cells of every launch / summed launch time, CUDA events around each launch on its stream"}}
     sim.close()
     return res

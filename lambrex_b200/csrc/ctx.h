@@ -48,6 +48,9 @@ struct Ctx {
   static constexpr int PROF_MAX = 8192;
   cudaEvent_t* prof_ev = nullptr;       // [2 * PROF_MAX], created on first use
   int prof_n = 0;
+  unsigned char* prof_kind = nullptr;   // [PROF_MAX] what each bracket holds: 0 fused level pass, 1 gather plan, 2 average_down
+  double prof_kind_ms[4] = {0, 0, 0, 0};   // last lbx_prof_end, per kind
+  uint64_t prof_kind_n[4] = {0, 0, 0, 0};
   double prof_cells = 0.0;              // valid cells of this rank's boxes over the bracketed launches
   uint64_t prof_dropped = 0;
   int conc_next = -1;              // >= 0: inside a concurrent section; index of the stream in use

@@ -322,6 +322,8 @@ int lbx_finalize(void) {
   if (g.prof_ev) {
     for (int i = 0; i < 2 * lbx::Ctx::PROF_MAX; ++i) cudaEventDestroy(g.prof_ev[i]);
     delete[] g.prof_ev;
+    delete[] g.prof_kind;
+    g.prof_kind = nullptr;
   }
   cudaEventDestroy(g.t0);
   cudaEventDestroy(g.t1);

@@ -82,6 +82,24 @@ using lbx::fail;
 lbx::Ctx& g = lbx::g_ctx;
 const lbx::Launchers& L() { return g.literal ? lbx::launchers_literal() : lbx::launchers_fast(); }
 
+// live timing brackets (lbx_prof_begin / lbx_prof_end): -1 when profiling is off or the bracket cannot be taken
+int prof_open(int kind) {
+  if (!g.prof) return -1;
+  if (g.prof_n >= lbx::Ctx::PROF_MAX || g.conc_next >= 0) { if (kind == 0) ++g.prof_dropped; return -1; }
+  const int i = g.prof_n++;
+  g.prof_kind[i] = (unsigned char)kind;
+  cudaEventRecord(g.prof_ev[2 * i], g.cur);
+  return i;
+}
+void prof_close(int i) {
+  if (i >= 0) cudaEventRecord(g.prof_ev[2 * i + 1], g.cur);
+}
+struct ProfScope {          // brackets everything a function queues, its barriers included
+  int i;
+  explicit ProfScope(int kind) : i(prof_open(kind)) {}
+  ~ProfScope() { prof_close(i); }
+};
+
 uint64_t mix(uint64_t h, uint64_t v) {
   h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
   return h;
@@ -359,6 +377,7 @@ int lbx_mf_average_down(const lbx_mf* fine, lbx_mf* crse, int ratio) {
           f.vhi[d] + fine->ngrow != (c.vhi[d] + crse->ngrow) * ratio + ratio - 1)
         return fail("lbx_mf_average_down: fine box (with ghosts) is not the refinement of the coarse box (with ghosts)");
     }
+  const ProfScope timed_scope(2);
   lbx::k_mf_average_down<<<lbx::mf_grid(crse->max_cells(crse->ngrow), crse->nlocal), lbx::MFT, 0, g.cur>>>(
       fine->table, crse->table, crse->nlocal, crse->ngrow, ratio);
   return lbx::after_launch("lbx_mf_average_down");
@@ -663,6 +682,7 @@ int lbx_prof_begin(void) {
   if (!g.prof_ev) {
     g.prof_ev = new cudaEvent_t[2 * lbx::Ctx::PROF_MAX];
     for (int i = 0; i < 2 * lbx::Ctx::PROF_MAX; ++i) LBX_CUDA(cudaEventCreate(&g.prof_ev[i]));
+    g.prof_kind = new unsigned char[lbx::Ctx::PROF_MAX];
   }
   g.prof = true;
   g.prof_n = 0;
@@ -675,16 +695,24 @@ int lbx_prof_end(double* ms_total, uint64_t* launches, double* valid_cells, uint
   if (!g.prof) return fail("lbx_prof_end: lbx_prof_begin was not called");
   g.prof = false;
   LBX_CUDA(cudaStreamSynchronize(g.cur));
-  double ms = 0.0;
+  for (int k = 0; k < 4; ++k) { g.prof_kind_ms[k] = 0.0; g.prof_kind_n[k] = 0; }
   for (int i = 0; i < g.prof_n; ++i) {
     float t = 0.f;
     LBX_CUDA(cudaEventElapsedTime(&t, g.prof_ev[2 * i], g.prof_ev[2 * i + 1]));
-    ms += t;
+    g.prof_kind_ms[g.prof_kind[i] & 3] += t;
+    ++g.prof_kind_n[g.prof_kind[i] & 3];
   }
-  if (ms_total) *ms_total = ms;
-  if (launches) *launches = (uint64_t)g.prof_n;
+  if (ms_total) *ms_total = g.prof_kind_ms[0];
+  if (launches) *launches = g.prof_kind_n[0];
   if (valid_cells) *valid_cells = g.prof_cells;
   if (dropped) *dropped = g.prof_dropped;
+  return 0;
+}
+
+int lbx_prof_breakdown(double* ms4, uint64_t* n4) {
+  LBX_NEED_INIT();
+  if (!ms4 || !n4) return fail("lbx_prof_breakdown: null output");
+  for (int k = 0; k < 4; ++k) { ms4[k] = g.prof_kind_ms[k]; n4[k] = g.prof_kind_n[k]; }
   return 0;
 }
 
@@ -851,6 +879,7 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
     return 0;
   }
   if (validate_plan(p, dst, src0, src1)) return 1;
+  const ProfScope timed_scope(1);
   if (op == LBX_OP_COPY && dst->dtype == LBX_F64 && src0 && lbx::g_row_kernel && !lbx::g_debug_skip && dst->rows_ok &&
       plan_shell_only(p, dst)) {
     lbx_resolved res;
@@ -1001,9 +1030,8 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
                         (size_t)ro_warps * LBX_NV * ro_pitch * sizeof(double) <= 199 * 1024;
   lbx_resolved res;
   if (use_rows && plan && plan_resolved(plan, dst, src0, src1, &res)) return 1;
-  const bool timed = g.prof && g.prof_n < lbx::Ctx::PROF_MAX && g.conc_next < 0;
-  if (g.prof && !timed) ++g.prof_dropped;
-  if (timed) LBX_CUDA(cudaEventRecord(g.prof_ev[2 * g.prof_n], g.cur));
+  const int pi = prof_open(0);
+  const bool timed = pi >= 0;
   if (use_rows) {
     lbx::ROArgs a;
     memset(&a, 0, sizeof(a));
@@ -1028,8 +1056,7 @@ static int collide_stream_common(const lbx_mf* src_valid, const lbx_mf* src_ghos
                           (zero_invalid ? 1 : 0) | (level_step ? 2 : 0));
   }
   if (timed) {
-    LBX_CUDA(cudaEventRecord(g.prof_ev[2 * g.prof_n + 1], g.cur));
-    ++g.prof_n;
+    prof_close(pi);
     for (const auto& f : dst->host)
       if (f.local) g.prof_cells += (double)(f.vhi[0] - f.vlo[0] + 1) * (f.vhi[1] - f.vlo[1] + 1) * (f.vhi[2] - f.vlo[2] + 1);
   }

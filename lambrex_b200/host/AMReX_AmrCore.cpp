@@ -292,7 +292,7 @@ void AmrMesh::MakeNewGrids(Real time) {
   finest_level = 0;
   {
     const BoxArray ba = MakeBaseGrids();
-    const DistributionMapping dm(ba);
+    const DistributionMapping dm = MakeDistributionMap(ba);
     MakeNewLevelFromScratch(0, time, ba, dm);
     SetBoxArray(0, ba);
     SetDistributionMap(0, dm);
@@ -305,7 +305,7 @@ void AmrMesh::MakeNewGrids(Real time) {
       MakeNewGrids(finest_level, time, new_finest, new_grids);
       if (new_finest <= finest_level) break;
       finest_level = new_finest;
-      const DistributionMapping dm(new_grids[new_finest]);
+      const DistributionMapping dm = MakeDistributionMap(new_grids[new_finest]);
       MakeNewLevelFromScratch(new_finest, time, new_grids[new_finest], dm);
       SetBoxArray(new_finest, new_grids[new_finest]);
       SetDistributionMap(new_finest, dm);
@@ -345,7 +345,7 @@ void AmrCore::regrid(int lbase, Real time, bool) {
         DistributionMapping level_dmap = dmap[lev];
         if (ba_changed) {
           level_grids = new_grids[lev];
-          level_dmap = DistributionMapping(level_grids);
+          level_dmap = MakeDistributionMap(level_grids);
         }
         RemakeLevel(lev, time, level_grids, level_dmap);
         lap("RemakeLevel", lev);
@@ -354,7 +354,7 @@ void AmrCore::regrid(int lbase, Real time, bool) {
       }
       coarse_ba_changed = ba_changed;
     } else {                                   // a new level
-      const DistributionMapping new_dmap(new_grids[lev]);
+      const DistributionMapping new_dmap = MakeDistributionMap(new_grids[lev]);
       MakeNewLevelFromCoarse(lev, time, new_grids[lev], new_dmap);
       lap("MakeNewLevelFromCoarse", lev);
       SetBoxArray(lev, new_grids[lev]);

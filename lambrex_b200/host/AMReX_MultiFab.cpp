@@ -471,6 +471,10 @@ std::string geom_key(const FabArrayBase& fa, bool flat, int storage_ng) {
   uint64_t h = 1469598103934665603ull;
   for (long i = 0; i < fa.size(); ++i)
     for (int d = 0; d < 3; ++d) { h = fnv(h, fa.box((int)i).smallEnd(d)); h = fnv(h, fa.box((int)i).bigEnd(d)); }
+  // ... and of who owns the boxes: plans are built per rank from the boxes it owns, and the same BoxArray can be
+  // distributed in two ways in one process (one slab per rank for a uniform run, interleaved runs for a hierarchy)
+  if (DistributionMapping::NProcs() > 1 && fa.DistributionMap().size() == fa.size())
+    for (long i = 0; i < fa.size(); ++i) h = fnv(h, fa.DistributionMap()[i]);
   char buf[96];
   std::snprintf(buf, sizeof(buf), "%016llx:%ld:%d:%d", (unsigned long long)h, fa.size(), flat ? 1 : 0, storage_ng);
   return buf;

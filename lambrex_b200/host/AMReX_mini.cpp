@@ -251,15 +251,16 @@ bool z_layers(const BoxArray& ba, std::vector<std::pair<int, int>>& layers) {
 }
 }  // namespace
 
-DistributionMapping::DistributionMapping(const BoxArray& ba, int nprocs) {
+DistributionMapping::DistributionMapping(const BoxArray& ba, int nprocs, int runs_per_rank) {
   const long n = ba.size();
   p_.assign(n, 0);
   if (nprocs <= 1 || n == 0) return;
+  if (runs_per_rank < 1) runs_per_rank = 1;
   // (1) a BoxArray made of whole x-y layers (every level 0): contiguous runs of layers per rank, balanced by
   // plane count -- each rank owns ONE z-slab, which is what the distributed uniform path stores as a single
   // ghost-free fab per GPU (SlabOwnership below) and a spatially compact share for the AMR path
   std::vector<std::pair<int, int>> layers;
-  if (z_layers(ba, layers) && (int)layers.size() >= nprocs) {
+  if (runs_per_rank == 1 && z_layers(ba, layers) && (int)layers.size() >= nprocs) {
     const Box mb = ba.minimalBox();
     const double total = (double)mb.length(2);
     std::map<int, int> owner_of_zlo;
@@ -300,7 +301,8 @@ DistributionMapping::DistributionMapping(const BoxArray& ba, int nprocs) {
   for (long q = 0; q < n; ++q) {
     const long i = order[q];
     const double mid = acc + 0.5 * ba[i].numPts();
-    p_[i] = std::min(nprocs - 1, (int)(mid / total * nprocs));
+    const int run = std::min(nprocs * runs_per_rank - 1, (int)(mid / total * (nprocs * runs_per_rank)));
+    p_[i] = run % nprocs;
     acc += (double)ba[i].numPts();
   }
 }

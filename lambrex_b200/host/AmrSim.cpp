@@ -130,7 +130,7 @@ Box AmrSim::LocalBox() {
   const int np = DistributionMapping::NProcs();
   if (np <= 1) return geom[0].Domain();
   const BoxArray ba = grids[0].empty() ? MakeBaseGrids() : grids[0];
-  const DistributionMapping dm = (dmap[0].size() == ba.size()) ? dmap[0] : DistributionMapping(ba);
+  const DistributionMapping dm = (dmap[0].size() == ba.size()) ? dmap[0] : MakeDistributionMap(ba);
   std::vector<Box> slabs;
   if (!amrex::SlabOwnership(ba, dm, np, &slabs)) amrex::Abort("LocalBox: level 0 is not owned as one slab per rank");
   return slabs[DistributionMapping::MyProc()];

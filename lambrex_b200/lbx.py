@@ -134,6 +134,7 @@ SYMBOLS = {
     "lbx_par_step_finish": (_i, []),
     "lbx_prof_begin": (_i, []),
     "lbx_prof_end": (_i, [ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64)]),
+    "lbx_prof_breakdown": (_i, [ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64)]),
     "lbx_plan_create": (_i, [ctypes.POINTER(lbx_gather), _i, ctypes.POINTER(_vp)]),
     "lbx_plan_apply": (_i, [_vp, _vp, _vp, _vp, _i]),
     "lbx_plan_destroy": (_i, [_vp]),
@@ -233,7 +234,11 @@ def prof_end():
     """{ms, launches, valid_cells, dropped} of the lbx_mf_collide_stream* launches since prof_begin()."""
     ms, n, cells, dr = _d(0), ctypes.c_uint64(0), _d(0), ctypes.c_uint64(0)
     check(lib().lbx_prof_end(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(cells), ctypes.byref(dr)))
-    return {"ms": ms.value, "launches": int(n.value), "valid_cells": cells.value, "dropped": int(dr.value)}
+    ms4, n4 = (_d * 4)(), (ctypes.c_uint64 * 4)()
+    check(lib().lbx_prof_breakdown(ms4, n4))
+    return {"ms": ms.value, "launches": int(n.value), "valid_cells": cells.value, "dropped": int(dr.value),
+            "by_kind": {"fused_pass": [ms4[0], int(n4[0])], "gather_plans": [ms4[1], int(n4[1])],
+                        "average_down": [ms4[2], int(n4[2])]}}
 
 
 class Timer:

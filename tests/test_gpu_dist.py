@@ -1,4 +1,6 @@
-"""Multi-GPU parity, run when >= 2 GPUs are visible (skipped on a 1-GPU box): one process per GPU under torchrun,
+"""Multi-rank parity: one process per rank under torchrun (one GPU each when the box has them; on a 1-GPU box the
+ranks SHARE the device -- CUDA-IPC and the device-side barriers work across processes of one GPU, so the whole
+distributed host logic, the peer pointers and the barrier protocol are exercised there too, only NVLink is not),
 AmrSim after lambrexInitParallel on every rank, compared BIT FOR BIT with the same problem run alone on one GPU
 (tools/amr_dist_check.py): the uniform path with level 0 stored as one slab per rank and the face exchange fused
 into the step kernel (peer stores over NVLink), the per-box distributed AMR path (2 and 3 levels, mid-run regrid),
@@ -32,11 +34,20 @@ def _torchrun(script, nproc, port, *args):
 
 @pytest.mark.parametrize("coupling", ["rohde", "subcycle"])
 def test_distributed_amrsim_bit_equal_single_gpu(coupling):
-    if _gpus() < 2:
-        pytest.skip("needs 2 GPUs")
+    """2 ranks: every rank owns boxes of every level.  Runs on one GPU too (the two ranks share it)."""
     r = _torchrun("amr_dist_check.py", 2, 29541 if coupling == "rohde" else 29542, *(["--subcycle"] if coupling == "subcycle" else []))
     assert r.returncode == 0 and "AMR_DIST_CHECK_OK" in r.stdout, r.stdout[-4000:] + r.stderr[-3000:]
     assert r.stdout.count("bit-equal=True") >= 8, r.stdout[-4000:]
+
+
+def test_eight_rank_layout_bit_equal_single_gpu():
+    """8 ranks (sharing the visible GPUs): the layout of the 8-GPU runs -- interleaved ownership of a hierarchy's
+    levels, ranks that own no box of a level, the same BoxArray distributed in two ways in one process (a uniform
+    run's slabs, then a hierarchy's interleaved runs: plans are cached per ownership), equal barrier counts on
+    every rank."""
+    r = _torchrun("amr_dist_check.py", 8, 29544)
+    assert r.returncode == 0 and "AMR_DIST_CHECK_OK" in r.stdout, r.stdout[-4000:] + r.stderr[-3000:]
+    assert r.stdout.count("bit-equal=True") >= 8 and "BARRIER COUNTS DIFFER" not in r.stdout, r.stdout[-4000:]
 
 
 def test_bench_multi_gpu_goes_through_amrsim():

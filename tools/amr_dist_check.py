@@ -100,8 +100,11 @@ def local_io_check(rank, world):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    # more ranks than GPUs (debugging the host logic of an 8-rank layout on one GPU): the ranks share devices -- CUDA-IPC
+    # and the device-side barriers work across processes of one GPU (time-sliced, slow), NCCL does not
+    shared = torch.cuda.device_count() < world
+    torch.cuda.set_device(local % torch.cuda.device_count())
+    dist.init_process_group("gloo" if shared else "cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     amrsim.lambrexInitParallel()
     ok = True
     cases = [
@@ -109,6 +112,8 @@ def main():
         ("2 levels", (16, 12, 20), 1, [((3, 2, 4), (11, 9, 14))], 8, 3),
         ("3 levels", (16, 16, 16), 2, [((3, 3, 3), (12, 12, 12)), ((10, 10, 10), (21, 21, 21))], 8, 2),
     ]
+    if "--only-2level" in sys.argv:
+        cases = cases[1:2]
     if "--big" in sys.argv:
         cases = [("64^3 L2", (64, 64, 64), 1, [((16, 16, 16), (47, 47, 47))], 16, 3),
                  ("128^3 L2", (128, 128, 128), 1, [((32, 32, 32), (95, 95, 95))], 32, 3),
@@ -183,6 +188,15 @@ def main():
             print("amr_dist_check %-8s world=%d owners per level=%s bit-equal=%s" % (name, world, owners, bool(flag.item())),
                   flush=True)
         ok = ok and bool(flag.item())
+        # every rank must have gone through the same number of device barriers: a rank that skips or adds one pairs
+        # its later barriers with the wrong ones of its peers (no deadlock, silently unordered reads)
+        bc = torch.zeros(world, dtype=torch.int64)
+        bc[rank] = lbx.par_info()["barriers"]
+        dist.all_reduce(bc, op=dist.ReduceOp.SUM)
+        if int(bc.min()) != int(bc.max()):
+            if rank == 0:
+                print("amr_dist_check %-8s BARRIER COUNTS DIFFER across ranks: %s" % (name, bc.tolist()), flush=True)
+            ok = False
     ok = local_io_check(rank, world) and ok
     info = lbx.par_info()
     if rank == 0:

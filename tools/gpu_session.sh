@@ -23,7 +23,7 @@ for stage in "$@"; do
              timeout 300 python tools/amr_bench.py --grid 256 --levels 2 --steps 16 --coupling subcycle 2>/dev/null | grep '^{' >> $O/${T}_amr.jsonl
              timeout 300 python tools/amr_bench.py --grid 256 --levels 3 --steps 12 --regrid-every 4 2>/dev/null | grep '^{' >> $O/${T}_amr.jsonl ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-               --log-file $O/${T}_launches_bench.csv python bench.py --steps 10 --warmup 3 --no-cpu > $O/${T}_launches_bench.out 2>&1 ;;
+               --log-file $O/${T}_launches_bench.csv python bench.py --steps 10 --warmup 3 --no-cpu --no-amr > $O/${T}_launches_bench.out 2>&1 ;;
     dist)    NG=${NGPUS:-2}
              ( time timeout 1200 python -m pytest tests/test_gpu_dist.py tests/test_gpu_slab.py -x -q -m gpu ) > $O/${T}_pytest_dist.log 2>&1 ;;
     benchN)  NG=${NGPUS:-2}
