@@ -165,9 +165,13 @@ int lbx_meta_cluster(const int *points /* [3 * npoints] */, int npoints, double 
 int lbx_meta_parallel_init(int rank, int nranks,
                            int (*allgather)(const void *send, size_t bytes, void *recv, void *user), void *user);
 int lbx_meta_parallel_finalise(void);
-/* box ownership of a distributed run (amrex::DistributionMapping(ba, nprocs)): owners[i] = rank of box i --
- * contiguous chunks of the box list balanced by cell count; the same on every rank by construction */
+/* box ownership of a distributed run (amrex::DistributionMapping(ba, nprocs)): owners[i] = rank of box i, the same
+ * on every rank by construction.  lbx_meta_distribution: a uniform run (one z-slab per rank where the layers divide,
+ * else one contiguous share of the (z, y, x)-ordered boxes balanced by cells).  _runs: runs_per_rank > 1 is what a
+ * hierarchy's levels get (AmrMesh::MakeDistributionMap): nprocs * runs_per_rank runs of equal cell count dealt to the
+ * ranks in turn. */
 int lbx_meta_distribution(const int *in_boxes, int n, int nprocs, int *owners);
+int lbx_meta_distribution_runs(const int *in_boxes, int n, int nprocs, int runs_per_rank, int *owners);
 /* A field-less AmrCore with the reference's static-box tagging (TagCell, src/AmrSim.cpp:413-417):
  * create, InitFromScratch, then set / unset static boxes (each triggers regrid(level)), query grids. */
 typedef struct lbx_meta_mesh lbx_meta_mesh;

@@ -81,6 +81,7 @@ SYMBOLS = {
     "lbx_meta_base_grids": (_i, [_ip, _i, _ip, _i]), "lbx_meta_max_size": (_i, [_ip, _i, _i, _ip, _i]),
     "lbx_meta_simplify": (_i, [_ip, _i, _ip, _i]), "lbx_meta_complement": (_i, [_ip, _ip, _i, _ip, _i]),
     "lbx_meta_cluster": (_i, [_ip, _i, _d, _ip, _i]), "lbx_meta_distribution": (_i, [_ip, _i, _i, _ip]),
+    "lbx_meta_distribution_runs": (_i, [_ip, _i, _i, _i, _ip]),
     "lbx_meta_parallel_init": (_i, [_i, _i, _vp, _vp]), "lbx_meta_parallel_finalise": (_i, []),
     "lbx_meta_mesh_create": (_i, [_ip, _i, _i, ctypes.POINTER(_vp)]), "lbx_meta_mesh_destroy": (_i, [_vp]),
     "lbx_meta_mesh_set_static": (_i, [_vp, _i, _ip, _ip]), "lbx_meta_mesh_unset_static": (_i, [_vp, _i]),
@@ -538,10 +539,10 @@ def metaParallelFinalise():
     _check(lib().lbx_meta_parallel_finalise())
 
 
-def meta_distribution(boxes, nprocs):
+def meta_distribution(boxes, nprocs, runs_per_rank=1):
     arr, n = _boxes_in(boxes)
     out = (_i * max(n, 1))()
-    _check(lib().lbx_meta_distribution(arr, n, int(nprocs), out))
+    _check(lib().lbx_meta_distribution_runs(arr, n, int(nprocs), int(runs_per_rank), out))
     return [int(out[i]) for i in range(n)]
 
 

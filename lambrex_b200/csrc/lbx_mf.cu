@@ -900,8 +900,7 @@ int lbx_plan_apply(lbx_plan* p, lbx_mf* dst, const lbx_mf* src0, const lbx_mf* s
   const int nd = (int)p->dsts.size();
 #define LBX_PLAN_LAUNCH(T, ADD, NC) \
   lbx::k_plan_apply<T, ADD, NC, false><<<grid, lbx::MFT, 0, g.cur>>>(p->d_dsts, nd, p->d_descs, dst->table, t0, t1, dst->ncomp)
-  static const bool avg_cpar = [] { const char* e = getenv("LBX_AVG_CPAR"); return !(e && e[0] == '0'); }();
-  if (dst->dtype == LBX_F64 && p->has_avg && (avg_cpar || dst->ncomp != LBX_NV)) {
+  if (dst->dtype == LBX_F64 && p->has_avg) {
     // averaging plans (sum_fine_to_coarse fused, average_down): 8 fine cells per coarse value -- component-parallel
     // launch, one thread per (cell, component), or a 15-component thread sits on 60 dependent 16-byte loads
     const dim3 gridc = lbx::mf_grid(p->max_cells, nd, 0, dst->ncomp);

@@ -397,12 +397,15 @@ int lbx_meta_parallel_finalise(void) {
   });
 }
 int lbx_meta_distribution(const int* in_boxes, int n, int nprocs, int* owners) {
+  return lbx_meta_distribution_runs(in_boxes, n, nprocs, 1, owners);
+}
+int lbx_meta_distribution_runs(const int* in_boxes, int n, int nprocs, int runs_per_rank, int* owners) {
   return guarded([&] {
     amrex::BoxList bl;
     for (int i = 0; i < n; ++i)
       bl.push_back(amrex::Box(amrex::IntVect(in_boxes[6 * i], in_boxes[6 * i + 1], in_boxes[6 * i + 2]),
                               amrex::IntVect(in_boxes[6 * i + 3], in_boxes[6 * i + 4], in_boxes[6 * i + 5])));
-    const amrex::DistributionMapping dm(amrex::BoxArray(bl), nprocs);
+    const amrex::DistributionMapping dm(amrex::BoxArray(bl), nprocs, runs_per_rank);
     for (int i = 0; i < n; ++i) owners[i] = dm[i];
   });
 }

@@ -156,3 +156,17 @@ def test_box_ownership_of_a_distributed_level():
     assert cells.max() <= 1.01 * cells.mean()
     zmin = [min(b[0][2] for b, o in zip(fine, own) if o == r) for r in range(8)]
     assert zmin == sorted(zmin)                                                   # ranks follow z
+    # a hierarchy's levels: two interleaved runs per rank, so that the part of a level under the next finer one (the
+    # central half) is spread over ALL ranks -- with one share per rank four of eight ranks owned all of it
+    for level in (ba, fine):
+        own = amrsim.meta_distribution(level, 8, runs_per_rank=2)
+        zs = sorted({b[0][2] for b in level})
+        zlo, zhi = zs[len(zs) // 4], zs[3 * len(zs) // 4]
+        cells, central = np.zeros(8), np.zeros(8)
+        for (lo, hi), r in zip(level, own):
+            c = np.prod([h - l + 1 for l, h in zip(lo, hi)])
+            cells[r] += c
+            if zlo <= lo[2] < zhi:
+                central[r] += c
+        assert cells.max() <= 1.02 * cells.mean()
+        assert central.min() > 0 and central.max() <= 1.35 * central.mean()
