@@ -29,7 +29,10 @@ def _torchrun(script, nproc, port, *args):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", script), *args]
-    return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0 and nproc > _gpus() and ("busy or unavailable" in (r.stdout + r.stderr) or "exclusive" in (r.stdout + r.stderr).lower()):
+        pytest.skip("the GPU is in an exclusive compute mode: %d ranks cannot share it" % nproc)
+    return r
 
 
 @pytest.mark.parametrize("coupling", ["rohde", "subcycle"])
